@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference modules (build container only).
+
+Run once here:  python tests/golden/make_golden.py     (needs /root/reference; CPU, fp32)
+Writes tests/golden/<case>.npz with the reference's pre-clamp output ``pre``
+(torch.clamp patched to identity; the clamped output is checked to equal clamp(pre, 0, 1)).  Inputs and
+weights are NOT stored: they are recomputed from ``oracle.weights`` (RandomState streams).
+Cases are listed in tests/golden/cases.py, shared with the tests.
+"""
+import importlib, os, sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+from oracle.weights import synth_state_dict, synth_frames      # noqa: E402
+from tests.golden.cases import CASES                             # noqa: E402
+
+
+def run_ref(model, sd, x, kw):
+    M = importlib.import_module(f"models.{model}.model").TransformerModel().eval()
+    M.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = M(x, **kw)
+        real = torch.clamp
+        torch.clamp = lambda t, *a, **k: t
+        try:
+            pre = M(x, **kw)
+        finally:
+            torch.clamp = real
+    return out, pre
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    for name, c in CASES.items():
+        sd = synth_state_dict(c["model"], c["wseed"], c.get("gain", 1.0))
+        B, _, H, W = c["shape"]
+        x = synth_frames(B, H, W, seed=c["xseed"])
+        out, pre = run_ref(c["model"], sd, x, c["kw"])
+        st = c.get("stride", 1)
+        assert torch.equal(out, pre.clamp(0.0, 1.0))          # so only the pre-clamp tensor is stored
+        np.savez_compressed(os.path.join(HERE, name + ".npz"),
+                            pre=pre.numpy()[..., ::st, ::st], shape=np.array(out.shape))
+        print(name, tuple(out.shape), "mean %.4f sat0 %.3f sat1 %.3f" % (
+            out.mean().item(), (out == 0).float().mean().item(), (out == 1).float().mean().item()))
+
+
+if __name__ == "__main__":
+    main()

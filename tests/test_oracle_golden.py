@@ -1,0 +1,50 @@
+"""CPU: the oracle restatement vs golden vectors produced by the unmodified reference modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import upscaler_oracle as orc
+from oracle.weights import synth_state_dict, synth_frames
+from tests.golden.cases import CASES
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# fp32 oracle vs fp32 reference: both are fp32 evaluations of the same graph with different
+# summation orders; the bicubic tap arithmetic is restated bit-for-bit.  Tolerance in the test:
+TOL_FP32 = 2e-5
+
+
+def load_case(name):
+    c = CASES[name]
+    B, _, H, W = c["shape"]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    return c, synth_state_dict(c["model"], c["wseed"], c.get("gain", 1.0)), synth_frames(B, H, W, seed=c["xseed"]), g
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if CASES[n]["shape"][2] < 400])
+def test_oracle_matches_reference_golden(name):
+    c, sd, x, g = load_case(name)
+    pre = orc.forward(c["model"], sd, x, pre_clamp=True, **c["kw"]).numpy()
+    assert tuple(g["shape"]) == pre.shape
+    st = c.get("stride", 1)
+    err = np.abs(pre[..., ::st, ::st] - g["pre"]).max()
+    assert err < TOL_FP32, f"{name}: max-abs {err}"
+    out = orc.forward(c["model"], sd, x, **c["kw"]).numpy()
+    assert out.min() >= 0.0 and out.max() <= 1.0
+
+
+def test_oracle_residual_720p_golden():
+    c, sd, x, g = load_case("residual_720p_1080p")
+    pre = orc.forward(c["model"], sd, x, pre_clamp=True, **c["kw"]).numpy()
+    err = np.abs(pre[..., ::8, ::8] - g["pre"]).max()
+    assert err < 1e-4, f"max-abs {err}"      # 8 global-attention blocks over 3600 tokens in fp32
+
+
+def test_oracle_error_behaviour():
+    sd = synth_state_dict("FastTransformer", 0)
+    with pytest.raises(ValueError, match="was not built"):
+        orc.fast_forward(sd, torch.rand(1, 3, 16, 16), upscale_factor=5)
+    sdr = synth_state_dict("ResidualTransformer", 0)
+    with pytest.raises(RuntimeError, match="must match"):
+        orc.residual_forward(sdr, torch.rand(1, 3, 64, 64))
