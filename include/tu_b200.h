@@ -1,0 +1,151 @@
+/*
+ * tu_b200.h — C ABI of libtu_b200.so, the B200 (sm_100a) engine for the forward pass of
+ * TransformerUpscaler's models.  This is the drop-in boundary for the hot path: everything the
+ * reference's `models/<Name>/model.py::TransformerModel.forward` computes through torch ops
+ * (reference: models/WindowTransformer/model.py:224-305, models/FastTransformer/model.py:231-327,
+ * models/ResidualTransformer/model.py:114-165) is reachable through these entry points.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller owns every buffer; the library never allocates or frees device memory, never
+ *     synchronises the device, and enqueues all work on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = success, negative = error; tu_last_error() gives the message (thread-local);
+ *   - dtype codes: TU_F32 = 0, TU_BF16 = 1;
+ *   - activations inside the engine are NHWC (64 channels); images at the boundary are NCHW, like
+ *     the reference's tensors.
+ */
+#ifndef TU_B200_H
+#define TU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TU_F32 0
+#define TU_BF16 1
+
+#define TU_OK 0
+#define TU_ERR_ARG (-1)      /* bad argument (shape / dtype / null pointer)              */
+#define TU_ERR_SCALE (-2)    /* FastTransformer scale not in {2,3,4,6} (utils.py:96-97)   */
+#define TU_ERR_TOKENS (-3)   /* ResidualTransformer token count != 3600 (model.py:140)    */
+#define TU_ERR_WORKSPACE (-4)/* workspace too small                                       */
+#define TU_ERR_CUDA (-5)     /* a CUDA launch failed                                      */
+
+#define TU_MODEL_WINDOW 0
+#define TU_MODEL_FAST 1
+#define TU_MODEL_RESIDUAL 2
+
+int tu_version(void);
+const char *tu_last_error(void);
+/* 1 if the tcgen05 (tensor-core) kernels are used for compute dtype TU_BF16, 0 if the CUDA-core path. */
+int tu_bf16_uses_tcgen05(void);
+void tu_set_bf16_tcgen05(int enable);
+
+/* ---- packed weights -------------------------------------------------------------------------
+ * All pointers are device pointers to tensors repacked by the host side
+ * (transformerupscaler_b200/packing.py documents each layout).  `T` = the compute dtype of the
+ * call (float for TU_F32, bf16 for TU_BF16); biases, LayerNorm affine, the dense relative-position
+ * bias and pos_embed are always fp32.
+ */
+typedef struct TuBlockWeights {
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;       /* (dim)                                   */
+    const void *qkv_w;  const float *qkv_b;           /* T (3dim, dim); rows [q;k;v], q rows and  */
+                                                      /*   q bias pre-scaled by head_dim^-0.5     */
+    const void *proj_w; const float *proj_b;          /* T (dim, dim)                             */
+    const void *fc1_w;  const float *fc1_b;           /* T (4dim, dim)                            */
+    const void *fc2_w;  const float *fc2_b;           /* T (dim, 4dim)                            */
+    const float *rel_bias;                            /* (heads, 64 key j, 64 query i) or NULL    */
+} TuBlockWeights;
+
+typedef struct TuUpsamplerStage {
+    const void *w;      /* T: (r*r phases, 9 taps, Cin, Cout=64) for the 64-ch branch             */
+                        /* float: (27, 3*r*r) for the 3-ch branch (tap-major, out-channel minor)  */
+    const float *b;     /* same out-channel order as w's last dim(s)                              */
+    int r;              /* PixelShuffle factor of this stage                                      */
+} TuUpsamplerStage;
+
+typedef struct TuModelWeights {
+    int model;                  /* TU_MODEL_*                                                     */
+    int dim, heads, n_blocks;   /* 128/8/8 (Window, Residual), 192/12/6 (Fast)                    */
+    const float *conv1_w;       /* (27, 64) fp32: [(ky*3+kx)*3+ci][co]                            */
+    const float *conv1_b;
+    const void *conv2_w;        /* T (9, 64 cout, 64 cin)  [tap][co][ci]                          */
+    const float *conv2_b;
+    const void *down_w;         /* T (9,64,64) or NULL (Fast)                                     */
+    const float *down_b;
+    const void *embed_w;        /* T (dim, 4096) with K ordered (ky, kx, ci)                      */
+    const float *embed_b;
+    const float *pos_embed;     /* fp32 (3600, dim) or NULL                                       */
+    const TuBlockWeights *blocks; /* HOST pointer to n_blocks structs                             */
+    const void *unembed_w;      /* T (4096, dim): row n = (ky*8+kx)*64 + co                       */
+    const float *unembed_b;     /* (64)                                                           */
+    const void *dec1_w;         /* T (9,64,64)                                                    */
+    const float *dec1_b;
+    const float *dec2_w;        /* fp32 (9, 64 ci, 3 co)                                          */
+    const float *dec2_b;        /* (3)                                                            */
+    /* FastTransformer only */
+    TuUpsamplerStage up1[4][2];     /* indexed by scale slot {2,3,4,6} -> 0..3, stage 0/1         */
+    TuUpsamplerStage fin[4][2];
+    const float *up1conv_w;     /* fp32 (9, 64, 3), no bias                                       */
+    const float *finconv_w;     /* fp32 (27, 3)                                                   */
+    const float *finconv_b;     /* (3)                                                            */
+} TuModelWeights;
+
+/* ---- whole-model forward (what TransformerModel.forward calls) --------------------------------
+ * x:   (B,3,H,W) NCHW, dtype in_dtype.     out: (B,3,outH,outW) NCHW, dtype out_dtype, clamped to [0,1]
+ *      (or un-clamped when clamp == 0; tests compare pre-clamp tensors).
+ * compute_dtype: TU_F32 (exact fp32 FFMA path) or TU_BF16 (bf16 operands, fp32 accumulate).
+ * scale: FastTransformer integer factor (ignored by the others).  For FastTransformer the library
+ *      writes the (scale*H, scale*W) image; an antialiased Resize to res_out, when required, is
+ *      tu_resize_bilinear_aa.
+ */
+size_t tu_forward_workspace_bytes(int model, int B, int H, int W, int outH, int outW, int scale, int compute_dtype);
+int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, void *out, int out_dtype,
+               int B, int H, int W, int outH, int outW, int scale, int compute_dtype, int clamp,
+               void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- single ops (exported for the per-op parity tests and for composition) ---------------------- */
+/* conv1: 3->64 3x3 p1 + ReLU, NCHW in -> NHWC out */
+int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const float *b, void *out, int dtype,
+                 int B, int H, int W, void *stream);
+/* 64->(64*nchunk) 3x3 p1 conv on NHWC, stride 1|2, optional ReLU, optional PixelShuffle(r) store
+ * (then nchunk = r*r and chunk p holds phase (i,j) = (p/r, p%r) for all 64 channels). */
+int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype,
+                   int B, int H, int W, int stride, int relu, int nchunk, int ps_r, void *stream);
+/* 64->3 3x3 p1 conv, NHWC in -> planar fp32 (B,3,H,W) out */
+int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const float *b, float *out,
+                       int B, int H, int W, int relu, void *stream);
+/* 3->3r^2 3x3 conv + PixelShuffle(r) on planar fp32 */
+int tu_conv3x3_c3_ps(const float *in, const float *w, const float *b, float *out, int B, int H, int W, int r,
+                     void *stream);
+/* out = clamp?(conv3x3_3to3(in) + addend) -> NCHW image of out_dtype */
+int tu_final_conv_add(const float *in, const float *w, const float *b, const float *addend, void *out,
+                      int out_dtype, int B, int H, int W, int clamp, void *stream);
+/* patch embed (Conv2d k8 s8) as GEMM; reflect-pads feat to x8 when reflect != 0; writes fp32 tokens
+ * window-ordered into zero-initialised (B*nWy*nWx*64, dim) (window != 0) or row-major + pos_embed. */
+int tu_patch_embed(const void *feat, int dtype, const void *w, const float *b, const float *pos_embed,
+                   float *tokens, int B, int H, int W, int Ht, int Wt, int dim, int window, int reflect,
+                   void *stream);
+/* patch unembed (ConvTranspose2d k8 s8) + crop + skip add -> NHWC (B,Hc,Wc,64) */
+int tu_patch_unembed(const float *tokens, const void *w, const float *b, const void *skip, int skipH, int skipW,
+                     void *out, int dtype, int B, int Ht, int Wt, int Hc, int Wc, int dim, int window,
+                     void *stream);
+/* one pre-LN transformer block in place on the fp32 token stream x (M, dim).
+ * window != 0: M = nWin*64, 8x8 window attention with rel_bias; else global attention over S tokens per frame. */
+size_t tu_block_workspace_bytes(int M, int dim, int dtype);
+int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
+                         int dtype, void *workspace, size_t workspace_bytes, void *stream);
+/* out = clamp?(bicubic(x -> outH,outW) + bicubic(res -> outH,outW)); res may be NULL */
+int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW,
+                         void *out, int out_dtype, int B, int outH, int outW, int clamp, void *stream);
+/* antialiased bilinear resize (torchvision Resize on a tensor) of an NCHW image, then optional clamp */
+int tu_resize_bilinear_aa(const void *in, int dtype, void *out, int B, int H, int W, int outH, int outW,
+                          int clamp, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TU_B200_H */

@@ -1,0 +1,112 @@
+"""Helpers for the GPU parity tests: call single ops of libtu_b200 through its C ABI on torch CUDA tensors."""
+import ctypes as C
+
+import torch
+
+from transformerupscaler_b200 import _lib
+
+DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def chk(rc):
+    _lib.check(rc)
+
+
+def stem_conv(x, w27x64, b, dtype):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, H, W, 64, dtype=dtype, device=x.device)
+    chk(lib.tu_stem_conv(p(x), DT[x.dtype], p(w27x64), p(b), p(out), DT[dtype], B, H, W, stream()))
+    return out
+
+
+def conv3x3_c64(x, w, b, stride=1, relu=0, nchunk=1, ps_r=0):
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if ps_r:
+        out = torch.empty(B, Ho * ps_r, Wo * ps_r, 64, dtype=x.dtype, device=x.device)
+    else:
+        out = torch.empty(B, Ho, Wo, 64 * nchunk, dtype=x.dtype, device=x.device)
+    chk(lib.tu_conv3x3_c64(p(x), p(w), p(b), p(out), DT[x.dtype], B, H, W, stride, relu, nchunk, ps_r, stream()))
+    return out
+
+
+def conv64to3(x, w, b, relu=0):
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
+    chk(lib.tu_conv3x3_c64_to3(p(x), DT[x.dtype], p(w), p(b), p(out), B, H, W, relu, stream()))
+    return out
+
+
+def conv3_ps(x, w, b, r):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, 3, H * r, W * r, dtype=torch.float32, device=x.device)
+    chk(lib.tu_conv3x3_c3_ps(p(x), p(w), p(b), p(out), B, H, W, r, stream()))
+    return out
+
+
+def final_conv_add(x, w, b, addend, out_dtype, clamp):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, 3, H, W, dtype=out_dtype, device=x.device)
+    chk(lib.tu_final_conv_add(p(x), p(w), p(b), p(addend), p(out), DT[out_dtype], B, H, W, int(clamp), stream()))
+    return out
+
+
+def patch_embed(feat, w, b, pos, Ht, Wt, dim, window, reflect):
+    lib = _lib.load()
+    B, H, W, _ = feat.shape
+    if window:
+        M = B * ((Ht + 7) // 8) * ((Wt + 7) // 8) * 64
+    else:
+        M = B * Ht * Wt
+    tok = torch.zeros(M, dim, dtype=torch.float32, device=feat.device)
+    chk(lib.tu_patch_embed(p(feat), DT[feat.dtype], p(w), p(b), p(pos), p(tok), B, H, W, Ht, Wt, dim, int(window),
+                           int(reflect), stream()))
+    return tok
+
+
+def patch_unembed(tok, w, b, skip, B, Ht, Wt, Hc, Wc, dim, window):
+    lib = _lib.load()
+    out = torch.empty(B, Hc, Wc, 64, dtype=skip.dtype, device=skip.device)
+    chk(lib.tu_patch_unembed(p(tok), p(w), p(b), p(skip), skip.shape[1], skip.shape[2], p(out), DT[skip.dtype], B, Ht, Wt,
+                             Hc, Wc, dim, int(window), stream()))
+    return out
+
+
+def transformer_block(x, bw, dim, heads, window, S, dtype):
+    lib = _lib.load()
+    M = x.shape[0]
+    n = lib.tu_block_workspace_bytes(M, dim, DT[dtype])
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    chk(lib.tu_transformer_block(p(x), C.byref(bw), M, dim, heads, int(window), S, DT[dtype], p(ws), n, stream()))
+    return x
+
+
+def bicubic_add_clamp(x, res, outH, outW, out_dtype, clamp):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, 3, outH, outW, dtype=out_dtype, device=x.device)
+    rH, rW = (res.shape[2], res.shape[3]) if res is not None else (0, 0)
+    chk(lib.tu_bicubic_add_clamp(p(x), DT[x.dtype], H, W, p(res), rH, rW, p(out), DT[out_dtype], B, outH, outW,
+                                 int(clamp), stream()))
+    return out
+
+
+def resize_aa(x, outH, outW, clamp):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, 3, outH, outW, dtype=x.dtype, device=x.device)
+    chk(lib.tu_resize_bilinear_aa(p(x), DT[x.dtype], p(out), B, H, W, outH, outW, int(clamp), stream()))
+    return out

@@ -1,0 +1,195 @@
+"""GPU: single ops of libtu_b200 (through the C ABI) vs the CPU oracle's restatement of the same op."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import upscaler_oracle as orc
+from oracle.weights import synth_state_dict, synth_frames
+
+pytestmark = pytest.mark.gpu
+
+F32, BF16 = torch.float32, torch.bfloat16
+# fp32 ops: exact-FFMA kernels vs fp32 CPU, differing only in summation order
+TOL32 = 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from transformerupscaler_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def _maxerr(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+def _tol(dtype, scale=1.0):
+    return TOL32 * max(scale, 1.0) if dtype == F32 else 2e-2 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("in_dt,dt", [(F32, F32), (F32, BF16), (BF16, BF16)])
+def test_stem_conv(dev, in_dt, dt):
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200.packing import PackedWeights
+    sd = synth_state_dict("WindowTransformer", 0)
+    x = synth_frames(2, 37, 53, seed=1).to(in_dt)
+    ref = orc.conv3x3_nhwc(x.float().permute(0, 2, 3, 1).contiguous(), sd["conv1.weight"], sd["conv1.bias"], relu=True)
+    w = sd["conv1.weight"].permute(2, 3, 1, 0).reshape(27, 64).contiguous().to(dev)
+    out = G.stem_conv(x.to(dev), w, sd["conv1.bias"].to(dev), dt)
+    assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("stride,relu,shape", [(1, 1, (2, 19, 45)), (2, 0, (1, 33, 41)), (2, 0, (1, 32, 48)), (1, 0, (1, 8, 130))])
+def test_conv3x3_c64(dev, dt, stride, relu, shape):
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(5)
+    B, H, W = shape
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)).to(dt)
+    w = torch.from_numpy(rs.uniform(-0.05, 0.05, (64, 64, 3, 3)).astype(np.float32)).to(dt)
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 64).astype(np.float32))
+    ref = orc.conv3x3_nhwc(x.float(), w.float(), b, stride=stride, relu=bool(relu))
+    wp = w.float().permute(2, 3, 0, 1).reshape(9, 64, 64).contiguous().to(dev, dt)
+    out = G.conv3x3_c64(x.to(dev), wp, b.to(dev), stride=stride, relu=relu)
+    assert out.shape == ref.shape
+    assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("r", [2, 3, 6])
+def test_conv3x3_pixelshuffle(dev, dt, r):
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(6)
+    B, H, W = 1, 13, 21
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)).to(dt)
+    w = torch.from_numpy(rs.uniform(-0.05, 0.05, (64 * r * r, 64, 3, 3)).astype(np.float32)).to(dt)
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 64 * r * r).astype(np.float32))
+    ref = orc.pixel_shuffle_nhwc(orc.conv3x3_nhwc(x.float(), w.float(), b), r)
+    wp = w.float().reshape(64, r * r, 64, 3, 3).permute(1, 3, 4, 0, 2).reshape(r * r, 9, 64, 64).contiguous().to(dev, dt)
+    bp = b.reshape(64, r * r).t().reshape(-1).contiguous().to(dev)
+    out = G.conv3x3_c64(x.to(dev), wp, bp, nchunk=r * r, ps_r=r)
+    assert out.shape == ref.shape
+    assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("bias,relu", [(True, 0), (False, 1)])
+def test_conv64to3(dev, dt, bias, relu):
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(7)
+    x = torch.from_numpy(rs.uniform(-1, 1, (2, 17, 150, 64)).astype(np.float32)).to(dt)
+    w = torch.from_numpy(rs.uniform(-0.05, 0.05, (3, 64, 3, 3)).astype(np.float32))
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 3).astype(np.float32)) if bias else None
+    ref = orc.conv3x3_nhwc(x.float(), w, b, relu=bool(relu)).permute(0, 3, 1, 2)
+    wp = w.permute(2, 3, 1, 0).reshape(9, 64, 3).contiguous().to(dev)
+    out = G.conv64to3(x.to(dev), wp, None if b is None else b.to(dev), relu=relu)
+    assert _maxerr(out, ref) < TOL32 * 4
+
+
+@pytest.mark.parametrize("r", [2, 3, 6])
+def test_conv3_ps_and_final(dev, r):
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(8)
+    B, H, W = 2, 11, 70
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, 3, H, W)).astype(np.float32))
+    w = torch.from_numpy(rs.uniform(-0.2, 0.2, (3 * r * r, 3, 3, 3)).astype(np.float32))
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 3 * r * r).astype(np.float32))
+    ref = orc.pixel_shuffle_nhwc(orc.conv3x3_nhwc(x.permute(0, 2, 3, 1).contiguous(), w, b), r)
+    wp = w.permute(2, 3, 1, 0).reshape(27, 3 * r * r).contiguous().to(dev)
+    out = G.conv3_ps(x.to(dev), wp, b.to(dev), r)
+    assert _maxerr(out, ref.permute(0, 3, 1, 2)) < TOL32
+    # final 3->3 conv + addend + clamp
+    w2 = torch.from_numpy(rs.uniform(-0.2, 0.2, (3, 3, 3, 3)).astype(np.float32))
+    b2 = torch.from_numpy(rs.uniform(-0.1, 0.1, 3).astype(np.float32))
+    add = torch.from_numpy(rs.uniform(0, 1, tuple(out.shape)).astype(np.float32))
+    ref2 = (orc.conv3x3_nhwc(ref, w2, b2).permute(0, 3, 1, 2) + add).clamp(0, 1)
+    out2 = G.final_conv_add(out, w2.permute(2, 3, 1, 0).reshape(27, 3).contiguous().to(dev), b2.to(dev), add.to(dev), F32, True)
+    assert _maxerr(out2, ref2) < TOL32
+
+
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("model,Hf,Wf", [("WindowTransformer", 36, 52), ("FastTransformer", 36, 52), ("FastTransformer", 64, 80)])
+def test_patch_embed_unembed(dev, dt, model, Hf, Wf):
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(9)
+    sd = synth_state_dict(model, 3)
+    dim = sd["patch_embed.weight"].shape[0]
+    fast = model == "FastTransformer"
+    B = 2
+    feat = torch.from_numpy(rs.uniform(-1, 1, (B, Hf, Wf, 64)).astype(np.float32)).to(dt)
+    Ht, Wt = ((Hf + 7) // 8, (Wf + 7) // 8) if fast else (Hf // 8, Wf // 8)
+    fpad = orc.reflect_pad_nhwc(feat.float(), Ht * 8 - Hf, Wt * 8 - Wf) if fast else feat.float()
+    we = sd["patch_embed.weight"].to(dt).float()
+    tok_ref = orc.patch_embed_nhwc(fpad, we, sd["patch_embed.bias"])            # (B,Ht,Wt,dim)
+    wp = we.permute(0, 2, 3, 1).reshape(dim, 4096).contiguous().to(dev, dt)
+    tok = G.patch_embed(feat.to(dev), wp, sd["patch_embed.bias"].to(dev), None, Ht, Wt, dim, True, fast)
+    nWy, nWx = (Ht + 7) // 8, (Wt + 7) // 8
+    grid = tok.reshape(B, nWy, nWx, 8, 8, dim).permute(0, 1, 3, 2, 4, 5).reshape(B, nWy * 8, nWx * 8, dim)
+    scale = tok_ref.abs().max().item()
+    assert _maxerr(grid[:, :Ht, :Wt], tok_ref) < _tol(dt, scale)
+    assert grid[:, Ht:].abs().max().item() == 0 and grid[:, :, Wt:].abs().max().item() == 0
+    # unembed + crop + skip
+    wu = sd["patch_unembed.weight"].to(dt).float()
+    Hc, Wc = (Hf, Wf) if fast else (min(Hf, 8 * Ht), min(Wf, 8 * Wt))
+    ref = orc.patch_unembed_nhwc(grid[:, :Ht, :Wt].cpu().contiguous(), wu, sd["patch_unembed.bias"])[:, :Hc, :Wc] + feat.float()[:, :Hc, :Wc]
+    wup = wu.permute(2, 3, 1, 0).reshape(4096, dim).contiguous().to(dev, dt)
+    out = G.patch_unembed(tok, wup, sd["patch_unembed.bias"].to(dev), feat.to(dev), B, Ht, Wt, Hc, Wc, dim, True)
+    assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("model", ["WindowTransformer", "FastTransformer", "ResidualTransformer"])
+def test_transformer_block(dev, dt, model):
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200.packing import PackedWeights
+    rs = np.random.RandomState(10)
+    sd = synth_state_dict(model, 4)
+    pw = PackedWeights(model, sd, dt, dev)
+    dim, heads = pw.dim, pw.heads
+    if model == "ResidualTransformer":
+        B, S = 2, 300
+        x = torch.from_numpy(rs.standard_normal((B, S, dim)).astype(np.float32))
+        sdq = {k: (v.to(dt).float() if v.dim() == 2 else v) for k, v in sd.items()}
+        ref = orc.mha_block(x, sdq, "transformer_blocks.1.", heads, F32)
+        out = G.transformer_block(x.reshape(B * S, dim).to(dev).clone(), pw.blocks[1], dim, heads, False, S, dt)
+        out = out.reshape(B, S, dim)
+    else:
+        nW = 5
+        x = torch.from_numpy(rs.standard_normal((nW, 64, dim)).astype(np.float32))
+        sdq = {k: (v.to(dt).float() if (v.dim() == 2 and "table" not in k) else v) for k, v in sd.items()}
+        ref = orc.window_block(x, sdq, "window_blocks.1.", heads, F32)
+        out = G.transformer_block(x.reshape(nW * 64, dim).to(dev).clone(), pw.blocks[1], dim, heads, True, 0, dt)
+        out = out.reshape(nW, 64, dim)
+    tol = 5e-5 if dt == F32 else 6e-2       # bf16: activations (LN out, qkv, attn out, MLP hidden) rounded to bf16
+    assert _maxerr(out, ref) < tol
+
+
+@pytest.mark.parametrize("in_dt,out_dt", [(F32, F32), (BF16, BF16), (F32, BF16)])
+@pytest.mark.parametrize("geom", [((72, 104), (36, 52), (108, 156)), ((64, 80), (32, 40), (128, 160)), ((45, 37), (20, 16), (200, 111))])
+def test_bicubic_add_clamp(dev, in_dt, out_dt, geom):
+    from tests import gpu_helpers as G
+    (H, W), (rH, rW), (oH, oW) = geom
+    x = synth_frames(2, H, W, seed=3).to(in_dt)
+    rs = np.random.RandomState(11)
+    res = torch.from_numpy(rs.uniform(-0.3, 0.3, (2, 3, rH, rW)).astype(np.float32))
+    ref = orc.bicubic_nchw(x.float(), (oH, oW)) + orc.bicubic_nchw(res, (oH, oW))
+    out = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, False)
+    tol = 2e-6 if out_dt == F32 else 8e-3        # bf16 store: half-ulp of values up to ~1.3
+    assert _maxerr(out, ref) < tol
+    outc = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, True)
+    assert _maxerr(outc, ref.clamp(0, 1)) < tol
+    # x only (residual absent)
+    out1 = G.bicubic_add_clamp(x.to(dev), None, oH, oW, out_dt, False)
+    assert _maxerr(out1, orc.bicubic_nchw(x.float(), (oH, oW))) < tol
+
+
+@pytest.mark.parametrize("geom", [((80, 112), (60, 84)), ((144, 192), (100, 150)), ((50, 70), (50, 35))])
+def test_resize_aa(dev, geom):
+    from tests import gpu_helpers as G
+    (H, W), (oH, oW) = geom
+    x = synth_frames(2, H, W, seed=5)
+    ref = orc.aa_bilinear_resize_nchw(x, (oH, oW))
+    out = G.resize_aa(x.to(dev), oH, oW, False)
+    assert _maxerr(out, ref) < 2e-6

@@ -1,0 +1,308 @@
+// C-ABI entry points of libtu_b200: error plumbing, the GEMM-shaped single ops, and the whole-model
+// forward drivers that enqueue every kernel of a TransformerModel.forward on the caller's stream.
+#include <string.h>
+
+#include "gemm_simt.cuh"
+#include "tc/tc_api.cuh"
+
+namespace tu {
+
+static thread_local std::string g_err;
+static int g_use_tc = 1;
+
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string("tu: CUDA error in ") + what + ": " + cudaGetErrorString(e);
+    return TU_ERR_CUDA;
+}
+
+template <typename T> int transformer_block_simt(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
+
+static inline bool tc_on(int dtype) { return dtype == TU_BF16 && g_use_tc && tc_available(); }
+
+// ------------------------------------------------------------------ op launchers (typed)
+template <typename T>
+static int conv3x3_c64(const T *in, const T *w, const float *b, T *out, int B, int H, int W, int stride, int relu,
+                       int nchunk, int ps_r, cudaStream_t st) {
+    const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+    const int M = B * Ho * Wo;
+    AConv3x3<T> a{in, M, H, W, Ho, Wo, stride};
+    WDesc<T> wd{w, 64, 64L * 64, 9L * 64 * 64};
+    EpiConv<T> e{out, b, Ho, Wo, relu, ps_r, nchunk * 64};
+    return launch_gemm_simt<T>(a, wd, M, nchunk * 64, 576, e, st, "conv3x3_c64");
+}
+
+template <typename T>
+static int patch_embed(const T *feat, const T *w, const float *b, const float *pos, float *tok, int B, int H, int W,
+                       int Ht, int Wt, int dim, int window, int reflect, cudaStream_t st) {
+    const int M = B * Ht * Wt;
+    APatch<T> a{feat, M, H, W, Ht, Wt, reflect};
+    WDesc<T> wd{w, 4096, 0, 64L * 4096};
+    EpiEmbed e{tok, b, pos, Ht, Wt, dim, window, (Ht + 7) / 8, (Wt + 7) / 8};
+    return launch_gemm_simt<T>(a, wd, M, dim, 4096, e, st, "patch_embed");
+}
+
+template <typename T>
+static int patch_unembed(const float *tok, const T *w, const float *b, const T *skip, int skipH, int skipW, T *out, int B,
+                         int Ht, int Wt, int Hc, int Wc, int dim, int window, cudaStream_t st) {
+    const int M = B * Ht * Wt;
+    ATokens a{tok, M, Ht, Wt, dim, window, (Ht + 7) / 8, (Wt + 7) / 8};
+    WDesc<T> wd{w, dim, 0, 64L * dim};
+    EpiUnembed<T> e{out, b, skip, Ht, Wt, Hc, Wc, skipH, skipW};
+    return launch_gemm_simt<T>(a, wd, M, 4096, dim, e, st, "patch_unembed");
+}
+
+// ------------------------------------------------------------------ workspace arena
+struct Arena {
+    char *base;
+    size_t off, cap;
+    bool dry;
+    void *get(size_t bytes) {
+        size_t o = off;
+        off += align_up(bytes, 1024);
+        return dry ? (void *)nullptr : (void *)(base + o);
+    }
+};
+
+static int scale_slot(int s) { return s == 2 ? 0 : s == 3 ? 1 : s == 4 ? 2 : s == 6 ? 3 : -1; }
+
+// Runs (or, with a.dry, only sizes) one forward.  TI/TO are handled by dtype codes in the leaf launchers.
+template <typename T>
+static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, void *out, int out_dtype, int B, int H,
+                        int W, int outH, int outW, int scale, int clamp, Arena &a, cudaStream_t st) {
+    const int dt = sizeof(T) == 2 ? TU_BF16 : TU_F32;
+    const bool dry = a.dry;
+    const int model = w->model, dim = w->dim, heads = w->heads;
+    const bool fast = model == TU_MODEL_FAST, window = model != TU_MODEL_RESIDUAL;
+    int rc;
+    void *stv = (void *)st;
+
+    if (fast && scale_slot(scale) < 0) {
+        set_error("Requested scale=" + std::to_string(scale) + " was not built.");
+        return TU_ERR_SCALE;
+    }
+    // feature-map geometry
+    const int Hd = fast ? H : (H - 1) / 2 + 1, Wd = fast ? W : (W - 1) / 2 + 1;   // grid the tokens come from
+    const int Ht = fast ? (H + 7) / 8 : Hd / 8, Wt = fast ? (W + 7) / 8 : Wd / 8;  // Fast reflect-pads up, others floor
+    if (Ht < 1 || Wt < 1) {
+        set_error("tu: input too small for an 8x8 patch grid");
+        return TU_ERR_ARG;
+    }
+    if (model == TU_MODEL_RESIDUAL) {
+        if (Ht * Wt != 3600) {
+            set_error("The size of tensor a (" + std::to_string(Ht * Wt) +
+                      ") must match the size of tensor b (3600) at non-singleton dimension 1");
+            return TU_ERR_TOKENS;
+        }
+        if (Hd != 8 * Ht || Wd != 8 * Wt) {
+            set_error("tu: ResidualTransformer skip connection needs a feature map that is a multiple of 8");
+            return TU_ERR_ARG;
+        }
+    }
+    const int nWy = (Ht + 7) / 8, nWx = (Wt + 7) / 8;
+    const int Mtok = window ? B * nWy * nWx * 64 : B * Ht * Wt;
+    const int Hc = fast ? H : min(Hd, 8 * Ht), Wc = fast ? W : min(Wd, 8 * Wt);
+
+    const size_t full = (size_t)B * H * W * 64 * sizeof(T);
+    T *f1 = (T *)a.get(full);
+    T *f2 = (T *)a.get(full);
+    T *fd = fast ? f2 : (T *)a.get((size_t)B * Hd * Wd * 64 * sizeof(T));
+    float *tok = (float *)a.get((size_t)Mtok * dim * sizeof(float));
+    const size_t bws = tu_block_workspace_bytes(Mtok, dim, dt);
+    void *blk = a.get(bws);
+    T *comb = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
+    T *dec = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
+    float *res = (float *)a.get((size_t)B * 3 * Hc * Wc * sizeof(float));
+
+    // ---- encoder
+    if (!dry) {
+        if ((rc = tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_b, f1, dt, B, H, W, stv))) return rc;
+        if ((rc = tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv))) return rc;
+        if (!fast)
+            if ((rc = tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv))) return rc;
+    }
+
+    // ---- FastTransformer branch A: sub-pixel upsample of feat, then 64->3 (+ReLU)
+    float *upA = nullptr;
+    if (fast) {
+        const int slot = scale_slot(scale);
+        const int nst = scale == 4 ? 2 : 1;
+        const T *cur = f2;
+        int ch = H, cw = W;
+        for (int s = 0; s < nst; ++s) {
+            const TuUpsamplerStage &sg = w->up1[slot][s];
+            const int r = sg.r;
+            T *nxt = (T *)a.get((size_t)B * ch * r * cw * r * 64 * sizeof(T));
+            if (!dry)
+                if ((rc = tu_conv3x3_c64(cur, sg.w, sg.b, nxt, dt, B, ch, cw, 1, 0, r * r, r, stv))) return rc;
+            cur = nxt;
+            ch *= r;
+            cw *= r;
+        }
+        upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
+        if (!dry)
+            if ((rc = tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, nullptr, upA, B, ch, cw, 1, stv))) return rc;
+    }
+
+    // ---- tokens
+    if (!dry) {
+        if (window && (Ht % 8 || Wt % 8)) {
+            cudaError_t e = cudaMemsetAsync(tok, 0, (size_t)Mtok * dim * sizeof(float), st);   // zero pad tokens
+            if (e != cudaSuccess) return cuda_fail(e, "memset tokens");
+        }
+        if ((rc = tu_patch_embed(fd, dt, w->embed_w, w->embed_b, w->pos_embed, tok, B, Hd, Wd, Ht, Wt, dim, window ? 1 : 0,
+                                 fast ? 1 : 0, stv)))
+            return rc;
+        for (int i = 0; i < w->n_blocks; ++i)
+            if ((rc = tu_transformer_block(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws, stv)))
+                return rc;
+        if ((rc = tu_patch_unembed(tok, w->unembed_w, w->unembed_b, fd, Hd, Wd, comb, dt, B, Ht, Wt, Hc, Wc, dim,
+                                   window ? 1 : 0, stv)))
+            return rc;
+        // ---- decoder
+        if ((rc = tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv))) return rc;
+        if ((rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_b, res, B, Hc, Wc, 0, stv))) return rc;
+    }
+
+    if (!fast) {
+        if (!dry)
+            if ((rc = tu_bicubic_add_clamp(x, in_dtype, H, W, res, Hc, Wc, out, out_dtype, B, outH, outW, clamp, stv)))
+                return rc;
+        return TU_OK;
+    }
+    // ---- FastTransformer branch B: sub-pixel upsample of the residual image, 3->3 conv, sum, clamp
+    {
+        const int slot = scale_slot(scale);
+        const int nst = scale == 4 ? 2 : 1;
+        const float *cur = res;
+        int ch = H, cw = W;
+        for (int s = 0; s < nst; ++s) {
+            const TuUpsamplerStage &sg = w->fin[slot][s];
+            const int r = sg.r;
+            float *nxt = (float *)a.get((size_t)B * 3 * ch * r * cw * r * sizeof(float));
+            if (!dry)
+                if ((rc = tu_conv3x3_c3_ps(cur, (const float *)sg.w, sg.b, nxt, B, ch, cw, r, stv))) return rc;
+            cur = nxt;
+            ch *= r;
+            cw *= r;
+        }
+        if (!dry) {
+            if (ch != outH || cw != outW) {
+                set_error("tu: FastTransformer output buffer must be (scale*H, scale*W)");
+                return TU_ERR_ARG;
+            }
+            if ((rc = tu_final_conv_add(cur, w->finconv_w, w->finconv_b, upA, out, out_dtype, B, ch, cw, clamp, stv)))
+                return rc;
+        }
+    }
+    return TU_OK;
+}
+
+}  // namespace tu
+
+using namespace tu;
+
+extern "C" int tu_version(void) { return 100; }
+extern "C" const char *tu_last_error(void) { return g_err.c_str(); }
+extern "C" int tu_bf16_uses_tcgen05(void) { return g_use_tc && tc_available(); }
+extern "C" void tu_set_bf16_tcgen05(int enable) { g_use_tc = enable; }
+
+extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype, int B, int H, int W,
+                              int stride, int relu, int nchunk, int ps_r, void *stream) {
+    TU_CHECK_ARG(in && w && out && B > 0 && H > 0 && W > 0, "conv3x3_c64: bad argument");
+    TU_CHECK_ARG(stride == 1 || stride == 2, "conv3x3_c64: stride must be 1 or 2");
+    TU_CHECK_ARG(nchunk >= 1 && (ps_r == 0 || (ps_r * ps_r == nchunk && stride == 1)), "conv3x3_c64: bad chunking");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc_on(dtype)) {
+        int rc = tc_conv3x3_c64((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
+        if (rc != TU_TC_UNSUPPORTED) return rc;
+    }
+    if (dtype == TU_F32)
+        return conv3x3_c64<float>((const float *)in, (const float *)w, b, (float *)out, B, H, W, stride, relu, nchunk, ps_r, st);
+    if (dtype == TU_BF16)
+        return conv3x3_c64<bf16>((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
+    TU_CHECK_ARG(false, "conv3x3_c64: bad dtype");
+}
+
+extern "C" int tu_patch_embed(const void *feat, int dtype, const void *w, const float *b, const float *pos_embed,
+                              float *tokens, int B, int H, int W, int Ht, int Wt, int dim, int window, int reflect,
+                              void *stream) {
+    TU_CHECK_ARG(feat && w && b && tokens && B > 0 && Ht > 0 && Wt > 0, "patch_embed: bad argument");
+    TU_CHECK_ARG(reflect ? (8 * Ht - H < 8 && 8 * Wt - W < 8 && 8 * Ht >= H && 8 * Wt >= W) : (8 * Ht <= H && 8 * Wt <= W),
+                 "patch_embed: token grid does not match the feature map");
+    TU_CHECK_ARG(!reflect || ((8 * Ht - H) < H && (8 * Wt - W) < W), "patch_embed: reflect pad larger than the input");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TU_F32)
+        return patch_embed<float>((const float *)feat, (const float *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, reflect, st);
+    if (dtype == TU_BF16)
+        return patch_embed<bf16>((const bf16 *)feat, (const bf16 *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, reflect, st);
+    TU_CHECK_ARG(false, "patch_embed: bad dtype");
+}
+
+extern "C" int tu_patch_unembed(const float *tokens, const void *w, const float *b, const void *skip, int skipH, int skipW,
+                                void *out, int dtype, int B, int Ht, int Wt, int Hc, int Wc, int dim, int window,
+                                void *stream) {
+    TU_CHECK_ARG(tokens && w && b && skip && out && B > 0 && Ht > 0 && Wt > 0, "patch_unembed: bad argument");
+    TU_CHECK_ARG(Hc <= skipH && Wc <= skipW && Hc <= 8 * Ht && Wc <= 8 * Wt, "patch_unembed: crop larger than its sources");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TU_F32)
+        return patch_unembed<float>(tokens, (const float *)w, b, (const float *)skip, skipH, skipW, (float *)out, B, Ht, Wt, Hc, Wc, dim, window, st);
+    if (dtype == TU_BF16)
+        return patch_unembed<bf16>(tokens, (const bf16 *)w, b, (const bf16 *)skip, skipH, skipW, (bf16 *)out, B, Ht, Wt, Hc, Wc, dim, window, st);
+    TU_CHECK_ARG(false, "patch_unembed: bad dtype");
+}
+
+static int check_forward_args(const TuModelWeights *w, int B, int H, int W, int outH, int outW, int compute_dtype) {
+    TU_CHECK_ARG(w, "forward: null weights");
+    TU_CHECK_ARG(w->model >= 0 && w->model <= 2, "forward: bad model id");
+    TU_CHECK_ARG(B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "forward: bad shape");
+    TU_CHECK_ARG(compute_dtype == TU_F32 || compute_dtype == TU_BF16, "forward: bad compute dtype");
+    TU_CHECK_ARG((long)B * H * W < (1L << 31) / 64 * 16, "forward: batch too large for 32-bit pixel indexing");
+    return TU_OK;
+}
+
+extern "C" size_t tu_forward_workspace_bytes(int model, int B, int H, int W, int outH, int outW, int scale,
+                                             int compute_dtype) {
+    TuModelWeights w;
+    memset(&w, 0, sizeof(w));
+    w.model = model;
+    w.dim = model == TU_MODEL_FAST ? 192 : 128;
+    w.heads = w.dim / 16;
+    w.n_blocks = model == TU_MODEL_FAST ? 6 : 8;
+    for (int s = 0; s < 4; ++s) {
+        const int r0 = s == 0 ? 2 : s == 1 ? 3 : s == 2 ? 2 : 6;
+        w.up1[s][0].r = w.fin[s][0].r = r0;
+        w.up1[s][1].r = w.fin[s][1].r = 2;
+    }
+    if (check_forward_args(&w, B, H, W, outH, outW, compute_dtype)) return 0;
+    Arena a{nullptr, 0, 0, true};
+    int rc = compute_dtype == TU_F32
+                 ? forward_impl<float>(&w, nullptr, TU_F32, nullptr, TU_F32, B, H, W, outH, outW, scale, 1, a, 0)
+                 : forward_impl<bf16>(&w, nullptr, TU_F32, nullptr, TU_F32, B, H, W, outH, outW, scale, 1, a, 0);
+    return rc == TU_OK ? a.off : 0;
+}
+
+extern "C" int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, void *out, int out_dtype, int B, int H,
+                          int W, int outH, int outW, int scale, int compute_dtype, int clamp, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+    int rc = check_forward_args(w, B, H, W, outH, outW, compute_dtype);
+    if (rc) return rc;
+    TU_CHECK_ARG(x && out && workspace, "forward: null buffer");
+    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16) && (out_dtype == TU_F32 || out_dtype == TU_BF16), "forward: bad i/o dtype");
+    TU_CHECK_ARG(w->blocks && w->n_blocks > 0 && w->dim == w->heads * 16, "forward: bad transformer configuration");
+    // size pass, then the real pass
+    Arena dry{nullptr, 0, 0, true};
+    rc = compute_dtype == TU_F32
+             ? forward_impl<float>(w, x, in_dtype, out, out_dtype, B, H, W, outH, outW, scale, clamp, dry, 0)
+             : forward_impl<bf16>(w, x, in_dtype, out, out_dtype, B, H, W, outH, outW, scale, clamp, dry, 0);
+    if (rc) return rc;
+    if (dry.off > workspace_bytes) {
+        set_error("tu: forward workspace too small: need " + std::to_string(dry.off) + " bytes");
+        return TU_ERR_WORKSPACE;
+    }
+    Arena a{(char *)workspace, 0, workspace_bytes, false};
+    cudaStream_t st = (cudaStream_t)stream;
+    return compute_dtype == TU_F32
+               ? forward_impl<float>(w, x, in_dtype, out, out_dtype, B, H, W, outH, outW, scale, clamp, a, st)
+               : forward_impl<bf16>(w, x, in_dtype, out, out_dtype, B, H, W, outH, outW, scale, clamp, a, st);
+}

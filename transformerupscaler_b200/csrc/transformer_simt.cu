@@ -1,0 +1,250 @@
+// Pre-LN transformer block pieces on CUDA cores (exact fp32 math): LayerNorm, 8x8 window attention with
+// dense relative-position bias, flash-style global attention, and the block driver that strings them
+// together with the SIMT GEMMs.
+// Reference: WindowAttention / WindowTransformerBlock (WindowTransformer/model.py:63-170,
+// FastTransformer/model.py:65-172) and TransformerBlock with nn.MultiheadAttention
+// (ResidualTransformer/model.py:22-50).
+#include "gemm_simt.cuh"
+
+namespace tu {
+
+// ------------------------------------------------------------------ LayerNorm (eps 1e-5, biased variance)
+// fp32 stream x (M, D) -> T (M, D).  One warp per token; D = 32 * PER.
+template <typename T, int PER>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict__ x, const float *__restrict__ g,
+                                                        const float *__restrict__ b, T *__restrict__ out, int M) {
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    constexpr int D = 32 * PER;
+    const float *row = x + (long)warp * D;
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = row[lane + 32 * i]; s += v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int c = lane + 32 * i;
+        out[(long)warp * D + c] = from_f<T>((v[i] - mean) * rstd * g[c] + b[c]);
+    }
+}
+
+// ------------------------------------------------------------------ window attention (64 tokens, head_dim 16)
+// qkv (nWin*64, 3*dim) T with q pre-scaled; out (nWin*64, dim) T.  One CTA per (window, head), one
+// query per thread; K, V of the head in shared memory (broadcast reads); softmax over 64 keys in registers.
+// bias_t[h][j][i] (key-major) so that the 64 threads of a CTA read consecutive floats.
+template <typename T>
+__global__ void __launch_bounds__(64) window_attn_kernel(const T *__restrict__ qkv, const float *__restrict__ bias_t,
+                                                         T *__restrict__ out, int dim, int heads) {
+    __shared__ float ks[64][16];
+    __shared__ float vs[64][16];
+    const int win = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
+    const T *base = qkv + ((long)win * 64 + i) * (3 * dim) + h * 16;
+    float q[16];
+#pragma unroll
+    for (int d = 0; d < 16; d += 4) {
+        float4 a = load4(base + d), k4 = load4(base + dim + d), v4 = load4(base + 2 * dim + d);
+        q[d] = a.x; q[d + 1] = a.y; q[d + 2] = a.z; q[d + 3] = a.w;
+        ks[i][d] = k4.x; ks[i][d + 1] = k4.y; ks[i][d + 2] = k4.z; ks[i][d + 3] = k4.w;
+        vs[i][d] = v4.x; vs[i][d + 1] = v4.y; vs[i][d + 2] = v4.z; vs[i][d + 3] = v4.w;
+    }
+    __syncthreads();
+    const float *bp = bias_t + (long)h * 4096 + i;
+    float s[64];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) a = fmaf(q[d], ks[j][d], a);
+        a += bp[j * 64];
+        s[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float p = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
+    }
+    T *op = out + ((long)win * 64 + i) * dim + h * 16;
+#pragma unroll
+    for (int d = 0; d < 16; d += 4) store4(op + d, make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]));
+}
+
+// ------------------------------------------------------------------ global attention (S tokens per frame, head_dim 16)
+// qkv (B*S, 3*dim) T with q pre-scaled; out (B*S, dim) T.  CTA = 128 queries of one (frame, head);
+// keys/values streamed through shared memory in tiles of 128 with an online softmax (never materialises SxS).
+template <typename T>
+__global__ void __launch_bounds__(128) global_attn_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int dim) {
+    __shared__ float ks[128][16];
+    __shared__ float vs[128][16];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int qi = blockIdx.x * 128 + threadIdx.x;
+    const bool active = qi < S;
+    const long frame = (long)b * S;
+    float q[16], o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { q[d] = 0.f; o[d] = 0.f; }
+    if (active) {
+        const T *qp = qkv + (frame + qi) * (3 * dim) + h * 16;
+#pragma unroll
+        for (int d = 0; d < 16; d += 4) {
+            float4 a = load4(qp + d);
+            q[d] = a.x; q[d + 1] = a.y; q[d + 2] = a.z; q[d + 3] = a.w;
+        }
+    }
+    float mx = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < S; k0 += 128) {
+        __syncthreads();
+        int kj = k0 + threadIdx.x;
+        if (kj < S) {
+            const T *kp = qkv + (frame + kj) * (3 * dim) + dim + h * 16;
+#pragma unroll
+            for (int d = 0; d < 16; d += 4) {
+                float4 k4 = load4(kp + d), v4 = load4(kp + dim + d);
+                ks[threadIdx.x][d] = k4.x; ks[threadIdx.x][d + 1] = k4.y; ks[threadIdx.x][d + 2] = k4.z; ks[threadIdx.x][d + 3] = k4.w;
+                vs[threadIdx.x][d] = v4.x; vs[threadIdx.x][d + 1] = v4.y; vs[threadIdx.x][d + 2] = v4.z; vs[threadIdx.x][d + 3] = v4.w;
+            }
+        }
+        __syncthreads();
+        const int nk = min(128, S - k0);
+        // two passes over the tile: tile max first, then one rescale of the running state
+        float tmx = mx;
+        for (int j = 0; j < nk; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) a = fmaf(q[d], ks[j][d], a);
+            tmx = fmaxf(tmx, a);
+        }
+        const float corr = expf(mx - tmx);   // exp(-inf) = 0 on the first tile
+        l *= corr;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] *= corr;
+        mx = tmx;
+        for (int j = 0; j < nk; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) a = fmaf(q[d], ks[j][d], a);
+            float p = expf(a - mx);
+            l += p;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) o[d] = fmaf(p, vs[j][d], o[d]);
+        }
+    }
+    if (!active) return;
+    const float inv = 1.0f / l;
+    T *op = out + (frame + qi) * dim + h * 16;
+#pragma unroll
+    for (int d = 0; d < 16; d += 4)
+        store4(op + d, make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv));
+}
+
+// ------------------------------------------------------------------ host launchers
+template <typename T>
+int launch_layernorm(const float *x, const float *g, const float *b, T *out, int M, int dim, cudaStream_t st) {
+    dim3 grid(ceil_div(M, 8));
+    if (dim == 128)
+        layernorm_kernel<T, 4><<<grid, 256, 0, st>>>(x, g, b, out, M);
+    else if (dim == 192)
+        layernorm_kernel<T, 6><<<grid, 256, 0, st>>>(x, g, b, out, M);
+    else {
+        set_error("tu: layernorm supports dim 128 or 192");
+        return TU_ERR_ARG;
+    }
+    TU_CHECK_LAUNCH("layernorm");
+    return TU_OK;
+}
+
+// workspace: ln (M,dim) T | qkv (M,3dim) T [reused as mlp hidden (M,4dim) T] | attn (M,dim) T
+static size_t block_ws(int M, int dim, int dtype) {
+    size_t e = dtype_size(dtype);
+    return align_up((size_t)M * dim * e, 256) + align_up((size_t)M * 4 * dim * e, 256) + align_up((size_t)M * dim * e, 256);
+}
+
+template <typename T>
+int transformer_block_simt(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, void *ws,
+                           cudaStream_t st) {
+    char *p = (char *)ws;
+    T *ln = (T *)p;
+    p += align_up((size_t)M * dim * sizeof(T), 256);
+    T *big = (T *)p;
+    p += align_up((size_t)M * 4 * dim * sizeof(T), 256);
+    T *att = (T *)p;
+    int rc;
+    if ((rc = launch_layernorm<T>(x, w->ln1_w, w->ln1_b, ln, M, dim, st))) return rc;
+    {
+        ARows<T> a{ln, M, dim};
+        WDesc<T> wd{(const T *)w->qkv_w, dim, 0, 64L * dim};
+        EpiStore<T, 0> e{big, w->qkv_b, 3L * dim};
+        if ((rc = launch_gemm_simt<T>(a, wd, M, 3 * dim, dim, e, st, "qkv"))) return rc;
+    }
+    if (window) {
+        dim3 grid(M / 64, heads);
+        window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
+        TU_CHECK_LAUNCH("window_attn");
+    } else {
+        dim3 grid(ceil_div(S, 128), heads, M / S);
+        global_attn_kernel<T><<<grid, 128, 0, st>>>(big, att, S, dim);
+        TU_CHECK_LAUNCH("global_attn");
+    }
+    {
+        ARows<T> a{att, M, dim};
+        WDesc<T> wd{(const T *)w->proj_w, dim, 0, 64L * dim};
+        EpiResidual e{x, w->proj_b, dim};
+        if ((rc = launch_gemm_simt<T>(a, wd, M, dim, dim, e, st, "proj"))) return rc;
+    }
+    if ((rc = launch_layernorm<T>(x, w->ln2_w, w->ln2_b, ln, M, dim, st))) return rc;
+    {
+        ARows<T> a{ln, M, dim};
+        WDesc<T> wd{(const T *)w->fc1_w, dim, 0, 64L * dim};
+        EpiStore<T, 2> e{big, w->fc1_b, 4L * dim};
+        if ((rc = launch_gemm_simt<T>(a, wd, M, 4 * dim, dim, e, st, "fc1"))) return rc;
+    }
+    {
+        ARows<T> a{big, M, 4L * dim};
+        WDesc<T> wd{(const T *)w->fc2_w, 4 * dim, 0, 64L * 4 * dim};
+        EpiResidual e{x, w->fc2_b, dim};
+        if ((rc = launch_gemm_simt<T>(a, wd, M, dim, 4 * dim, e, st, "fc2"))) return rc;
+    }
+    return TU_OK;
+}
+
+template int transformer_block_simt<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
+template int transformer_block_simt<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
+
+}  // namespace tu
+
+using namespace tu;
+
+extern "C" size_t tu_block_workspace_bytes(int M, int dim, int dtype) { return block_ws(M, dim, dtype); }
+
+extern "C" int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
+                                    int dtype, void *workspace, size_t workspace_bytes, void *stream) {
+    TU_CHECK_ARG(x && w && workspace && M > 0, "transformer_block: bad argument");
+    TU_CHECK_ARG(dim == heads * 16 && (dim == 128 || dim == 192), "transformer_block: dim must be heads*16 and 128|192");
+    TU_CHECK_ARG(window ? (M % 64 == 0 && w->rel_bias) : (S > 0 && M % S == 0), "transformer_block: bad token count");
+    if (workspace_bytes < block_ws(M, dim, dtype)) {
+        set_error("tu: transformer_block workspace too small");
+        return TU_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TU_F32) return transformer_block_simt<float>(x, w, M, dim, heads, window, S, workspace, st);
+    if (dtype == TU_BF16) return transformer_block_simt<bf16>(x, w, M, dim, heads, window, S, workspace, st);
+    TU_CHECK_ARG(false, "transformer_block: bad dtype");
+}

@@ -1,0 +1,65 @@
+// Shared device/host helpers for libtu_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/tu_b200.h"
+
+namespace tu {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (host) -------------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define TU_CHECK_ARG(cond, msg)                         \
+    do {                                                \
+        if (!(cond)) {                                  \
+            ::tu::set_error(std::string("tu: ") + msg); \
+            return TU_ERR_ARG;                          \
+        }                                               \
+    } while (0)
+
+#define TU_CHECK_LAUNCH(what)                                   \
+    do {                                                        \
+        cudaError_t _e = cudaGetLastError();                    \
+        if (_e != cudaSuccess) return ::tu::cuda_fail(_e, what); \
+    } while (0)
+
+// ---- scalar load/store with dtype conversion --------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements -> float4 (pointer must be aligned to 4 elements)
+__device__ __forceinline__ float4 load4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 load4(const bf16 *p) {
+    uint2 u = *reinterpret_cast<const uint2 *>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&u.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162 *>(&u.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void store4(bf16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t *>(&a);
+    u.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = u;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline size_t dtype_size(int dtype) { return dtype == TU_BF16 ? 2 : 4; }
+
+}  // namespace tu

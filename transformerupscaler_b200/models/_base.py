@@ -1,0 +1,133 @@
+"""Shared scaffolding of the drop-in model classes.
+
+The classes below only *hold parameters* under the reference's names and shapes so that
+``load_state_dict(strict=True)`` of reference checkpoints works; none of their
+``forward`` methods does arithmetic.  ``EngineModel.forward`` routes the whole forward pass into
+libtu_b200 through the ``tu::forward`` custom op.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import engine
+from ..packing import PackedWeights
+
+
+def _relative_position_index(ws: int) -> torch.Tensor:
+    ys, xs = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
+    ys, xs = ys.reshape(-1), xs.reshape(-1)
+    return (ys[:, None] - ys[None, :] + ws - 1) * (2 * ws - 1) + (xs[:, None] - xs[None, :] + ws - 1)
+
+
+class _ParamsOnly(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - never used
+        raise RuntimeError("this sub-module only stores parameters; call TransformerModel.forward")
+
+
+class WindowAttention(_ParamsOnly):
+    """Parameter holder for reference WindowAttention (WindowTransformer/model.py:63-100)."""
+
+    def __init__(self, dim: int, window_size: int, num_heads: int, dropout: float = 0.0):
+        super().__init__()
+        assert (dim // num_heads) * num_heads == dim, "dim must be divisible by num_heads"
+        self.dim, self.window_size, self.num_heads = dim, window_size, num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.attn_drop = nn.Dropout(dropout)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(dropout)
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * window_size - 1) ** 2, num_heads))
+        self.register_buffer("relative_position_index", _relative_position_index(window_size))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
+
+
+def _mlp(dim: int, hidden: int, dropout: float) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim), nn.Dropout(dropout))
+
+
+class WindowTransformerBlock(_ParamsOnly):
+    """Parameter holder for reference WindowTransformerBlock (WindowTransformer/model.py:133-149)."""
+
+    def __init__(self, dim: int, window_size: int, num_heads: int, mlp_ratio: float = 4.0, dropout: float = 0.1):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = WindowAttention(dim, window_size, num_heads, dropout)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = _mlp(dim, int(dim * mlp_ratio), dropout)
+
+
+class GlobalTransformerBlock(_ParamsOnly):
+    """Parameter holder for ResidualTransformer's TransformerBlock (ResidualTransformer/model.py:22-38)."""
+
+    def __init__(self, embed_dim: int, num_heads: int, mlp_ratio: float = 4.0, dropout: float = 0.1):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        self.mlp = _mlp(embed_dim, int(embed_dim * mlp_ratio), dropout)
+
+
+class EngineModel(nn.Module):
+    """Base of the three TransformerModel classes: precision selection, weight packing cache, dispatch."""
+
+    ENGINE_MODEL = ""          # "WindowTransformer" | "FastTransformer" | "ResidualTransformer"
+    AUTOCAST_OUT_FP32 = True   # reference output dtype under autocast: fp32 (Window/Residual), low precision (Fast)
+
+    def __init__(self):
+        super().__init__()
+        self._tu_cache = {}
+        # None = follow the reference's dtype semantics; "fp32" / "bf16" force the compute path
+        self.engine_precision: Optional[str] = None
+
+    # -- packing ------------------------------------------------------------------------------
+    def _packed(self, compute_bf16: bool, device: torch.device) -> int:
+        sd = {k: v for k, v in self.state_dict(keep_vars=True).items()}
+        key = (compute_bf16, str(device), tuple((k, v.data_ptr(), v._version) for k, v in sd.items()))
+        hit = self._tu_cache.get("key")
+        if hit != key:
+            old = self._tu_cache.get("handle")
+            if old is not None:
+                engine.release_weights(old)
+            pw = PackedWeights(self.ENGINE_MODEL, sd, torch.bfloat16 if compute_bf16 else torch.float32, device)
+            self._tu_cache = {"key": key, "handle": engine.register_weights(pw)}
+        return self._tu_cache["handle"]
+
+    def _select_precision(self, x: torch.Tensor) -> Tuple[bool, torch.dtype]:
+        """(compute in bf16?, output dtype) mirroring what the reference returns for this input/autocast state."""
+        pdt = self.conv1.weight.dtype
+        if pdt not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"unsupported parameter dtype {pdt}: the engine runs fp32 or bf16 modules")
+        autocast = x.is_cuda and torch.is_autocast_enabled("cuda")
+        if self.engine_precision == "fp32":
+            bf16 = False
+        elif self.engine_precision == "bf16":
+            bf16 = True
+        else:
+            bf16 = autocast or pdt == torch.bfloat16
+        if pdt == torch.bfloat16:
+            out_dt = torch.bfloat16
+        elif autocast and not self.AUTOCAST_OUT_FP32:
+            out_dt = torch.bfloat16
+        else:
+            out_dt = torch.float32
+        return bf16, out_dt
+
+    def forward(self, x: torch.Tensor, res_out: Tuple[int, int] = (1080, 1920), upscale_factor: int = None,
+                require_ratio: bool = True) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError("transformerupscaler_b200 is a forward-only inference engine: call .eval() first "
+                               "(dropout is treated as identity; there is no backward)")
+        if not x.is_cuda:
+            raise RuntimeError("transformerupscaler_b200 has no CPU path: move the model and the input to a CUDA device")
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        bf16, out_dt = self._select_precision(x)
+        handle = self._packed(bf16, x.device)
+        out = engine.run_forward(handle, self.ENGINE_MODEL, x, res_out, upscale_factor, require_ratio, bf16, out_dt)
+        if x.is_cuda and torch.is_autocast_enabled("cuda") and not self.AUTOCAST_OUT_FP32:
+            want = torch.get_autocast_dtype("cuda")
+            if out.dtype != want:
+                out = out.to(want)
+        return out

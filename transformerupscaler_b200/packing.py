@@ -1,0 +1,122 @@
+"""state_dict -> packed device weights for libtu_b200 (layouts documented in include/tu_b200.h).
+
+One-off host-side plumbing (torch permutes / casts on the model's device), cached per
+(parameter versions, compute dtype).  ``T`` below is the compute dtype (fp32 or bf16); biases,
+LayerNorm affine, the dense relative-position bias and pos_embed stay fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+
+SCALES = (2, 3, 4, 6)
+
+
+def dense_rel_bias_t(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """(heads, key j, query i) fp32 from the (225, heads) table and the (64,64) index buffer
+    (reference: WindowTransformer/model.py:118-122 gathers table[index] -> (i, j, heads))."""
+    b = table.float()[index.reshape(-1).long()].reshape(64, 64, -1)      # (i, j, h)
+    return b.permute(2, 1, 0).contiguous()                               # (h, j, i)
+
+
+class PackedWeights:
+    """Keeps the packed tensors alive and exposes the TuModelWeights struct."""
+
+    def __init__(self, model: str, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device: torch.device):
+        self.model, self.dtype, self.device = model, dtype, device
+        self.keep: List[torch.Tensor] = []
+        f32 = torch.float32
+
+        def dev(t: torch.Tensor, dt) -> torch.Tensor:
+            t = t.detach().to(device=device, dtype=dt).contiguous()
+            self.keep.append(t)
+            return t
+
+        def ptr(t) -> int:
+            return 0 if t is None else t.data_ptr()
+
+        def conv64(w):      # (64*nchunk? , 64, 3, 3) plain conv -> [tap][co][ci]
+            return dev(w.float().permute(2, 3, 0, 1).reshape(9, w.shape[0], 64), dtype)
+
+        def conv_small_in(w):   # (co, 3, 3, 3) -> (27, co): [(ky*3+kx)*3+ci][co]
+            return dev(w.float().permute(2, 3, 1, 0).reshape(27, w.shape[0]), f32)
+
+        def conv_to3(w):        # (3, 64, 3, 3) -> (9, 64, 3)
+            return dev(w.float().permute(2, 3, 1, 0).reshape(9, 64, 3), f32)
+
+        mw = _lib.TuModelWeights()
+        mw.model = _lib.MODEL_IDS[model]
+        fast, resid = model == "FastTransformer", model == "ResidualTransformer"
+        dim = sd["patch_embed.weight"].shape[0]
+        heads = dim // 16
+        bprefix = "transformer_blocks." if resid else "window_blocks."
+        nb = 1 + max(int(k[len(bprefix):].split(".")[0]) for k in sd if k.startswith(bprefix))
+        mw.dim, mw.heads, mw.n_blocks = dim, heads, nb
+
+        mw.conv1_w = ptr(conv_small_in(sd["conv1.weight"]))
+        mw.conv1_b = ptr(dev(sd["conv1.bias"], f32))
+        mw.conv2_w = ptr(conv64(sd["conv2.weight"]))
+        mw.conv2_b = ptr(dev(sd["conv2.bias"], f32))
+        if not fast:
+            mw.down_w = ptr(conv64(sd["downsample.weight"]))
+            mw.down_b = ptr(dev(sd["downsample.bias"], f32))
+        # patch embed (dim, 64, 8, 8) -> (dim, ky, kx, ci)
+        mw.embed_w = ptr(dev(sd["patch_embed.weight"].float().permute(0, 2, 3, 1).reshape(dim, 4096), dtype))
+        mw.embed_b = ptr(dev(sd["patch_embed.bias"], f32))
+        if resid:
+            mw.pos_embed = ptr(dev(sd["pos_embed"].reshape(-1, dim), f32))
+        # patch unembed: ConvTranspose2d weight (dim, 64, 8, 8) -> (ky, kx, co) x dim
+        mw.unembed_w = ptr(dev(sd["patch_unembed.weight"].float().permute(2, 3, 1, 0).reshape(4096, dim), dtype))
+        mw.unembed_b = ptr(dev(sd["patch_unembed.bias"], f32))
+        mw.dec1_w = ptr(conv64(sd["decoder_conv1.weight"]))
+        mw.dec1_b = ptr(dev(sd["decoder_conv1.bias"], f32))
+        mw.dec2_w = ptr(conv_to3(sd["decoder_conv2.weight"]))
+        mw.dec2_b = ptr(dev(sd["decoder_conv2.bias"], f32))
+
+        # transformer blocks (q rows and q bias pre-scaled by head_dim^-0.5 = 0.25: exact in fp32 and bf16)
+        self.blocks = (_lib.TuBlockWeights * nb)()
+        for i in range(nb):
+            p = f"{bprefix}{i}."
+            bw = self.blocks[i]
+            for nm, key in (("ln1_w", "norm1.weight"), ("ln1_b", "norm1.bias"), ("ln2_w", "norm2.weight"), ("ln2_b", "norm2.bias")):
+                setattr(bw, nm, ptr(dev(sd[p + key], f32)))
+            if resid:
+                qw, qb = sd[p + "attn.in_proj_weight"].float().clone(), sd[p + "attn.in_proj_bias"].float().clone()
+                pw, pb = sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"]
+            else:
+                qw, qb = sd[p + "attn.qkv.weight"].float().clone(), sd[p + "attn.qkv.bias"].float().clone()
+                pw, pb = sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"]
+                bw.rel_bias = ptr(dev(dense_rel_bias_t(sd[p + "attn.relative_position_bias_table"],
+                                                       sd[p + "attn.relative_position_index"]), f32))
+            qw[:dim] *= 0.25
+            qb[:dim] *= 0.25
+            bw.qkv_w, bw.qkv_b = ptr(dev(qw, dtype)), ptr(dev(qb, f32))
+            bw.proj_w, bw.proj_b = ptr(dev(pw, dtype)), ptr(dev(pb, f32))
+            bw.fc1_w, bw.fc1_b = ptr(dev(sd[p + "mlp.0.weight"], dtype)), ptr(dev(sd[p + "mlp.0.bias"], f32))
+            bw.fc2_w, bw.fc2_b = ptr(dev(sd[p + "mlp.2.weight"], dtype)), ptr(dev(sd[p + "mlp.2.bias"], f32))
+        mw.blocks = C.cast(self.blocks, C.POINTER(_lib.TuBlockWeights))
+
+        if fast:
+            for slot, s in enumerate(SCALES):
+                stages = [(0, 2), (2, 2)] if s == 4 else [(0, s)]
+                for si, (idx, r) in enumerate(stages):
+                    # 64-channel branch: (64 r^2, 64, 3, 3), out channel o = c*r^2 + phase -> [phase][tap][c][ci]
+                    w = sd[f"up1.upsamplers.{s}.{idx}.weight"].float()
+                    b = sd[f"up1.upsamplers.{s}.{idx}.bias"].float()
+                    wp = w.reshape(64, r * r, 64, 3, 3).permute(1, 3, 4, 0, 2).reshape(r * r, 9, 64, 64)
+                    mw.up1[slot][si].w = ptr(dev(wp, dtype))
+                    mw.up1[slot][si].b = ptr(dev(b.reshape(64, r * r).t().reshape(-1), f32))
+                    mw.up1[slot][si].r = r
+                    # 3-channel branch: (3 r^2, 3, 3, 3) -> (27, 3 r^2), original out-channel order
+                    mw.fin[slot][si].w = ptr(conv_small_in(sd[f"final_upscale.upsamplers.{s}.{idx}.weight"]))
+                    mw.fin[slot][si].b = ptr(dev(sd[f"final_upscale.upsamplers.{s}.{idx}.bias"], f32))
+                    mw.fin[slot][si].r = r
+            mw.up1conv_w = ptr(conv_to3(sd["up1_conv.conv.weight"]))
+            mw.finconv_w = ptr(conv_small_in(sd["final_upscale_conv.weight"]))
+            mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
+        self.struct = mw
+        self.dim, self.heads, self.n_blocks = dim, heads, nb
