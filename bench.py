@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark: WindowTransformer 720p -> 1080p frames/s in bf16 (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one TransformerModel.forward over a batch of 8 synthetic 720p frames per GPU (weak scaling: frames are
+independent, so every rank upscales its own 8 frames; NCCL only carries the barrier and the max-over-ranks of the
+timings).  Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric
+through the public API with pinned HOST buffers (H2D + forward + D2H inside the timed region, overlapped on three
+streams); `roofline` = the dominant kernel (conv2, 64->64 3x3 at 720p) timed live with CUDA events; `cpu_baseline` =
+the reference's own modules timed on this box's host cores (rank 0, N=1 only).
+
+--impl reference: times the reference's CPU implementation (baseline/_ref, unmodified; else the oracle port) on one
+frame of the same workload per step, on all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 8
+H, W, OH, OW = 720, 1280, 1080, 1920
+CONV2_FLOP_PER_FRAME = 2.0 * 576 * 64 * H * W          # 67.95 GFLOP: 2*Cin*9*Cout*H*W
+WORKLOAD = "WindowTransformer 720p->1080p, batch 8 frames per GPU, bf16 (BASELINE.json configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1393.1), d.get("hbm_gbs", 6540.8), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def reference_cpu_fps(steps, warmup):
+    """Reference forward on host CPU: one 720p frame per step (a bounded sample of the batch-8 workload)."""
+    import importlib
+    import torch
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    from oracle.weights import synth_state_dict, synth_frames
+    sd = synth_state_dict("WindowTransformer", 0)
+    x = synth_frames(1, H, W, seed=123)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if os.path.isdir(os.path.join(ref_dir, "models", "WindowTransformer")):
+        sys.path.insert(0, ref_dir)
+        M = importlib.import_module("models.WindowTransformer.model").TransformerModel().eval()
+        sys.path.pop(0)
+        M.load_state_dict(sd, strict=True)
+        kind = "reference"
+
+        def fn():
+            with torch.no_grad():
+                return M(x, res_out=(OH, OW))
+    else:
+        from oracle import upscaler_oracle as orc
+        kind = "port"
+
+        def fn():
+            return orc.window_forward(sd, x, res_out=(OH, OW))
+    for _ in range(max(warmup, 1)):
+        fn()
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+    mean = sum(ts) / len(ts)
+    return 1.0 / mean, mean * 1e3, kind, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fps, ms, kind, cores = reference_cpu_fps(max(args.steps, 1), max(args.warmup, 1))
+    sample = "1 frame (B=1) of the batch-8 720p->1080p workload per step, fp32, torch CPU, all host threads"
+    line = {"impl": "reference", "metric": "frames_per_s_720p_to_1080p", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tcgen05", action="store_true", help="force the CUDA-core bf16 path (A/B only)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from oracle.weights import synth_state_dict, synth_frames
+    from transformerupscaler_b200 import _lib
+    from transformerupscaler_b200.models.WindowTransformer.model import TransformerModel
+    from transformerupscaler_b200.pipeline import FramePipeline
+
+    lib = _lib.load()          # raises if the CUDA library is missing: no fallback
+    if args.no_tcgen05:
+        lib.tu_set_bf16_tcgen05(0)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+
+    sd = synth_state_dict("WindowTransformer", 0)
+    model = TransformerModel().eval()
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).bfloat16()
+    # each rank owns its own frames (shard by frame, no data-path collective); two input buffers alternate
+    xs = [synth_frames(FRAMES_PER_GPU, H, W, seed=123 + 7 * rank + i).to(dev).bfloat16() for i in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    with torch.no_grad():
+        for i in range(warmup):
+            y = model(xs[i & 1])
+        barrier()
+        lib.tu_profile_enable(1)
+        n0 = lib.tu_launch_count()
+        clocks = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            y = model(xs[i & 1])
+        e1.record()
+        barrier()
+        launches = lib.tu_launch_count() - n0
+        ms_total = e0.elapsed_time(e1)
+        lib.tu_profile_enable(0)
+        kms, kn = C.c_double(0), C.c_int(0)
+        lib.tu_profile_collect(C.byref(kms), C.byref(kn))
+        clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    ms_per_step = ms_total / steps
+    fps = world * FRAMES_PER_GPU * steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end through the public API with pinned host buffers (`e2e`)
+    e2e_steps = steps
+    hin = [xs[i].cpu().pin_memory() for i in range(2)]
+    hout = [torch.empty((FRAMES_PER_GPU, 3, OH, OW), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+    pipe = FramePipeline(model, depth=2, device=dev, res_out=(OH, OW))
+    for i in range(warmup):
+        pipe.submit(hin[i & 1], hout[i & 1])
+    pipe.drain()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        pipe.submit(hin[i & 1], hout[i & 1])
+    pipe.drain()
+    dt = time.perf_counter() - t0
+    checksum = float(hout[(e2e_steps - 1) & 1].float().mean())     # the D2H result is read on the host
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = world * FRAMES_PER_GPU * e2e_steps / t.item()
+    h2d = hin[0].numel() * hin[0].element_size()
+    d2h = hout[0].numel() * hout[0].element_size()
+
+    if rank == 0:
+        tf_peak, hbm_peak, peak_src = peaks()
+        achieved = None
+        if kn.value > 0 and kms.value > 0:
+            achieved = CONV2_FLOP_PER_FRAME * FRAMES_PER_GPU / (kms.value / kn.value * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "conv2_traffic_bytes.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "frames_per_s_720p_to_1080p", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_PER_GPU, "parallelism": f"frame-sharded x{world}, no collective",
+                       "l2": "per-step working set ~2.5 GB (inputs + NHWC intermediates) >> 126 MB L2; two input buffers alternate",
+                       "tcgen05": bool(lib.tu_bf16_uses_tcgen05()), "output_mean": checksum},
+            "roofline": {"bound": "tensor", "kernel": "conv2 64->64 3x3 @720p (implicit GEMM, M=B*H*W, N=64, K=576)",
+                         "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernel_ms": (kms.value / kn.value) if kn.value else None,
+                         "kernel_share_of_step": (kms.value / ms_total) if kn.value else None},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "pinned host bf16 frames -> H2D -> model(x) -> D2H, 3 streams, depth-2 pipeline, wall clock"},
+            "gpu_launches": int(launches), "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cfps, cms, kind, cores = reference_cpu_fps(3, 1)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": kind,
+                                    "sample": "1 frame (B=1) of the same 720p->1080p workload, fp32, mean of 3 after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

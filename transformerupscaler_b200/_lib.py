@@ -53,6 +53,9 @@ SIGNATURES = {
     "tu_last_error": (C.c_char_p, []),
     "tu_bf16_uses_tcgen05": (i32, []),
     "tu_set_bf16_tcgen05": (None, [i32]),
+    "tu_launch_count": (C.c_longlong, []),
+    "tu_profile_enable": (None, [i32]),
+    "tu_profile_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "tu_forward_workspace_bytes": (sz, [i32] * 8),
     "tu_forward": (i32, [C.POINTER(TuModelWeights), vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "tu_stem_conv": (i32, [vp, i32, fp, fp, vp, i32, i32, i32, i32, vp]),

@@ -2,6 +2,10 @@
 // forward drivers that enqueue every kernel of a TransformerModel.forward on the caller's stream.
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "gemm_simt.cuh"
 #include "tc/tc_api.cuh"
 
@@ -9,6 +13,31 @@ namespace tu {
 
 static thread_local std::string g_err;
 static int g_use_tc = 1;
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// bench-only kernel timing hook (see tu_profile_enable in tu_b200.h)
+static int g_prof_on = 0;
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static cudaEvent_t g_prof_open = nullptr;
+static void prof_begin(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof_open = e;
+}
+static void prof_end(cudaStream_t st) {
+    if (!g_prof_on || !g_prof_open) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_events.emplace_back(g_prof_open, e);
+    g_prof_open = nullptr;
+}
 
 void set_error(const std::string &msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char *what) {
@@ -117,7 +146,10 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     // ---- encoder
     if (!dry) {
         if ((rc = tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_b, f1, dt, B, H, W, stv))) return rc;
-        if ((rc = tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv))) return rc;
+        prof_begin(st);
+        rc = tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv);
+        prof_end(st);
+        if (rc) return rc;
         if (!fast)
             if ((rc = tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv))) return rc;
     }
@@ -206,6 +238,26 @@ extern "C" int tu_version(void) { return 100; }
 extern "C" const char *tu_last_error(void) { return g_err.c_str(); }
 extern "C" int tu_bf16_uses_tcgen05(void) { return g_use_tc && tc_available(); }
 extern "C" void tu_set_bf16_tcgen05(int enable) { g_use_tc = enable; }
+extern "C" long long tu_launch_count(void) { return g_launches.load(); }
+extern "C" void tu_profile_enable(int on) { g_prof_on = on; }
+extern "C" int tu_profile_collect(double *total_ms, int *launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    int n = 0;
+    for (auto &pr : g_prof_events) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            tot += ms;
+            ++n;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_events.clear();
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return TU_OK;
+}
 
 extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype, int B, int H, int W,
                               int stride, int relu, int nchunk, int ps_r, void *stream) {

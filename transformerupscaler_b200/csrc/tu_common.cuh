@@ -15,6 +15,7 @@ typedef __nv_bfloat16 bf16;
 // ---- error plumbing (host) -------------------------------------------------------------------
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
+void count_launch();   // every kernel launch of the library is counted (tu_launch_count)
 
 #define TU_CHECK_ARG(cond, msg)                         \
     do {                                                \
@@ -28,6 +29,7 @@ int cuda_fail(cudaError_t e, const char *what);
     do {                                                        \
         cudaError_t _e = cudaGetLastError();                    \
         if (_e != cudaSuccess) return ::tu::cuda_fail(_e, what); \
+        ::tu::count_launch();                                   \
     } while (0)
 
 // ---- scalar load/store with dtype conversion --------------------------------------------------

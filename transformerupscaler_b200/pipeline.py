@@ -1,0 +1,51 @@
+"""Host-buffer frame pipeline: pinned host frames -> device -> TransformerModel.forward -> pinned host frames,
+with the H2D copy, the forward and the D2H copy of consecutive batches overlapped on three CUDA streams.
+
+This is the end-to-end entry a video caller uses (the reference's speed_test.py / app_overlay.py do a
+synchronous batch-1 `.to(device)` -> model -> `.cpu()` loop, speed_test.py:60-67, app_overlay.py:365-391).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+
+class FramePipeline:
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, **forward_kw):
+        self.model, self.kw, self.depth = model, forward_kw, depth
+        self.device = device or next(model.parameters()).device
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.dev_in: List[Optional[torch.Tensor]] = [None] * depth
+        self.dev_out: List[Optional[torch.Tensor]] = [None] * depth
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+
+    @torch.no_grad()
+    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+        """Enqueue one batch: host_in (pinned, NCHW) is upscaled into host_out (pinned). Returns immediately."""
+        slot = self.n % self.depth
+        if self.n >= self.depth:
+            self.ev_out[slot].synchronize()          # slot's previous result has left the device
+        if self.dev_in[slot] is None or self.dev_in[slot].shape != host_in.shape or self.dev_in[slot].dtype != host_in.dtype:
+            self.dev_in[slot] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.device)
+        with torch.cuda.stream(self.s_in):
+            self.dev_in[slot].copy_(host_in, non_blocking=True)
+            self.ev_in[slot].record(self.s_in)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(self.ev_in[slot])
+            out = self.model(self.dev_in[slot], **self.kw)
+            self.ev_comp[slot].record(self.s_comp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_comp[slot])
+            host_out.copy_(out, non_blocking=True)
+            self.ev_out[slot].record(self.s_out)
+        out.record_stream(self.s_out)
+        self.dev_out[slot] = out
+        self.n += 1
+
+    def drain(self) -> None:
+        for s in (self.s_in, self.s_comp, self.s_out):
+            s.synchronize()
