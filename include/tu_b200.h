@@ -51,6 +51,8 @@ long long tu_launch_count(void);
  * device), returns the summed kernel time in milliseconds and the number of launches, and clears. */
 void tu_profile_enable(int on);
 int tu_profile_collect(double *total_ms, int *launches);
+/* bring-up switches (not part of the stable interface): key "tc_base_off_mode" in {0,1} */
+int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------
  * All pointers are device pointers to tensors repacked by the host side

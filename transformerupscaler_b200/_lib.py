@@ -53,6 +53,7 @@ SIGNATURES = {
     "tu_last_error": (C.c_char_p, []),
     "tu_bf16_uses_tcgen05": (i32, []),
     "tu_set_bf16_tcgen05": (None, [i32]),
+    "tu_debug_set": (i32, [C.c_char_p, i32]),
     "tu_launch_count": (C.c_longlong, []),
     "tu_profile_enable": (None, [i32]),
     "tu_profile_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -238,6 +238,14 @@ extern "C" int tu_version(void) { return 100; }
 extern "C" const char *tu_last_error(void) { return g_err.c_str(); }
 extern "C" int tu_bf16_uses_tcgen05(void) { return g_use_tc && tc_available(); }
 extern "C" void tu_set_bf16_tcgen05(int enable) { g_use_tc = enable; }
+extern "C" int tu_debug_set(const char *key, int value) {
+    if (key && !strcmp(key, "tc_base_off_mode")) {
+        tc_set_base_off_mode(value);
+        return TU_OK;
+    }
+    set_error("tu: unknown debug key");
+    return TU_ERR_ARG;
+}
 extern "C" long long tu_launch_count(void) { return g_launches.load(); }
 extern "C" void tu_profile_enable(int on) { g_prof_on = on; }
 extern "C" int tu_profile_collect(double *total_ms, int *launches) {

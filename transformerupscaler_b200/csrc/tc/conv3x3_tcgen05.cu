@@ -1,7 +1,371 @@
+// 3x3 / pad-1 convolution with 64 input channels as an implicit GEMM on the 5th-gen tensor cores.
+//
+// Reference call sites: conv2 / downsample / decoder_conv1 (WindowTransformer/model.py:202,205,221;
+// FastTransformer/model.py:204,228; ResidualTransformer/model.py:85,88,111) and the Upsampler convs
+// 64 -> 64 r^2 followed by PixelShuffle(r) (FastTransformer/utils.py:49-98) — 85-95 % of every model's FLOPs.
+//
+// Mapping (per CTA, persistent over tiles):
+//   * NHWC bf16 activations: one pixel = 64 channels = 128 bytes = exactly one row of a 128-byte-swizzled
+//     K-major UMMA operand.  A tile is TILE_R output rows x 128 output pixels.
+//   * TMA brings each needed input row segment (136 pixels: 128 + halo, zero-filled outside the image, so
+//     padding costs nothing) into a ring of shared-memory slots ONCE; the nine filter taps are nine UMMA
+//     descriptors into the same bytes: tap (ky,kx) of output row r reads slot row r+ky starting kx pixels
+//     (= kx*128 bytes) in.  Stride 2 views the image as (W/2) "super-pixels" of 128 channels and loads the even
+//     and the odd pixels of a row as two dense slots.
+//   * the 9 x (64 co x 64 ci) filter bank of the current 64-channel output chunk stays resident in shared
+//     memory (72 KB); accumulators live in TMEM: 2 sets x TILE_R rows x 64 fp32 columns = all 512 columns, so
+//     the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * warp 0: TMA producer, warp 1: MMA issuer (one thread), warps 4-7: epilogue (tcgen05.ld -> +bias, ReLU,
+//     bf16 -> 128-byte global stores, optionally at PixelShuffle-ed addresses).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "ptx.cuh"
 #include "tc_api.cuh"
+
 namespace tu {
-int tc_available() { return 0; }
-int tc_conv3x3_c64(const bf16 *, const bf16 *, const float *, bf16 *, int, int, int, int, int, int, int, cudaStream_t) {
-    return TU_TC_UNSUPPORTED;
+
+namespace {
+
+constexpr int TILE_R = 4;                 // output rows per tile
+constexpr int TILE_M = 128;               // output pixels per row segment = UMMA M
+constexpr int BOXW = 136;                 // pixels per TMA box (128 + halo, keeps slots 1024-byte aligned)
+constexpr int UNIT_BYTES = BOXW * 128;    // 17408 = 17 * 1024
+constexpr int RING_UNITS = 6;
+constexpr int W_BYTES = 9 * 64 * 128;     // 73728
+constexpr int SMEM_BYTES = W_BYTES + RING_UNITS * UNIT_BYTES + 256 + 1024;
+constexpr int NUM_THREADS = 256;
+
+struct ConvParams {
+    int B, H, W, Ho, Wo;
+    int stride, relu, nchunk, ps_r;
+    int tiles_x, tiles_y, tiles_per_chunk, total_tiles;
+    const float *bias;
+    bf16 *out;
+    int base_off_mode;
+};
+
+struct Barriers {
+    uint64_t full[RING_UNITS];
+    uint64_t empty[RING_UNITS];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint64_t w_full;
+    uint64_t w_free;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t adesc(uint32_t addr, int mode) {
+    return ptx::make_sdesc_sw128(addr, mode ? ((addr >> 7) & 7u) : 0u);
 }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_sm = smem0;
+    const uint32_t ring_sm = smem0 + W_BYTES;
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + W_BYTES + RING_UNITS * UNIT_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stride;
+    const int units_per_step = S;                       // stride 2: even + odd slot per input row
+    const int nslots = RING_UNITS / units_per_step;     // 6 or 3
+    const int nsteps = S == 1 ? TILE_R + 2 : 2 * TILE_R + 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RING_UNITS; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
+        }
+        ptx::mbar_init(ptx::smem_u32(&bars->w_full), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars->w_free), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
+        ptx::tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_act);
+        ptx::prefetch_tmap(&tmap_w);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0 && lane == 0) {
+        // ================================ TMA producer ================================
+        int slot = 0;
+        uint32_t phase = 0;
+        int cur_chunk = -1;
+        uint32_t wphase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int chunk = t / p.tiles_per_chunk;
+            int rem = t - chunk * p.tiles_per_chunk;
+            const int tx = rem % p.tiles_x;
+            rem /= p.tiles_x;
+            const int ty = rem % p.tiles_y;
+            const int b = rem / p.tiles_y;
+            if (chunk != cur_chunk) {
+                if (cur_chunk >= 0) {   // all MMAs that read the old filter bank must have retired
+                    ptx::mbar_wait(ptx::smem_u32(&bars->w_free), wphase);
+                    wphase ^= 1;
+                }
+                ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
+                for (int tap = 0; tap < 9; ++tap)
+                    ptx::tma_load_2d(w_sm + tap * 8192, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * 9 + tap) * 64);
+                cur_chunk = chunk;
+            }
+            const int x0 = tx * TILE_M, y0 = ty * TILE_R;
+            for (int j = 0; j < nsteps; ++j) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), phase ^ 1);
+                const uint32_t dst = ring_sm + slot * units_per_step * UNIT_BYTES;
+                const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
+                ptx::mbar_expect_tx(fb, units_per_step * UNIT_BYTES);
+                if (S == 1) {
+                    ptx::tma_load_4d(dst, &tmap_act, fb, 0, x0 - 1, y0 - 1 + j, b);
+                } else {
+                    const int iy = 2 * y0 - 1 + j;
+                    ptx::tma_load_4d(dst, &tmap_act, fb, 0, x0, iy, b);                     // even pixels 2x
+                    ptx::tma_load_4d(dst + UNIT_BYTES, &tmap_act, fb, 64, x0 - 1, iy, b);   // odd pixels 2x+1, from x0-1
+                }
+                if (++slot == nslots) { slot = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, 64);
+        int slot = 0;
+        uint32_t phase = 0;
+        int cur_chunk = -1;
+        uint32_t wphase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int chunk = t / p.tiles_per_chunk;
+            const int set = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            if (chunk != cur_chunk) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->w_full), wphase);
+                wphase ^= 1;
+                cur_chunk = chunk;
+            }
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t acc0 = tmem_base + set * (TILE_R * 64);
+            for (int j = 0; j < nsteps; ++j) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), phase);
+                ptx::tc_fence_after();
+                const uint32_t src = ring_sm + slot * units_per_step * UNIT_BYTES;
+                if (S == 1) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int r = j - ky;
+                        if (r < 0 || r >= TILE_R) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const uint64_t ad = adesc(src + kx * 128 + k4 * 32, p.base_off_mode);
+                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * 8192 + k4 * 32, 0);
+                                ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
+                            }
+                        }
+                    }
+                } else {
+                    // input row iy = 2*y0 - 1 + j feeds output row r with ky = j - 2r in {0,1,2}
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int r = (j >> 1) - q;
+                        const int ky = j - 2 * r;
+                        if (r < 0 || r >= TILE_R || ky > 2) continue;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            // kx=0: odd slot row 0; kx=1: even slot row 0; kx=2: odd slot row 1
+                            const uint32_t a0 = kx == 1 ? src : src + UNIT_BYTES + (kx == 2 ? 128 : 0);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const uint64_t ad = adesc(a0 + k4 * 32, p.base_off_mode);
+                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * 8192 + k4 * 32, 0);
+                                ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
+                            }
+                        }
+                    }
+                }
+                ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));     // slot reusable once these MMAs retire
+                if (++slot == nslots) { slot = 0; phase ^= 1; }
+            }
+            ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));       // accumulators of this tile complete
+            // does the next tile of this CTA switch to another filter bank?
+            const int tn = t + gridDim.x;
+            if (tn < p.total_tiles && tn / p.tiles_per_chunk != chunk) ptx::umma_commit(ptx::smem_u32(&bars->w_free));
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp - 4;                     // TMEM lane quadrant of this warp
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int chunk = t / p.tiles_per_chunk;
+            int rem = t - chunk * p.tiles_per_chunk;
+            const int tx = rem % p.tiles_x;
+            rem /= p.tiles_x;
+            const int ty = rem % p.tiles_y;
+            const int b = rem / p.tiles_y;
+            const int set = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
+            ptx::tc_fence_after();
+            const int px = tx * TILE_M + q * 32 + lane;
+            const float *bias = p.bias ? p.bias + chunk * 64 : nullptr;
+#pragma unroll 1
+            for (int r = 0; r < TILE_R; ++r) {
+                const int y = ty * TILE_R + r;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (TILE_R * 64) + r * 64;
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_x32(taddr, v0);
+                ptx::tmem_ld_x32(taddr + 32, v1);
+                ptx::tmem_ld_wait();
+                if (y < p.Ho && px < p.Wo) {
+                    bf16 *o;
+                    if (p.ps_r) {
+                        const int rr = p.ps_r, pi = chunk / rr, pj = chunk % rr;
+                        o = p.out + ((((long)b * p.Ho + y) * rr + pi) * ((long)p.Wo * rr) + (long)px * rr + pj) * 64;
+                    } else {
+                        o = p.out + (((long)b * p.Ho + y) * p.Wo + px) * 64;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float a = __uint_as_float(v0[c + e]) + (bias ? __ldg(bias + c + e) : 0.f);
+                            f[e] = p.relu ? fmaxf(a, 0.f) : a;
+                        }
+                        uint4 u;
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                        *reinterpret_cast<uint4 *>(o + c) = u;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float a = __uint_as_float(v1[c + e]) + (bias ? __ldg(bias + 32 + c + e) : 0.f);
+                            f[e] = p.relu ? fmaxf(a, 0.f) : a;
+                        }
+                        uint4 u;
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                        *reinterpret_cast<uint4 *>(o + 32 + c) = u;
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+int g_sm_count = 0;
+int g_base_off_mode = 1;
+bool g_attr_set = false;
+
+}  // namespace
+
+int tc_available() { return get_encode() != nullptr; }
+void tc_set_base_off_mode(int m) { g_base_off_mode = m; }
+
+int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
+                   int nchunk, int ps_r, cudaStream_t st) {
+    if (nchunk > 1 && ps_r == 0) return TU_TC_UNSUPPORTED;
+    if (stride == 2 && (W & 1)) return TU_TC_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(w) & 127) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return TU_TC_UNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return TU_TC_UNSUPPORTED;
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "conv3x3_tc smem attribute");
+        g_attr_set = true;
+    }
+    CUtensorMap tm_act, tm_w;
+    {
+        cuuint64_t dims[4], strides[3];
+        cuuint32_t box[4] = {64, (cuuint32_t)BOXW, 1, 1}, estr[4] = {1, 1, 1, 1};
+        if (stride == 1) {
+            dims[0] = 64; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)B;
+            strides[0] = 128; strides[1] = (cuuint64_t)W * 128; strides[2] = (cuuint64_t)H * W * 128;
+        } else {
+            dims[0] = 128; dims[1] = (cuuint64_t)(W / 2); dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)B;
+            strides[0] = 256; strides[1] = (cuuint64_t)W * 128; strides[2] = (cuuint64_t)H * W * 128;
+        }
+        CUresult r = enc(&tm_act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tu: cuTensorMapEncodeTiled(activations) failed with code " + std::to_string((int)r));
+            return TU_ERR_CUDA;
+        }
+        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * 9 * 64}, ws[1] = {128};
+        cuuint32_t wb[2] = {64, 64}, we[2] = {1, 1};
+        r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tu: cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+            return TU_ERR_CUDA;
+        }
+    }
+    ConvParams p;
+    p.B = B; p.H = H; p.W = W;
+    p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+    p.stride = stride; p.relu = relu; p.nchunk = nchunk; p.ps_r = ps_r;
+    p.tiles_x = ceil_div(p.Wo, TILE_M); p.tiles_y = ceil_div(p.Ho, TILE_R);
+    p.tiles_per_chunk = p.tiles_x * p.tiles_y * B;
+    p.total_tiles = p.tiles_per_chunk * nchunk;
+    p.bias = bias; p.out = out; p.base_off_mode = g_base_off_mode;
+    const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+    conv3x3_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
+    TU_CHECK_LAUNCH("conv3x3_tc");
+    return TU_OK;
+}
+
 }  // namespace tu

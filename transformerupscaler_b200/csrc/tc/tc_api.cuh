@@ -8,6 +8,8 @@ constexpr int TU_TC_UNSUPPORTED = 1;   // shape not covered by the tensor-core k
 
 // 1 when the tcgen05 kernels were compiled in and may be used on this device.
 int tc_available();
+// debug: 0 = UMMA descriptor base_offset 0, 1 = base_offset (addr>>7)&7 for row-shifted operand views
+void tc_set_base_off_mode(int m);
 
 // 3x3 / pad 1 convolution, 64 input channels, NHWC bf16, fp32 accumulation in TMEM.
 // w: [chunk][tap][co 64][ci 64] bf16.  Returns TU_OK, an error code, or TU_TC_UNSUPPORTED.
