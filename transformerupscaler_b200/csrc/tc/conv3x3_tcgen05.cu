@@ -301,7 +301,8 @@ EncodeTiledFn get_encode() {
 }
 
 int g_sm_count = 0;
-int g_base_off_mode = 1;
+int g_base_off_mode = 0;   // measured on B200: the UMMA swizzle is a function of the absolute smem address (like TMA's),
+                           // so row-shifted operand views need base_offset 0 (tools/tc_probe.py, profiles/r01_tc_probe.log)
 bool g_attr_set = false;
 
 }  // namespace
