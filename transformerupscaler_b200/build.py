@@ -18,6 +18,7 @@ SOURCES = [
     "transformer_simt.cu",
     "resample.cu",
     "tc/conv3x3_tcgen05.cu",
+    "tc/gemm_tcgen05.cu",
 ]
 
 NVCC_FLAGS = [

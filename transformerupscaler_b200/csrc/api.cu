@@ -45,9 +45,8 @@ int cuda_fail(cudaError_t e, const char *what) {
     return TU_ERR_CUDA;
 }
 
-template <typename T> int transformer_block_simt(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
-
-static inline bool tc_on(int dtype) { return dtype == TU_BF16 && g_use_tc && tc_available(); }
+bool tc_enabled() { return g_use_tc && tc_available(); }
+static inline bool tc_on(int dtype) { return dtype == TU_BF16 && tc_enabled(); }
 
 // ------------------------------------------------------------------ op launchers (typed)
 template <typename T>
@@ -137,6 +136,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     T *f2 = (T *)a.get(full);
     T *fd = fast ? f2 : (T *)a.get((size_t)B * Hd * Wd * 64 * sizeof(T));
     float *tok = (float *)a.get((size_t)Mtok * dim * sizeof(float));
+    bf16 *tok16 = (bf16 *)a.get((size_t)Mtok * dim * sizeof(bf16));   // bf16 copy of the final stream (tensor-core unembed)
     const size_t bws = tu_block_workspace_bytes(Mtok, dim, dt);
     void *blk = a.get(bws);
     T *comb = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
@@ -185,12 +185,18 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         if ((rc = tu_patch_embed(fd, dt, w->embed_w, w->embed_b, w->pos_embed, tok, B, Hd, Wd, Ht, Wt, dim, window ? 1 : 0,
                                  fast ? 1 : 0, stv)))
             return rc;
+        const bool tc = tc_on(dt);
         for (int i = 0; i < w->n_blocks; ++i)
-            if ((rc = tu_transformer_block(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws, stv)))
+            if ((rc = transformer_block_ex(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws,
+                                           (tc && i == w->n_blocks - 1) ? tok16 : nullptr, st)))
                 return rc;
-        if ((rc = tu_patch_unembed(tok, w->unembed_w, w->unembed_b, fd, Hd, Wd, comb, dt, B, Ht, Wt, Hc, Wc, dim,
-                                   window ? 1 : 0, stv)))
-            return rc;
+        rc = TU_TC_UNSUPPORTED;
+        if (tc)
+            rc = tc_patch_unembed(tok16, (const bf16 *)w->unembed_w, w->unembed_b, (const bf16 *)fd, Hd, Wd, (bf16 *)comb, B, Ht, Wt,
+                                  Hc, Wc, dim, window ? 1 : 0, st);
+        if (rc == TU_TC_UNSUPPORTED)
+            rc = tu_patch_unembed(tok, w->unembed_w, w->unembed_b, fd, Hd, Wd, comb, dt, B, Ht, Wt, Hc, Wc, dim, window ? 1 : 0, stv);
+        if (rc) return rc;
         // ---- decoder
         if ((rc = tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv))) return rc;
         if ((rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_b, res, B, Hc, Wc, 0, stv))) return rc;
@@ -292,6 +298,10 @@ extern "C" int tu_patch_embed(const void *feat, int dtype, const void *w, const 
                  "patch_embed: token grid does not match the feature map");
     TU_CHECK_ARG(!reflect || ((8 * Ht - H) < H && (8 * Wt - W) < W), "patch_embed: reflect pad larger than the input");
     cudaStream_t st = (cudaStream_t)stream;
+    if (tc_on(dtype) && (!reflect || (H % 8 == 0 && W % 8 == 0))) {
+        int rc = tc_patch_embed((const bf16 *)feat, (const bf16 *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, st);
+        if (rc != TU_TC_UNSUPPORTED) return rc;
+    }
     if (dtype == TU_F32)
         return patch_embed<float>((const float *)feat, (const float *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, reflect, st);
     if (dtype == TU_BF16)

@@ -283,23 +283,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    });
-    return fn;
-}
-
 int g_sm_count = 0;
 int g_base_off_mode = 0;   // measured on B200: the UMMA swizzle is a function of the absolute smem address (like TMA's),
                            // so row-shifted operand views need base_offset 0 (tools/tc_probe.py, profiles/r01_tc_probe.log)
@@ -307,7 +290,20 @@ bool g_attr_set = false;
 
 }  // namespace
 
-int tc_available() { return get_encode() != nullptr; }
+TcEncodeFn tc_encode_fn() {
+    static TcEncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TcEncodeFn)p;
+    });
+    return fn;
+}
+
+int tc_available() { return tc_encode_fn() != nullptr; }
 void tc_set_base_off_mode(int m) { g_base_off_mode = m; }
 
 int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
@@ -316,7 +312,7 @@ int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, 
     if (stride == 2 && (W & 1)) return TU_TC_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(w) & 127) || (reinterpret_cast<uintptr_t>(out) & 15))
         return TU_TC_UNSUPPORTED;
-    EncodeTiledFn enc = get_encode();
+    TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
     if (!g_sm_count) {
         int dev = 0;

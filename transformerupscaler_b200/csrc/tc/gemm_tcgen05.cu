@@ -1,0 +1,412 @@
+// C[M,N] = A[M,K] * W[N,K]^T on the 5th-gen tensor cores (bf16 operands, fp32 accumulation in TMEM), with the
+// epilogues the transformer part of the models needs.
+//
+// Reference call sites: qkv / proj / mlp Linear layers (WindowTransformer/model.py:77-79,144-148,113,129,168;
+// ResidualTransformer/model.py:31-37), patch_embed = Conv2d k8 s8 (W:208,251; F:215,268; R:93,135) and
+// patch_unembed = ConvTranspose2d k8 s8 + crop + skip add (W:218,287-294; F:225,302-309; R:108,150-153).
+//
+// Per CTA (persistent over output tiles of 128 rows x BN columns, n fastest so an A block is re-read from L2):
+//   warp 0: TMA producer — A tile (128 rows x 64 k, 128-byte swizzle) and W tile (BN rows x 64 k) per stage, 4 stages.
+//           A is either a plain row-major matrix or, for patch embed, a rank-5 view of the NHWC feature map
+//           (c, kx, tx, ky, b*ty) so that the 8x8x64 patch gather is done by the TMA engine: stage s = pixel
+//           (ky,kx) = s/8, s%8 of every patch of the tile, 64 channels = one swizzle row.
+//   warp 1: one thread issues 4 tcgen05.mma (128 x BN x 16) per stage into one of two TMEM accumulator sets.
+//   warps 4-7: epilogue, thread = output row: tcgen05.ld 32 columns at a time, then
+//           STORE  : + bias, optional exact GELU, bf16 row-major
+//           RESID  : x[m][n] += acc + bias on the fp32 token stream (optionally also a bf16 copy for the next GEMM)
+//           EMBED  : + bias (+ pos_embed), fp32 token written at its window-ordered row
+//           UNEMBED: column n = (ky,kx,c) scattered to pixel (8ty+ky, 8tx+kx), + bias + skip, cropped, bf16 NHWC
+#include <cuda.h>
+
+#include <mutex>
+
+#include "ptx.cuh"
+#include "tc_api.cuh"
+
+namespace tu {
+
+namespace {
+
+constexpr int BM = 128, BK = 64, NSTAGE = 4, NUM_THREADS = 256;
+constexpr int A_STAGE = BM * BK * 2;   // 16384
+
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_EMBED = 2, EPI_UNEMBED = 3 };
+
+struct GemmParams {
+    int M, N, K, BN;
+    int tiles_m, tiles_n, total_tiles;
+    int amode;          // 0: plain 2D A; 1: patch-embed rank-5 A
+    int epi, act;       // act: 0 none, 2 gelu (STORE only)
+    const float *bias;
+    // STORE
+    bf16 *out;
+    // RESID
+    float *x;
+    bf16 *x_bf16;       // optional bf16 copy of the updated stream
+    // EMBED / UNEMBED geometry
+    const float *pos;
+    float *tok;
+    int B, Ht, Wt, nWy, nWx, window, dim;
+    int tiles_tx;       // embed: x-tiles of 16 tokens
+    const bf16 *skip;
+    int skipH, skipW, Hc, Wc;
+};
+
+struct Barriers {
+    uint64_t full[NSTAGE];
+    uint64_t empty[NSTAGE];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ long win_row(int b, int ty, int tx, int nWy, int nWx) {
+    return (((long)b * nWy + (ty >> 3)) * nWx + (tx >> 3)) * 64 + (ty & 7) * 8 + (tx & 7);
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int w_stage = p.BN * 128;
+    const int stage_bytes = A_STAGE + w_stage;
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + NSTAGE * stage_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = p.K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
+        ptx::tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_w);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0 && lane == 0) {
+        // ================================ TMA producer ================================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+            const int n0 = tn * p.BN;
+            for (int s = 0; s < nk; ++s) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
+                const uint32_t dst = smem0 + stage * stage_bytes;
+                const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
+                ptx::mbar_expect_tx(fb, stage_bytes);
+                if (p.amode == 0) {
+                    ptx::tma_load_2d(dst, &tmap_a, fb, s * BK, tm * BM);
+                } else {
+                    const int tx0 = (tm % p.tiles_tx) * 16, r0 = (tm / p.tiles_tx) * 8;
+                    ptx::tma_load_5d(dst, &tmap_a, fb, 0, s & 7, tx0, s >> 3, r0);
+                }
+                ptx::tma_load_2d(dst + A_STAGE, &tmap_w, fb, s * BK, n0);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int set = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), aphase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t acc = tmem_base + set * 256;
+            for (int s = 0; s < nk; ++s) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+                ptx::tc_fence_after();
+                const uint32_t a_sm = smem0 + stage * stage_bytes, w_sm = a_sm + A_STAGE;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    ptx::umma_bf16(acc, ptx::make_sdesc_sw128(a_sm + k4 * 32, 0), ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc,
+                                   (s | k4) != 0);
+                ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp - 4;
+        const int i = q * 32 + lane;                  // row of the tile owned by this thread
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+            const int n0 = tn * p.BN;
+            const int set = it & 1;
+            const uint32_t aphase = (it >> 1) & 1;
+            // ---- row geometry
+            bool valid;
+            long row = 0;            // STORE/RESID: m ; EMBED: token stream row
+            int b = 0, ty = 0, tx = 0;
+            if (p.epi == EPI_EMBED) {
+                tx = (tm % p.tiles_tx) * 16 + (i & 15);
+                const int bty = (tm / p.tiles_tx) * 8 + (i >> 4);
+                b = bty / p.Ht;
+                ty = bty - b * p.Ht;
+                valid = tx < p.Wt && b < p.B;
+                row = p.window ? win_row(b, ty, tx, p.nWy, p.nWx) : ((long)b * p.Ht + ty) * p.Wt + tx;
+            } else {
+                const int m = tm * BM + i;
+                valid = m < p.M;
+                row = m;
+                if (p.epi == EPI_UNEMBED) {
+                    if (p.window) {
+                        const int wi = m >> 6, tk = m & 63;
+                        const int wx = wi % p.nWx, rest = wi / p.nWx;
+                        const int wy = rest % p.nWy;
+                        b = rest / p.nWy;
+                        ty = wy * 8 + (tk >> 3);
+                        tx = wx * 8 + (tk & 7);
+                    } else {
+                        tx = m % p.Wt;
+                        const int rest = m / p.Wt;
+                        ty = rest % p.Ht;
+                        b = rest / p.Ht;
+                    }
+                    valid = valid && ty < p.Ht && tx < p.Wt;
+                }
+            }
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
+            ptx::tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256;
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_x32(tbase + c0, v);
+                ptx::tmem_ld_wait();
+                if (!valid) continue;
+                const int n = n0 + c0;
+                if (p.epi == EPI_STORE) {
+                    bf16 *o = p.out + row * p.N + n;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float a = __uint_as_float(v[c + e]) + __ldg(p.bias + n + c + e);
+                            f[e] = p.act == 2 ? gelu_f(a) : a;
+                        }
+                        uint4 u;
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                        h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                        *reinterpret_cast<uint4 *>(o + c) = u;
+                    }
+                } else if (p.epi == EPI_RESID) {
+                    float *xr = p.x + row * p.N + n;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        float4 o = *reinterpret_cast<const float4 *>(xr + c);
+                        o.x += __uint_as_float(v[c + 0]) + __ldg(p.bias + n + c + 0);
+                        o.y += __uint_as_float(v[c + 1]) + __ldg(p.bias + n + c + 1);
+                        o.z += __uint_as_float(v[c + 2]) + __ldg(p.bias + n + c + 2);
+                        o.w += __uint_as_float(v[c + 3]) + __ldg(p.bias + n + c + 3);
+                        *reinterpret_cast<float4 *>(xr + c) = o;
+                        if (p.x_bf16) {
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                            uint2 u;
+                            u.x = *reinterpret_cast<uint32_t *>(&h0);
+                            u.y = *reinterpret_cast<uint32_t *>(&h1);
+                            *reinterpret_cast<uint2 *>(p.x_bf16 + row * p.N + n + c) = u;
+                        }
+                    }
+                } else if (p.epi == EPI_EMBED) {
+                    float *o = p.tok + row * p.dim + n;
+                    const float *pe = p.pos ? p.pos + ((long)ty * p.Wt + tx) * p.dim + n : nullptr;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        float4 r;
+                        r.x = __uint_as_float(v[c + 0]) + __ldg(p.bias + n + c + 0);
+                        r.y = __uint_as_float(v[c + 1]) + __ldg(p.bias + n + c + 1);
+                        r.z = __uint_as_float(v[c + 2]) + __ldg(p.bias + n + c + 2);
+                        r.w = __uint_as_float(v[c + 3]) + __ldg(p.bias + n + c + 3);
+                        if (pe) {
+                            const float4 pv = *reinterpret_cast<const float4 *>(pe + c);
+                            r.x += pv.x; r.y += pv.y; r.z += pv.z; r.w += pv.w;
+                        }
+                        *reinterpret_cast<float4 *>(o + c) = r;
+                    }
+                } else {   // EPI_UNEMBED: 32 columns = half of one pixel's 64 channels
+                    const int pix = n >> 6, ch = n & 63;
+                    const int y = ty * 8 + (pix >> 3), xx = tx * 8 + (pix & 7);
+                    if (y < p.Hc && xx < p.Wc) {
+                        const bf16 *sk = p.skip + (((long)b * p.skipH + y) * p.skipW + xx) * 64 + ch;
+                        bf16 *o = p.out + (((long)b * p.Hc + y) * p.Wc + xx) * 64 + ch;
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            const uint4 su = *reinterpret_cast<const uint4 *>(sk + c);
+                            const __nv_bfloat162 *sh = reinterpret_cast<const __nv_bfloat162 *>(&su);
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const float2 s2 = __bfloat1622float2(sh[e >> 1]);
+                                f[e] = __uint_as_float(v[c + e]) + __ldg(p.bias + ch + c + e) + s2.x;
+                                f[e + 1] = __uint_as_float(v[c + e + 1]) + __ldg(p.bias + ch + c + e + 1) + s2.y;
+                            }
+                            uint4 u;
+                            __nv_bfloat162 h;
+                            h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                            h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                            *reinterpret_cast<uint4 *>(o + c) = u;
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+int g_sm_count = 0;
+int g_smem_set = 0;
+
+int pick_bn(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    return 0;
+}
+
+int encode_2d(CUtensorMap *tm, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    TcEncodeFn enc = tc_encode_fn();
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows}, es[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tu: cuTensorMapEncodeTiled(gemm 2d) failed with code " + std::to_string((int)r));
+        return TU_ERR_CUDA;
+    }
+    return TU_OK;
+}
+
+int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStream_t st) {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + 1024;
+    if (smem > g_smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "gemm_tc smem attribute");
+        g_smem_set = smem;
+    }
+    p.tiles_n = p.N / p.BN;
+    p.total_tiles = p.tiles_m * p.tiles_n;
+    const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ta, tw, p);
+    TU_CHECK_LAUNCH("gemm_tc");
+    return TU_OK;
+}
+
+}  // namespace
+
+int tc_linear(const bf16 *A, const bf16 *W, const float *bias, int M, int N, int K, int act, bf16 *out, float *resid_x,
+              bf16 *resid_bf16, cudaStream_t st) {
+    const int BN = pick_bn(N);
+    if (!tc_encode_fn() || !BN || K % 64 || (reinterpret_cast<uintptr_t>(A) & 127) || (reinterpret_cast<uintptr_t>(W) & 127))
+        return TU_TC_UNSUPPORTED;
+    CUtensorMap ta, tw;
+    int rc;
+    if ((rc = encode_2d(&ta, A, M, K, BM))) return rc;
+    if ((rc = encode_2d(&tw, W, N, K, BN))) return rc;
+    GemmParams p = {};
+    p.M = M; p.N = N; p.K = K; p.BN = BN;
+    p.tiles_m = ceil_div(M, BM);
+    p.amode = 0;
+    p.bias = bias;
+    if (resid_x) {
+        p.epi = EPI_RESID; p.x = resid_x; p.x_bf16 = resid_bf16;
+    } else {
+        p.epi = EPI_STORE; p.act = act; p.out = out;
+    }
+    return launch(ta, tw, p, st);
+}
+
+int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
+                   int Ht, int Wt, int dim, int window, cudaStream_t st) {
+    const int BN = pick_bn(dim);
+    if (!tc_encode_fn() || !BN || H != 8 * Ht || Wd < 8 * Wt || (reinterpret_cast<uintptr_t>(feat) & 127) ||
+        (reinterpret_cast<uintptr_t>(W) & 127))
+        return TU_TC_UNSUPPORTED;
+    CUtensorMap ta, tw;
+    {
+        // rank-5 view of NHWC(64): (c, kx, tx, ky, b*ty)
+        cuuint64_t dims[5] = {64, 8, (cuuint64_t)Wt, 8, (cuuint64_t)B * Ht};
+        cuuint64_t strides[4] = {128, 1024, (cuuint64_t)Wd * 128, (cuuint64_t)Wd * 128 * 8};
+        cuuint32_t box[5] = {64, 1, 16, 1, 8}, es[5] = {1, 1, 1, 1, 1};
+        CUresult r = tc_encode_fn()(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)feat, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tu: cuTensorMapEncodeTiled(patch embed) failed with code " + std::to_string((int)r));
+            return TU_ERR_CUDA;
+        }
+    }
+    int rc;
+    if ((rc = encode_2d(&tw, W, dim, 4096, BN))) return rc;
+    GemmParams p = {};
+    p.M = B * Ht * Wt; p.N = dim; p.K = 4096; p.BN = BN;
+    p.tiles_tx = ceil_div(Wt, 16);
+    p.tiles_m = p.tiles_tx * ceil_div(B * Ht, 8);
+    p.amode = 1;
+    p.epi = EPI_EMBED;
+    p.bias = bias; p.pos = pos; p.tok = tok;
+    p.B = B; p.Ht = Ht; p.Wt = Wt; p.nWy = (Ht + 7) / 8; p.nWx = (Wt + 7) / 8; p.window = window; p.dim = dim;
+    return launch(ta, tw, p, st);
+}
+
+int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, const bf16 *skip, int skipH, int skipW, bf16 *out,
+                     int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, cudaStream_t st) {
+    if (!tc_encode_fn() || dim % 64 || (reinterpret_cast<uintptr_t>(tok_bf16) & 127) || (reinterpret_cast<uintptr_t>(W) & 127))
+        return TU_TC_UNSUPPORTED;
+    const int nWy = (Ht + 7) / 8, nWx = (Wt + 7) / 8;
+    const int M = window ? B * nWy * nWx * 64 : B * Ht * Wt;
+    CUtensorMap ta, tw;
+    int rc;
+    if ((rc = encode_2d(&ta, tok_bf16, M, dim, BM))) return rc;
+    if ((rc = encode_2d(&tw, W, 4096, dim, 256))) return rc;
+    GemmParams p = {};
+    p.M = M; p.N = 4096; p.K = dim; p.BN = 256;
+    p.tiles_m = ceil_div(M, BM);
+    p.amode = 0;
+    p.epi = EPI_UNEMBED;
+    p.bias = bias; p.out = out; p.skip = skip; p.skipH = skipH; p.skipW = skipW; p.Hc = Hc; p.Wc = Wc;
+    p.B = B; p.Ht = Ht; p.Wt = Wt; p.nWy = nWy; p.nWx = nWx; p.window = window; p.dim = dim;
+    return launch(ta, tw, p, st);
+}
+
+}  // namespace tu

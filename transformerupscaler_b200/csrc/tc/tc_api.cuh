@@ -1,5 +1,7 @@
 // Internal interface between the C-ABI layer and the tcgen05 (5th-gen tensor core) kernels.
 #pragma once
+#include <cuda.h>
+
 #include "../tu_common.cuh"
 
 namespace tu {
@@ -8,12 +10,34 @@ constexpr int TU_TC_UNSUPPORTED = 1;   // shape not covered by the tensor-core k
 
 // 1 when the tcgen05 kernels were compiled in and may be used on this device.
 int tc_available();
+// tc_available() and not switched off by tu_set_bf16_tcgen05(0)
+bool tc_enabled();
 // debug: 0 = UMMA descriptor base_offset 0, 1 = base_offset (addr>>7)&7 for row-shifted operand views
 void tc_set_base_off_mode(int m);
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda); nullptr without a driver
+typedef CUresult (*TcEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TcEncodeFn tc_encode_fn();
+
+// C = A W^T GEMMs of the transformer part (gemm_tcgen05.cu).  All return TU_OK, an error, or TU_TC_UNSUPPORTED.
+//   out != nullptr : out[M][N] = act(A W^T + bias) as bf16 (act 0 none, 2 exact GELU)
+//   resid_x != nullptr : resid_x[M][N] += A W^T + bias (fp32), and resid_bf16 (optional) receives a bf16 copy
+int tc_linear(const bf16 *A, const bf16 *W, const float *bias, int M, int N, int K, int act, bf16 *out, float *resid_x,
+              bf16 *resid_bf16, cudaStream_t st);
+int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
+                   int Ht, int Wt, int dim, int window, cudaStream_t st);
+int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, const bf16 *skip, int skipH, int skipW, bf16 *out,
+                     int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, cudaStream_t st);
 
 // 3x3 / pad 1 convolution, 64 input channels, NHWC bf16, fp32 accumulation in TMEM.
 // w: [chunk][tap][co 64][ci 64] bf16.  Returns TU_OK, an error code, or TU_TC_UNSUPPORTED.
 int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
                    int nchunk, int ps_r, cudaStream_t st);
+
+// one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
+int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
+                         void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st);
 
 }  // namespace tu

@@ -5,6 +5,7 @@
 // FastTransformer/model.py:65-172) and TransformerBlock with nn.MultiheadAttention
 // (ResidualTransformer/model.py:22-50).
 #include "gemm_simt.cuh"
+#include "tc/tc_api.cuh"
 
 namespace tu {
 
@@ -177,9 +178,34 @@ static size_t block_ws(int M, int dim, int dtype) {
     return align_up((size_t)M * dim * e, 256) + align_up((size_t)M * 4 * dim * e, 256) + align_up((size_t)M * dim * e, 256);
 }
 
+// Dense layer of the block: tensor-core GEMM for bf16 when enabled, else the exact-fp32 SIMT GEMM.
+//   mode 0: out = A W^T + b   mode 2: out = gelu(A W^T + b)   mode 1: x += A W^T + b (fp32 stream)
 template <typename T>
-int transformer_block_simt(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, void *ws,
-                           cudaStream_t st) {
+static int block_linear(const T *A, long lda, const void *W, const float *bias, int M, int N, int K, int mode, T *out, float *x,
+                        bf16 *x_bf16, bool tc, cudaStream_t st, const char *what) {
+    if (tc && sizeof(T) == 2 && lda == K) {
+        int rc = tc_linear((const bf16 *)A, (const bf16 *)W, bias, M, N, K, mode == 2 ? 2 : 0, mode == 1 ? nullptr : (bf16 *)out,
+                           mode == 1 ? x : nullptr, mode == 1 ? x_bf16 : nullptr, st);
+        if (rc != TU_TC_UNSUPPORTED) return rc;
+    }
+    ARows<T> a{A, M, lda};
+    WDesc<T> wd{(const T *)W, K, 0, 64L * K};
+    if (mode == 1) {
+        EpiResidual e{x, bias, N};
+        return launch_gemm_simt<T>(a, wd, M, N, K, e, st, what);
+    }
+    if (mode == 2) {
+        EpiStore<T, 2> e{out, bias, N};
+        return launch_gemm_simt<T>(a, wd, M, N, K, e, st, what);
+    }
+    EpiStore<T, 0> e{out, bias, N};
+    return launch_gemm_simt<T>(a, wd, M, N, K, e, st, what);
+}
+
+// x_bf16_out (optional, tensor-core path only): receives a bf16 copy of the block's output stream
+template <typename T>
+int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, void *ws,
+                           bool tc, bf16 *x_bf16_out, cudaStream_t st) {
     char *p = (char *)ws;
     T *ln = (T *)p;
     p += align_up((size_t)M * dim * sizeof(T), 256);
@@ -188,12 +214,7 @@ int transformer_block_simt(float *x, const TuBlockWeights *w, int M, int dim, in
     T *att = (T *)p;
     int rc;
     if ((rc = launch_layernorm<T>(x, w->ln1_w, w->ln1_b, ln, M, dim, st))) return rc;
-    {
-        ARows<T> a{ln, M, dim};
-        WDesc<T> wd{(const T *)w->qkv_w, dim, 0, 64L * dim};
-        EpiStore<T, 0> e{big, w->qkv_b, 3L * dim};
-        if ((rc = launch_gemm_simt<T>(a, wd, M, 3 * dim, dim, e, st, "qkv"))) return rc;
-    }
+    if ((rc = block_linear<T>(ln, dim, w->qkv_w, w->qkv_b, M, 3 * dim, dim, 0, big, nullptr, nullptr, tc, st, "qkv"))) return rc;
     if (window) {
         dim3 grid(M / 64, heads);
         window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
@@ -203,30 +224,36 @@ int transformer_block_simt(float *x, const TuBlockWeights *w, int M, int dim, in
         global_attn_kernel<T><<<grid, 128, 0, st>>>(big, att, S, dim);
         TU_CHECK_LAUNCH("global_attn");
     }
-    {
-        ARows<T> a{att, M, dim};
-        WDesc<T> wd{(const T *)w->proj_w, dim, 0, 64L * dim};
-        EpiResidual e{x, w->proj_b, dim};
-        if ((rc = launch_gemm_simt<T>(a, wd, M, dim, dim, e, st, "proj"))) return rc;
-    }
+    if ((rc = block_linear<T>(att, dim, w->proj_w, w->proj_b, M, dim, dim, 1, nullptr, x, nullptr, tc, st, "proj"))) return rc;
     if ((rc = launch_layernorm<T>(x, w->ln2_w, w->ln2_b, ln, M, dim, st))) return rc;
-    {
-        ARows<T> a{ln, M, dim};
-        WDesc<T> wd{(const T *)w->fc1_w, dim, 0, 64L * dim};
-        EpiStore<T, 2> e{big, w->fc1_b, 4L * dim};
-        if ((rc = launch_gemm_simt<T>(a, wd, M, 4 * dim, dim, e, st, "fc1"))) return rc;
-    }
-    {
-        ARows<T> a{big, M, 4L * dim};
-        WDesc<T> wd{(const T *)w->fc2_w, 4 * dim, 0, 64L * 4 * dim};
-        EpiResidual e{x, w->fc2_b, dim};
-        if ((rc = launch_gemm_simt<T>(a, wd, M, dim, 4 * dim, e, st, "fc2"))) return rc;
+    if ((rc = block_linear<T>(ln, dim, w->fc1_w, w->fc1_b, M, 4 * dim, dim, 2, big, nullptr, nullptr, tc, st, "fc1"))) return rc;
+    if ((rc = block_linear<T>(big, 4L * dim, w->fc2_w, w->fc2_b, M, dim, 4 * dim, 1, nullptr, x, x_bf16_out, tc, st, "fc2"))) return rc;
+    return TU_OK;
+}
+
+template int transformer_block_impl<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, bool, bf16 *, cudaStream_t);
+template int transformer_block_impl<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, bool, bf16 *, cudaStream_t);
+
+static int block_check(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype, void *workspace,
+                       size_t workspace_bytes) {
+    TU_CHECK_ARG(x && w && workspace && M > 0, "transformer_block: bad argument");
+    TU_CHECK_ARG(dim == heads * 16 && (dim == 128 || dim == 192), "transformer_block: dim must be heads*16 and 128|192");
+    TU_CHECK_ARG(window ? (M % 64 == 0 && w->rel_bias) : (S > 0 && M % S == 0), "transformer_block: bad token count");
+    TU_CHECK_ARG(dtype == TU_F32 || dtype == TU_BF16, "transformer_block: bad dtype");
+    if (workspace_bytes < block_ws(M, dim, dtype)) {
+        set_error("tu: transformer_block workspace too small");
+        return TU_ERR_WORKSPACE;
     }
     return TU_OK;
 }
 
-template int transformer_block_simt<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
-template int transformer_block_simt<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, cudaStream_t);
+int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
+                         void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st) {
+    int rc = block_check(x, w, M, dim, heads, window, S, dtype, workspace, workspace_bytes);
+    if (rc) return rc;
+    if (dtype == TU_F32) return transformer_block_impl<float>(x, w, M, dim, heads, window, S, workspace, false, nullptr, st);
+    return transformer_block_impl<bf16>(x, w, M, dim, heads, window, S, workspace, tc_enabled(), x_bf16_out, st);
+}
 
 }  // namespace tu
 
@@ -236,15 +263,5 @@ extern "C" size_t tu_block_workspace_bytes(int M, int dim, int dtype) { return b
 
 extern "C" int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                                     int dtype, void *workspace, size_t workspace_bytes, void *stream) {
-    TU_CHECK_ARG(x && w && workspace && M > 0, "transformer_block: bad argument");
-    TU_CHECK_ARG(dim == heads * 16 && (dim == 128 || dim == 192), "transformer_block: dim must be heads*16 and 128|192");
-    TU_CHECK_ARG(window ? (M % 64 == 0 && w->rel_bias) : (S > 0 && M % S == 0), "transformer_block: bad token count");
-    if (workspace_bytes < block_ws(M, dim, dtype)) {
-        set_error("tu: transformer_block workspace too small");
-        return TU_ERR_WORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == TU_F32) return transformer_block_simt<float>(x, w, M, dim, heads, window, S, workspace, st);
-    if (dtype == TU_BF16) return transformer_block_simt<bf16>(x, w, M, dim, heads, window, S, workspace, st);
-    TU_CHECK_ARG(false, "transformer_block: bad dtype");
+    return transformer_block_ex(x, w, M, dim, heads, window, S, dtype, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
 }
