@@ -67,7 +67,7 @@ typedef struct TuBlockWeights {
     const void *proj_w; const float *proj_b;          /* T (dim, dim)                             */
     const void *fc1_w;  const float *fc1_b;           /* T (4dim, dim)                            */
     const void *fc2_w;  const float *fc2_b;           /* T (dim, 4dim)                            */
-    const float *rel_bias;                            /* (heads, 64 key j, 64 query i) or NULL    */
+    const float *rel_bias;                            /* (heads, 64 query i, 64 key j) or NULL    */
 } TuBlockWeights;
 
 typedef struct TuUpsamplerStage {
@@ -82,6 +82,7 @@ typedef struct TuModelWeights {
     int dim, heads, n_blocks;   /* 128/8/8 (Window, Residual), 192/12/6 (Fast)                    */
     const float *conv1_w;       /* (27, 64) fp32: [(ky*3+kx)*3+ci][co]                            */
     const float *conv1_b;
+    const void *conv1_w64;      /* bf16 (64 co, 64 k): k = (ky*3+kx)*3+ci for k < 27, zero above; tensor-core stem, or NULL */
     const void *conv2_w;        /* T (9, 64 cout, 64 cin)  [tap][co][ci]                          */
     const float *conv2_b;
     const void *down_w;         /* T (9,64,64) or NULL (Fast)                                     */
@@ -96,10 +97,12 @@ typedef struct TuModelWeights {
     const float *dec1_b;
     const float *dec2_w;        /* fp32 (9, 64 ci, 3 co)                                          */
     const float *dec2_b;        /* (3)                                                            */
+    const void *dec2_w16;       /* bf16 (9, 16 co [3 real + 13 zero], 64 ci) for the tensor-core head, or NULL */
     /* FastTransformer only */
     TuUpsamplerStage up1[4][2];     /* indexed by scale slot {2,3,4,6} -> 0..3, stage 0/1         */
     TuUpsamplerStage fin[4][2];
     const float *up1conv_w;     /* fp32 (9, 64, 3), no bias                                       */
+    const void *up1conv_w16;    /* bf16 (9, 16, 64) or NULL                                        */
     const float *finconv_w;     /* fp32 (27, 3)                                                   */
     const float *finconv_b;     /* (3)                                                            */
 } TuModelWeights;
@@ -118,15 +121,17 @@ int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, void *out, 
                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- single ops (exported for the per-op parity tests and for composition) ---------------------- */
-/* conv1: 3->64 3x3 p1 + ReLU, NCHW in -> NHWC out */
-int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const float *b, void *out, int dtype,
+/* conv1: 3->64 3x3 p1 + ReLU, NCHW in -> NHWC out.  w64 (optional, bf16 (64,64)) enables the tensor-core kernel
+ * for dtype TU_BF16. */
+int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const void *w64, const float *b, void *out, int dtype,
                  int B, int H, int W, void *stream);
 /* 64->(64*nchunk) 3x3 p1 conv on NHWC, stride 1|2, optional ReLU, optional PixelShuffle(r) store
  * (then nchunk = r*r and chunk p holds phase (i,j) = (p/r, p%r) for all 64 channels). */
 int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype,
                    int B, int H, int W, int stride, int relu, int nchunk, int ps_r, void *stream);
-/* 64->3 3x3 p1 conv, NHWC in -> planar fp32 (B,3,H,W) out */
-int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const float *b, float *out,
+/* 64->3 3x3 p1 conv, NHWC in -> planar fp32 (B,3,H,W) out.  w16 (optional, bf16 (9,16,64)) enables the
+ * tensor-core kernel for dtype TU_BF16; w (fp32 (9,64,3)) is always required. */
+int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const void *w16, const float *b, float *out,
                        int B, int H, int W, int relu, void *stream);
 /* 3->3r^2 3x3 conv + PixelShuffle(r) on planar fp32 */
 int tu_conv3x3_c3_ps(const float *in, const float *w, const float *b, float *out, int B, int H, int W, int r,

@@ -20,11 +20,11 @@ def chk(rc):
     _lib.check(rc)
 
 
-def stem_conv(x, w27x64, b, dtype):
+def stem_conv(x, w27x64, b, dtype, w64=None):
     lib = _lib.load()
     B, _, H, W = x.shape
     out = torch.empty(B, H, W, 64, dtype=dtype, device=x.device)
-    chk(lib.tu_stem_conv(p(x), DT[x.dtype], p(w27x64), p(b), p(out), DT[dtype], B, H, W, stream()))
+    chk(lib.tu_stem_conv(p(x), DT[x.dtype], p(w27x64), p(w64), p(b), p(out), DT[dtype], B, H, W, stream()))
     return out
 
 
@@ -40,11 +40,11 @@ def conv3x3_c64(x, w, b, stride=1, relu=0, nchunk=1, ps_r=0):
     return out
 
 
-def conv64to3(x, w, b, relu=0):
+def conv64to3(x, w, b, relu=0, w16=None):
     lib = _lib.load()
     B, H, W, _ = x.shape
     out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
-    chk(lib.tu_conv3x3_c64_to3(p(x), DT[x.dtype], p(w), p(b), p(out), B, H, W, relu, stream()))
+    chk(lib.tu_conv3x3_c64_to3(p(x), DT[x.dtype], p(w), p(w16), p(b), p(out), B, H, W, relu, stream()))
     return out
 
 

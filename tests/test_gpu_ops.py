@@ -39,6 +39,17 @@ def test_stem_conv(dev, in_dt, dt):
     w = sd["conv1.weight"].permute(2, 3, 1, 0).reshape(27, 64).contiguous().to(dev)
     out = G.stem_conv(x.to(dev), w, sd["conv1.bias"].to(dev), dt)
     assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
+    if dt == BF16:      # tensor-core stem: bf16 operands (image and filter rounded to bf16), fp32 accumulate
+        w64 = torch.zeros(64, 64)
+        w64[:, :27] = sd["conv1.weight"].permute(0, 2, 3, 1).reshape(64, 27)
+        ref16 = orc.conv3x3_nhwc(x.to(BF16).float().permute(0, 2, 3, 1).contiguous(), sd["conv1.weight"].to(BF16).float(),
+                                 sd["conv1.bias"], relu=True)
+        for shape_x in (x, synth_frames(1, 5, 300, seed=2).to(in_dt)):
+            if shape_x is not x:
+                ref16 = orc.conv3x3_nhwc(shape_x.to(BF16).float().permute(0, 2, 3, 1).contiguous(),
+                                         sd["conv1.weight"].to(BF16).float(), sd["conv1.bias"], relu=True)
+            out16 = G.stem_conv(shape_x.to(dev), w, sd["conv1.bias"].to(dev), dt, w64=w64.to(dev, BF16))
+            assert _maxerr(out16, ref16) < 1e-2
 
 
 @pytest.mark.parametrize("dt", [F32, BF16])
@@ -86,6 +97,12 @@ def test_conv64to3(dev, dt, bias, relu):
     wp = w.permute(2, 3, 1, 0).reshape(9, 64, 3).contiguous().to(dev)
     out = G.conv64to3(x.to(dev), wp, None if b is None else b.to(dev), relu=relu)
     assert _maxerr(out, ref) < TOL32 * 4
+    if dt == BF16:      # tensor-core head: bf16 weights (3 of 16 output channels real)
+        w16 = torch.zeros(9, 16, 64)
+        w16[:, :3] = w.permute(2, 3, 0, 1).reshape(9, 3, 64)
+        ref16 = orc.conv3x3_nhwc(x.float(), w.to(BF16).float(), b, relu=bool(relu)).permute(0, 3, 1, 2)
+        out16 = G.conv64to3(x.to(dev), wp, None if b is None else b.to(dev), relu=relu, w16=w16.to(dev, BF16))
+        assert _maxerr(out16, ref16) < 1e-3
 
 
 @pytest.mark.parametrize("r", [2, 3, 6])

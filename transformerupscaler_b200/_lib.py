@@ -31,7 +31,7 @@ class TuUpsamplerStage(C.Structure):
 class TuModelWeights(C.Structure):
     _fields_ = [
         ("model", C.c_int), ("dim", C.c_int), ("heads", C.c_int), ("n_blocks", C.c_int),
-        ("conv1_w", C.c_void_p), ("conv1_b", C.c_void_p),
+        ("conv1_w", C.c_void_p), ("conv1_b", C.c_void_p), ("conv1_w64", C.c_void_p),
         ("conv2_w", C.c_void_p), ("conv2_b", C.c_void_p),
         ("down_w", C.c_void_p), ("down_b", C.c_void_p),
         ("embed_w", C.c_void_p), ("embed_b", C.c_void_p),
@@ -39,10 +39,10 @@ class TuModelWeights(C.Structure):
         ("blocks", C.POINTER(TuBlockWeights)),
         ("unembed_w", C.c_void_p), ("unembed_b", C.c_void_p),
         ("dec1_w", C.c_void_p), ("dec1_b", C.c_void_p),
-        ("dec2_w", C.c_void_p), ("dec2_b", C.c_void_p),
+        ("dec2_w", C.c_void_p), ("dec2_b", C.c_void_p), ("dec2_w16", C.c_void_p),
         ("up1", (TuUpsamplerStage * 2) * 4),
         ("fin", (TuUpsamplerStage * 2) * 4),
-        ("up1conv_w", C.c_void_p),
+        ("up1conv_w", C.c_void_p), ("up1conv_w16", C.c_void_p),
         ("finconv_w", C.c_void_p), ("finconv_b", C.c_void_p),
     ]
 
@@ -59,9 +59,9 @@ SIGNATURES = {
     "tu_profile_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "tu_forward_workspace_bytes": (sz, [i32] * 8),
     "tu_forward": (i32, [C.POINTER(TuModelWeights), vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
-    "tu_stem_conv": (i32, [vp, i32, fp, fp, vp, i32, i32, i32, i32, vp]),
+    "tu_stem_conv": (i32, [vp, i32, fp, vp, fp, vp, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c64": (i32, [vp, vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
-    "tu_conv3x3_c64_to3": (i32, [vp, i32, fp, fp, fp, i32, i32, i32, i32, vp]),
+    "tu_conv3x3_c64_to3": (i32, [vp, i32, fp, vp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c3_ps": (i32, [fp, fp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_final_conv_add": (i32, [fp, fp, fp, fp, vp, i32, i32, i32, i32, i32, vp]),
     "tu_patch_embed": (i32, [vp, i32, vp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -19,6 +19,7 @@ SOURCES = [
     "resample.cu",
     "tc/conv3x3_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
+    "tc/stem_tcgen05.cu",
 ]
 
 NVCC_FLAGS = [

@@ -145,7 +145,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
 
     // ---- encoder
     if (!dry) {
-        if ((rc = tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_b, f1, dt, B, H, W, stv))) return rc;
+        if ((rc = tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv))) return rc;
         prof_begin(st);
         rc = tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv);
         prof_end(st);
@@ -173,7 +173,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         }
         upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
         if (!dry)
-            if ((rc = tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, nullptr, upA, B, ch, cw, 1, stv))) return rc;
+            if ((rc = tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv))) return rc;
     }
 
     // ---- tokens
@@ -199,7 +199,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         if (rc) return rc;
         // ---- decoder
         if ((rc = tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv))) return rc;
-        if ((rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_b, res, B, Hc, Wc, 0, stv))) return rc;
+        if ((rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv))) return rc;
     }
 
     if (!fast) {

@@ -70,6 +70,78 @@ __global__ void __launch_bounds__(256) bicubic_add_clamp_kernel(const TI *__rest
     }
 }
 
+// Tiled separable version for up-scaling (at most TR source rows feed the 16 output rows of a tile):
+// per tile, every needed source row is first resampled horizontally into shared memory (4 taps), then the 16
+// output rows take their 4 vertical taps from shared memory.  Same operation order as ATen (horizontal sum
+// inside each source row, then the vertical sum), ~6x fewer instructions per output than the direct kernel.
+constexpr int BT_W = 128, BT_H = 16, BT_R = 24;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) bicubic_add_clamp_tiled_kernel(const TI *__restrict__ x, int H, int W,
+                                                                      const float *__restrict__ res, int rH, int rW,
+                                                                      TO *__restrict__ out, int oH, int oW, int clamp) {
+    __shared__ float hx[BT_R][BT_W];
+    __shared__ float hr[BT_R][BT_W];
+    __shared__ int yidx[2][BT_H][4];
+    __shared__ float yw[2][BT_H][4];
+    const int t = threadIdx.x, cx = t & (BT_W - 1), half = t >> 7;
+    const int ox0 = blockIdx.x * BT_W, oy0 = blockIdx.y * BT_H, b = blockIdx.z;
+    const int ox = ox0 + cx;
+    const Cubic tx = cubic_taps(min(ox, oW - 1), W, oW);
+    Cubic tr = tx;
+    if (res) tr = cubic_taps(min(ox, oW - 1), rW, oW);
+    if (t < 2 * BT_H) {
+        const int s = t / BT_H, r = t % BT_H;
+        const Cubic c = cubic_taps(min(oy0 + r, oH - 1), s ? rH : H, oH);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { yidx[s][r][i] = c.idx[i]; yw[s][r][i] = c.w[i]; }
+    }
+    __syncthreads();
+    const int lo_x = yidx[0][0][0], n_x = yidx[0][BT_H - 1][3] - lo_x + 1;
+    const int lo_r = yidx[1][0][0], n_r = res ? yidx[1][BT_H - 1][3] - lo_r + 1 : 0;
+#pragma unroll 1
+    for (int c = 0; c < 3; ++c) {
+        const TI *px = x + (((long)b * 3 + c) * H + lo_x) * W;
+        for (int s = half; s < n_x; s += 2) {
+            const TI *row = px + (long)s * W;
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v += to_f(row[tx.idx[j]]) * tx.w[j];
+            hx[s][cx] = v;
+        }
+        if (res) {
+            const float *pr = res + (((long)b * 3 + c) * rH + lo_r) * rW;
+            for (int s = half; s < n_r; s += 2) {
+                const float *row = pr + (long)s * rW;
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v += row[tr.idx[j]] * tr.w[j];
+                hr[s][cx] = v;
+            }
+        }
+        __syncthreads();
+        if (ox < oW) {
+#pragma unroll
+            for (int k = 0; k < BT_H / 2; ++k) {
+                const int r = half * (BT_H / 2) + k, oy = oy0 + r;
+                if (oy >= oH) break;
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v += hx[yidx[0][r][i] - lo_x][cx] * yw[0][r][i];
+                if (res) {
+                    float u = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u += hr[yidx[1][r][i] - lo_r][cx] * yw[1][r][i];
+                    v += u;
+                }
+                if (clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+                out[(((long)b * 3 + c) * oH + oy) * oW + ox] = from_f<TO>(v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // triangle-filter taps for one output index: [lo, lo+n) and the normalisation 1/sum
 __device__ __forceinline__ void aa_range(int dst, int in_size, int out_size, int &lo, int &n, float &center, float &inv,
                                          float &norm) {
@@ -119,12 +191,18 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     TU_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "bicubic_add_clamp: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(outW, 64), ceil_div(outH, 4), B);
-#define TU_BIC(TI, TO) \
-    bicubic_add_clamp_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI *)x, H, W, res, rH, rW, (TO *)out, outH, outW, clamp)
-    if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC(float, float);
-    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC(float, bf16);
-    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC(bf16, float);
-    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC(bf16, bf16);
+    // tiled kernel when the 16 output rows of a tile never need more than BT_R source rows (any up-scaling)
+    const bool tiled = (long)BT_H * H <= (long)(BT_R - 5) * outH && (!res || (long)BT_H * rH <= (long)(BT_R - 5) * outH);
+    dim3 tgrid(ceil_div(outW, BT_W), ceil_div(outH, BT_H), B);
+#define TU_BIC(TI, TO)                                                                                                          \
+    if (tiled)                                                                                                                  \
+        bicubic_add_clamp_tiled_kernel<TI, TO><<<tgrid, 256, 0, st>>>((const TI *)x, H, W, res, rH, rW, (TO *)out, outH, outW, clamp); \
+    else                                                                                                                        \
+        bicubic_add_clamp_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI *)x, H, W, res, rH, rW, (TO *)out, outH, outW, clamp)
+    if (in_dtype == TU_F32 && out_dtype == TU_F32) { TU_BIC(float, float); }
+    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) { TU_BIC(float, bf16); }
+    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) { TU_BIC(bf16, float); }
+    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) { TU_BIC(bf16, bf16); }
     else TU_CHECK_ARG(false, "bicubic_add_clamp: bad dtype");
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");

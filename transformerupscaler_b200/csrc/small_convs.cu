@@ -5,6 +5,7 @@
 // final_upscale = Upsampler(n_feats=3) (utils.py:43-98; model.py:211,316), final_upscale_conv + sum
 // + clamp (model.py:212,317-327).
 #include "tu_common.cuh"
+#include "tc/tc_api.cuh"
 
 namespace tu {
 
@@ -168,10 +169,15 @@ __global__ void __launch_bounds__(256) final_conv_add_kernel(const float *__rest
 
 using namespace tu;
 
-extern "C" int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const float *b, void *out, int dtype, int B,
-                            int H, int W, void *stream) {
+extern "C" int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const void *w64, const float *b, void *out,
+                            int dtype, int B, int H, int W, void *stream) {
     TU_CHECK_ARG(x && w27x64 && b && out && B > 0 && H > 0 && W > 0, "stem_conv: bad argument");
+    TU_CHECK_ARG(in_dtype == TU_F32 || in_dtype == TU_BF16, "stem_conv: bad input dtype");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TU_BF16 && w64 && tc_enabled()) {
+        int rc = tc_stem_conv(x, in_dtype, (const bf16 *)w64, b, (bf16 *)out, B, H, W, st);
+        if (rc != TU_TC_UNSUPPORTED) return rc;
+    }
     dim3 grid(ceil_div(W, 16), ceil_div(H, 16), B);
     if (in_dtype == TU_F32 && dtype == TU_F32)
         stem_conv_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, w27x64, b, (float *)out, H, W);
@@ -187,10 +193,14 @@ extern "C" int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, co
     return TU_OK;
 }
 
-extern "C" int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const float *b, float *out, int B, int H,
-                                  int W, int relu, void *stream) {
+extern "C" int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const void *w16, const float *b, float *out, int B,
+                                  int H, int W, int relu, void *stream) {
     TU_CHECK_ARG(in && w && out && B > 0 && H > 0 && W > 0, "conv3x3_c64_to3: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TU_BF16 && w16 && tc_enabled()) {
+        int rc = tc_conv3x3_c64_to3((const bf16 *)in, (const bf16 *)w16, b, out, B, H, W, relu, st);
+        if (rc != TU_TC_UNSUPPORTED) return rc;
+    }
     dim3 grid(ceil_div(W, 128), H, B);
     if (dtype == TU_F32)
         conv64to3_kernel<float><<<grid, 128, 0, st>>>((const float *)in, w, b, out, H, W, relu);

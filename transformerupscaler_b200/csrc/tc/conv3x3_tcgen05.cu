@@ -33,8 +33,8 @@ constexpr int TILE_M = 128;               // output pixels per row segment = UMM
 constexpr int BOXW = 136;                 // pixels per TMA box (128 + halo, keeps slots 1024-byte aligned)
 constexpr int UNIT_BYTES = BOXW * 128;    // 17408 = 17 * 1024
 constexpr int RING_UNITS = 6;
-constexpr int W_BYTES = 9 * 64 * 128;     // 73728
-constexpr int SMEM_BYTES = W_BYTES + RING_UNITS * UNIT_BYTES + 256 + 1024;
+constexpr int W_BYTES_MAX = 9 * 64 * 128;  // 73728 (64 output channels); 9*16*128 for the 64->3 head (3 padded to 16)
+constexpr int SMEM_BYTES = W_BYTES_MAX + RING_UNITS * UNIT_BYTES + 256 + 1024;
 constexpr int NUM_THREADS = 256;
 
 struct ConvParams {
@@ -43,6 +43,7 @@ struct ConvParams {
     int tiles_x, tiles_y, tiles_per_chunk, total_tiles;
     const float *bias;
     bf16 *out;
+    float *out3;        // NOUT == 16: planar fp32 (B,3,Ho,Wo)
     int base_off_mode;
 };
 
@@ -60,13 +61,15 @@ __device__ __forceinline__ uint64_t adesc(uint32_t addr, int mode) {
     return ptx::make_sdesc_sw128(addr, mode ? ((addr >> 7) & 7u) : 0u);
 }
 
+template <int NOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr int W_TAP = NOUT * 128, W_BYTES = 9 * W_TAP;
     const uint32_t w_sm = smem0;
-    const uint32_t ring_sm = smem0 + W_BYTES;
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + W_BYTES + RING_UNITS * UNIT_BYTES);
+    const uint32_t ring_sm = smem0 + W_BYTES_MAX;
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + W_BYTES_MAX + RING_UNITS * UNIT_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stride;
     const int units_per_step = S;                       // stride 2: even + odd slot per input row
@@ -119,7 +122,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 }
                 ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
                 for (int tap = 0; tap < 9; ++tap)
-                    ptx::tma_load_2d(w_sm + tap * 8192, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * 9 + tap) * 64);
+                    ptx::tma_load_2d(w_sm + tap * W_TAP, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * 9 + tap) * NOUT);
                 cur_chunk = chunk;
             }
             const int x0 = tx * TILE_M, y0 = ty * TILE_R;
@@ -140,7 +143,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         }
     } else if (warp == 1 && lane == 0) {
         // ================================ MMA issuer ================================
-        const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, 64);
+        const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, NOUT);
         int slot = 0;
         uint32_t phase = 0;
         int cur_chunk = -1;
@@ -172,7 +175,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 const uint64_t ad = adesc(src + kx * 128 + k4 * 32, p.base_off_mode);
-                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * 8192 + k4 * 32, 0);
+                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * W_TAP + k4 * 32, 0);
                                 ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
                             }
                         }
@@ -191,7 +194,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
                                 const uint64_t ad = adesc(a0 + k4 * 32, p.base_off_mode);
-                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * 8192 + k4 * 32, 0);
+                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * W_TAP + k4 * 32, 0);
                                 ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
                             }
                         }
@@ -226,6 +229,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             for (int r = 0; r < TILE_R; ++r) {
                 const int y = ty * TILE_R + r;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (TILE_R * 64) + r * 64;
+                if (NOUT == 16) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(taddr, v);       // columns 16..31 belong to nobody (row stride is 64 columns)
+                    ptx::tmem_ld_wait();
+                    if (y < p.Ho && px < p.Wo) {
+                        const long plane = (long)p.Ho * p.Wo;
+                        float *o = p.out3 + (long)b * 3 * plane + (long)y * p.Wo + px;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            float a = __uint_as_float(v[c]) + (bias ? __ldg(bias + c) : 0.f);
+                            o[c * plane] = p.relu ? fmaxf(a, 0.f) : a;
+                        }
+                    }
+                    continue;
+                }
                 uint32_t v0[32], v1[32];
                 ptx::tmem_ld_x32(taddr, v0);
                 ptx::tmem_ld_x32(taddr + 32, v1);
@@ -306,10 +324,8 @@ TcEncodeFn tc_encode_fn() {
 int tc_available() { return tc_encode_fn() != nullptr; }
 void tc_set_base_off_mode(int m) { g_base_off_mode = m; }
 
-int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
-                   int nchunk, int ps_r, cudaStream_t st) {
-    if (nchunk > 1 && ps_r == 0) return TU_TC_UNSUPPORTED;
-    if (stride == 2 && (W & 1)) return TU_TC_UNSUPPORTED;
+static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, float *out3, int nout, int B, int H, int W,
+                       int stride, int relu, int nchunk, int ps_r, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(w) & 127) || (reinterpret_cast<uintptr_t>(out) & 15))
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
@@ -320,7 +336,8 @@ int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, 
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv3x3_tc smem attribute");
         g_attr_set = true;
     }
@@ -342,8 +359,8 @@ int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, 
             set_error("tu: cuTensorMapEncodeTiled(activations) failed with code " + std::to_string((int)r));
             return TU_ERR_CUDA;
         }
-        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * 9 * 64}, ws[1] = {128};
-        cuuint32_t wb[2] = {64, 64}, we[2] = {1, 1};
+        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * 9 * nout}, ws[1] = {128};
+        cuuint32_t wb[2] = {64, (cuuint32_t)nout}, we[2] = {1, 1};
         r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -358,11 +375,26 @@ int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, 
     p.tiles_x = ceil_div(p.Wo, TILE_M); p.tiles_y = ceil_div(p.Ho, TILE_R);
     p.tiles_per_chunk = p.tiles_x * p.tiles_y * B;
     p.total_tiles = p.tiles_per_chunk * nchunk;
-    p.bias = bias; p.out = out; p.base_off_mode = g_base_off_mode;
+    p.bias = bias; p.out = out; p.out3 = out3; p.base_off_mode = g_base_off_mode;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
-    conv3x3_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
+    if (nout == 64)
+        conv3x3_tc_kernel<64><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
+    else
+        conv3x3_tc_kernel<16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
     TU_CHECK_LAUNCH("conv3x3_tc");
     return TU_OK;
+}
+
+int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
+                   int nchunk, int ps_r, cudaStream_t st) {
+    if (nchunk > 1 && ps_r == 0) return TU_TC_UNSUPPORTED;
+    if (stride == 2 && (W & 1)) return TU_TC_UNSUPPORTED;
+    return launch_conv(in, w, bias, out, nullptr, 64, B, H, W, stride, relu, nchunk, ps_r, st);
+}
+
+int tc_conv3x3_c64_to3(const bf16 *in, const bf16 *w16, const float *bias, float *out, int B, int H, int W, int relu,
+                       cudaStream_t st) {
+    return launch_conv(in, w16, bias, reinterpret_cast<bf16 *>(out), out, 16, B, H, W, 1, relu, 1, 0, st);
 }
 
 }  // namespace tu

@@ -1,0 +1,227 @@
+// conv1 (3 -> 64, 3x3, pad 1, + ReLU) on the tensor cores: NCHW image in, NHWC bf16 features out.
+// Reference: conv1 + relu (WindowTransformer/model.py:200,244; FastTransformer/model.py:202,251;
+// ResidualTransformer/model.py:83,128).
+//
+// The op is HBM-bound on its 128-byte-per-pixel output (K = 27 only), so the point of using tcgen05 here is to
+// take the 1728 FMAs per pixel off the CUDA cores: four "builder" warps write the im2col rows (27 taps padded to
+// 32 bf16 = four 16-byte chunks per pixel) straight into a 128-byte-swizzled K-major operand tile in shared
+// memory, one thread issues two 128x64x16 UMMAs per 128-pixel row segment, and four epilogue warps drain TMEM
+// (+bias, ReLU, bf16) into full 128-byte pixel stores.  Tiles are row segments of 128 pixels; the CTA is
+// persistent and double-buffers both the operand tile and the accumulator.
+#include <cuda.h>
+
+#include "ptx.cuh"
+#include "tc_api.cuh"
+
+namespace tu {
+
+namespace {
+
+constexpr int NUM_THREADS = 288;      // warps 0-3 epilogue, 4-7 builders, 8 MMA / TMEM / weight TMA
+constexpr int A_BYTES = 128 * 128;    // 128 pixels x 128-byte rows
+constexpr int W_BYTES = 64 * 128;     // 64 output channels x (64 k, 27 real)
+constexpr int SMEM_BYTES = 2 * A_BYTES + W_BYTES + 128 + 1024;
+
+struct StemParams {
+    int B, H, W, tiles_x, total_tiles;
+    const float *bias;
+    bf16 *out;
+};
+
+struct Barriers {
+    uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], w_full;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict__ x, const StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+    const uint32_t a_sm = smem0, w_sm = smem0 + 2 * A_BYTES;
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + 2 * A_BYTES + W_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 128);
+            ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
+        }
+        ptx::mbar_init(ptx::smem_u32(&bars->w_full), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 8) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 128);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ================================ weights + MMA issuer ================================
+            ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
+            ptx::tma_load_2d(w_sm, &tmap_w, ptx::smem_u32(&bars->w_full), 0, 0);
+            ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
+            const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), ph ^ 1);
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_full[buf]), ph);
+                ptx::tc_fence_after();
+                const uint32_t a = a_sm + buf * A_BYTES;
+#pragma unroll
+                for (int k4 = 0; k4 < 2; ++k4)     // k = 0..31 (27 taps + 5 zeros); chunks 4-7 of a row are never read
+                    ptx::umma_bf16(tmem_base + buf * 64, ptx::make_sdesc_sw128(a + k4 * 32, 0),
+                                   ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc, k4 != 0);
+                ptx::umma_commit(ptx::smem_u32(&bars->a_empty[buf]));
+                ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ builders: im2col rows -> swizzled smem ================================
+        const int i = (warp - 4) * 32 + lane;            // pixel of the segment = operand row
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int tx = t % p.tiles_x;
+            int rem = t / p.tiles_x;
+            const int y = rem % p.H, b = rem / p.H;
+            const int px = tx * 128 + i;
+            float v[32];
+#pragma unroll
+            for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y + ky - 1;
+                const bool rowok = iy >= 0 && iy < p.H;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const TI *row = x + (((long)b * 3 + c) * p.H + (rowok ? iy : 0)) * p.W;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = px + kx - 1;
+                        v[(ky * 3 + kx) * 3 + c] = (rowok && ix >= 0 && ix < p.W) ? to_f(row[ix]) : 0.f;
+                    }
+                }
+            }
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[buf]), ph ^ 1);
+            uint8_t *rowp = smem_al + buf * A_BYTES + i * 128;
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                uint4 u;
+                u.x = pack2(v[ch * 8 + 0], v[ch * 8 + 1]);
+                u.y = pack2(v[ch * 8 + 2], v[ch * 8 + 3]);
+                u.z = pack2(v[ch * 8 + 4], v[ch * 8 + 5]);
+                u.w = pack2(v[ch * 8 + 6], v[ch * 8 + 7]);
+                *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
+            }
+            ptx::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
+            ptx::mbar_arrive(ptx::smem_u32(&bars->a_full[buf]));
+        }
+    } else {
+        // ================================ epilogue ================================
+        const int q = warp;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int tx = t % p.tiles_x;
+            int rem = t / p.tiles_x;
+            const int y = rem % p.H, b = rem / p.H;
+            const int px = tx * 128 + q * 32 + lane;
+            const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), ph);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64;
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld_x32(taddr, v0);
+            ptx::tmem_ld_x32(taddr + 32, v1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));   // values are in registers now
+            if (px < p.W) {
+                bf16 *o = p.out + (((long)b * p.H + y) * p.W + px) * 64;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 u;
+                    u.x = pack2(fmaxf(__uint_as_float(v0[c + 0]) + __ldg(p.bias + c + 0), 0.f), fmaxf(__uint_as_float(v0[c + 1]) + __ldg(p.bias + c + 1), 0.f));
+                    u.y = pack2(fmaxf(__uint_as_float(v0[c + 2]) + __ldg(p.bias + c + 2), 0.f), fmaxf(__uint_as_float(v0[c + 3]) + __ldg(p.bias + c + 3), 0.f));
+                    u.z = pack2(fmaxf(__uint_as_float(v0[c + 4]) + __ldg(p.bias + c + 4), 0.f), fmaxf(__uint_as_float(v0[c + 5]) + __ldg(p.bias + c + 5), 0.f));
+                    u.w = pack2(fmaxf(__uint_as_float(v0[c + 6]) + __ldg(p.bias + c + 6), 0.f), fmaxf(__uint_as_float(v0[c + 7]) + __ldg(p.bias + c + 7), 0.f));
+                    *reinterpret_cast<uint4 *>(o + c) = u;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 u;
+                    u.x = pack2(fmaxf(__uint_as_float(v1[c + 0]) + __ldg(p.bias + 32 + c + 0), 0.f), fmaxf(__uint_as_float(v1[c + 1]) + __ldg(p.bias + 32 + c + 1), 0.f));
+                    u.y = pack2(fmaxf(__uint_as_float(v1[c + 2]) + __ldg(p.bias + 32 + c + 2), 0.f), fmaxf(__uint_as_float(v1[c + 3]) + __ldg(p.bias + 32 + c + 3), 0.f));
+                    u.z = pack2(fmaxf(__uint_as_float(v1[c + 4]) + __ldg(p.bias + 32 + c + 4), 0.f), fmaxf(__uint_as_float(v1[c + 5]) + __ldg(p.bias + 32 + c + 5), 0.f));
+                    u.w = pack2(fmaxf(__uint_as_float(v1[c + 6]) + __ldg(p.bias + 32 + c + 6), 0.f), fmaxf(__uint_as_float(v1[c + 7]) + __ldg(p.bias + 32 + c + 7), 0.f));
+                    *reinterpret_cast<uint4 *>(o + 32 + c) = u;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) ptx::tmem_dealloc(tmem_base, 128);
+}
+
+int g_sm_count = 0;
+bool g_attr_set = false;
+
+}  // namespace
+
+// w64: bf16 (64 co, 64 k) with k = (ky*3+kx)*3 + ci for k < 27 and zeros above
+int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st) {
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || (reinterpret_cast<uintptr_t>(w64) & 127) || (reinterpret_cast<uintptr_t>(out) & 15)) return TU_TC_UNSUPPORTED;
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem attribute");
+        g_attr_set = true;
+    }
+    CUtensorMap tw;
+    cuuint64_t wd[2] = {64, 64}, ws[1] = {128};
+    cuuint32_t wb[2] = {64, 64}, we[2] = {1, 1};
+    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)w64, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tu: cuTensorMapEncodeTiled(stem weights) failed with code " + std::to_string((int)r));
+        return TU_ERR_CUDA;
+    }
+    StemParams p;
+    p.B = B; p.H = H; p.W = W;
+    p.tiles_x = ceil_div(W, 128);
+    p.total_tiles = p.tiles_x * H * B;
+    p.bias = bias; p.out = out;
+    const int grid = p.total_tiles < 2 * g_sm_count ? p.total_tiles : 2 * g_sm_count;
+    if (in_dtype == TU_F32)
+        stem_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, (const float *)x, p);
+    else
+        stem_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, (const bf16 *)x, p);
+    TU_CHECK_LAUNCH("stem_tc");
+    return TU_OK;
+}
+
+}  // namespace tu

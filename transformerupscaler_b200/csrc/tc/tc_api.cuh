@@ -36,6 +36,13 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
 int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
                    int nchunk, int ps_r, cudaStream_t st);
 
+// conv1 3 -> 64 + ReLU, NCHW (fp32|bf16) -> NHWC bf16 (stem_tcgen05.cu)
+int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st);
+
+// 64 -> 3 head (decoder_conv2 / up1_conv): w16 = bf16 [9 taps][16 co (3 real, 13 zero)][64 ci]; planar fp32 (B,3,H,W) out
+int tc_conv3x3_c64_to3(const bf16 *in, const bf16 *w16, const float *bias, float *out, int B, int H, int W, int relu,
+                       cudaStream_t st);
+
 // one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
 int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
                          void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float *__restrict_
 // ------------------------------------------------------------------ window attention (64 tokens, head_dim 16)
 // qkv (nWin*64, 3*dim) T with q pre-scaled; out (nWin*64, dim) T.  One CTA per (window, head), one
 // query per thread; K, V of the head in shared memory (broadcast reads); softmax over 64 keys in registers.
-// bias_t[h][j][i] (key-major) so that the 64 threads of a CTA read consecutive floats.
+// bias[h][i][j] dense (heads, query, key) fp32.
 template <typename T>
 __global__ void __launch_bounds__(64) window_attn_kernel(const T *__restrict__ qkv, const float *__restrict__ bias_t,
                                                          T *__restrict__ out, int dim, int heads) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(64) window_attn_kernel(const T *__restrict__ q
         vs[i][d] = v4.x; vs[i][d + 1] = v4.y; vs[i][d + 2] = v4.z; vs[i][d + 3] = v4.w;
     }
     __syncthreads();
-    const float *bp = bias_t + (long)h * 4096 + i;
+    const float *bp = bias_t + ((long)h * 64 + i) * 64;
     float s[64];
     float mx = -INFINITY;
 #pragma unroll
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(64) window_attn_kernel(const T *__restrict__ q
         float a = 0.f;
 #pragma unroll
         for (int d = 0; d < 16; ++d) a = fmaf(q[d], ks[j][d], a);
-        a += bp[j * 64];
+        a += bp[j];
         s[j] = a;
         mx = fmaxf(mx, a);
     }
@@ -86,6 +86,96 @@ __global__ void __launch_bounds__(64) window_attn_kernel(const T *__restrict__ q
     T *op = out + ((long)win * 64 + i) * dim + h * 16;
 #pragma unroll
     for (int d = 0; d < 16; d += 4) store4(op + d, make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]));
+}
+
+// ------------------------------------------------------------------ window attention on mma.sync (bf16)
+// Same contract as window_attn_kernel for T = bf16.  CTA = (window, head), 4 warps x 16 query rows.
+// S = Q K^T via 8 m16n8k16 MMAs per warp (K fragments straight from global), + bias, softmax in the accumulator
+// fragments (quad shuffles), P re-used in place as the A operand of the 8 P V MMAs (V via ldmatrix.trans from
+// shared memory), normalisation by the row sum in fp32 at the end.  64x64x16 problems are far too small for a
+// 128-row tcgen05 tile, so the warp-level tensor path is the right tool for this 0.8 % of the FLOPs.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(128) window_attn_mma_kernel(const bf16 *__restrict__ qkv, const float *__restrict__ bias,
+                                                              bf16 *__restrict__ out, int dim) {
+    __shared__ __align__(16) bf16 vs[64][24];     // V of this head, row pitch 48 B (conflict-free ldmatrix)
+    const int win = blockIdx.x, h = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const long ld = 3L * dim;
+    const bf16 *base = qkv + (long)win * 64 * ld + h * 16;
+    {   // stage V: 64 rows x 32 B
+        const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+        *reinterpret_cast<uint4 *>(&vs[r][hf * 8]) = *reinterpret_cast<const uint4 *>(base + r * ld + 2 * dim + hf * 8);
+    }
+    const int r0 = warp * 16 + g;                 // this thread's query rows: r0 and r0 + 8
+    uint32_t qa[4];
+    qa[0] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2);
+    qa[1] = *reinterpret_cast<const uint32_t *>(base + (long)(r0 + 8) * ld + tq * 2);
+    qa[2] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2 + 8);
+    qa[3] = *reinterpret_cast<const uint32_t *>(base + (long)(r0 + 8) * ld + tq * 2 + 8);
+    float s[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const bf16 *kp = base + (long)(n * 8 + g) * ld + dim + tq * 2;      // key j = n*8 + g, d = tq*2 (+8)
+        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kp), b1 = *reinterpret_cast<const uint32_t *>(kp + 8);
+        s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+        mma_bf16_16816(s[n], qa, b0, b1);
+    }
+    const float *bp0 = bias + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        const float2 ba = *reinterpret_cast<const float2 *>(bp0 + n * 8), bb = *reinterpret_cast<const float2 *>(bp1 + n * 8);
+        s[n][0] += ba.x; s[n][1] += ba.y; s[n][2] += bb.x; s[n][3] += bb.y;
+        m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+        m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+    const float L2E = 1.4426950408889634f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        s[n][0] = exp2f((s[n][0] - m0) * L2E); s[n][1] = exp2f((s[n][1] - m0) * L2E);
+        s[n][2] = exp2f((s[n][2] - m1) * L2E); s[n][3] = exp2f((s[n][3] - m1) * L2E);
+        l0 += s[n][0] + s[n][1];
+        l1 += s[n][2] + s[n][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    __syncthreads();                               // V staged
+    float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {                  // 16 keys per step
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * t][0], s[2 * t][1]);
+        pa[1] = pack_bf16x2(s[2 * t][2], s[2 * t][3]);
+        pa[2] = pack_bf16x2(s[2 * t + 1][0], s[2 * t + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * t + 1][2], s[2 * t + 1][3]);
+        // four 8x8 matrices: (keys 0-7 | 8-15) x (d 0-7 | 8-15), transposed on load -> B fragments
+        uint32_t v0, v1, v2, v3;
+        const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&vs[t * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][(lane >> 4) * 8]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                     : "r"(addr));
+        mma_bf16_16816(o[0], pa, v0, v1);
+        mma_bf16_16816(o[1], pa, v2, v3);
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    bf16 *op0 = out + ((long)win * 64 + r0) * dim + h * 16 + tq * 2, *op1 = op0 + 8L * dim;
+    *reinterpret_cast<uint32_t *>(op0) = pack_bf16x2(o[0][0] * i0, o[0][1] * i0);
+    *reinterpret_cast<uint32_t *>(op0 + 8) = pack_bf16x2(o[1][0] * i0, o[1][1] * i0);
+    *reinterpret_cast<uint32_t *>(op1) = pack_bf16x2(o[0][2] * i1, o[0][3] * i1);
+    *reinterpret_cast<uint32_t *>(op1 + 8) = pack_bf16x2(o[1][2] * i1, o[1][3] * i1);
 }
 
 // ------------------------------------------------------------------ global attention (S tokens per frame, head_dim 16)
@@ -215,7 +305,11 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
     int rc;
     if ((rc = launch_layernorm<T>(x, w->ln1_w, w->ln1_b, ln, M, dim, st))) return rc;
     if ((rc = block_linear<T>(ln, dim, w->qkv_w, w->qkv_b, M, 3 * dim, dim, 0, big, nullptr, nullptr, tc, st, "qkv"))) return rc;
-    if (window) {
+    if (window && tc && sizeof(T) == 2) {
+        dim3 grid(M / 64, heads);
+        window_attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16 *)big, w->rel_bias, (bf16 *)att, dim);
+        TU_CHECK_LAUNCH("window_attn_mma");
+    } else if (window) {
         dim3 grid(M / 64, heads);
         window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
         TU_CHECK_LAUNCH("window_attn");

@@ -17,10 +17,10 @@ SCALES = (2, 3, 4, 6)
 
 
 def dense_rel_bias_t(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
-    """(heads, key j, query i) fp32 from the (225, heads) table and the (64,64) index buffer
-    (reference: WindowTransformer/model.py:118-122 gathers table[index] -> (i, j, heads))."""
+    """(heads, query i, key j) fp32 from the (225, heads) table and the (64,64) index buffer
+    (reference: WindowTransformer/model.py:118-122 gathers table[index] -> (i, j, heads) -> permute(2,0,1))."""
     b = table.float()[index.reshape(-1).long()].reshape(64, 64, -1)      # (i, j, h)
-    return b.permute(2, 1, 0).contiguous()                               # (h, j, i)
+    return b.permute(2, 0, 1).contiguous()                               # (h, i, j)
 
 
 class PackedWeights:
@@ -48,6 +48,11 @@ class PackedWeights:
         def conv_to3(w):        # (3, 64, 3, 3) -> (9, 64, 3)
             return dev(w.float().permute(2, 3, 1, 0).reshape(9, 64, 3), f32)
 
+        def conv_to3_tc(w):     # (3, 64, 3, 3) -> bf16 (9 taps, 16 co [3 real], 64 ci) for the tensor-core head
+            t = torch.zeros(9, 16, 64, dtype=torch.float32, device=w.device)
+            t[:, :3] = w.float().permute(2, 3, 0, 1).reshape(9, 3, 64)
+            return dev(t, torch.bfloat16)
+
         mw = _lib.TuModelWeights()
         mw.model = _lib.MODEL_IDS[model]
         fast, resid = model == "FastTransformer", model == "ResidualTransformer"
@@ -59,6 +64,10 @@ class PackedWeights:
 
         mw.conv1_w = ptr(conv_small_in(sd["conv1.weight"]))
         mw.conv1_b = ptr(dev(sd["conv1.bias"], f32))
+        if dtype == torch.bfloat16:     # tensor-core stem: (64 co, 64 k), k = (ky*3+kx)*3+ci, zero-padded from 27
+            w64 = torch.zeros(64, 64, dtype=torch.float32, device=sd["conv1.weight"].device)
+            w64[:, :27] = sd["conv1.weight"].float().permute(0, 2, 3, 1).reshape(64, 27)
+            mw.conv1_w64 = ptr(dev(w64, torch.bfloat16))
         mw.conv2_w = ptr(conv64(sd["conv2.weight"]))
         mw.conv2_b = ptr(dev(sd["conv2.bias"], f32))
         if not fast:
@@ -76,6 +85,8 @@ class PackedWeights:
         mw.dec1_b = ptr(dev(sd["decoder_conv1.bias"], f32))
         mw.dec2_w = ptr(conv_to3(sd["decoder_conv2.weight"]))
         mw.dec2_b = ptr(dev(sd["decoder_conv2.bias"], f32))
+        if dtype == torch.bfloat16:
+            mw.dec2_w16 = ptr(conv_to3_tc(sd["decoder_conv2.weight"]))
 
         # transformer blocks (q rows and q bias pre-scaled by head_dim^-0.5 = 0.25: exact in fp32 and bf16)
         self.blocks = (_lib.TuBlockWeights * nb)()
@@ -116,6 +127,8 @@ class PackedWeights:
                     mw.fin[slot][si].b = ptr(dev(sd[f"final_upscale.upsamplers.{s}.{idx}.bias"], f32))
                     mw.fin[slot][si].r = r
             mw.up1conv_w = ptr(conv_to3(sd["up1_conv.conv.weight"]))
+            if dtype == torch.bfloat16:
+                mw.up1conv_w16 = ptr(conv_to3_tc(sd["up1_conv.conv.weight"]))
             mw.finconv_w = ptr(conv_small_in(sd["final_upscale_conv.weight"]))
             mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
         self.struct = mw
