@@ -1,0 +1,120 @@
+"""CPU: host-side mirror of the reference interface — state_dict compatibility, precision selection, the shape logic
+of the three forwards, error behaviour, and frame sharding over a 2-rank gloo group."""
+import importlib
+import os
+
+import pytest
+import torch
+
+from oracle.weights import _spec, synth_state_dict
+
+MODELS = ["WindowTransformer", "FastTransformer", "ResidualTransformer"]
+
+
+def make(name):
+    return importlib.import_module(f"transformerupscaler_b200.models.{name}.model").TransformerModel()
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_state_dict_keys_and_shapes_match_reference_spec(name):
+    m = make(name)
+    sd = m.state_dict()
+    spec = {k: tuple(shape) for k, shape, _, _ in _spec(name)}
+    assert set(sd) == set(spec)
+    for k, v in sd.items():
+        assert tuple(v.shape) == spec[k], k
+    m.load_state_dict(synth_state_dict(name, 3), strict=True)
+    # root-level drop-in alias used by importlib.import_module(f"models.{name}.model")
+    alias = importlib.import_module(f"models.{name}.model").TransformerModel
+    assert alias is type(m)
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_cpu_tensor_and_training_mode_are_rejected(name):
+    m = make(name)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        m(torch.rand(1, 3, 32, 32))
+    m.eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.rand(1, 3, 32, 32))
+
+
+def test_fast_forward_shape_logic(monkeypatch):
+    from transformerupscaler_b200 import engine
+    calls = []
+
+    def fake_forward(x, handle, oh, ow, scale, cbf, obf, clamp):
+        calls.append(("fwd", oh, ow, scale, clamp))
+        return torch.zeros(x.shape[0], 3, oh, ow)
+
+    def fake_resize(x, oh, ow, clamp):
+        calls.append(("resize", oh, ow, clamp))
+        return torch.zeros(x.shape[0], 3, oh, ow)
+
+    monkeypatch.setattr(engine, "tu_forward", fake_forward)
+    monkeypatch.setattr(engine, "tu_resize_aa", fake_resize)
+    x = torch.zeros(1, 3, 40, 56)
+    # upscale_factor overrides res_out; no resize because the size already matches
+    out = engine.run_forward(1, "FastTransformer", x, (1080, 1920), 3, True, False, torch.float32)
+    assert tuple(out.shape) == (1, 3, 120, 168) and calls == [("fwd", 120, 168, 3, True)]
+    # res_out path: factor = ceil(max ratio) = 2, then antialiased resize + clamp afterwards
+    calls.clear()
+    out = engine.run_forward(1, "FastTransformer", x, (60, 84), None, True, False, torch.float32)
+    assert tuple(out.shape) == (1, 3, 60, 84)
+    assert calls == [("fwd", 80, 112, 2, False), ("resize", 60, 84, True)]
+    # require_ratio=False (train.py:124) keeps the integer-factor size
+    calls.clear()
+    out = engine.run_forward(1, "FastTransformer", x, (60, 84), None, False, False, torch.float32)
+    assert tuple(out.shape) == (1, 3, 80, 112)
+    # the reference compares with (H_out, H_out): a square target equal to that skips the resize
+    calls.clear()
+    engine.run_forward(1, "FastTransformer", torch.zeros(1, 3, 40, 40), (80, 80), None, True, False, torch.float32)
+    assert calls == [("fwd", 80, 80, 2, True)]
+    with pytest.raises(ValueError, match="scale=5 was not built"):
+        engine.run_forward(1, "FastTransformer", x, (200, 280), None, True, False, torch.float32)
+    # Window / Residual: upscale_factor overrides res_out
+    calls.clear()
+    engine.run_forward(1, "WindowTransformer", x, (1080, 1920), 2, True, False, torch.float32)
+    assert calls == [("fwd", 80, 112, 0, True)]
+
+
+def test_frame_shard_partitions():
+    from transformerupscaler_b200.sharding import frame_shard
+    for total, world in [(64, 8), (64, 3), (5, 8), (8, 1)]:
+        cover = []
+        for r in range(world):
+            a, b = frame_shard(total, r, world)
+            cover += list(range(a, b))
+        assert cover == list(range(total))
+    assert frame_shard(64, 1, 2) == (32, 64)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from transformerupscaler_b200.sharding import frame_shard, gather_frames, max_over_ranks
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    total = 5
+    frames = torch.arange(total, dtype=torch.float32).reshape(total, 1, 1, 1).expand(total, 3, 2, 2).contiguous()
+    a, b = frame_shard(total, rank, world)
+    local = frames[a:b] * 2.0                      # stand-in for "upscale my frames"
+    full = gather_frames(local, total)
+    ms = max_over_ranks(10.0 + rank)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, torch.equal(full, frames * 2.0), ms))
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True]       # every rank reassembles the 1-GPU batch order
+    assert [r[2] for r in res] == [11.0, 11.0]       # max over ranks
