@@ -91,6 +91,10 @@ typedef struct TuModelWeights {
     const float *embed_b;
     const float *pos_embed;     /* fp32 (3600, dim) or NULL                                       */
     const TuBlockWeights *blocks; /* HOST pointer to n_blocks structs                             */
+    /* fused window-transformer stack (dim 128, bf16, tcgen05) or NULL: see packing.py / window_stack_tcgen05.cu */
+    const void *stack_w;        /* bf16 (n_blocks*24*128, 64): weight slabs [128 n][64 k] in consumption order   */
+    const float *stack_p;       /* fp32 n_blocks*1664 + 128: per block c0|ln1w|ln1b|qkvb|c1|ln2w|ln2b|fc1b, then c_final */
+    const float *stack_rel;     /* fp32 (n_blocks, heads, 64, 64) dense relative-position bias            */
     const void *unembed_w;      /* T (4096, dim): row n = (ky*8+kx)*64 + co                       */
     const float *unembed_b;     /* (64)                                                           */
     const void *dec1_w;         /* T (9,64,64)                                                    */

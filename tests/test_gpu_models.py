@@ -100,6 +100,26 @@ def test_window_720p_fullsize_vs_oracle_and_batch_independence():
     assert torch.equal(ob3[0], ob1[0])
 
 
+def test_fused_window_stack_matches_per_block_path():
+    """The one-kernel transformer stack (TMEM-resident residual stream) vs the per-block tensor-core path."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    M, sd = build("WindowTransformer", 23)
+    x = synth_frames(2, 192, 256, seed=79).cuda()
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            lib.tu_debug_set(b"fused_stack", 1)
+            a = M(x, upscale_factor=2)
+            lib.tu_debug_set(b"fused_stack", 0)
+            b = M(x, upscale_factor=2)
+    finally:
+        lib.tu_debug_set(b"fused_stack", 1)
+    ref = orc.window_forward(sd, x.cpu(), upscale_factor=2)
+    assert (a.cpu() - ref).abs().max().item() < TOL_BF16
+    assert (b.cpu() - ref).abs().max().item() < TOL_BF16
+    assert (a - b).abs().max().item() < 1e-2
+
+
 def test_fast_360x640_x2_cfg1_vs_oracle():
     M, sd = build("FastTransformer", 22)
     x = synth_frames(1, 360, 640, seed=78)

@@ -37,6 +37,7 @@ class TuModelWeights(C.Structure):
         ("embed_w", C.c_void_p), ("embed_b", C.c_void_p),
         ("pos_embed", C.c_void_p),
         ("blocks", C.POINTER(TuBlockWeights)),
+        ("stack_w", C.c_void_p), ("stack_p", C.c_void_p), ("stack_rel", C.c_void_p),
         ("unembed_w", C.c_void_p), ("unembed_b", C.c_void_p),
         ("dec1_w", C.c_void_p), ("dec1_b", C.c_void_p),
         ("dec2_w", C.c_void_p), ("dec2_b", C.c_void_p), ("dec2_w16", C.c_void_p),

@@ -20,6 +20,7 @@ SOURCES = [
     "tc/conv3x3_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
     "tc/stem_tcgen05.cu",
+    "tc/window_stack_tcgen05.cu",
 ]
 
 NVCC_FLAGS = [

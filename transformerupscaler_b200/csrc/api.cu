@@ -13,6 +13,7 @@ namespace tu {
 
 static thread_local std::string g_err;
 static int g_use_tc = 1;
+static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -186,7 +187,12 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
                                  fast ? 1 : 0, stv)))
             return rc;
         const bool tc = tc_on(dt);
-        for (int i = 0; i < w->n_blocks; ++i)
+        rc = TU_TC_UNSUPPORTED;
+        if (tc && window && dim == 128 && w->stack_w && g_use_stack)
+            rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+        if (rc != TU_TC_UNSUPPORTED && rc != TU_OK) return rc;
+        const bool stack_done = rc == TU_OK;
+        for (int i = 0; i < w->n_blocks && !stack_done; ++i)
             if ((rc = transformer_block_ex(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws,
                                            (tc && i == w->n_blocks - 1) ? tok16 : nullptr, st)))
                 return rc;
@@ -247,6 +253,10 @@ extern "C" void tu_set_bf16_tcgen05(int enable) { g_use_tc = enable; }
 extern "C" int tu_debug_set(const char *key, int value) {
     if (key && !strcmp(key, "tc_base_off_mode")) {
         tc_set_base_off_mode(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "fused_stack")) {
+        g_use_stack = value;
         return TU_OK;
     }
     set_error("tu: unknown debug key");

@@ -18,18 +18,19 @@ namespace tu {
 namespace {
 
 constexpr int NUM_THREADS = 288;      // warps 0-3 epilogue, 4-7 builders, 8 MMA / TMEM / weight TMA
-constexpr int A_BYTES = 128 * 128;    // 128 pixels x 128-byte rows
+constexpr int ROWS = 4;               // image rows per tile (halo rows are loaded once for all four)
+constexpr int A_BYTES = 128 * 128;    // one operand tile: 128 pixels x 128-byte rows
 constexpr int W_BYTES = 64 * 128;     // 64 output channels x (64 k, 27 real)
-constexpr int SMEM_BYTES = 2 * A_BYTES + W_BYTES + 128 + 1024;
+constexpr int SMEM_BYTES = ROWS * A_BYTES + W_BYTES + 256 + 256 + 1024;
 
 struct StemParams {
-    int B, H, W, tiles_x, total_tiles;
+    int B, H, W, tiles_x, tiles_y, total_tiles;
     const float *bias;
     bf16 *out;
 };
 
 struct Barriers {
-    uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], w_full;
+    uint64_t a_full, a_empty, acc_full[ROWS], acc_empty[ROWS], w_full;
     uint32_t tmem_base;
 };
 
@@ -44,14 +45,16 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
-    const uint32_t a_sm = smem0, w_sm = smem0 + 2 * A_BYTES;
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + 2 * A_BYTES + W_BYTES);
+    const uint32_t a_sm = smem0, w_sm = smem0 + ROWS * A_BYTES;
+    float *bias_s = reinterpret_cast<float *>(smem_al + ROWS * A_BYTES + W_BYTES);
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 128);
-            ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars->a_full), 128);
+        ptx::mbar_init(ptx::smem_u32(&bars->a_empty), 1);
+        for (int i = 0; i < ROWS; ++i) {
             ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
         }
@@ -59,7 +62,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
         ptx::fence_barrier_init();
     }
     if (warp == 8) {
-        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 128);
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 256);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -74,111 +77,128 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
             ptx::tma_load_2d(w_sm, &tmap_w, ptx::smem_u32(&bars->w_full), 0, 0);
             ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
             const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
-            int it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[buf]), ph ^ 1);
-                ptx::mbar_wait(ptx::smem_u32(&bars->a_full[buf]), ph);
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_full), ph);
                 ptx::tc_fence_after();
-                const uint32_t a = a_sm + buf * A_BYTES;
 #pragma unroll
-                for (int k4 = 0; k4 < 2; ++k4)     // k = 0..31 (27 taps + 5 zeros); chunks 4-7 of a row are never read
-                    ptx::umma_bf16(tmem_base + buf * 64, ptx::make_sdesc_sw128(a + k4 * 32, 0),
-                                   ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc, k4 != 0);
-                ptx::umma_commit(ptx::smem_u32(&bars->a_empty[buf]));
-                ptx::umma_commit(ptx::smem_u32(&bars->acc_full[buf]));
+                for (int r = 0; r < ROWS; ++r) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[r]), ph ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t a = a_sm + r * A_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < 2; ++k4)     // k = 0..31 (27 taps + 5 zeros); chunks 4-7 of a row are never read
+                        ptx::umma_bf16(tmem_base + r * 64, ptx::make_sdesc_sw128(a + k4 * 32, 0),
+                                       ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc, k4 != 0);
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_full[r]));
+                }
+                ptx::umma_commit(ptx::smem_u32(&bars->a_empty));
             }
         }
     } else if (warp >= 4) {
         // ================================ builders: im2col rows -> swizzled smem ================================
         const int i = (warp - 4) * 32 + lane;            // pixel of the segment = operand row
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        float v[3][ROWS + 2][3];                         // [channel][input row][kx]
+        auto load_tile = [&](int t) {
             const int tx = t % p.tiles_x;
             int rem = t / p.tiles_x;
-            const int y = rem % p.H, b = rem / p.H;
-            const int px = tx * 128 + i;
-            float v[32];
+            const int ty = rem % p.tiles_y, b = rem / p.tiles_y;
+            const int px = tx * 128 + i, y0 = ty * ROWS;
 #pragma unroll
-            for (int k = 27; k < 32; ++k) v[k] = 0.f;
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = y + ky - 1;
-                const bool rowok = iy >= 0 && iy < p.H;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
+                for (int r = 0; r < ROWS + 2; ++r) {
+                    const int iy = y0 + r - 1;
+                    const bool rowok = iy >= 0 && iy < p.H;
                     const TI *row = x + (((long)b * 3 + c) * p.H + (rowok ? iy : 0)) * p.W;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const int ix = px + kx - 1;
-                        v[(ky * 3 + kx) * 3 + c] = (rowok && ix >= 0 && ix < p.W) ? to_f(row[ix]) : 0.f;
+                        v[c][r][kx] = (rowok && ix >= 0 && ix < p.W) ? to_f(row[ix]) : 0.f;
                     }
                 }
-            }
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[buf]), ph ^ 1);
-            uint8_t *rowp = smem_al + buf * A_BYTES + i * 128;
+        };
+        uint32_t ph = 0;
+        if (blockIdx.x < p.total_tiles) load_tile(blockIdx.x);
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), ph ^ 1);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                uint4 u;
-                u.x = pack2(v[ch * 8 + 0], v[ch * 8 + 1]);
-                u.y = pack2(v[ch * 8 + 2], v[ch * 8 + 3]);
-                u.z = pack2(v[ch * 8 + 4], v[ch * 8 + 5]);
-                u.w = pack2(v[ch * 8 + 6], v[ch * 8 + 7]);
-                *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
+            for (int r = 0; r < ROWS; ++r) {
+                uint8_t *rowp = smem_al + r * A_BYTES + i * 128;
+                float k[32];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) k[(ky * 3 + kx) * 3 + c] = v[c][r + ky][kx];
+#pragma unroll
+                for (int z = 27; z < 32; ++z) k[z] = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint4 u;
+                    u.x = pack2(k[ch * 8 + 0], k[ch * 8 + 1]);
+                    u.y = pack2(k[ch * 8 + 2], k[ch * 8 + 3]);
+                    u.z = pack2(k[ch * 8 + 4], k[ch * 8 + 5]);
+                    u.w = pack2(k[ch * 8 + 6], k[ch * 8 + 7]);
+                    *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
+                }
             }
             ptx::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
-            ptx::mbar_arrive(ptx::smem_u32(&bars->a_full[buf]));
+            ptx::mbar_arrive(ptx::smem_u32(&bars->a_full));
+            if (t + gridDim.x < p.total_tiles) load_tile(t + gridDim.x);   // next tile's pixels fly while this one is consumed
         }
     } else {
         // ================================ epilogue ================================
         const int q = warp;
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
             const int tx = t % p.tiles_x;
             int rem = t / p.tiles_x;
-            const int y = rem % p.H, b = rem / p.H;
+            const int ty = rem % p.tiles_y, b = rem / p.tiles_y;
             const int px = tx * 128 + q * 32 + lane;
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[buf]), ph);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64;
-            uint32_t v0[32], v1[32];
-            ptx::tmem_ld_x32(taddr, v0);
-            ptx::tmem_ld_x32(taddr + 32, v1);
-            ptx::tmem_ld_wait();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[buf]));   // values are in registers now
-            if (px < p.W) {
-                bf16 *o = p.out + (((long)b * p.H + y) * p.W + px) * 64;
+#pragma unroll 1
+            for (int r = 0; r < ROWS; ++r) {
+                const int y = ty * ROWS + r;
+                ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[r]), ph);
+                ptx::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + r * 64;
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_x32(taddr, v0);
+                ptx::tmem_ld_x32(taddr + 32, v1);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[r]));   // values are in registers now
+                if (px < p.W && y < p.H) {
+                    bf16 *o = p.out + (((long)b * p.H + y) * p.W + px) * 64;
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 u;
-                    u.x = pack2(fmaxf(__uint_as_float(v0[c + 0]) + __ldg(p.bias + c + 0), 0.f), fmaxf(__uint_as_float(v0[c + 1]) + __ldg(p.bias + c + 1), 0.f));
-                    u.y = pack2(fmaxf(__uint_as_float(v0[c + 2]) + __ldg(p.bias + c + 2), 0.f), fmaxf(__uint_as_float(v0[c + 3]) + __ldg(p.bias + c + 3), 0.f));
-                    u.z = pack2(fmaxf(__uint_as_float(v0[c + 4]) + __ldg(p.bias + c + 4), 0.f), fmaxf(__uint_as_float(v0[c + 5]) + __ldg(p.bias + c + 5), 0.f));
-                    u.w = pack2(fmaxf(__uint_as_float(v0[c + 6]) + __ldg(p.bias + c + 6), 0.f), fmaxf(__uint_as_float(v0[c + 7]) + __ldg(p.bias + c + 7), 0.f));
-                    *reinterpret_cast<uint4 *>(o + c) = u;
-                }
+                    for (int c = 0; c < 32; c += 8) {
+                        const float4 ba = *reinterpret_cast<const float4 *>(bias_s + c), bb = *reinterpret_cast<const float4 *>(bias_s + c + 4);
+                        uint4 u;
+                        u.x = pack2(fmaxf(__uint_as_float(v0[c + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[c + 1]) + ba.y, 0.f));
+                        u.y = pack2(fmaxf(__uint_as_float(v0[c + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[c + 3]) + ba.w, 0.f));
+                        u.z = pack2(fmaxf(__uint_as_float(v0[c + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v0[c + 5]) + bb.y, 0.f));
+                        u.w = pack2(fmaxf(__uint_as_float(v0[c + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v0[c + 7]) + bb.w, 0.f));
+                        *reinterpret_cast<uint4 *>(o + c) = u;
+                    }
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    uint4 u;
-                    u.x = pack2(fmaxf(__uint_as_float(v1[c + 0]) + __ldg(p.bias + 32 + c + 0), 0.f), fmaxf(__uint_as_float(v1[c + 1]) + __ldg(p.bias + 32 + c + 1), 0.f));
-                    u.y = pack2(fmaxf(__uint_as_float(v1[c + 2]) + __ldg(p.bias + 32 + c + 2), 0.f), fmaxf(__uint_as_float(v1[c + 3]) + __ldg(p.bias + 32 + c + 3), 0.f));
-                    u.z = pack2(fmaxf(__uint_as_float(v1[c + 4]) + __ldg(p.bias + 32 + c + 4), 0.f), fmaxf(__uint_as_float(v1[c + 5]) + __ldg(p.bias + 32 + c + 5), 0.f));
-                    u.w = pack2(fmaxf(__uint_as_float(v1[c + 6]) + __ldg(p.bias + 32 + c + 6), 0.f), fmaxf(__uint_as_float(v1[c + 7]) + __ldg(p.bias + 32 + c + 7), 0.f));
-                    *reinterpret_cast<uint4 *>(o + 32 + c) = u;
+                    for (int c = 0; c < 32; c += 8) {
+                        const float4 ba = *reinterpret_cast<const float4 *>(bias_s + 32 + c), bb = *reinterpret_cast<const float4 *>(bias_s + 36 + c);
+                        uint4 u;
+                        u.x = pack2(fmaxf(__uint_as_float(v1[c + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v1[c + 1]) + ba.y, 0.f));
+                        u.y = pack2(fmaxf(__uint_as_float(v1[c + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v1[c + 3]) + ba.w, 0.f));
+                        u.z = pack2(fmaxf(__uint_as_float(v1[c + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[c + 5]) + bb.y, 0.f));
+                        u.w = pack2(fmaxf(__uint_as_float(v1[c + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[c + 7]) + bb.w, 0.f));
+                        *reinterpret_cast<uint4 *>(o + 32 + c) = u;
+                    }
                 }
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 8) ptx::tmem_dealloc(tmem_base, 128);
+    if (warp == 8) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 int g_sm_count = 0;
@@ -213,7 +233,8 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
     StemParams p;
     p.B = B; p.H = H; p.W = W;
     p.tiles_x = ceil_div(W, 128);
-    p.total_tiles = p.tiles_x * H * B;
+    p.tiles_y = ceil_div(H, ROWS);
+    p.total_tiles = p.tiles_x * p.tiles_y * B;
     p.bias = bias; p.out = out;
     const int grid = p.total_tiles < 2 * g_sm_count ? p.total_tiles : 2 * g_sm_count;
     if (in_dtype == TU_F32)

@@ -1,0 +1,495 @@
+// The whole window-transformer stack (all blocks) of WindowTransformer in ONE persistent kernel.
+//
+// Reference: the loop `for block in self.window_blocks: tokens_windows = block(tokens_windows)`
+// (WindowTransformer/model.py:272-273) over WindowTransformerBlock (model.py:133-170) with WindowAttention
+// (model.py:63-131).  Windows are never shifted, so a window's 64 tokens only ever interact with each other:
+// a CTA takes 128 tokens (two windows) through all 8 blocks without touching HBM in between.
+//
+// On-chip data layout (dim = 128):
+//   TMEM columns [0,128)   X: the fp32 residual stream, one TMEM lane per token.  proj and fc2 are issued with
+//                          accumulate=1 straight onto X, so the two residual adds of a block cost nothing; their
+//                          constant biases are folded into a running offset vector c that LayerNorm adds on read.
+//   TMEM columns [128,512) ACC: qkv (384 columns), then the two 256-wide halves of the MLP hidden layer.
+//   smem A32  (32 KB)      LayerNorm output / attention output as a 128-byte-swizzled K-major UMMA A operand.
+//   smem STG  (99 KB)      q,k,v of the 128 tokens in bf16 for the attention (mma.sync); later aliased by
+//                          HID: GELU(fc1) half-tiles (64 KB) as the A operand of fc2.
+//   smem ring (5 x 16 KB)  weight slabs [128 n x 64 k] streamed by TMA in exactly the order the MMAs consume them
+//                          (24 slabs = 384 KB per block, pre-packed on the host).
+// Roles: warps 0-7 "math" (LN, epilogues, attention; thread = token row x column half), warp 8 TMA producer,
+// warp 9 MMA issuer + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc_ready (MMA -> math).
+#include <cuda.h>
+
+#include "ptx.cuh"
+#include "tc_api.cuh"
+
+namespace tu {
+
+namespace {
+
+constexpr int DIM = 128, HEADS = 8, HID = 512;
+constexpr int NUM_THREADS = 320;
+constexpr int SLAB = 128 * 128;                 // 16 KB: 128 rows x 64 bf16
+constexpr int NRING = 5;
+constexpr int SLABS_PER_BLOCK = 24;
+constexpr int STG_PITCH = 3 * DIM * 2 + 16;     // 784 B per token row (conflict-free fragment loads)
+constexpr int OFF_A32 = 0;
+constexpr int OFF_STG = 2 * SLAB;               // 32768
+constexpr int STG_BYTES = 99 * 1024;            // >= 128 * 784 = 100352 and >= 4 slabs (HID)
+constexpr int OFF_RING = OFF_STG + STG_BYTES;
+constexpr int OFF_PAR = OFF_RING + NRING * SLAB;
+constexpr int PAR_FLOATS = 1664;                // c0 | ln1w | ln1b | qkvb(384) | c1 | ln2w | ln2b | fc1b(512)
+constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
+constexpr int OFF_BAR = OFF_STAT + 128 * 2 * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int P_C0 = 0, P_LN1W = 128, P_LN1B = 256, P_QKVB = 384, P_C1 = 768, P_LN2W = 896, P_LN2B = 1024, P_FC1B = 1152;
+
+struct StackParams {
+    float *tok;            // (M, 128) fp32 token stream, window-ordered; updated in place
+    bf16 *tok16;           // optional bf16 copy of the result
+    const float *par;      // nblocks * PAR_FLOATS + 128 (final offset vector)
+    const float *rel_bias; // nblocks x (8, 64, 64) fp32 dense relative-position bias
+    int n_tiles, n_blocks;
+};
+
+struct Barriers {
+    uint64_t full[NRING], empty[NRING];
+    uint64_t a_ready, acc_ready;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = 1.0f - poly * t * exp2f(-z * z * 1.4426950408889634f);   // erf(|x|/sqrt2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// LayerNorm of this thread's 64 columns of row i (x already includes the folded bias offset), two-pass statistics
+// shared with the partner thread holding the other half of the row; result -> A32 slab `hf`, swizzled.
+__device__ __forceinline__ void layernorm_to_a32(float (&x)[64], const float *gam, const float *bet, float *stat, uint8_t *a32,
+                                                 int i, int hf) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) s += x[j];
+    stat[i * 2 + hf] = s;
+    math_barrier();
+    const float mean = (stat[i * 2] + stat[i * 2 + 1]) * (1.0f / DIM);
+    math_barrier();
+    float qv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; qv = fmaf(d, d, qv); }
+    stat[i * 2 + hf] = qv;
+    math_barrier();
+    const float rstd = rsqrtf((stat[i * 2] + stat[i * 2 + 1]) * (1.0f / DIM) + 1e-5f);
+    uint8_t *rowp = a32 + hf * SLAB + i * 128;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (x[ch * 8 + e] - mean) * rstd * gam[ch * 8 + e] + bet[ch * 8 + e];
+        uint4 u;
+        u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+        *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+    Barriers *bars = reinterpret_cast<Barriers *>(sm + OFF_BAR);
+    float *par = reinterpret_cast<float *>(sm + OFF_PAR);
+    float *stat = reinterpret_cast<float *>(sm + OFF_STAT);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NRING; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+        }
+        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), 256);
+        ptx::mbar_init(ptx::smem_u32(&bars->acc_ready), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
+        ptx::tmem_relinquish();
+    }
+    if (warp == 8 && lane == 0) ptx::prefetch_tmap(&tmap_w);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t TX = tmem_base, TACC = tmem_base + 128;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            // ================================ TMA producer: weight slabs in consumption order ================================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int s = 0; s < p.n_blocks * SLABS_PER_BLOCK; ++s) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
+                    const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
+                    ptx::mbar_expect_tx(fb, SLAB);
+                    ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB, &tmap_w, fb, 0, s * 128);
+                    if (++stage == NRING) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            // ================================ MMA issuer ================================
+            const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+            int stage = 0;
+            uint32_t phase = 0, aph = 0;
+            // one weight slab: D[128 x 128] (+)= A_slab[128 x 64] * W_slab[128 x 64]^T
+            auto slab_mma = [&](uint32_t d_tmem, uint32_t a_addr, bool first_clears) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+                ptx::tc_fence_after();
+                const uint32_t w = smem0 + OFF_RING + stage * SLAB;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4)
+                    ptx::umma_bf16(d_tmem, ptx::make_sdesc_sw128(a_addr + k4 * 32, 0), ptx::make_sdesc_sw128(w + k4 * 32, 0), idesc,
+                                   (first_clears && k4 == 0) ? 0u : 1u);
+                ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
+                if (++stage == NRING) { stage = 0; phase ^= 1; }
+            };
+            auto wait_a = [&]() {
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), aph);
+                aph ^= 1;
+                ptx::tc_fence_after();
+            };
+            const uint32_t a32 = smem0 + OFF_A32, hid = smem0 + OFF_STG;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int bk = 0; bk < p.n_blocks; ++bk) {
+                    wait_a();                                       // LN1 output in A32
+                    for (int nc = 0; nc < 3; ++nc)
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
+                    wait_a();                                       // attention output in A32
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, a32 + ks * SLAB, false);            // x += att Wp^T
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
+                    wait_a();                                       // LN2 output in A32
+                    for (int nc = 0; nc < 2; ++nc)
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);   // fc1, half 0
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
+                    wait_a();                                       // GELU(half 0) in HID, ACC drained
+                    for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SLAB, false);            // x += h0 W2[:, h0]^T
+                    for (int nc = 0; nc < 2; ++nc)
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);   // fc1, half 1
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
+                    wait_a();                                       // GELU(half 1) in HID
+                    for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SLAB, false);
+                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
+                }
+        }
+    } else {
+        // ================================ math warps ================================
+        const int q = warp & 3, hf = warp >> 2;
+        const int i = q * 32 + lane;                        // token row of the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int mt = threadIdx.x;                          // 0..255
+        uint8_t *a32 = sm + OFF_A32, *stg = sm + OFF_STG;
+        uint32_t cph = 0;
+        auto wait_acc = [&]() {
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc_ready), cph);
+            cph ^= 1;
+            ptx::tc_fence_after();
+        };
+        auto signal_a = [&]() {
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
+        };
+        // x row half (+ offset vector) -> registers
+        auto load_x = [&](float (&x)[64], const float *cvec) {
+            uint32_t v[32];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                ptx::tmem_ld_x32(TX + lane_base + hf * 64 + h2 * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[h2 * 32 + j] = __uint_as_float(v[j]) + cvec[hf * 64 + h2 * 32 + j];
+            }
+        };
+
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            // ---- tokens -> TMEM X
+            {
+                const float *src = p.tok + ((long)t * 128 + i) * DIM + hf * 64;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 f = *reinterpret_cast<const float4 *>(src + h2 * 32 + j);
+                        v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
+                    }
+                    tmem_st_x32(TX + lane_base + hf * 64 + h2 * 32, v);
+                }
+                tmem_st_wait();
+                ptx::tc_fence_before();
+            }
+            for (int bk = 0; bk < p.n_blocks; ++bk) {
+                // ---- per-block parameters -> smem
+                math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
+                ptx::tc_fence_after();
+                {
+                    const float4 *g = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
+                    float4 *d = reinterpret_cast<float4 *>(par);
+                    for (int e = mt; e < PAR_FLOATS / 4; e += 256) d[e] = g[e];
+                }
+                math_barrier();
+                // ---- LN1(x + c0) -> A32
+                {
+                    float x[64];
+                    load_x(x, par + P_C0);
+                    layernorm_to_a32(x, par + P_LN1W + hf * 64, par + P_LN1B + hf * 64, stat, a32, i, hf);
+                }
+                signal_a();
+                // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows
+                wait_acc();
+                {
+                    uint8_t *rowp = stg + i * STG_PITCH;
+#pragma unroll 1
+                    for (int nc = 0; nc < 3; ++nc) {
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint32_t v[32];
+                            const int col = nc * 128 + hf * 64 + h2 * 32;
+                            ptx::tmem_ld_x32(TACC + lane_base + col, v);
+                            ptx::tmem_ld_wait();
+                            const float *bb = par + P_QKVB + col;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint4 u;
+                                u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
+                                u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
+                                u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
+                                u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
+                                *reinterpret_cast<uint4 *>(rowp + (col + j) * 2) = u;
+                            }
+                        }
+                    }
+                }
+                math_barrier();
+                // ---- window attention: 2 windows x 8 heads x 4 row groups = 64 warp tasks, 8 per warp
+                {
+                    const int g = lane >> 2, tq = lane & 3;
+                    const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
+#pragma unroll 1
+                    for (int task = warp; task < 64; task += 8) {
+                        const int win = task >> 5, h = (task >> 2) & 7, rg = task & 3;
+                        const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
+                        const int r0 = rg * 16 + g;
+                        uint32_t qa[4];
+                        qa[0] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (h * 16 + tq * 2) * 2);
+                        qa[1] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (h * 16 + tq * 2) * 2);
+                        qa[2] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (h * 16 + tq * 2 + 8) * 2);
+                        qa[3] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (h * 16 + tq * 2 + 8) * 2);
+                        float s[8][4];
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            const uint8_t *kp = wbase + (n * 8 + g) * STG_PITCH + (DIM + h * 16 + tq * 2) * 2;
+                            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kp), b1 = *reinterpret_cast<const uint32_t *>(kp + 16);
+                            s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+                            mma16816(s[n], qa, b0, b1);
+                        }
+                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+                        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            const float2 ba = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
+                            const float2 bb = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                            s[n][0] += ba.x; s[n][1] += ba.y; s[n][2] += bb.x; s[n][3] += bb.y;
+                            m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+                            m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+                        }
+                        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+                        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+                        float l0 = 0.f, l1 = 0.f;
+                        const float L2E = 1.4426950408889634f;
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            s[n][0] = exp2f((s[n][0] - m0) * L2E); s[n][1] = exp2f((s[n][1] - m0) * L2E);
+                            s[n][2] = exp2f((s[n][2] - m1) * L2E); s[n][3] = exp2f((s[n][3] - m1) * L2E);
+                            l0 += s[n][0] + s[n][1];
+                            l1 += s[n][2] + s[n][3];
+                        }
+                        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+                        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+                        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                        for (int kt = 0; kt < 4; ++kt) {
+                            uint32_t pa[4];
+                            pa[0] = pk(s[2 * kt][0], s[2 * kt][1]);
+                            pa[1] = pk(s[2 * kt][2], s[2 * kt][3]);
+                            pa[2] = pk(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+                            pa[3] = pk(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+                            uint32_t v0, v1, v2, v3;
+                            const uint32_t addr = ptx::smem_u32(wbase + (kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STG_PITCH +
+                                                                (2 * DIM + h * 16 + (lane >> 4) * 8) * 2);
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                         : "r"(addr));
+                            mma16816(o[0], pa, v0, v1);
+                            mma16816(o[1], pa, v2, v3);
+                        }
+                        const float i0 = 1.f / l0, i1 = 1.f / l1;
+                        // attention output -> A32 (row = token of the tile, column = h*16 + d), swizzled
+                        const int row0 = win * 64 + r0, row1 = row0 + 8;
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int col = h * 16 + nt * 8 + tq * 2;
+                            const int ks = col >> 6, ch = (col & 63) >> 3, bo = (col & 7) * 2;
+                            *reinterpret_cast<uint32_t *>(a32 + ks * SLAB + row0 * 128 + ((ch ^ (row0 & 7)) << 4) + bo) = pk(o[nt][0] * i0, o[nt][1] * i0);
+                            *reinterpret_cast<uint32_t *>(a32 + ks * SLAB + row1 * 128 + ((ch ^ (row1 & 7)) << 4) + bo) = pk(o[nt][2] * i1, o[nt][3] * i1);
+                        }
+                    }
+                }
+                signal_a();
+                // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
+                wait_acc();
+                {
+                    float x[64];
+                    load_x(x, par + P_C1);
+                    layernorm_to_a32(x, par + P_LN2W + hf * 64, par + P_LN2B + hf * 64, stat, a32, i, hf);
+                }
+                signal_a();
+                // ---- MLP: two halves of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    wait_acc();
+#pragma unroll 1
+                    for (int nc = 0; nc < 2; ++nc) {
+                        uint8_t *rowp = stg + (nc * 2 + hf) * SLAB + i * 128;        // HID K-slab = hidden column / 64
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint32_t v[32];
+                            ptx::tmem_ld_x32(TACC + lane_base + nc * 128 + hf * 64 + h2 * 32, v);
+                            ptx::tmem_ld_wait();
+                            const float *bb = par + P_FC1B + half * 256 + nc * 128 + hf * 64 + h2 * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                float y[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) y[e] = gelu_fast(__uint_as_float(v[j + e]) + bb[j + e]);
+                                uint4 u;
+                                u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+                                const int ch = (h2 * 32 + j) >> 3;
+                                *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
+                            }
+                        }
+                    }
+                    signal_a();
+                }
+                wait_acc();      // fc2 of the second half accumulated: X holds the block output (minus folded biases)
+            }
+            // ---- X (+ final offset) -> global
+            {
+                const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS;
+                float *dst = p.tok + ((long)t * 128 + i) * DIM + hf * 64;
+                bf16 *dst16 = p.tok16 ? p.tok16 + ((long)t * 128 + i) * DIM + hf * 64 : nullptr;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(TX + lane_base + hf * 64 + h2 * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 f;
+                        f.x = __uint_as_float(v[j]) + __ldg(cfin + hf * 64 + h2 * 32 + j);
+                        f.y = __uint_as_float(v[j + 1]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 1);
+                        f.z = __uint_as_float(v[j + 2]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 2);
+                        f.w = __uint_as_float(v[j + 3]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 3);
+                        *reinterpret_cast<float4 *>(dst + h2 * 32 + j) = f;
+                        if (dst16) {
+                            uint2 u;
+                            u.x = pk(f.x, f.y); u.y = pk(f.z, f.w);
+                            *reinterpret_cast<uint2 *>(dst16 + h2 * 32 + j) = u;
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+int g_sm_count = 0;
+bool g_attr_set = false;
+
+}  // namespace
+
+// stack_w: bf16 (n_blocks * 24 * 128, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*1664 + 128;
+// rel_bias: fp32 n_blocks x (8,64,64).  tok: (M,128) fp32 with M % 128 == 0.
+int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
+                    const float *rel_bias, cudaStream_t st) {
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
+        (reinterpret_cast<uintptr_t>(tok) & 15))
+        return TU_TC_UNSUPPORTED;
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(window_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "window_stack smem attribute");
+        g_attr_set = true;
+    }
+    CUtensorMap tw;
+    cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * SLABS_PER_BLOCK * 128}, ws[1] = {128};
+    cuuint32_t wb[2] = {64, 128}, we[2] = {1, 1};
+    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tu: cuTensorMapEncodeTiled(window stack weights) failed with code " + std::to_string((int)r));
+        return TU_ERR_CUDA;
+    }
+    StackParams p;
+    p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
+    p.n_tiles = M / 128; p.n_blocks = n_blocks;
+    const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
+    window_stack_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, p);
+    TU_CHECK_LAUNCH("window_stack");
+    return TU_OK;
+}
+
+}  // namespace tu

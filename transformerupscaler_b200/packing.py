@@ -110,6 +110,8 @@ class PackedWeights:
             bw.fc1_w, bw.fc1_b = ptr(dev(sd[p + "mlp.0.weight"], dtype)), ptr(dev(sd[p + "mlp.0.bias"], f32))
             bw.fc2_w, bw.fc2_b = ptr(dev(sd[p + "mlp.2.weight"], dtype)), ptr(dev(sd[p + "mlp.2.bias"], f32))
         mw.blocks = C.cast(self.blocks, C.POINTER(_lib.TuBlockWeights))
+        if dtype == torch.bfloat16 and not resid and dim == 128:
+            self._pack_fused_stack(sd, mw, nb, dim, bprefix, dev, ptr)
 
         if fast:
             for slot, s in enumerate(SCALES):
@@ -133,3 +135,43 @@ class PackedWeights:
             mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
         self.struct = mw
         self.dim, self.heads, self.n_blocks = dim, heads, nb
+
+    @staticmethod
+    def _slabs(w: torch.Tensor, n_chunks: int, k_slabs: int):
+        """(n_chunks*128, k_slabs*64) weight -> list of [128 n][64 k] slabs, n-chunk major, k-slab minor."""
+        return [w[nc * 128:(nc + 1) * 128, ks * 64:(ks + 1) * 64] for nc in range(n_chunks) for ks in range(k_slabs)]
+
+    def _pack_fused_stack(self, sd, mw, nb, dim, bprefix, dev, ptr):
+        """Weights / parameters of all blocks in the order window_stack_tcgen05.cu consumes them.
+
+        Per block 24 slabs: qkv (3 n-chunks x 2 k-slabs, q rows pre-scaled), proj (2 k-slabs), then per hidden half
+        h in {0,1}: fc1 rows [256h, 256h+256) (2 n-chunks x 2 k-slabs) and fc2 columns [256h, 256h+256) (4 k-slabs).
+        The proj / fc2 biases are not added inside the kernel: they are folded into offset vectors c0 (before LN1),
+        c1 (before LN2) and c_final that are added when the residual stream is read.
+        """
+        f32 = torch.float32
+        slabs, pars, rels = [], [], []
+        c = torch.zeros(dim, dtype=torch.float64)
+        for i in range(nb):
+            p = f"{bprefix}{i}."
+            qw, qb = sd[p + "attn.qkv.weight"].float().cpu().clone(), sd[p + "attn.qkv.bias"].float().cpu().clone()
+            qw[:dim] *= 0.25
+            qb[:dim] *= 0.25
+            pw, pb = sd[p + "attn.proj.weight"].float().cpu(), sd[p + "attn.proj.bias"].float().cpu()
+            w1, b1 = sd[p + "mlp.0.weight"].float().cpu(), sd[p + "mlp.0.bias"].float().cpu()
+            w2, b2 = sd[p + "mlp.2.weight"].float().cpu(), sd[p + "mlp.2.bias"].float().cpu()
+            slabs += self._slabs(qw, 3, 2) + self._slabs(pw, 1, 2)
+            for h in range(2):
+                slabs += self._slabs(w1[h * 256:(h + 1) * 256], 2, 2) + self._slabs(w2[:, h * 256:(h + 1) * 256], 1, 4)
+            c0 = c.clone()
+            c1 = c0 + pb.double()
+            c = c1 + b2.double()
+            pars += [c0.float(), sd[p + "norm1.weight"].float().cpu(), sd[p + "norm1.bias"].float().cpu(), qb,
+                     c1.float(), sd[p + "norm2.weight"].float().cpu(), sd[p + "norm2.bias"].float().cpu(), b1]
+            rels.append(dense_rel_bias_t(sd[p + "attn.relative_position_bias_table"].cpu(),
+                                         sd[p + "attn.relative_position_index"].cpu()))
+        pars.append(c.float())
+        assert len(slabs) == 24 * nb
+        mw.stack_w = ptr(dev(torch.stack(slabs).reshape(-1, 64), torch.bfloat16))
+        mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
+        mw.stack_rel = ptr(dev(torch.stack(rels), f32))
