@@ -190,7 +190,15 @@ def main():
         ms_total = e0.elapsed_time(e1)
         lib.tu_profile_enable(0)
         kms, kn = C.c_double(0), C.c_int(0)
-        lib.tu_profile_collect(C.byref(kms), C.byref(kn))
+        lib.tu_profile_collect(b"conv2", C.byref(kms), C.byref(kn))
+        breakdown = {}
+        nbuf = lib.tu_profile_report(None, 0)
+        buf = C.create_string_buffer(max(nbuf, 16))
+        lib.tu_profile_report(buf, len(buf))
+        for ln in buf.value.decode().splitlines():
+            name, tot, cnt = ln.split()
+            breakdown[name] = round(float(tot) / max(int(cnt), 1), 5)      # mean ms per launch, live CUDA events
+        lib.tu_profile_reset()
         clk = clocks.stop() if clocks else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -244,7 +252,8 @@ def main():
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": (kms.value / kn.value) if kn.value else None,
-                         "kernel_share_of_step": (kms.value / ms_total) if kn.value else None},
+                         "kernel_share_of_step": (kms.value / ms_total) if kn.value else None,
+                         "kernel_ms_per_launch": breakdown},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "how": "pinned host bf16 frames -> H2D -> model(x) -> D2H, 3 streams, depth-2 pipeline, wall clock"},
             "gpu_launches": int(launches), "clocks": clk,

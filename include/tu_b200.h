@@ -45,12 +45,17 @@ int tu_bf16_uses_tcgen05(void);
 void tu_set_bf16_tcgen05(int enable);
 /* number of kernels this library has launched in the calling process (monotonic) */
 long long tu_launch_count(void);
-/* Measurement hook for bench.py: when enabled, tu_forward brackets its dominant kernel (conv2, the
- * 64->64 3x3 convolution at input resolution) with CUDA events on the caller's stream.
- * tu_profile_collect synchronises those events (the only call in the library that waits on the
- * device), returns the summed kernel time in milliseconds and the number of launches, and clears. */
+/* Measurement hook for bench.py: when enabled, tu_forward brackets every kernel it launches with CUDA events on
+ * the caller's stream, tagged with the reference op it implements ("conv1", "conv2", "downsample", "patch_embed",
+ * "transformer_blocks", "patch_unembed", "decoder_conv1", "decoder_conv2", "bicubic_add_clamp", "up1", "up1_conv",
+ * "final_upscale", "final_conv_add").  tu_profile_collect / tu_profile_report synchronise those events (the only
+ * calls in the library that wait on the device): collect sums the milliseconds and launches recorded under `name`
+ * (NULL = all); report writes "name total_ms launches\n" lines into buf (returns the needed size when buf is NULL);
+ * tu_profile_reset drops the records. */
 void tu_profile_enable(int on);
-int tu_profile_collect(double *total_ms, int *launches);
+int tu_profile_collect(const char *name, double *total_ms, int *launches);
+int tu_profile_report(char *buf, size_t cap);
+void tu_profile_reset(void);
 /* bring-up switches (not part of the stable interface): key "tc_base_off_mode" in {0,1} */
 int tu_debug_set(const char *key, int value);
 

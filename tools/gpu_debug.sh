@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 60 tools/probes/tma_probe
+for k in bicubic; do
+  timeout 300 python -m pytest tests/test_gpu_ops.py -q -m gpu -x --timeout 120 -p no:cacheprovider -k "$k" > gpurun_out/dbg_$k.log 2>&1
+  echo "$k rc=$? $(tail -1 gpurun_out/dbg_$k.log)"
+done

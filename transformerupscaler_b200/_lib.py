@@ -57,7 +57,9 @@ SIGNATURES = {
     "tu_debug_set": (i32, [C.c_char_p, i32]),
     "tu_launch_count": (C.c_longlong, []),
     "tu_profile_enable": (None, [i32]),
-    "tu_profile_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "tu_profile_collect": (i32, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "tu_profile_report": (i32, [C.c_char_p, sz]),
+    "tu_profile_reset": (None, []),
     "tu_forward_workspace_bytes": (sz, [i32] * 8),
     "tu_forward": (i32, [C.POINTER(TuModelWeights), vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "tu_stem_conv": (i32, [vp, i32, fp, vp, fp, vp, i32, i32, i32, i32, vp]),

@@ -18,10 +18,12 @@ static int g_use_stack = 1;   // fused window-transformer stack kernel (debug sw
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// bench-only kernel timing hook (see tu_profile_enable in tu_b200.h)
+// bench-only kernel timing hook (see tu_profile_enable in tu_b200.h): every launch of tu_forward is bracketed by a
+// pair of CUDA events on the caller's stream and tagged with the name of the reference op it implements
 static int g_prof_on = 0;
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_events;
 static cudaEvent_t g_prof_open = nullptr;
 static void prof_begin(cudaStream_t st) {
     if (!g_prof_on) return;
@@ -30,15 +32,23 @@ static void prof_begin(cudaStream_t st) {
     cudaEventRecord(e, st);
     g_prof_open = e;
 }
-static void prof_end(cudaStream_t st) {
+static void prof_end(cudaStream_t st, const char *name) {
     if (!g_prof_on || !g_prof_open) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof_events.emplace_back(g_prof_open, e);
+    g_prof_events.push_back({name, g_prof_open, e});
     g_prof_open = nullptr;
 }
+// run one launcher call, bracketed when profiling is on
+#define TU_STEP(name, call)            \
+    do {                               \
+        prof_begin(st);                \
+        rc = (call);                   \
+        prof_end(st, name);            \
+        if (rc) return rc;             \
+    } while (0)
 
 void set_error(const std::string &msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char *what) {
@@ -146,13 +156,9 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
 
     // ---- encoder
     if (!dry) {
-        if ((rc = tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv))) return rc;
-        prof_begin(st);
-        rc = tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv);
-        prof_end(st);
-        if (rc) return rc;
-        if (!fast)
-            if ((rc = tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv))) return rc;
+        TU_STEP("conv1", tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv));
+        TU_STEP("conv2", tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv));
+        if (!fast) TU_STEP("downsample", tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv));
     }
 
     // ---- FastTransformer branch A: sub-pixel upsample of feat, then 64->3 (+ReLU)
@@ -166,15 +172,13 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             const TuUpsamplerStage &sg = w->up1[slot][s];
             const int r = sg.r;
             T *nxt = (T *)a.get((size_t)B * ch * r * cw * r * 64 * sizeof(T));
-            if (!dry)
-                if ((rc = tu_conv3x3_c64(cur, sg.w, sg.b, nxt, dt, B, ch, cw, 1, 0, r * r, r, stv))) return rc;
+            if (!dry) TU_STEP("up1", tu_conv3x3_c64(cur, sg.w, sg.b, nxt, dt, B, ch, cw, 1, 0, r * r, r, stv));
             cur = nxt;
             ch *= r;
             cw *= r;
         }
         upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
-        if (!dry)
-            if ((rc = tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv))) return rc;
+        if (!dry) TU_STEP("up1_conv", tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv));
     }
 
     // ---- tokens
@@ -183,10 +187,10 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             cudaError_t e = cudaMemsetAsync(tok, 0, (size_t)Mtok * dim * sizeof(float), st);   // zero pad tokens
             if (e != cudaSuccess) return cuda_fail(e, "memset tokens");
         }
-        if ((rc = tu_patch_embed(fd, dt, w->embed_w, w->embed_b, w->pos_embed, tok, B, Hd, Wd, Ht, Wt, dim, window ? 1 : 0,
-                                 fast ? 1 : 0, stv)))
-            return rc;
+        TU_STEP("patch_embed", tu_patch_embed(fd, dt, w->embed_w, w->embed_b, w->pos_embed, tok, B, Hd, Wd, Ht, Wt, dim, window ? 1 : 0,
+                                              fast ? 1 : 0, stv));
         const bool tc = tc_on(dt);
+        prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
         if (tc && window && dim == 128 && w->stack_w && g_use_stack)
             rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
@@ -196,22 +200,23 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             if ((rc = transformer_block_ex(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws,
                                            (tc && i == w->n_blocks - 1) ? tok16 : nullptr, st)))
                 return rc;
+        prof_end(st, "transformer_blocks");
+        prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
         if (tc)
             rc = tc_patch_unembed(tok16, (const bf16 *)w->unembed_w, w->unembed_b, (const bf16 *)fd, Hd, Wd, (bf16 *)comb, B, Ht, Wt,
                                   Hc, Wc, dim, window ? 1 : 0, st);
         if (rc == TU_TC_UNSUPPORTED)
             rc = tu_patch_unembed(tok, w->unembed_w, w->unembed_b, fd, Hd, Wd, comb, dt, B, Ht, Wt, Hc, Wc, dim, window ? 1 : 0, stv);
+        prof_end(st, "patch_unembed");
         if (rc) return rc;
         // ---- decoder
-        if ((rc = tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv))) return rc;
-        if ((rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv))) return rc;
+        TU_STEP("decoder_conv1", tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv));
+        TU_STEP("decoder_conv2", tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv));
     }
 
     if (!fast) {
-        if (!dry)
-            if ((rc = tu_bicubic_add_clamp(x, in_dtype, H, W, res, Hc, Wc, out, out_dtype, B, outH, outW, clamp, stv)))
-                return rc;
+        if (!dry) TU_STEP("bicubic_add_clamp", tu_bicubic_add_clamp(x, in_dtype, H, W, res, Hc, Wc, out, out_dtype, B, outH, outW, clamp, stv));
         return TU_OK;
     }
     // ---- FastTransformer branch B: sub-pixel upsample of the residual image, 3->3 conv, sum, clamp
@@ -224,8 +229,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             const TuUpsamplerStage &sg = w->fin[slot][s];
             const int r = sg.r;
             float *nxt = (float *)a.get((size_t)B * 3 * ch * r * cw * r * sizeof(float));
-            if (!dry)
-                if ((rc = tu_conv3x3_c3_ps(cur, (const float *)sg.w, sg.b, nxt, B, ch, cw, r, stv))) return rc;
+            if (!dry) TU_STEP("final_upscale", tu_conv3x3_c3_ps(cur, (const float *)sg.w, sg.b, nxt, B, ch, cw, r, stv));
             cur = nxt;
             ch *= r;
             cw *= r;
@@ -235,8 +239,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
                 set_error("tu: FastTransformer output buffer must be (scale*H, scale*W)");
                 return TU_ERR_ARG;
             }
-            if ((rc = tu_final_conv_add(cur, w->finconv_w, w->finconv_b, upA, out, out_dtype, B, ch, cw, clamp, stv)))
-                return rc;
+            TU_STEP("final_conv_add", tu_final_conv_add(cur, w->finconv_w, w->finconv_b, upA, out, out_dtype, B, ch, cw, clamp, stv));
         }
     }
     return TU_OK;
@@ -264,23 +267,55 @@ extern "C" int tu_debug_set(const char *key, int value) {
 }
 extern "C" long long tu_launch_count(void) { return g_launches.load(); }
 extern "C" void tu_profile_enable(int on) { g_prof_on = on; }
-extern "C" int tu_profile_collect(double *total_ms, int *launches) {
+// waits for the recorded events (the only calls in the library that wait on the device)
+extern "C" int tu_profile_collect(const char *name, double *total_ms, int *launches) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     double tot = 0.0;
     int n = 0;
     for (auto &pr : g_prof_events) {
+        if (name && strcmp(name, pr.name)) continue;
         float ms = 0.f;
-        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        if (cudaEventSynchronize(pr.b) == cudaSuccess && cudaEventElapsedTime(&ms, pr.a, pr.b) == cudaSuccess) {
             tot += ms;
             ++n;
         }
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
     }
-    g_prof_events.clear();
     if (total_ms) *total_ms = tot;
     if (launches) *launches = n;
     return TU_OK;
+}
+extern "C" int tu_profile_report(char *buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<const char *> names;
+    std::vector<double> ms;
+    std::vector<int> cnt;
+    for (auto &pr : g_prof_events) {
+        float t = 0.f;
+        if (cudaEventSynchronize(pr.b) != cudaSuccess || cudaEventElapsedTime(&t, pr.a, pr.b) != cudaSuccess) continue;
+        size_t i = 0;
+        for (; i < names.size(); ++i)
+            if (!strcmp(names[i], pr.name)) break;
+        if (i == names.size()) { names.push_back(pr.name); ms.push_back(0.0); cnt.push_back(0); }
+        ms[i] += t;
+        cnt[i] += 1;
+    }
+    std::string out;
+    for (size_t i = 0; i < names.size(); ++i) {
+        char line[160];
+        snprintf(line, sizeof(line), "%s %.6f %d\n", names[i], ms[i], cnt[i]);
+        out += line;
+    }
+    if (!buf || cap == 0) return (int)out.size() + 1;
+    snprintf(buf, cap, "%s", out.c_str());
+    return TU_OK;
+}
+extern "C" void tu_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &pr : g_prof_events) {
+        cudaEventDestroy(pr.a);
+        cudaEventDestroy(pr.b);
+    }
+    g_prof_events.clear();
 }
 
 extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype, int B, int H, int W,

@@ -7,6 +7,10 @@
 //    Keys cubic A = -0.75, taps clamped to [0, in-1].
 //  * antialiased bilinear resize (torchvision Resize on a tensor = ATen _upsample_bilinear2d_aa), used by
 //    FastTransformer when the integer factor overshoots res_out (FastTransformer/model.py:323-325).
+#include <cuda.h>
+
+#include "tc/ptx.cuh"
+#include "tc/tc_api.cuh"
 #include "tu_common.cuh"
 
 namespace tu {
@@ -36,109 +40,152 @@ __device__ __forceinline__ Cubic cubic_taps(int dst, int in_size, int out_size) 
     return c;
 }
 
+// A thread owns one output column of a 32-row strip and slides a 4-row window of horizontally-resampled source rows
+// down the strip, for the 3 channels and both sources at once.  A source row is resampled horizontally exactly once
+// per strip, the per-row vertical taps come from a small shared table computed once per CTA.  Operation order per
+// output is ATen's: horizontal 4-tap sum inside each source row, then the vertical 4-tap sum.
+//
+// Source pixels come from one of two places:
+//   * TMA variant (row pitch of both sources a multiple of 16 bytes): one thread issues two cp.async.bulk.tensor loads
+//     that bring the whole source footprint of the tile (3 channels x rows x cols, out-of-image parts zero-filled and
+//     never addressed because taps are clamped) into shared memory; the strip walk then runs at shared-memory latency.
+//   * direct variant (any shape): taps are read from global memory.
+constexpr int BS_W = 128, BS_H = 32;
+
 template <typename TS>
-__device__ __forceinline__ float cubic_sample(const TS *__restrict__ plane, int W, const Cubic &cy, const Cubic &cx) {
-    float out = 0.f;
+struct GlobalSrc {          // image of one frame: (3, H, W)
+    const TS *img;
+    long plane;
+    int W;
+    __device__ __forceinline__ float at(int ch, int row, int col) const { return to_f(img[ch * plane + (long)row * W + col]); }
+};
+template <typename TS>
+struct TileSrc {            // shared-memory tile (3, nr, pitch) whose element (0,0) is source pixel (r0, c0)
+    const TS *s;
+    int r0, c0, nr, pitch;
+    __device__ __forceinline__ float at(int ch, int row, int col) const { return to_f(s[(ch * nr + (row - r0)) * pitch + (col - c0)]); }
+};
+
+template <typename Src>
+__device__ __forceinline__ float hrow(const Src &src, int ch, int row, const Cubic &cx) {
+    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const TS *row = plane + (long)cy.idx[i] * W;
-        float t = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) t += to_f(row[cx.idx[j]]) * cx.w[j];
-        out += t * cy.w[i];
-    }
-    return out;
+    for (int j = 0; j < 4; ++j) t += src.at(ch, row, cx.idx[j]) * cx.w[j];
+    return t;
 }
 
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) bicubic_add_clamp_kernel(const TI *__restrict__ x, int H, int W,
-                                                                const float *__restrict__ res, int rH, int rW,
-                                                                TO *__restrict__ out, int oH, int oW, int clamp) {
-    const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int b = blockIdx.z;
-    if (ox >= oW || oy >= oH) return;
-    const Cubic cy = cubic_taps(oy, H, oH), cx = cubic_taps(ox, W, oW);
-    Cubic ry, rx;
-    if (res) { ry = cubic_taps(oy, rH, oH); rx = cubic_taps(ox, rW, oW); }
+// slide the 3-channel window so that it covers unclamped rows base-1 .. base+2 (rows are clamped on load)
+template <typename Src>
+__device__ __forceinline__ void slide(float (&win)[3][4], int &cur, int base, const Src &src, int H, const Cubic &cx) {
+    if (cur != base) {
+        const int step = base - cur;
+        if (step < 0 || step > 3) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float v = cubic_sample<TI>(x + ((long)b * 3 + c) * H * W, W, cy, cx);
-        if (res) v += cubic_sample<float>(res + ((long)b * 3 + c) * rH * rW, rW, ry, rx);
-        if (clamp) v = fminf(fmaxf(v, 0.f), 1.f);
-        out[(((long)b * 3 + c) * oH + oy) * oW + ox] = from_f<TO>(v);
-    }
-}
-
-// Tiled separable version for up-scaling (at most TR source rows feed the 16 output rows of a tile):
-// per tile, every needed source row is first resampled horizontally into shared memory (4 taps), then the 16
-// output rows take their 4 vertical taps from shared memory.  Same operation order as ATen (horizontal sum
-// inside each source row, then the vertical sum), ~6x fewer instructions per output than the direct kernel.
-constexpr int BT_W = 128, BT_H = 16, BT_R = 24;
-
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(256) bicubic_add_clamp_tiled_kernel(const TI *__restrict__ x, int H, int W,
-                                                                      const float *__restrict__ res, int rH, int rW,
-                                                                      TO *__restrict__ out, int oH, int oW, int clamp) {
-    __shared__ float hx[BT_R][BT_W];
-    __shared__ float hr[BT_R][BT_W];
-    __shared__ int yidx[2][BT_H][4];
-    __shared__ float yw[2][BT_H][4];
-    const int t = threadIdx.x, cx = t & (BT_W - 1), half = t >> 7;
-    const int ox0 = blockIdx.x * BT_W, oy0 = blockIdx.y * BT_H, b = blockIdx.z;
-    const int ox = ox0 + cx;
-    const Cubic tx = cubic_taps(min(ox, oW - 1), W, oW);
-    Cubic tr = tx;
-    if (res) tr = cubic_taps(min(ox, oW - 1), rW, oW);
-    if (t < 2 * BT_H) {
-        const int s = t / BT_H, r = t % BT_H;
-        const Cubic c = cubic_taps(min(oy0 + r, oH - 1), s ? rH : H, oH);
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { yidx[s][r][i] = c.idx[i]; yw[s][r][i] = c.w[i]; }
-    }
-    __syncthreads();
-    const int lo_x = yidx[0][0][0], n_x = yidx[0][BT_H - 1][3] - lo_x + 1;
-    const int lo_r = yidx[1][0][0], n_r = res ? yidx[1][BT_H - 1][3] - lo_r + 1 : 0;
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) {
-        const TI *px = x + (((long)b * 3 + c) * H + lo_x) * W;
-        for (int s = half; s < n_x; s += 2) {
-            const TI *row = px + (long)s * W;
-            float v = 0.f;
+                for (int i = 0; i < 4; ++i) win[c][i] = hrow(src, c, min(max(base - 1 + i, 0), H - 1), cx);
+        } else {
+            for (int s = 0; s < step; ++s) {
+                const int row = min(max(cur + s + 3, 0), H - 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v += to_f(row[tx.idx[j]]) * tx.w[j];
-            hx[s][cx] = v;
-        }
-        if (res) {
-            const float *pr = res + (((long)b * 3 + c) * rH + lo_r) * rW;
-            for (int s = half; s < n_r; s += 2) {
-                const float *row = pr + (long)s * rW;
-                float v = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v += row[tr.idx[j]] * tr.w[j];
-                hr[s][cx] = v;
+                for (int c = 0; c < 3; ++c) {
+                    win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = win[c][3];
+                    win[c][3] = hrow(src, c, row, cx);
+                }
             }
         }
-        __syncthreads();
-        if (ox < oW) {
+        cur = base;
+    }
+}
+
+__device__ __forceinline__ int src_floor(int dst, int in_size, int out_size) {
+    const float scale = (float)in_size / (float)out_size;
+    return min((int)floorf(fmaf(scale, (float)dst + 0.5f, -0.5f)), in_size - 1);
+}
+
+struct BicubicTileGeom { int xr, xc, rr, rc; };     // TMA box sizes: rows / cols of the x tile and of the residual tile
+
+template <typename TI, typename TO, bool TMA>
+__global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                       const __grid_constant__ CUtensorMap tmap_r,
+                                                                       const BicubicTileGeom g, const TI *__restrict__ x, int H, int W,
+                                                                       const float *__restrict__ res, int rH, int rW,
+                                                                       TO *__restrict__ out, int oH, int oW, int clamp) {
+    __shared__ float yw[2][BS_H][4];
+    __shared__ int ybase[2][BS_H];
+    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ uint8_t tile_dyn[];
+    uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
+    const int t = threadIdx.x;
+    const int ox0 = blockIdx.x * BS_W, ox = ox0 + t, oy0 = blockIdx.y * BS_H, b = blockIdx.z;
+    int xr0 = 0, xc0 = 0, rr0 = 0, rc0 = 0;
+    const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
+    const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
+    if (TMA) {
+        // the innermost box coordinate must start on a 16-byte boundary (measured: tools/probes/tma_probe.cu): round the
+        // first column down to a multiple of 16 / sizeof(element); the box is that much wider (see the host side)
+        constexpr int XA = 16 / (int)sizeof(TI);
+        xr0 = src_floor(oy0, H, oH) - 1; xc0 = (src_floor(ox0, W, oW) - 1) & ~(XA - 1);
+        if (res) { rr0 = src_floor(oy0, rH, oH) - 1; rc0 = (src_floor(ox0, rW, oW) - 1) & ~3; }
+        if (t == 0) {
+            const uint32_t bar_a = ptx::smem_u32(&bar);
+            ptx::mbar_init(bar_a, 1);
+            ptx::fence_barrier_init();
+            ptx::mbar_expect_tx(bar_a, x_bytes + (res ? 3u * g.rr * g.rc * 4u : 0u));
+            ptx::tma_load_4d(ptx::smem_u32(tile_raw), &tmap_x, bar_a, xc0, xr0, 0, b);
+            if (res) ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
+        }
+    }
+    if (t < 2 * BS_H) {
+        const int s = t / BS_H, r = t % BS_H;
+        const int in_size = s ? rH : H;
+        const float scale = (float)in_size / (float)oH;
+        const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        const float A = -0.75f;
+        ybase[s][r] = i0;
+        yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
+    }
+    __syncthreads();
+    if (TMA) ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    if (ox >= oW) return;
+    const Cubic cx = cubic_taps(ox, W, oW);
+    Cubic cr = cx;
+    if (res) cr = cubic_taps(ox, rW, oW);
+    const long xplane = (long)H * W, rplane = (long)rH * rW, oplane = (long)oH * oW;
+    TO *ob = out + (long)b * 3 * oplane + ox;
+    float wx[3][4], wr[3][4];
+    int curx = -1000000, curr = -1000000;
+    const int nrows = min(BS_H, oH - oy0);
+    auto run = [&](const auto &sx, const auto &sr) {
+        for (int r = 0; r < nrows; ++r) {
+            slide(wx, curx, ybase[0][r], sx, H, cx);
+            if (res) slide(wr, curr, ybase[1][r], sr, rH, cr);
+            const float4 a = *reinterpret_cast<const float4 *>(yw[0][r]);
+            const float4 gg = *reinterpret_cast<const float4 *>(yw[1][r]);
 #pragma unroll
-            for (int k = 0; k < BT_H / 2; ++k) {
-                const int r = half * (BT_H / 2) + k, oy = oy0 + r;
-                if (oy >= oH) break;
+            for (int c = 0; c < 3; ++c) {
                 float v = 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v += hx[yidx[0][r][i] - lo_x][cx] * yw[0][r][i];
+                v += wx[c][0] * a.x; v += wx[c][1] * a.y; v += wx[c][2] * a.z; v += wx[c][3] * a.w;
                 if (res) {
                     float u = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) u += hr[yidx[1][r][i] - lo_r][cx] * yw[1][r][i];
+                    u += wr[c][0] * gg.x; u += wr[c][1] * gg.y; u += wr[c][2] * gg.z; u += wr[c][3] * gg.w;
                     v += u;
                 }
                 if (clamp) v = fminf(fmaxf(v, 0.f), 1.f);
-                out[(((long)b * 3 + c) * oH + oy) * oW + ox] = from_f<TO>(v);
+                ob[c * oplane + (long)(oy0 + r) * oW] = from_f<TO>(v);
             }
         }
-        __syncthreads();
+    };
+    if (TMA) {
+        const TileSrc<TI> sx{reinterpret_cast<const TI *>(tile_raw), xr0, xc0, g.xr, g.xc};
+        const TileSrc<float> sr{reinterpret_cast<const float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc};
+        run(sx, sr);
+    } else {
+        const GlobalSrc<TI> sx{x + (long)b * 3 * xplane, xplane, W};
+        const GlobalSrc<float> sr{res ? res + (long)b * 3 * rplane : nullptr, rplane, rW};
+        run(sx, sr);
     }
 }
 
@@ -186,24 +233,60 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const T *__restrict__ in
 
 using namespace tu;
 
+// (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
+static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, int B, int H, int W, int box_rows, int box_cols) {
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || box_rows > 256 || box_cols > 256) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)W * elem_bytes, (cuuint64_t)H * W * elem_bytes, (cuuint64_t)3 * H * W * elem_bytes};
+    cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 3, 1}, es[4] = {1, 1, 1, 1};
+    return enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr, dims, strides,
+               box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW, void *out,
                                     int out_dtype, int B, int outH, int outW, int clamp, void *stream) {
     TU_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "bicubic_add_clamp: bad argument");
+    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16) && (out_dtype == TU_F32 || out_dtype == TU_BF16), "bicubic_add_clamp: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ceil_div(outW, 64), ceil_div(outH, 4), B);
-    // tiled kernel when the 16 output rows of a tile never need more than BT_R source rows (any up-scaling)
-    const bool tiled = (long)BT_H * H <= (long)(BT_R - 5) * outH && (!res || (long)BT_H * rH <= (long)(BT_R - 5) * outH);
-    dim3 tgrid(ceil_div(outW, BT_W), ceil_div(outH, BT_H), B);
+    dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, BS_H), B);
+    // source footprint of a 32 x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
+    const int eb = in_dtype == TU_BF16 ? 2 : 4;
+    BicubicTileGeom g;
+    g.xr = (int)((long)(BS_H - 1) * H / outH) + 6;
+    g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 7) & ~7;          // + alignment slack of the first column
+    g.rr = res ? (int)((long)(BS_H - 1) * rH / outH) + 6 : 0;
+    g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 6 + 3 + 3) & ~3 : 0;
+    const size_t x_bytes = ((size_t)3 * g.xr * g.xc * eb + 127) & ~(size_t)127;
+    const size_t tile_bytes = x_bytes + (size_t)3 * g.rr * g.rc * 4;
+    CUtensorMap tx, tr;
+    memset(&tx, 0, sizeof(tx));
+    memset(&tr, 0, sizeof(tr));
+    bool tma = tile_bytes <= 96 * 1024 && ((size_t)W * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (!res || (((size_t)rW * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0));
+    tma = tma && encode_image_map(&tx, x, eb, B, H, W, g.xr, g.xc) && (!res || encode_image_map(&tr, res, 4, B, rH, rW, g.rr, g.rc));
 #define TU_BIC(TI, TO)                                                                                                          \
-    if (tiled)                                                                                                                  \
-        bicubic_add_clamp_tiled_kernel<TI, TO><<<tgrid, 256, 0, st>>>((const TI *)x, H, W, res, rH, rW, (TO *)out, outH, outW, clamp); \
-    else                                                                                                                        \
-        bicubic_add_clamp_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI *)x, H, W, res, rH, rW, (TO *)out, outH, outW, clamp)
-    if (in_dtype == TU_F32 && out_dtype == TU_F32) { TU_BIC(float, float); }
-    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) { TU_BIC(float, bf16); }
-    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) { TU_BIC(bf16, float); }
-    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) { TU_BIC(bf16, bf16); }
-    else TU_CHECK_ARG(false, "bicubic_add_clamp: bad dtype");
+    do {                                                                                                                        \
+        if (tma) {                                                                                                              \
+            static bool attr_done = false;                                                                                      \
+            if (!attr_done) {                                                                                                   \
+                cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, true>,                              \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                  \
+                if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                            \
+                attr_done = true;                                                                                               \
+            }                                                                                                                   \
+            bicubic_add_clamp_strip_kernel<TI, TO, true><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW, \
+                                                                                          (TO *)out, outH, outW, clamp);        \
+        } else {                                                                                                                \
+            bicubic_add_clamp_strip_kernel<TI, TO, false><<<grid, BS_W, 0, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW,     \
+                                                                                  (TO *)out, outH, outW, clamp);                \
+        }                                                                                                                       \
+    } while (0)
+    if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC(float, float);
+    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC(float, bf16);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC(bf16, float);
+    else TU_BIC(bf16, bf16);
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
     return TU_OK;

@@ -19,6 +19,8 @@
 //     bf16 -> 128-byte global stores, optionally at PixelShuffle-ed addresses).
 #include <cuda.h>
 
+#include <string.h>
+
 #include <mutex>
 
 #include "ptx.cuh"
@@ -34,7 +36,8 @@ constexpr int BOXW = 136;                 // pixels per TMA box (128 + halo, kee
 constexpr int UNIT_BYTES = BOXW * 128;    // 17408 = 17 * 1024
 constexpr int RING_UNITS = 6;
 constexpr int W_BYTES_MAX = 9 * 64 * 128;  // 73728 (64 output channels); 9*16*128 for the 64->3 head (3 padded to 16)
-constexpr int SMEM_BYTES = W_BYTES_MAX + RING_UNITS * UNIT_BYTES + 256 + 1024;
+constexpr int STG_BYTES = 4 * 2 * 4096;     // epilogue staging: 4 warps x 2 buffers x (32 pixels x 128 B), source of the TMA stores
+constexpr int SMEM_BYTES = W_BYTES_MAX + RING_UNITS * UNIT_BYTES + STG_BYTES + 256 + 1024;
 constexpr int NUM_THREADS = 256;
 
 struct ConvParams {
@@ -44,7 +47,6 @@ struct ConvParams {
     const float *bias;
     bf16 *out;
     float *out3;        // NOUT == 16: planar fp32 (B,3,Ho,Wo)
-    int base_off_mode;
 };
 
 struct Barriers {
@@ -57,24 +59,23 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint64_t adesc(uint32_t addr, int mode) {
-    return ptx::make_sdesc_sw128(addr, mode ? ((addr >> 7) & 7u) : 0u);
-}
-
-template <int NOUT>
+template <int NOUT, int S>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr int W_TAP = NOUT * 128, W_BYTES = 9 * W_TAP;
     const uint32_t w_sm = smem0;
     const uint32_t ring_sm = smem0 + W_BYTES_MAX;
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + W_BYTES_MAX + RING_UNITS * UNIT_BYTES);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = p.stride;
-    const int units_per_step = S;                       // stride 2: even + odd slot per input row
-    const int nslots = RING_UNITS / units_per_step;     // 6 or 3
-    const int nsteps = S == 1 ? TILE_R + 2 : 2 * TILE_R + 1;
+    const uint32_t stg_sm = ring_sm + RING_UNITS * UNIT_BYTES;      // 1024-byte aligned (UNIT_BYTES = 17 * 1024)
+    uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + W_BYTES_MAX + RING_UNITS * UNIT_BYTES + STG_BYTES);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    constexpr int units_per_step = S;                       // stride 2: even + odd slot per input row
+    constexpr int nslots = RING_UNITS / units_per_step;     // 6 or 3
+    constexpr int nsteps = S == 1 ? TILE_R + 2 : 2 * TILE_R + 1;
+    static_assert(nsteps % nslots == 0, "a tile must consume whole turns of the ring (slot index is then compile-time)");
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING_UNITS; ++i) {
@@ -96,6 +97,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_act);
         ptx::prefetch_tmap(&tmap_w);
+        if (NOUT == 64) ptx::prefetch_tmap(&tmap_out);
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -141,11 +143,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 if (++slot == nslots) { slot = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ================================ MMA issuer ================================
+        // The whole warp walks the loop converged; the elected lane's predicate guards each tcgen05 instruction.
+        // Slot, tap and k offsets are compile-time, so an MMA costs two adds on pre-encoded descriptor words.
+        const uint32_t leader = ptx::elect_one();
         const uint32_t idesc = ptx::make_idesc_bf16(TILE_M, NOUT);
-        int slot = 0;
-        uint32_t phase = 0;
+        const uint32_t w_lo = ptx::sdesc_lo(w_sm), ring_lo = ptx::sdesc_lo(ring_sm);
+        uint32_t tphase = 0;                     // ring phase at the start of the tile (flips once per tile)
         int cur_chunk = -1;
         uint32_t wphase = 0;
         int it = 0;
@@ -161,10 +166,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), aphase ^ 1);
             ptx::tc_fence_after();
             const uint32_t acc0 = tmem_base + set * (TILE_R * 64);
+#pragma unroll
             for (int j = 0; j < nsteps; ++j) {
-                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), phase);
+                const int slot = j % nslots;
+                ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), tphase ^ ((j / nslots) & 1));
                 ptx::tc_fence_after();
-                const uint32_t src = ring_sm + slot * units_per_step * UNIT_BYTES;
+                const uint32_t a0 = ring_lo + ((slot * units_per_step * UNIT_BYTES) >> 4);
                 if (S == 1) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
@@ -174,9 +181,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
-                                const uint64_t ad = adesc(src + kx * 128 + k4 * 32, p.base_off_mode);
-                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * W_TAP + k4 * 32, 0);
-                                ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
+                                const uint32_t ad = a0 + ((kx * 128 + k4 * 32) >> 4);
+                                const uint32_t bd = w_lo + (((ky * 3 + kx) * W_TAP + k4 * 32) >> 4);
+                                if ((ky | kx | k4) != 0) ptx::umma_bf16_lo<1>(acc0 + r * 64, ad, bd, idesc, leader);
+                                else ptx::umma_bf16_lo<0>(acc0 + r * 64, ad, bd, idesc, leader);
                             }
                         }
                     }
@@ -190,28 +198,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
                             // kx=0: odd slot row 0; kx=1: even slot row 0; kx=2: odd slot row 1
-                            const uint32_t a0 = kx == 1 ? src : src + UNIT_BYTES + (kx == 2 ? 128 : 0);
+                            const int aoff = kx == 1 ? 0 : UNIT_BYTES + (kx == 2 ? 128 : 0);
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {
-                                const uint64_t ad = adesc(a0 + k4 * 32, p.base_off_mode);
-                                const uint64_t bd = ptx::make_sdesc_sw128(w_sm + (ky * 3 + kx) * W_TAP + k4 * 32, 0);
-                                ptx::umma_bf16(acc0 + r * 64, ad, bd, idesc, (ky | kx | k4) != 0);
+                                const uint32_t ad = a0 + ((aoff + k4 * 32) >> 4);
+                                const uint32_t bd = w_lo + (((ky * 3 + kx) * W_TAP + k4 * 32) >> 4);
+                                if ((ky | kx | k4) != 0) ptx::umma_bf16_lo<1>(acc0 + r * 64, ad, bd, idesc, leader);
+                                else ptx::umma_bf16_lo<0>(acc0 + r * 64, ad, bd, idesc, leader);
                             }
                         }
                     }
                 }
-                ptx::umma_commit(ptx::smem_u32(&bars->empty[slot]));     // slot reusable once these MMAs retire
-                if (++slot == nslots) { slot = 0; phase ^= 1; }
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[slot]), leader);     // slot reusable once these MMAs retire
             }
-            ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));       // accumulators of this tile complete
+            tphase ^= (nsteps / nslots) & 1;
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_full[set]), leader);       // accumulators of this tile complete
             // does the next tile of this CTA switch to another filter bank?
             const int tn = t + gridDim.x;
-            if (tn < p.total_tiles && tn / p.tiles_per_chunk != chunk) ptx::umma_commit(ptx::smem_u32(&bars->w_free));
+            if (tn < p.total_tiles && tn / p.tiles_per_chunk != chunk) ptx::umma_commit_pred(ptx::smem_u32(&bars->w_free), leader);
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
+        // NOUT == 64: TMEM -> (+bias, ReLU, bf16) -> the pixel's 128 bytes into a swizzled staging buffer -> one TMA store per
+        // 32-pixel row segment and warp (a thread storing its own pixel would touch 32 different cache lines per instruction).
         const int q = warp - 4;                     // TMEM lane quadrant of this warp
         int it = 0;
+        uint32_t nstore = 0;
+        uint8_t *stg_w = smem_al + W_BYTES_MAX + RING_UNITS * UNIT_BYTES + q * 8192;
+        const uint32_t stg_w_sm = stg_sm + q * 8192;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int chunk = t / p.tiles_per_chunk;
             int rem = t - chunk * p.tiles_per_chunk;
@@ -223,7 +237,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
             ptx::tc_fence_after();
-            const int px = tx * TILE_M + q * 32 + lane;
+            const int px0 = tx * TILE_M + q * 32, px = px0 + lane;
             const float *bias = p.bias ? p.bias + chunk * 64 : nullptr;
 #pragma unroll 1
             for (int r = 0; r < TILE_R; ++r) {
@@ -233,6 +247,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                     uint32_t v[32];
                     ptx::tmem_ld_x32(taddr, v);       // columns 16..31 belong to nobody (row stride is 64 columns)
                     ptx::tmem_ld_wait();
+                    if (r == TILE_R - 1) {            // accumulators are in registers: hand the TMEM set back to the MMA warp
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
+                    }
                     if (y < p.Ho && px < p.Wo) {
                         const long plane = (long)p.Ho * p.Wo;
                         float *o = p.out3 + (long)b * 3 * plane + (long)y * p.Wo + px;
@@ -248,52 +267,49 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 ptx::tmem_ld_x32(taddr, v0);
                 ptx::tmem_ld_x32(taddr + 32, v1);
                 ptx::tmem_ld_wait();
-                if (y < p.Ho && px < p.Wo) {
-                    bf16 *o;
-                    if (p.ps_r) {
-                        const int rr = p.ps_r, pi = chunk / rr, pj = chunk % rr;
-                        o = p.out + ((((long)b * p.Ho + y) * rr + pi) * ((long)p.Wo * rr) + (long)px * rr + pj) * 64;
-                    } else {
-                        o = p.out + (((long)b * p.Ho + y) * p.Wo + px) * 64;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float a = __uint_as_float(v0[c + e]) + (bias ? __ldg(bias + c + e) : 0.f);
-                            f[e] = p.relu ? fmaxf(a, 0.f) : a;
-                        }
-                        uint4 u;
-                        __nv_bfloat162 h;
-                        h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
-                        *reinterpret_cast<uint4 *>(o + c) = u;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float a = __uint_as_float(v1[c + e]) + (bias ? __ldg(bias + 32 + c + e) : 0.f);
-                            f[e] = p.relu ? fmaxf(a, 0.f) : a;
-                        }
-                        uint4 u;
-                        __nv_bfloat162 h;
-                        h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
-                        h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
-                        *reinterpret_cast<uint4 *>(o + 32 + c) = u;
-                    }
+                if (r == TILE_R - 1) {
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
                 }
+                const uint32_t buf = nstore & 1;
+                if (lane == 0) ptx::bulk_wait_read<1>();      // the store that last used this buffer has read it
+                __syncwarp();
+                uint8_t *rowp = stg_w + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float a = __uint_as_float(c < 32 ? v0[c + e] : v1[c - 32 + e]) + (bias ? __ldg(bias + c + e) : 0.f);
+                        f[e] = p.relu ? fmaxf(a, 0.f) : a;
+                    }
+                    uint4 u;
+                    __nv_bfloat162 h;
+                    h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
+                    *reinterpret_cast<uint4 *>(rowp + ((((c >> 3) ^ (lane & 7))) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
+                }
+                ptx::fence_proxy_async();         // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    if (y < p.Ho && px0 < p.Wo) {
+                        if (p.ps_r) {
+                            const int rr = p.ps_r, pi = chunk / rr, pj = chunk % rr;
+                            ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, pj, (b * p.Ho + y) * rr + pi);
+                        } else {
+                            ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, y, b);
+                        }
+                    }
+                    ptx::bulk_commit();
+                }
+                ++nstore;
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
         }
+        if (lane == 0) ptx::bulk_wait<0>();          // all stores of this warp have left shared memory and are visible
+        __syncwarp();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -336,8 +352,9 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv3x3_tc smem attribute");
         g_attr_set = true;
     }
@@ -368,6 +385,26 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
             return TU_ERR_CUDA;
         }
     }
+    CUtensorMap tm_out;
+    memset(&tm_out, 0, sizeof(tm_out));
+    const int Ho_ = (H - 1) / stride + 1, Wo_ = (W - 1) / stride + 1;
+    if (nout == 64) {
+        cuuint64_t od[4], os[3];
+        cuuint32_t ob[4] = {64, 32, 1, 1}, oe[4] = {1, 1, 1, 1};
+        if (ps_r) {      // (c, px [stride r pixels], pj, (b*Ho + y)*r + pi): PixelShuffle addressing done by the TMA engine
+            od[0] = 64; od[1] = (cuuint64_t)Wo_; od[2] = (cuuint64_t)ps_r; od[3] = (cuuint64_t)B * Ho_ * ps_r;
+            os[0] = (cuuint64_t)ps_r * 128; os[1] = 128; os[2] = (cuuint64_t)Wo_ * ps_r * 128;
+        } else {
+            od[0] = 64; od[1] = (cuuint64_t)Wo_; od[2] = (cuuint64_t)Ho_; od[3] = (cuuint64_t)B;
+            os[0] = 128; os[1] = (cuuint64_t)Wo_ * 128; os[2] = (cuuint64_t)Ho_ * Wo_ * 128;
+        }
+        CUresult r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tu: cuTensorMapEncodeTiled(conv output) failed with code " + std::to_string((int)r));
+            return TU_ERR_CUDA;
+        }
+    }
     ConvParams p;
     p.B = B; p.H = H; p.W = W;
     p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
@@ -375,12 +412,14 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
     p.tiles_x = ceil_div(p.Wo, TILE_M); p.tiles_y = ceil_div(p.Ho, TILE_R);
     p.tiles_per_chunk = p.tiles_x * p.tiles_y * B;
     p.total_tiles = p.tiles_per_chunk * nchunk;
-    p.bias = bias; p.out = out; p.out3 = out3; p.base_off_mode = g_base_off_mode;
+    p.bias = bias; p.out = out; p.out3 = out3;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
-    if (nout == 64)
-        conv3x3_tc_kernel<64><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
+    if (nout == 64 && stride == 1)
+        conv3x3_tc_kernel<64, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
+    else if (nout == 64)
+        conv3x3_tc_kernel<64, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
     else
-        conv3x3_tc_kernel<16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, p);
+        conv3x3_tc_kernel<16, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
     TU_CHECK_LAUNCH("conv3x3_tc");
     return TU_OK;
 }

@@ -27,8 +27,10 @@ namespace tu {
 
 namespace {
 
-constexpr int BM = 128, BK = 64, NSTAGE = 4, NUM_THREADS = 256;
+constexpr int BM = 128, BK = 64, NSTAGE = 4, NUM_THREADS = 384;   // warps 0-3: TMA, MMA, TMEM alloc, spare; warps 4-11: epilogue
 constexpr int A_STAGE = BM * BK * 2;   // 16384
+constexpr int UE_PITCH = 68;           // floats per staged row of the unembed epilogue (64 + 4: conflict-free 16-byte accesses)
+constexpr int UE_BYTES = 8 * 32 * UE_PITCH * 4;
 
 enum { EPI_STORE = 0, EPI_RESID = 1, EPI_EMBED = 2, EPI_UNEMBED = 3 };
 
@@ -72,8 +74,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int w_stage = p.BN * 128;
     const int stage_bytes = A_STAGE + w_stage;
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_raw + (smem0 - ptx::smem_u32(smem_raw)) + NSTAGE * stage_bytes);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + NSTAGE * stage_bytes);
+    float *stage_f32 = reinterpret_cast<float *>(smem_al + NSTAGE * stage_bytes + 256);   // UNEMBED only: 8 warps x 32 rows x 68 floats
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int nk = p.K / BK;
 
     if (threadIdx.x == 0) {
@@ -83,7 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
-            ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
+            ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 8);
         }
         ptx::fence_barrier_init();
     }
@@ -122,9 +126,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ================================ MMA issuer ================================
+    } else if (warp == 1) {
+        // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
+        const uint32_t leader = ptx::elect_one();
         const uint32_t idesc = ptx::make_idesc_bf16(BM, p.BN);
+        const uint32_t smem_lo = ptx::sdesc_lo(smem0);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -137,19 +143,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int s = 0; s < nk; ++s) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
                 ptx::tc_fence_after();
-                const uint32_t a_sm = smem0 + stage * stage_bytes, w_sm = a_sm + A_STAGE;
+                const uint32_t a_lo = smem_lo + ((stage * stage_bytes) >> 4), w_lo = a_lo + (A_STAGE >> 4);
+                ptx::umma_bf16_lo_rt(acc, a_lo, w_lo, idesc, s != 0, leader);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    ptx::umma_bf16(acc, ptx::make_sdesc_sw128(a_sm + k4 * 32, 0), ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc,
-                                   (s | k4) != 0);
-                ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
+                for (int k4 = 1; k4 < 4; ++k4) ptx::umma_bf16_lo<1>(acc, a_lo + k4 * 2, w_lo + k4 * 2, idesc, leader);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(ptx::smem_u32(&bars->acc_full[set]));
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_full[set]), leader);
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
-        const int q = warp - 4;
+        // 8 warps: warp w drains TMEM lane quadrant q = w % 4 (a warp may only touch its own 32 lanes), columns of half w / 4
+        const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+        const int cbeg = half * (p.BN >> 1), cend = cbeg + (p.BN >> 1);
         const int i = q * 32 + lane;                  // row of the tile owned by this thread
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -189,11 +196,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     valid = valid && ty < p.Ht && tx < p.Wt;
                 }
             }
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256;
+            if (p.epi == EPI_UNEMBED) {
+                // BN = 128: this warp owns 64 columns = the 64 channels of ONE output pixel (dy,dx) of each of its 32 tokens.
+                // A thread owning a whole pixel would store it as eight 16-byte pieces, 32 different cache lines per warp
+                // instruction; instead the warp transposes through shared memory so that 8 lanes cover one pixel (128
+                // contiguous bytes) and an instruction touches 4 lines.  The skip-connection loads do not depend on the
+                // accumulator, so all 8 are issued before waiting for the MMAs (one DRAM latency per tile, overlapped).
+                float *stg = stage_f32 + (warp - 4) * (32 * UE_PITCH);
+                const uint32_t geo = valid ? ((uint32_t)b << 20) | ((uint32_t)ty << 10) | (uint32_t)tx : 0xFFFFFFFFu;
+                const int sub = lane >> 3, chunk = lane & 7;
+                const float4 bs0 = *reinterpret_cast<const float4 *>(p.bias + chunk * 8), bs1 = *reinterpret_cast<const float4 *>(p.bias + chunk * 8 + 4);
+                const int pix = (n0 + cbeg) >> 6;
+                const int dy = pix >> 3, dx = pix & 7;
+                bool ok[8];
+                long oo[8];
+                uint4 su[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {      // row j*4 + sub of the warp's 32 token rows
+                    const uint32_t g = __shfl_sync(0xffffffffu, geo, j * 4 + sub);
+                    const int gb = g >> 20, gy = ((g >> 10) & 1023) * 8 + dy, gx = (g & 1023) * 8 + dx;
+                    ok[j] = g != 0xFFFFFFFFu && gy < p.Hc && gx < p.Wc;
+                    oo[j] = (((long)gb * p.Hc + gy) * p.Wc + gx) * 64 + chunk * 8;
+                    const long so = ok[j] ? (((long)gb * p.skipH + gy) * p.skipW + gx) * 64 + chunk * 8 : (long)chunk * 8;
+                    su[j] = *reinterpret_cast<const uint4 *>(p.skip + so);
+                }
+                ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
+                ptx::tc_fence_after();
+                {
+                    uint32_t v0[32], v1[32];
+                    ptx::tmem_ld_x32(tbase + cbeg, v0);
+                    ptx::tmem_ld_x32(tbase + cbeg + 32, v1);
+                    ptx::tmem_ld_wait();
+                    float *row = stg + lane * UE_PITCH;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        *reinterpret_cast<float4 *>(row + c) = make_float4(__uint_as_float(v0[c]), __uint_as_float(v0[c + 1]), __uint_as_float(v0[c + 2]), __uint_as_float(v0[c + 3]));
+                        *reinterpret_cast<float4 *>(row + 32 + c) = make_float4(__uint_as_float(v1[c]), __uint_as_float(v1[c + 1]), __uint_as_float(v1[c + 2]), __uint_as_float(v1[c + 3]));
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));      // accumulator columns are in shared memory now
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float *sr = stg + (j * 4 + sub) * UE_PITCH + chunk * 8;
+                    const float4 a0 = *reinterpret_cast<const float4 *>(sr), a1 = *reinterpret_cast<const float4 *>(sr + 4);
+                    const __nv_bfloat162 *sh = reinterpret_cast<const __nv_bfloat162 *>(&su[j]);
+                    const float2 s0 = __bfloat1622float2(sh[0]), s1 = __bfloat1622float2(sh[1]), s2 = __bfloat1622float2(sh[2]), s3 = __bfloat1622float2(sh[3]);
+                    uint4 u;
+                    __nv_bfloat162 h;
+                    h = __floats2bfloat162_rn(a0.x + bs0.x + s0.x, a0.y + bs0.y + s0.y); u.x = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(a0.z + bs0.z + s1.x, a0.w + bs0.w + s1.y); u.y = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(a1.x + bs1.x + s2.x, a1.y + bs1.y + s2.y); u.z = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(a1.z + bs1.z + s3.x, a1.w + bs1.w + s3.y); u.w = *reinterpret_cast<uint32_t *>(&h);
+                    if (ok[j]) *reinterpret_cast<uint4 *>(p.out + oo[j]) = u;
+                }
+                __syncwarp();                      // staging rows are free for the next tile
+                continue;
+            }
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
             ptx::tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256;
 #pragma unroll 1
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 uint32_t v[32];
                 ptx::tmem_ld_x32(tbase + c0, v);
                 ptx::tmem_ld_wait();
@@ -251,32 +316,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         }
                         *reinterpret_cast<float4 *>(o + c) = r;
                     }
-                } else {   // EPI_UNEMBED: 32 columns = half of one pixel's 64 channels
-                    const int pix = n >> 6, ch = n & 63;
-                    const int y = ty * 8 + (pix >> 3), xx = tx * 8 + (pix & 7);
-                    if (y < p.Hc && xx < p.Wc) {
-                        const bf16 *sk = p.skip + (((long)b * p.skipH + y) * p.skipW + xx) * 64 + ch;
-                        bf16 *o = p.out + (((long)b * p.Hc + y) * p.Wc + xx) * 64 + ch;
-#pragma unroll
-                        for (int c = 0; c < 32; c += 8) {
-                            const uint4 su = *reinterpret_cast<const uint4 *>(sk + c);
-                            const __nv_bfloat162 *sh = reinterpret_cast<const __nv_bfloat162 *>(&su);
-                            float f[8];
-#pragma unroll
-                            for (int e = 0; e < 8; e += 2) {
-                                const float2 s2 = __bfloat1622float2(sh[e >> 1]);
-                                f[e] = __uint_as_float(v[c + e]) + __ldg(p.bias + ch + c + e) + s2.x;
-                                f[e + 1] = __uint_as_float(v[c + e + 1]) + __ldg(p.bias + ch + c + e + 1) + s2.y;
-                            }
-                            uint4 u;
-                            __nv_bfloat162 h;
-                            h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t *>(&h);
-                            h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t *>(&h);
-                            *reinterpret_cast<uint4 *>(o + c) = u;
-                        }
-                    }
                 }
             }
             ptx::tc_fence_before();
@@ -318,7 +357,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStre
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + 1024;
+    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + (p.epi == EPI_UNEMBED ? UE_BYTES : 0) + 1024;
     if (smem > g_smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "gemm_tc smem attribute");
@@ -391,16 +430,17 @@ int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const flo
 
 int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, const bf16 *skip, int skipH, int skipW, bf16 *out,
                      int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, cudaStream_t st) {
-    if (!tc_encode_fn() || dim % 64 || (reinterpret_cast<uintptr_t>(tok_bf16) & 127) || (reinterpret_cast<uintptr_t>(W) & 127))
+    if (!tc_encode_fn() || dim % 64 || (reinterpret_cast<uintptr_t>(tok_bf16) & 127) || (reinterpret_cast<uintptr_t>(W) & 127) ||
+        (reinterpret_cast<uintptr_t>(skip) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || B >= 2048 || Ht >= 1024 || Wt >= 1024)
         return TU_TC_UNSUPPORTED;
     const int nWy = (Ht + 7) / 8, nWx = (Wt + 7) / 8;
     const int M = window ? B * nWy * nWx * 64 : B * Ht * Wt;
     CUtensorMap ta, tw;
     int rc;
     if ((rc = encode_2d(&ta, tok_bf16, M, dim, BM))) return rc;
-    if ((rc = encode_2d(&tw, W, 4096, dim, 256))) return rc;
+    if ((rc = encode_2d(&tw, W, 4096, dim, 128))) return rc;
     GemmParams p = {};
-    p.M = M; p.N = 4096; p.K = dim; p.BN = 256;
+    p.M = M; p.N = 4096; p.K = dim; p.BN = 128;      // 2 pixels per token and tile: leaves shared memory for the epilogue transpose
     p.tiles_m = ceil_div(M, BM);
     p.amode = 0;
     p.epi = EPI_UNEMBED;

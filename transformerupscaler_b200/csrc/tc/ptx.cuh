@@ -63,6 +63,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *m, 
                  : "memory");
 }
 
+// ---- TMA stores (shared -> global), bulk-group completion -------------------------------------------
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- TMEM / tcgen05 -----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -88,6 +101,51 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- low-overhead issue path ------------------------------------------------------------------------
+// One UTCHMMA with N = 64 lasts only 32 cycles, so the issuing warp must spend just a few instructions per MMA.
+// The whole warp runs the issue loop converged (warp-uniform values stay in uniform registers), the elected lane's
+// predicate guards the instruction, and descriptors are a compile-time offset added to a pre-encoded low word:
+// high word (SBO 1024 B, version 1, SWIZZLE_128B) is the constant below.
+constexpr uint32_t SDESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // 0x40004040
+__device__ __forceinline__ uint32_t sdesc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
+}
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred pl, pa;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pl, %4, 0;\n\t"
+        "setp.ne.b32 pa, %6, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(leader), "r"(SDESC_HI_SW128), "n"(ACC)
+        : "memory");
+}
+// same, accumulate flag known only at run time
+__device__ __forceinline__ void umma_bf16_lo_rt(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred pl, pa;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 pl, %4, 0;\n\t"
+        "setp.ne.b32 pa, %6, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(leader), "r"(SDESC_HI_SW128), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %1, 0;\n\t"
+        "@pl tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+        "r"(leader)
+        : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base_lane + t), columns c..c+31

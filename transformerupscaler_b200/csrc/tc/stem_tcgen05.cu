@@ -48,7 +48,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
     const uint32_t a_sm = smem0, w_sm = smem0 + ROWS * A_BYTES;
     float *bias_s = reinterpret_cast<float *>(smem_al + ROWS * A_BYTES + W_BYTES);
     Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + 256);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
     if (threadIdx.x == 0) {
@@ -71,29 +71,30 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 8) {
-        if (lane == 0) {
-            // ================================ weights + MMA issuer ================================
+        // ================================ weights + MMA issuer (whole warp converged, elected lane issues) ================================
+        const uint32_t leader = ptx::elect_one();
+        if (leader) {
             ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
             ptx::tma_load_2d(w_sm, &tmap_w, ptx::smem_u32(&bars->w_full), 0, 0);
-            ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
-            const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
-            uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
-                ptx::mbar_wait(ptx::smem_u32(&bars->a_full), ph);
+        }
+        __syncwarp();
+        ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
+        const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
+        const uint32_t a_lo = ptx::sdesc_lo(a_sm), w_lo = ptx::sdesc_lo(w_sm);
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->a_full), ph);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[r]), ph ^ 1);
                 ptx::tc_fence_after();
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[r]), ph ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t a = a_sm + r * A_BYTES;
-#pragma unroll
-                    for (int k4 = 0; k4 < 2; ++k4)     // k = 0..31 (27 taps + 5 zeros); chunks 4-7 of a row are never read
-                        ptx::umma_bf16(tmem_base + r * 64, ptx::make_sdesc_sw128(a + k4 * 32, 0),
-                                       ptx::make_sdesc_sw128(w_sm + k4 * 32, 0), idesc, k4 != 0);
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_full[r]));
-                }
-                ptx::umma_commit(ptx::smem_u32(&bars->a_empty));
+                // k = 0..31 (27 taps + 5 zeros); chunks 4-7 of a row are never read
+                ptx::umma_bf16_lo<0>(tmem_base + r * 64, a_lo + ((r * A_BYTES) >> 4), w_lo, idesc, leader);
+                ptx::umma_bf16_lo<1>(tmem_base + r * 64, a_lo + ((r * A_BYTES + 32) >> 4), w_lo + 2, idesc, leader);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_full[r]), leader);
             }
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->a_empty), leader);
         }
     } else if (warp >= 4) {
         // ================================ builders: im2col rows -> swizzled smem ================================

@@ -132,7 +132,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     Barriers *bars = reinterpret_cast<Barriers *>(sm + OFF_BAR);
     float *par = reinterpret_cast<float *>(sm + OFF_PAR);
     float *stat = reinterpret_cast<float *>(sm + OFF_STAT);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NRING; ++i) {
@@ -169,52 +169,52 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
-            // ================================ MMA issuer ================================
-            const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
-            int stage = 0;
-            uint32_t phase = 0, aph = 0;
-            // one weight slab: D[128 x 128] (+)= A_slab[128 x 64] * W_slab[128 x 64]^T
-            auto slab_mma = [&](uint32_t d_tmem, uint32_t a_addr, bool first_clears) {
-                ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-                ptx::tc_fence_after();
-                const uint32_t w = smem0 + OFF_RING + stage * SLAB;
+        // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
+        const uint32_t leader = ptx::elect_one();
+        const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+        const uint32_t ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
+        int stage = 0;
+        uint32_t phase = 0, aph = 0;
+        // one weight slab: D[128 x 128] (+)= A_slab[128 x 64] * W_slab[128 x 64]^T
+        auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, bool first_clears) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+            ptx::tc_fence_after();
+            const uint32_t w_lo = ring_lo + ((stage * SLAB) >> 4);
+            ptx::umma_bf16_lo_rt(d_tmem, a_lo, w_lo, idesc, first_clears ? 0u : 1u, leader);
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    ptx::umma_bf16(d_tmem, ptx::make_sdesc_sw128(a_addr + k4 * 32, 0), ptx::make_sdesc_sw128(w + k4 * 32, 0), idesc,
-                                   (first_clears && k4 == 0) ? 0u : 1u);
-                ptx::umma_commit(ptx::smem_u32(&bars->empty[stage]));
-                if (++stage == NRING) { stage = 0; phase ^= 1; }
-            };
-            auto wait_a = [&]() {
-                ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), aph);
-                aph ^= 1;
-                ptx::tc_fence_after();
-            };
-            const uint32_t a32 = smem0 + OFF_A32, hid = smem0 + OFF_STG;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-                for (int bk = 0; bk < p.n_blocks; ++bk) {
-                    wait_a();                                       // LN1 output in A32
-                    for (int nc = 0; nc < 3; ++nc)
-                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
-                    wait_a();                                       // attention output in A32
-                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, a32 + ks * SLAB, false);            // x += att Wp^T
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
-                    wait_a();                                       // LN2 output in A32
-                    for (int nc = 0; nc < 2; ++nc)
-                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);   // fc1, half 0
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
-                    wait_a();                                       // GELU(half 0) in HID, ACC drained
-                    for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SLAB, false);            // x += h0 W2[:, h0]^T
-                    for (int nc = 0; nc < 2; ++nc)
-                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SLAB, ks == 0);   // fc1, half 1
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
-                    wait_a();                                       // GELU(half 1) in HID
-                    for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SLAB, false);
-                    ptx::umma_commit(ptx::smem_u32(&bars->acc_ready));
-                }
-        }
+            for (int k4 = 1; k4 < 4; ++k4) ptx::umma_bf16_lo<1>(d_tmem, a_lo + k4 * 2, w_lo + k4 * 2, idesc, leader);
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
+            if (++stage == NRING) { stage = 0; phase ^= 1; }
+        };
+        auto wait_a = [&]() {
+            ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), aph);
+            aph ^= 1;
+            ptx::tc_fence_after();
+        };
+        const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32), hid = ptx::sdesc_lo(smem0 + OFF_STG);
+        constexpr uint32_t SL = SLAB >> 4;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+            for (int bk = 0; bk < p.n_blocks; ++bk) {
+                wait_a();                                       // LN1 output in A32
+                for (int nc = 0; nc < 3; ++nc)
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                wait_a();                                       // attention output in A32
+                for (int ks = 0; ks < 2; ++ks) slab_mma(TX, a32 + ks * SL, false);            // x += att Wp^T
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                wait_a();                                       // LN2 output in A32
+                for (int nc = 0; nc < 2; ++nc)
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 0
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                wait_a();                                       // GELU(half 0) in HID, ACC drained
+                for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);            // x += h0 W2[:, h0]^T
+                for (int nc = 0; nc < 2; ++nc)
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 1
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                wait_a();                                       // GELU(half 1) in HID
+                for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+            }
     } else {
         // ================================ math warps ================================
         const int q = warp & 3, hf = warp >> 2;
