@@ -66,7 +66,17 @@ __device__ __forceinline__ long win_row(int b, int ty, int tx, int nWy, int nWx)
     return (((long)b * nWy + (ty >> 3)) * nWx + (tx >> 3)) * 64 + (ty & 7) * 8 + (tx & 7);
 }
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU = x * 0.5 (1 + tanh(p(x))), p an odd polynomial fitted to atanh(erf(x / sqrt 2)): |error| <= 2.6e-5 against the
+// exact erf form, far below the bf16 resolution of the stored activation (tools/fit_gelu.py)
+__device__ __forceinline__ float gelu_f(float x) {
+    const float x2 = fminf(x * x, 64.f);
+    float q = fmaf(-0.0003515167826820022f, x2, 0.03700564597780192f);
+    q = fmaf(q, x2, 0.7975078843613885f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {

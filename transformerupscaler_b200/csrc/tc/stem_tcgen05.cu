@@ -21,7 +21,8 @@ constexpr int NUM_THREADS = 288;      // warps 0-3 epilogue, 4-7 builders, 8 MMA
 constexpr int ROWS = 4;               // image rows per tile (halo rows are loaded once for all four)
 constexpr int A_BYTES = 128 * 128;    // one operand tile: 128 pixels x 128-byte rows
 constexpr int W_BYTES = 64 * 128;     // 64 output channels x (64 k, 27 real)
-constexpr int SMEM_BYTES = ROWS * A_BYTES + W_BYTES + 256 + 256 + 1024;
+constexpr int STG_BYTES = 4 * 2 * 4096;   // epilogue staging: 4 warps x 2 buffers x (32 pixels x 128 B), source of the TMA stores
+constexpr int SMEM_BYTES = ROWS * A_BYTES + W_BYTES + STG_BYTES + 256 + 256 + 1024;
 
 struct StemParams {
     int B, H, W, tiles_x, tiles_y, total_tiles;
@@ -41,13 +42,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 
 template <typename TI>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict__ x, const StemParams p) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, const TI *__restrict__ x,
+               const StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
     const uint32_t a_sm = smem0, w_sm = smem0 + ROWS * A_BYTES;
-    float *bias_s = reinterpret_cast<float *>(smem_al + ROWS * A_BYTES + W_BYTES);
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + 256);
+    const uint32_t stg_sm = w_sm + W_BYTES;        // 1024-byte aligned
+    float *bias_s = reinterpret_cast<float *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES);
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES + 256);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
@@ -151,13 +154,17 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
         }
     } else {
         // ================================ epilogue ================================
+        // TMEM -> (+bias, ReLU, bf16) -> the pixel's 128 bytes into a swizzled staging buffer -> one TMA store per 32-pixel
+        // row segment and warp (a thread storing its own pixel would touch 32 different cache lines per instruction).
         const int q = warp;
-        uint32_t ph = 0;
+        uint32_t ph = 0, nstore = 0;
+        uint8_t *stg_w = smem_al + ROWS * A_BYTES + W_BYTES + q * 8192;
+        const uint32_t stg_w_sm = stg_sm + q * 8192;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
             const int tx = t % p.tiles_x;
             int rem = t / p.tiles_x;
             const int ty = rem % p.tiles_y, b = rem / p.tiles_y;
-            const int px = tx * 128 + q * 32 + lane;
+            const int px0 = tx * 128 + q * 32;
 #pragma unroll 1
             for (int r = 0; r < ROWS; ++r) {
                 const int y = ty * ROWS + r;
@@ -170,32 +177,35 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TI *__restrict_
                 ptx::tmem_ld_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[r]));   // values are in registers now
-                if (px < p.W && y < p.H) {
-                    bf16 *o = p.out + (((long)b * p.H + y) * p.W + px) * 64;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        const float4 ba = *reinterpret_cast<const float4 *>(bias_s + c), bb = *reinterpret_cast<const float4 *>(bias_s + c + 4);
-                        uint4 u;
-                        u.x = pack2(fmaxf(__uint_as_float(v0[c + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[c + 1]) + ba.y, 0.f));
-                        u.y = pack2(fmaxf(__uint_as_float(v0[c + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[c + 3]) + ba.w, 0.f));
-                        u.z = pack2(fmaxf(__uint_as_float(v0[c + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v0[c + 5]) + bb.y, 0.f));
-                        u.w = pack2(fmaxf(__uint_as_float(v0[c + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v0[c + 7]) + bb.w, 0.f));
-                        *reinterpret_cast<uint4 *>(o + c) = u;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        const float4 ba = *reinterpret_cast<const float4 *>(bias_s + 32 + c), bb = *reinterpret_cast<const float4 *>(bias_s + 36 + c);
-                        uint4 u;
-                        u.x = pack2(fmaxf(__uint_as_float(v1[c + 0]) + ba.x, 0.f), fmaxf(__uint_as_float(v1[c + 1]) + ba.y, 0.f));
-                        u.y = pack2(fmaxf(__uint_as_float(v1[c + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v1[c + 3]) + ba.w, 0.f));
-                        u.z = pack2(fmaxf(__uint_as_float(v1[c + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[c + 5]) + bb.y, 0.f));
-                        u.w = pack2(fmaxf(__uint_as_float(v1[c + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[c + 7]) + bb.w, 0.f));
-                        *reinterpret_cast<uint4 *>(o + 32 + c) = u;
-                    }
+                if (lane == 0) {
+                    ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[r]));   // values are in registers now
+                    ptx::bulk_wait_read<1>();                               // the store that last used this buffer has read it
                 }
+                __syncwarp();
+                const uint32_t buf = nstore & 1;
+                uint8_t *rowp = stg_w + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    const float4 ba = *reinterpret_cast<const float4 *>(bias_s + c), bb = *reinterpret_cast<const float4 *>(bias_s + c + 4);
+                    const uint32_t *v = c < 32 ? &v0[c] : &v1[c - 32];
+                    uint4 u;
+                    u.x = pack2(fmaxf(__uint_as_float(v[0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[1]) + ba.y, 0.f));
+                    u.y = pack2(fmaxf(__uint_as_float(v[2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[3]) + ba.w, 0.f));
+                    u.z = pack2(fmaxf(__uint_as_float(v[4]) + bb.x, 0.f), fmaxf(__uint_as_float(v[5]) + bb.y, 0.f));
+                    u.w = pack2(fmaxf(__uint_as_float(v[6]) + bb.z, 0.f), fmaxf(__uint_as_float(v[7]) + bb.w, 0.f));
+                    *reinterpret_cast<uint4 *>(rowp + (((c >> 3) ^ (lane & 7)) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (y < p.H && px0 < p.W) ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, y, b);
+                    ptx::bulk_commit();
+                }
+                ++nstore;
             }
         }
+        if (lane == 0) ptx::bulk_wait<0>();
+        __syncwarp();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -231,6 +241,17 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
         set_error("tu: cuTensorMapEncodeTiled(stem weights) failed with code " + std::to_string((int)r));
         return TU_ERR_CUDA;
     }
+    CUtensorMap to;
+    {
+        cuuint64_t od[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B}, os[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+        cuuint32_t ob[4] = {64, 32, 1, 1}, oe[4] = {1, 1, 1, 1};
+        r = enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tu: cuTensorMapEncodeTiled(stem output) failed with code " + std::to_string((int)r));
+            return TU_ERR_CUDA;
+        }
+    }
     StemParams p;
     p.B = B; p.H = H; p.W = W;
     p.tiles_x = ceil_div(W, 128);
@@ -239,9 +260,9 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
     p.bias = bias; p.out = out;
     const int grid = p.total_tiles < 2 * g_sm_count ? p.total_tiles : 2 * g_sm_count;
     if (in_dtype == TU_F32)
-        stem_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, (const float *)x, p);
+        stem_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const float *)x, p);
     else
-        stem_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, (const bf16 *)x, p);
+        stem_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const bf16 *)x, p);
     TU_CHECK_LAUNCH("stem_tc");
     return TU_OK;
 }

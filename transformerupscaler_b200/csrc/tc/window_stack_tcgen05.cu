@@ -15,8 +15,9 @@
 //                          HID: GELU(fc1) half-tiles (64 KB) as the A operand of fc2.
 //   smem ring (5 x 16 KB)  weight slabs [128 n x 64 k] streamed by TMA in exactly the order the MMAs consume them
 //                          (24 slabs = 384 KB per block, pre-packed on the host).
-// Roles: warps 0-7 "math" (LN, epilogues, attention; thread = token row x column half), warp 8 TMA producer,
-// warp 9 MMA issuer + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc_ready (MMA -> math).
+// Roles: warps 0-15 "math" (LN, epilogues, attention; thread = token row x column quarter: warp w may only touch TMEM
+// lanes 32*(w%4).., so the four warps of a lane quadrant split the columns), warp 16 TMA producer, warp 17 MMA issuer
+// + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc_ready (MMA -> math).
 #include <cuda.h>
 
 #include "ptx.cuh"
@@ -27,7 +28,8 @@ namespace tu {
 namespace {
 
 constexpr int DIM = 128, HEADS = 8, HID = 512;
-constexpr int NUM_THREADS = 320;
+constexpr int NMATH = 16;                        // math warps
+constexpr int NUM_THREADS = (NMATH + 2) * 32;    // 576
 constexpr int SLAB = 128 * 128;                 // 16 KB: 128 rows x 64 bf16
 constexpr int NRING = 5;
 constexpr int SLABS_PER_BLOCK = 24;
@@ -39,7 +41,7 @@ constexpr int OFF_RING = OFF_STG + STG_BYTES;
 constexpr int OFF_PAR = OFF_RING + NRING * SLAB;
 constexpr int PAR_FLOATS = 1664;                // c0 | ln1w | ln1b | qkvb(384) | c1 | ln2w | ln2b | fc1b(512)
 constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
-constexpr int OFF_BAR = OFF_STAT + 128 * 2 * 4;
+constexpr int OFF_BAR = OFF_STAT + 128 * 4 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int P_C0 = 0, P_LN1W = 128, P_LN1B = 256, P_QKVB = 384, P_C1 = 768, P_LN2W = 896, P_LN2B = 1024, P_FC1B = 1152;
 
@@ -57,7 +59,7 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -77,16 +79,17 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-// exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution)
+// GELU(x) = x * Phi(x) with Phi(x) = 0.5 (1 + tanh(p(x))), p the odd polynomial fitted (minimax over |x| <= 8) to
+// atanh(erf(x / sqrt 2)): |error| <= 2.6e-5 against the exact erf form in exact arithmetic, plus tanh.approx's 2^-11
+// relative error -- both far below the bf16 resolution of the stored activation (tools/fit_gelu.py reproduces the fit).
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float e = 1.0f - poly * t * exp2f(-z * z * 1.4426950408889634f);   // erf(|x|/sqrt2)
-    return 0.5f * x * (1.0f + copysignf(e, x));
+    const float x2 = fminf(x * x, 64.f);            // beyond |x| = 8 the tanh is saturated; keeps p monotone
+    float q = fmaf(-0.0003515167826820022f, x2, 0.03700564597780192f);
+    q = fmaf(q, x2, 0.7975078843613885f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
 }
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -95,32 +98,34 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// LayerNorm of this thread's 64 columns of row i (x already includes the folded bias offset), two-pass statistics
-// shared with the partner thread holding the other half of the row; result -> A32 slab `hf`, swizzled.
-__device__ __forceinline__ void layernorm_to_a32(float (&x)[64], const float *gam, const float *bet, float *stat, uint8_t *a32,
-                                                 int i, int hf) {
+// LayerNorm of this thread's 32 columns of row i (x already includes the folded bias offset), two-pass statistics
+// shared with the three partner threads holding the rest of the row; result -> A32 slab part/2, swizzled.
+__device__ __forceinline__ void layernorm_to_a32(float (&x)[32], const float *gam, const float *bet, float *stat, uint8_t *a32,
+                                                 int i, int part) {
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) s += x[j];
-    stat[i * 2 + hf] = s;
+    for (int j = 0; j < 32; ++j) s += x[j];
+    stat[i * 4 + part] = s;
     math_barrier();
-    const float mean = (stat[i * 2] + stat[i * 2 + 1]) * (1.0f / DIM);
+    const float4 s4 = *reinterpret_cast<const float4 *>(stat + i * 4);
+    const float mean = ((s4.x + s4.y) + (s4.z + s4.w)) * (1.0f / DIM);
     math_barrier();
     float qv = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) { const float d = x[j] - mean; qv = fmaf(d, d, qv); }
-    stat[i * 2 + hf] = qv;
+    for (int j = 0; j < 32; ++j) { const float d = x[j] - mean; qv = fmaf(d, d, qv); }
+    stat[i * 4 + part] = qv;
     math_barrier();
-    const float rstd = rsqrtf((stat[i * 2] + stat[i * 2 + 1]) * (1.0f / DIM) + 1e-5f);
-    uint8_t *rowp = a32 + hf * SLAB + i * 128;
+    const float4 q4 = *reinterpret_cast<const float4 *>(stat + i * 4);
+    const float rstd = rsqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.0f / DIM) + 1e-5f);
+    uint8_t *rowp = a32 + (part >> 1) * SLAB + i * 128;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int ch = 0; ch < 4; ++ch) {
         float y[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = (x[ch * 8 + e] - mean) * rstd * gam[ch * 8 + e] + bet[ch * 8 + e];
         uint4 u;
         u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
-        *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
+        *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + ch) ^ (i & 7)) << 4)) = u;
     }
 }
 
@@ -139,22 +144,22 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
         }
-        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), 256);
+        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH * 32);
         ptx::mbar_init(ptx::smem_u32(&bars->acc_ready), 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == NMATH + 1) {
         ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
         ptx::tmem_relinquish();
     }
-    if (warp == 8 && lane == 0) ptx::prefetch_tmap(&tmap_w);
+    if (warp == NMATH && lane == 0) ptx::prefetch_tmap(&tmap_w);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const uint32_t TX = tmem_base, TACC = tmem_base + 128;
 
-    if (warp == 8) {
+    if (warp == NMATH) {
         if (lane == 0) {
             // ================================ TMA producer: weight slabs in consumption order ================================
             int stage = 0;
@@ -168,7 +173,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     if (++stage == NRING) { stage = 0; phase ^= 1; }
                 }
         }
-    } else if (warp == 9) {
+    } else if (warp == NMATH + 1) {
         // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
         const uint32_t leader = ptx::elect_one();
         const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
@@ -217,10 +222,10 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             }
     } else {
         // ================================ math warps ================================
-        const int q = warp & 3, hf = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;           // TMEM lane quadrant, column quarter
         const int i = q * 32 + lane;                        // token row of the tile == TMEM lane
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int mt = threadIdx.x;                          // 0..255
+        const int mt = threadIdx.x;                          // 0..511
         uint8_t *a32 = sm + OFF_A32, *stg = sm + OFF_STG;
         uint32_t cph = 0;
         auto wait_acc = [&]() {
@@ -233,32 +238,26 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             ptx::tc_fence_before();
             ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
         };
-        // x row half (+ offset vector) -> registers
-        auto load_x = [&](float (&x)[64], const float *cvec) {
+        // x row quarter (+ offset vector) -> registers
+        auto load_x = [&](float (&x)[32], const float *cvec) {
             uint32_t v[32];
+            ptx::tmem_ld_x32(TX + lane_base + part * 32, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                ptx::tmem_ld_x32(TX + lane_base + hf * 64 + h2 * 32, v);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[h2 * 32 + j] = __uint_as_float(v[j]) + cvec[hf * 64 + h2 * 32 + j];
-            }
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + cvec[part * 32 + j];
         };
 
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
             // ---- tokens -> TMEM X
             {
-                const float *src = p.tok + ((long)t * 128 + i) * DIM + hf * 64;
+                const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 32;
+                uint32_t v[32];
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    uint32_t v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 f = *reinterpret_cast<const float4 *>(src + h2 * 32 + j);
-                        v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
-                    }
-                    tmem_st_x32(TX + lane_base + hf * 64 + h2 * 32, v);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 f = *reinterpret_cast<const float4 *>(src + j);
+                    v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
                 }
+                tmem_st_x32(TX + lane_base + part * 32, v);
                 tmem_st_wait();
                 ptx::tc_fence_before();
             }
@@ -269,48 +268,45 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 {
                     const float4 *g = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
                     float4 *d = reinterpret_cast<float4 *>(par);
-                    for (int e = mt; e < PAR_FLOATS / 4; e += 256) d[e] = g[e];
+                    for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g[e];
                 }
                 math_barrier();
                 // ---- LN1(x + c0) -> A32
                 {
-                    float x[64];
+                    float x[32];
                     load_x(x, par + P_C0);
-                    layernorm_to_a32(x, par + P_LN1W + hf * 64, par + P_LN1B + hf * 64, stat, a32, i, hf);
+                    layernorm_to_a32(x, par + P_LN1W + part * 32, par + P_LN1B + part * 32, stat, a32, i, part);
                 }
                 signal_a();
                 // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows
                 wait_acc();
                 {
                     uint8_t *rowp = stg + i * STG_PITCH;
-#pragma unroll 1
+#pragma unroll
                     for (int nc = 0; nc < 3; ++nc) {
+                        uint32_t v[32];
+                        const int col = nc * 128 + part * 32;
+                        ptx::tmem_ld_x32(TACC + lane_base + col, v);
+                        ptx::tmem_ld_wait();
+                        const float *bb = par + P_QKVB + col;
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            uint32_t v[32];
-                            const int col = nc * 128 + hf * 64 + h2 * 32;
-                            ptx::tmem_ld_x32(TACC + lane_base + col, v);
-                            ptx::tmem_ld_wait();
-                            const float *bb = par + P_QKVB + col;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint4 u;
-                                u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
-                                u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
-                                u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
-                                u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
-                                *reinterpret_cast<uint4 *>(rowp + (col + j) * 2) = u;
-                            }
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 u;
+                            u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
+                            u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
+                            u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
+                            u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
+                            *reinterpret_cast<uint4 *>(rowp + (col + j) * 2) = u;
                         }
                     }
                 }
                 math_barrier();
-                // ---- window attention: 2 windows x 8 heads x 4 row groups = 64 warp tasks, 8 per warp
+                // ---- window attention: 2 windows x 8 heads x 4 row groups = 64 warp tasks, 4 per warp
                 {
                     const int g = lane >> 2, tq = lane & 3;
                     const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
 #pragma unroll 1
-                    for (int task = warp; task < 64; task += 8) {
+                    for (int task = warp; task < 64; task += NMATH) {
                         const int win = task >> 5, h = (task >> 2) & 7, rg = task & 3;
                         const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
                         const int r0 = rg * 16 + g;
@@ -341,10 +337,11 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
                         float l0 = 0.f, l1 = 0.f;
                         const float L2E = 1.4426950408889634f;
+                        const float mm0 = m0 * L2E, mm1 = m1 * L2E;
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
-                            s[n][0] = exp2f((s[n][0] - m0) * L2E); s[n][1] = exp2f((s[n][1] - m0) * L2E);
-                            s[n][2] = exp2f((s[n][2] - m1) * L2E); s[n][3] = exp2f((s[n][3] - m1) * L2E);
+                            s[n][0] = exp2f(fmaf(s[n][0], L2E, -mm0)); s[n][1] = exp2f(fmaf(s[n][1], L2E, -mm0));
+                            s[n][2] = exp2f(fmaf(s[n][2], L2E, -mm1)); s[n][3] = exp2f(fmaf(s[n][3], L2E, -mm1));
                             l0 += s[n][0] + s[n][1];
                             l1 += s[n][2] + s[n][3];
                         }
@@ -383,34 +380,32 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
                 wait_acc();
                 {
-                    float x[64];
+                    float x[32];
                     load_x(x, par + P_C1);
-                    layernorm_to_a32(x, par + P_LN2W + hf * 64, par + P_LN2B + hf * 64, stat, a32, i, hf);
+                    layernorm_to_a32(x, par + P_LN2W + part * 32, par + P_LN2B + part * 32, stat, a32, i, part);
                 }
                 signal_a();
                 // ---- MLP: two halves of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     wait_acc();
-#pragma unroll 1
+#pragma unroll
                     for (int nc = 0; nc < 2; ++nc) {
-                        uint8_t *rowp = stg + (nc * 2 + hf) * SLAB + i * 128;        // HID K-slab = hidden column / 64
+                        const int col = nc * 128 + part * 32;                       // column of this 256-wide half
+                        uint8_t *rowp = stg + (col >> 6) * SLAB + i * 128;          // HID K-slab = hidden column / 64
+                        uint32_t v[32];
+                        ptx::tmem_ld_x32(TACC + lane_base + col, v);
+                        ptx::tmem_ld_wait();
+                        const float *bb = par + P_FC1B + half * 256 + col;
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            uint32_t v[32];
-                            ptx::tmem_ld_x32(TACC + lane_base + nc * 128 + hf * 64 + h2 * 32, v);
-                            ptx::tmem_ld_wait();
-                            const float *bb = par + P_FC1B + half * 256 + nc * 128 + hf * 64 + h2 * 32;
+                        for (int j = 0; j < 32; j += 8) {
+                            float y[8];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                float y[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) y[e] = gelu_fast(__uint_as_float(v[j + e]) + bb[j + e]);
-                                uint4 u;
-                                u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
-                                const int ch = (h2 * 32 + j) >> 3;
-                                *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
-                            }
+                            for (int e = 0; e < 8; ++e) y[e] = gelu_fast(__uint_as_float(v[j + e]) + bb[j + e]);
+                            uint4 u;
+                            u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+                            const int ch = ((col & 63) + j) >> 3;
+                            *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
                         }
                     }
                     signal_a();
@@ -419,27 +414,24 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             }
             // ---- X (+ final offset) -> global
             {
-                const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS;
-                float *dst = p.tok + ((long)t * 128 + i) * DIM + hf * 64;
-                bf16 *dst16 = p.tok16 ? p.tok16 + ((long)t * 128 + i) * DIM + hf * 64 : nullptr;
+                const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS + part * 32;
+                float *dst = p.tok + ((long)t * 128 + i) * DIM + part * 32;
+                bf16 *dst16 = p.tok16 ? p.tok16 + ((long)t * 128 + i) * DIM + part * 32 : nullptr;
+                uint32_t v[32];
+                ptx::tmem_ld_x32(TX + lane_base + part * 32, v);
+                ptx::tmem_ld_wait();
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_x32(TX + lane_base + hf * 64 + h2 * 32, v);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 f;
-                        f.x = __uint_as_float(v[j]) + __ldg(cfin + hf * 64 + h2 * 32 + j);
-                        f.y = __uint_as_float(v[j + 1]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 1);
-                        f.z = __uint_as_float(v[j + 2]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 2);
-                        f.w = __uint_as_float(v[j + 3]) + __ldg(cfin + hf * 64 + h2 * 32 + j + 3);
-                        *reinterpret_cast<float4 *>(dst + h2 * 32 + j) = f;
-                        if (dst16) {
-                            uint2 u;
-                            u.x = pk(f.x, f.y); u.y = pk(f.z, f.w);
-                            *reinterpret_cast<uint2 *>(dst16 + h2 * 32 + j) = u;
-                        }
+                for (int j = 0; j < 32; j += 4) {
+                    float4 f;
+                    f.x = __uint_as_float(v[j]) + __ldg(cfin + j);
+                    f.y = __uint_as_float(v[j + 1]) + __ldg(cfin + j + 1);
+                    f.z = __uint_as_float(v[j + 2]) + __ldg(cfin + j + 2);
+                    f.w = __uint_as_float(v[j + 3]) + __ldg(cfin + j + 3);
+                    *reinterpret_cast<float4 *>(dst + j) = f;
+                    if (dst16) {
+                        uint2 u;
+                        u.x = pk(f.x, f.y); u.y = pk(f.z, f.w);
+                        *reinterpret_cast<uint2 *>(dst16 + j) = u;
                     }
                 }
                 ptx::tc_fence_before();
@@ -448,7 +440,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 9) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == NMATH + 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 int g_sm_count = 0;
