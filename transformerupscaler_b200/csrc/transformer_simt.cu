@@ -178,6 +178,157 @@ __global__ void __launch_bounds__(128) window_attn_mma_kernel(const bf16 *__rest
     *reinterpret_cast<uint32_t *>(op1 + 8) = pack_bf16x2(o[1][2] * i1, o[1][3] * i1);
 }
 
+// ------------------------------------------------------------------ global attention on the tensor cores (bf16, head_dim 16)
+// Flash-style: CTA = 128 queries of one (frame, head), warp = 32 query rows (two m16 tiles sharing every K/V fragment);
+// keys/values stream through shared memory in double-buffered tiles of 64 (cp.async) with an online softmax, so the
+// S x S score matrix never exists.  QK^T is one m16n8k16 step per 8 keys (K = head_dim = 16), PV four steps per tile.
+// Reference: nn.MultiheadAttention(128, 8, batch_first=True) inside TransformerBlock (ResidualTransformer/model.py:31,44);
+// q is pre-scaled by head_dim^-0.5 in the packed in_proj weights.
+constexpr int GA_KT = 64;          // keys per tile
+constexpr int GA_PITCH = 24;       // bf16 per staged row (48 B: conflict-free fragment loads and ldmatrix)
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;                 // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+__global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
+    __shared__ __align__(16) bf16 ks[2][GA_KT][GA_PITCH];
+    __shared__ __align__(16) bf16 vs[2][GA_KT][GA_PITCH];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const long ld = 3L * dim;
+    const bf16 *base = qkv + (long)b * S * ld + h * 16;
+    const int q0 = blockIdx.x * 128 + warp * 32;
+    const float L2E = 1.4426950408889634f;
+
+    auto stage = [&](int buf, int k0) {
+        const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+        const int key = k0 + r;
+        const bool ok = key < S;
+        const bf16 *src = base + (long)(ok ? key : 0) * ld + hf * 8;
+        cp_async16(&ks[buf][r][hf * 8], src + dim, ok);
+        cp_async16(&vs[buf][r][hf * 8], src + 2 * dim, ok);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // Q fragments of the two m16 tiles (rows beyond S read row S-1; their results are never stored)
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = min(q0 + mt * 16 + g, S - 1), r1 = min(q0 + mt * 16 + g + 8, S - 1);
+        qa[mt][0] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2);
+        qa[mt][1] = *reinterpret_cast<const uint32_t *>(base + (long)r1 * ld + tq * 2);
+        qa[mt][2] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2 + 8);
+        qa[mt][3] = *reinterpret_cast<const uint32_t *>(base + (long)r1 * ld + tq * 2 + 8);
+    }
+    float o[2][2][4], m[2][2], l[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        m[mt][0] = m[mt][1] = -INFINITY;
+        l[mt][0] = l[mt][1] = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+    }
+    const int ntiles = (S + GA_KT - 1) / GA_KT;
+    stage(0, 0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < ntiles) {
+            stage(buf ^ 1, (t + 1) * GA_KT);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int nk = min(GA_KT, S - t * GA_KT);
+        // K fragments of the tile: key n*8+g, dims tq*2.. (+8)
+        uint32_t kb[8][2];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            kb[n][0] = *reinterpret_cast<const uint32_t *>(&ks[buf][n * 8 + g][tq * 2]);
+            kb[n][1] = *reinterpret_cast<const uint32_t *>(&ks[buf][n * 8 + g][tq * 2 + 8]);
+        }
+        uint32_t vb[4][4];
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&vs[buf][kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][(lane >> 4) * 8]);
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(vb[kt][0]), "=r"(vb[kt][1]), "=r"(vb[kt][2]), "=r"(vb[kt][3])
+                         : "r"(addr));
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            float s[8][4];
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+                mma_bf16_16816(s[n], qa[mt], kb[n][0], kb[n][1]);
+            }
+            if (nk < GA_KT) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const int j = n * 8 + tq * 2;
+                    if (j >= nk) s[n][0] = s[n][2] = -INFINITY;
+                    if (j + 1 >= nk) s[n][1] = s[n][3] = -INFINITY;
+                }
+            }
+            float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                t0 = fmaxf(t0, fmaxf(s[n][0], s[n][1]));
+                t1 = fmaxf(t1, fmaxf(s[n][2], s[n][3]));
+            }
+            t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+            t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+            const float n0 = fmaxf(m[mt][0], t0), n1 = fmaxf(m[mt][1], t1);
+            const float c0 = exp2f((m[mt][0] - n0) * L2E), c1 = exp2f((m[mt][1] - n1) * L2E);   // exp2(-inf) = 0 on the first tile
+            m[mt][0] = n0; m[mt][1] = n1;
+            l[mt][0] *= c0; l[mt][1] *= c1;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { o[mt][nt][0] *= c0; o[mt][nt][1] *= c0; o[mt][nt][2] *= c1; o[mt][nt][3] *= c1; }
+            const float b0 = n0 * L2E, b1 = n1 * L2E;
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                s[n][0] = exp2f(fmaf(s[n][0], L2E, -b0)); s[n][1] = exp2f(fmaf(s[n][1], L2E, -b0));
+                s[n][2] = exp2f(fmaf(s[n][2], L2E, -b1)); s[n][3] = exp2f(fmaf(s[n][3], L2E, -b1));
+                l[mt][0] += s[n][0] + s[n][1];
+                l[mt][1] += s[n][2] + s[n][3];
+            }
+#pragma unroll
+            for (int kt = 0; kt < 4; ++kt) {
+                uint32_t pa[4];
+                pa[0] = pack_bf16x2(s[2 * kt][0], s[2 * kt][1]);
+                pa[1] = pack_bf16x2(s[2 * kt][2], s[2 * kt][3]);
+                pa[2] = pack_bf16x2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+                pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+                mma_bf16_16816(o[mt][0], pa, vb[kt][0], vb[kt][1]);
+                mma_bf16_16816(o[mt][1], pa, vb[kt][2], vb[kt][3]);
+            }
+        }
+        __syncthreads();       // everyone is done with this buffer before the next prefetch overwrites it
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        float l0 = l[mt][0], l1 = l[mt][1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        const int r0 = q0 + mt * 16 + g, r1 = r0 + 8;
+        bf16 *op0 = out + ((long)b * S + r0) * dim + h * 16 + tq * 2, *op1 = out + ((long)b * S + r1) * dim + h * 16 + tq * 2;
+        if (r0 < S) {
+            *reinterpret_cast<uint32_t *>(op0) = pack_bf16x2(o[mt][0][0] * i0, o[mt][0][1] * i0);
+            *reinterpret_cast<uint32_t *>(op0 + 8) = pack_bf16x2(o[mt][1][0] * i0, o[mt][1][1] * i0);
+        }
+        if (r1 < S) {
+            *reinterpret_cast<uint32_t *>(op1) = pack_bf16x2(o[mt][0][2] * i1, o[mt][0][3] * i1);
+            *reinterpret_cast<uint32_t *>(op1 + 8) = pack_bf16x2(o[mt][1][2] * i1, o[mt][1][3] * i1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ global attention (S tokens per frame, head_dim 16)
 // qkv (B*S, 3*dim) T with q pre-scaled; out (B*S, dim) T.  CTA = 128 queries of one (frame, head);
 // keys/values streamed through shared memory in tiles of 128 with an online softmax (never materialises SxS).
@@ -313,6 +464,10 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
         dim3 grid(M / 64, heads);
         window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
         TU_CHECK_LAUNCH("window_attn");
+    } else if (tc && sizeof(T) == 2) {
+        dim3 grid(ceil_div(S, 128), heads, M / S);
+        global_attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
+        TU_CHECK_LAUNCH("global_attn_mma");
     } else {
         dim3 grid(ceil_div(S, 128), heads, M / S);
         global_attn_kernel<T><<<grid, 128, 0, st>>>(big, att, S, dim);
