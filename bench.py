@@ -207,27 +207,35 @@ def main():
     ms_per_step = ms_total / steps
     fps = world * FRAMES_PER_GPU * steps / (ms_total * 1e-3)
 
-    # ---------------- end-to-end through the public API with pinned host buffers (`e2e`)
-    e2e_steps = steps
+    # ---------------- end-to-end through the public API with pinned HOST buffers (`e2e`)
+    # Frames cross PCIe as uint8 (what a video caller holds: inference.py:65-70 / app_overlay.py:298,383 convert uint8 <-> float
+    # around the model); the ToTensor scaling and the (out*255).clamp().to(uint8) are fused into the first / last kernel.
+    # The same pipeline with bf16 host tensors (the float signature of the reference) is reported beside it.
+    def run_e2e(hin, hout):
+        pipe = FramePipeline(model, depth=2, device=dev, res_out=(OH, OW))
+        for i in range(warmup):
+            pipe.submit(hin[i & 1], hout[i & 1])
+        pipe.drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            pipe.submit(hin[i & 1], hout[i & 1])
+        pipe.drain()
+        dt = time.perf_counter() - t0
+        chk = float(hout[(steps - 1) & 1].float().mean())          # the D2H result is read on the host
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * FRAMES_PER_GPU * steps / tt.item(), chk
+
+    hin8 = [(xs[i].float() * 255).round().clamp(0, 255).to(torch.uint8).cpu().pin_memory() for i in range(2)]
+    hout8 = [torch.empty((FRAMES_PER_GPU, 3, OH, OW), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    e2e_fps, checksum8 = run_e2e(hin8, hout8)
+    h2d = hin8[0].numel() * hin8[0].element_size()
+    d2h = hout8[0].numel() * hout8[0].element_size()
     hin = [xs[i].cpu().pin_memory() for i in range(2)]
     hout = [torch.empty((FRAMES_PER_GPU, 3, OH, OW), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
-    pipe = FramePipeline(model, depth=2, device=dev, res_out=(OH, OW))
-    for i in range(warmup):
-        pipe.submit(hin[i & 1], hout[i & 1])
-    pipe.drain()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        pipe.submit(hin[i & 1], hout[i & 1])
-    pipe.drain()
-    dt = time.perf_counter() - t0
-    checksum = float(hout[(e2e_steps - 1) & 1].float().mean())     # the D2H result is read on the host
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = world * FRAMES_PER_GPU * e2e_steps / t.item()
-    h2d = hin[0].numel() * hin[0].element_size()
-    d2h = hout[0].numel() * hout[0].element_size()
+    e2e_bf16_fps, checksum = run_e2e(hin, hout)
 
     if rank == 0:
         tf_peak, hbm_peak, peak_src = peaks()
@@ -255,7 +263,11 @@ def main():
                          "kernel_share_of_step": (kms.value / ms_total) if kn.value else None,
                          "kernel_ms_per_launch": breakdown},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": "pinned host bf16 frames -> H2D -> model(x) -> D2H, 3 streams, depth-2 pipeline, wall clock"},
+                    "how": "pinned host uint8 frames -> H2D -> model(x_u8) -> uint8 frames -> D2H, 3 streams, depth-2 pipeline, "
+                           "wall clock; x/255 and (out*255).clamp().to(uint8) fused into the first/last kernel",
+                    "output_mean_u8": checksum8,
+                    "bf16_host_tensors": {"value": e2e_bf16_fps, "h2d_bytes_per_step": hin[0].numel() * 2,
+                                          "d2h_bytes_per_step": hout[0].numel() * 2}},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -10,7 +10,7 @@
  *   - the caller owns every buffer; the library never allocates or frees device memory, never
  *     synchronises the device, and enqueues all work on `stream` (a cudaStream_t passed as void*);
  *   - return value 0 = success, negative = error; tu_last_error() gives the message (thread-local);
- *   - dtype codes: TU_F32 = 0, TU_BF16 = 1;
+ *   - dtype codes: TU_F32 = 0, TU_BF16 = 1, TU_U8 = 2 (image input / output only);
  *   - activations inside the engine are NHWC (64 channels); images at the boundary are NCHW, like
  *     the reference's tensors.
  */
@@ -26,6 +26,8 @@ extern "C" {
 
 #define TU_F32 0
 #define TU_BF16 1
+#define TU_U8 2   /* image I/O only (in_dtype / out_dtype of tu_forward, tu_stem_conv, tu_bicubic_add_clamp,        */
+                  /* tu_final_conv_add): uint8 frames, x/255 on read (ToTensor), trunc(clamp(v*255,0,255)) on write  */
 
 #define TU_OK 0
 #define TU_ERR_ARG (-1)      /* bad argument (shape / dtype / null pointer)              */

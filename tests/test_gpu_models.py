@@ -151,3 +151,28 @@ def test_native_library_is_loaded():
     assert lib.tu_version() >= 100
     with open("/proc/self/maps") as fh:
         assert "libtu_b200.so" in fh.read()
+
+
+@pytest.mark.parametrize("name", ["window_72x104_r1p5", "window_131x189_odd", "fast_40x56_x2", "residual_720p_1080p"])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_uint8_frames_match_float_path(name, bf16):
+    """uint8 frames in -> uint8 frames out (ToTensor on read, (out*255).clamp(0,255).to(uint8) on write, fused into the
+    first / last kernels; reference glue: inference.py:65-70, app_overlay.py:298,383) equals the float path fed x/255 and
+    converted the way the reference's overlay does, up to one grey level where the float result sits on an integer."""
+    c = CASES[name]
+    B, _, H, W = c["shape"]
+    M, sd = build(c["model"], c["wseed"], c.get("gain", 1.0))
+    if bf16:
+        M = M.bfloat16()
+    g = torch.Generator().manual_seed(c["xseed"])
+    xu = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda()
+    with torch.no_grad():
+        yu = M(xu, **c["kw"])
+        xf = xu.float() / 255.0
+        yf = M(xf.bfloat16() if bf16 else xf, **c["kw"])
+    assert yu.dtype == torch.uint8 and yu.shape == yf.shape
+    want = (yf.float() * 255).clamp(0, 255).to(torch.uint8)
+    diff = (yu.int() - want.int()).abs()
+    tol = 3 if bf16 else 1          # bf16 module: the float path rounds its output to bf16 (4e-3 near 1.0) before the *255
+    assert diff.max().item() <= tol, f"{name}: max grey-level difference {diff.max().item()}"
+    assert (diff > 0).float().mean().item() < (0.5 if bf16 else 0.02)

@@ -403,7 +403,8 @@ extern "C" int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, 
     int rc = check_forward_args(w, B, H, W, outH, outW, compute_dtype);
     if (rc) return rc;
     TU_CHECK_ARG(x && out && workspace, "forward: null buffer");
-    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16) && (out_dtype == TU_F32 || out_dtype == TU_BF16), "forward: bad i/o dtype");
+    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8) && (out_dtype == TU_F32 || out_dtype == TU_BF16 || out_dtype == TU_U8),
+                 "forward: bad i/o dtype");
     TU_CHECK_ARG(w->blocks && w->n_blocks > 0 && w->dim == w->heads * 16, "forward: bad transformer configuration");
     // size pass, then the real pass
     Arena dry{nullptr, 0, 0, true};

@@ -47,55 +47,79 @@ __device__ __forceinline__ Cubic cubic_taps(int dst, int in_size, int out_size) 
 //
 // Source pixels come from one of two places:
 //   * TMA variant (row pitch of both sources a multiple of 16 bytes): one thread issues two cp.async.bulk.tensor loads
-//     that bring the whole source footprint of the tile (3 channels x rows x cols, out-of-image parts zero-filled and
-//     never addressed because taps are clamped) into shared memory; the strip walk then runs at shared-memory latency.
+//     that bring the whole source footprint of the tile (3 channels x rows x cols) into shared memory; out-of-image
+//     parts are rewritten with the border pixel (replicate padding == clamped taps), so a thread's four taps are four
+//     contiguous elements and the strip walk runs at shared-memory latency with almost no address arithmetic.
 //   * direct variant (any shape): taps are read from global memory.
 constexpr int BS_W = 128, BS_H = 32;
 
+// element as stored -> float, and the factor applied once per 4-tap sum (uint8 frames: 1/255, ToTensor)
+__device__ __forceinline__ float raw_f(float v) { return v; }
+__device__ __forceinline__ float raw_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float raw_f(uint8_t v) { return (float)v; }
+template <typename TS> __device__ __forceinline__ float src_scale(float t) { return t; }
+template <> __device__ __forceinline__ float src_scale<uint8_t>(float t) { return t * 0.00392156862745098f; }
+
 template <typename TS>
-struct GlobalSrc {          // image of one frame: (3, H, W)
+struct GlobalSrc {          // image of one frame: (3, H, W); taps and rows clamped to the image like ATen
     const TS *img;
     long plane;
-    int W;
-    __device__ __forceinline__ float at(int ch, int row, int col) const { return to_f(img[ch * plane + (long)row * W + col]); }
-};
-template <typename TS>
-struct TileSrc {            // shared-memory tile (3, nr, pitch) whose element (0,0) is source pixel (r0, c0)
-    const TS *s;
-    int r0, c0, nr, pitch;
-    __device__ __forceinline__ float at(int ch, int row, int col) const { return to_f(s[(ch * nr + (row - r0)) * pitch + (col - c0)]); }
-};
-
-template <typename Src>
-__device__ __forceinline__ float hrow(const Src &src, int ch, int row, const Cubic &cx) {
-    float t = 0.f;
+    int H, W;
+    __device__ __forceinline__ float hrow(int ch, int row, const Cubic &cx) const {
+        const TS *p = img + ch * plane + (long)min(max(row, 0), H - 1) * W;
+        float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t += src.at(ch, row, cx.idx[j]) * cx.w[j];
-    return t;
-}
-
-// slide the 3-channel window so that it covers unclamped rows base-1 .. base+2 (rows are clamped on load)
+        for (int j = 0; j < 4; ++j) t += raw_f(p[cx.idx[j]]) * cx.w[j];
+        return src_scale<TS>(t);
+    }
+};
+// slide the 3-channel window so that it covers source rows base-1 .. base+2
 template <typename Src>
-__device__ __forceinline__ void slide(float (&win)[3][4], int &cur, int base, const Src &src, int H, const Cubic &cx) {
+__device__ __forceinline__ void slide(float (&win)[3][4], int &cur, int base, const Src &src, const Cubic &cx) {
     if (cur != base) {
         const int step = base - cur;
         if (step < 0 || step > 3) {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) win[c][i] = hrow(src, c, min(max(base - 1 + i, 0), H - 1), cx);
+                for (int i = 0; i < 4; ++i) win[c][i] = src.hrow(c, base - 1 + i, cx);
         } else {
             for (int s = 0; s < step; ++s) {
-                const int row = min(max(cur + s + 3, 0), H - 1);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = win[c][3];
-                    win[c][3] = hrow(src, c, row, cx);
+                    win[c][3] = src.hrow(c, cur + s + 3, cx);
                 }
             }
         }
         cur = base;
     }
+}
+
+// The TMA zero-fills the parts of the box that lie outside the image; bicubic taps clamp to the border instead.
+// Rewrite those columns / rows with the nearest image pixel so that a thread's four taps are always contiguous.
+template <typename TS>
+__device__ __forceinline__ void replicate_pad(TS *s, int r0, int c0, int nr, int nc, int H, int W) {
+    const int padL = max(0, -c0), padR = max(0, c0 + nc - W), padT = max(0, -r0), padB = max(0, r0 + nr - H);
+    if ((padL | padR | padT | padB) == 0) return;           // interior tile (uniform across the CTA)
+    if (padL | padR) {
+        for (int e = threadIdx.x; e < 3 * nr; e += BS_W) {
+            TS *p = s + e * nc;
+            const TS l = p[min(padL, nc - 1)], r = p[max(nc - 1 - padR, 0)];
+            for (int c = 0; c < padL; ++c) p[c] = l;
+            for (int c = nc - padR; c < nc; ++c) p[c] = r;
+        }
+        __syncthreads();
+    }
+    if (padT | padB) {
+        for (int e = threadIdx.x; e < 3 * nc; e += BS_W) {
+            TS *p = s + (e / nc) * nr * nc + (e % nc);
+            const TS tp = p[min(padT, nr - 1) * nc], bt = p[max(nr - 1 - padB, 0) * nc];
+            for (int r = 0; r < padT; ++r) p[r * nc] = tp;
+            for (int r = nr - padB; r < nr; ++r) p[r * nc] = bt;
+        }
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int src_floor(int dst, int in_size, int out_size) {
@@ -105,7 +129,59 @@ __device__ __forceinline__ int src_floor(int dst, int in_size, int out_size) {
 
 struct BicubicTileGeom { int xr, xc, rr, rc; };     // TMA box sizes: rows / cols of the x tile and of the residual tile
 
-template <typename TI, typename TO, bool TMA>
+// shared-memory element -> float with an immediate byte offset (the four taps of a row are contiguous)
+template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, float) {
+    float v;
+    asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF * 4));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, bf16) {
+    unsigned short h;
+    asm("ld.shared.u16 %0, [%1+%2];" : "=h"(h) : "r"(a), "n"(OFF * 2));
+    return __uint_as_float((uint32_t)h << 16);
+}
+template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, uint8_t) {
+    unsigned short h;
+    asm("ld.shared.u8 %0, [%1+%2];" : "=h"(h) : "r"(a), "n"(OFF));
+    return (float)h;
+}
+// 4-tap horizontal sum of one source row of the replicate-padded tile (ATen's left-to-right order)
+template <typename TS>
+__device__ __forceinline__ float hrow_tile(uint32_t a, const float (&w)[4]) {
+    float t = 0.f;
+    t += lds_raw<0>(a, TS()) * w[0];
+    t += lds_raw<1>(a, TS()) * w[1];
+    t += lds_raw<2>(a, TS()) * w[2];
+    t += lds_raw<3>(a, TS()) * w[3];
+    return src_scale<TS>(t);
+}
+// slide a 3-channel window of horizontally resampled rows to source rows base-1 .. base+2; ca[] = per-channel shared
+// address of the thread's first tap in tile row 0, trow0 = tile row of source row 0 (= -r0)
+template <typename TS>
+__device__ __forceinline__ void slide_tile(float (&win)[3][4], int &cur, int base, const uint32_t (&ca)[3], int trow0, uint32_t pitchB,
+                                           const float (&w)[4]) {
+    if (base == cur) return;
+    if (base == cur + 1) {                  // the only step an up-scaling strip ever takes after its first row
+        const uint32_t ro = (uint32_t)(base + 2 + trow0) * pitchB;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = win[c][3];
+            win[c][3] = hrow_tile<TS>(ca[c] + ro, w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ro = (uint32_t)(base - 1 + i + trow0) * pitchB;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) win[c][i] = hrow_tile<TS>(ca[c] + ro, w);
+        }
+    }
+    cur = base;
+}
+
+// MODE 0: taps from global memory (any shape, residual optional at run time); MODE 1 / 2: TMA-staged tile with / without
+// the residual source (compile-time, so the strip loop has no dead branches)
+template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                        const __grid_constant__ CUtensorMap tmap_r,
                                                                        const BicubicTileGeom g, const TI *__restrict__ x, int H, int W,
@@ -116,6 +192,8 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
     __shared__ __align__(8) uint64_t bar;
     extern __shared__ uint8_t tile_dyn[];
     uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
+    constexpr bool TMA = MODE != 0;
+    if (MODE == 2) res = nullptr;
     const int t = threadIdx.x;
     const int ox0 = blockIdx.x * BS_W, ox = ox0 + t, oy0 = blockIdx.y * BS_H, b = blockIdx.z;
     int xr0 = 0, xc0 = 0, rr0 = 0, rc0 = 0;
@@ -148,7 +226,11 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
         yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
     }
     __syncthreads();
-    if (TMA) ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    if (TMA) {
+        ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+        replicate_pad(reinterpret_cast<TI *>(tile_raw), xr0, xc0, g.xr, g.xc, H, W);
+        if (res) replicate_pad(reinterpret_cast<float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc, rH, rW);
+    }
     if (ox >= oW) return;
     const Cubic cx = cubic_taps(ox, W, oW);
     Cubic cr = cx;
@@ -160,8 +242,8 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
     const int nrows = min(BS_H, oH - oy0);
     auto run = [&](const auto &sx, const auto &sr) {
         for (int r = 0; r < nrows; ++r) {
-            slide(wx, curx, ybase[0][r], sx, H, cx);
-            if (res) slide(wr, curr, ybase[1][r], sr, rH, cr);
+            slide(wx, curx, ybase[0][r], sx, cx);
+            if (res) slide(wr, curr, ybase[1][r], sr, cr);
             const float4 a = *reinterpret_cast<const float4 *>(yw[0][r]);
             const float4 gg = *reinterpret_cast<const float4 *>(yw[1][r]);
 #pragma unroll
@@ -179,12 +261,40 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
         }
     };
     if (TMA) {
-        const TileSrc<TI> sx{reinterpret_cast<const TI *>(tile_raw), xr0, xc0, g.xr, g.xc};
-        const TileSrc<float> sr{reinterpret_cast<const float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc};
-        run(sx, sr);
+        // ---- fast path: explicit shared-memory addresses, immediate tap offsets, running output pointers
+        constexpr bool RES = MODE == 1;
+        const uint32_t xpitch = g.xc * sizeof(TI), rpitch = g.rc * 4u;
+        const uint32_t xs = ptx::smem_u32(tile_raw) + (uint32_t)(src_floor(ox, W, oW) - 1 - xc0) * (uint32_t)sizeof(TI);
+        const uint32_t xa[3] = {xs, xs + g.xr * xpitch, xs + 2u * g.xr * xpitch};
+        uint32_t ra[3] = {0u, 0u, 0u};
+        if (RES) {
+            const uint32_t rs = ptx::smem_u32(tile_raw) + x_bytes_al + (uint32_t)(src_floor(ox, rW, oW) - 1 - rc0) * 4u;
+            ra[0] = rs; ra[1] = rs + g.rr * rpitch; ra[2] = rs + 2u * g.rr * rpitch;
+        }
+        TO *o0 = ob + (long)oy0 * oW, *o1 = o0 + oplane, *o2 = o1 + oplane;
+        for (int r = 0; r < nrows; ++r) {
+            slide_tile<TI>(wx, curx, ybase[0][r], xa, -xr0, xpitch, cx.w);
+            if (RES) slide_tile<float>(wr, curr, ybase[1][r], ra, -rr0, rpitch, cr.w);
+            const float4 a = *reinterpret_cast<const float4 *>(yw[0][r]);
+            const float4 gg = *reinterpret_cast<const float4 *>(yw[1][r]);
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                v[c] = 0.f;
+                v[c] += wx[c][0] * a.x; v[c] += wx[c][1] * a.y; v[c] += wx[c][2] * a.z; v[c] += wx[c][3] * a.w;
+                if (RES) {
+                    float u = 0.f;
+                    u += wr[c][0] * gg.x; u += wr[c][1] * gg.y; u += wr[c][2] * gg.z; u += wr[c][3] * gg.w;
+                    v[c] += u;
+                }
+                if (clamp) v[c] = fminf(fmaxf(v[c], 0.f), 1.f);
+            }
+            *o0 = from_f<TO>(v[0]); *o1 = from_f<TO>(v[1]); *o2 = from_f<TO>(v[2]);
+            o0 += oW; o1 += oW; o2 += oW;
+        }
     } else {
-        const GlobalSrc<TI> sx{x + (long)b * 3 * xplane, xplane, W};
-        const GlobalSrc<float> sr{res ? res + (long)b * 3 * rplane : nullptr, rplane, rW};
+        const GlobalSrc<TI> sx{x + (long)b * 3 * xplane, xplane, H, W};
+        const GlobalSrc<float> sr{res ? res + (long)b * 3 * rplane : nullptr, rplane, rH, rW};
         run(sx, sr);
     }
 }
@@ -240,7 +350,7 @@ static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, i
     cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)W * elem_bytes, (cuuint64_t)H * W * elem_bytes, (cuuint64_t)3 * H * W * elem_bytes};
     cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 3, 1}, es[4] = {1, 1, 1, 1};
-    return enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr, dims, strides,
+    return enc(tm, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)ptr, dims, strides,
                box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -248,14 +358,15 @@ static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, i
 extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW, void *out,
                                     int out_dtype, int B, int outH, int outW, int clamp, void *stream) {
     TU_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "bicubic_add_clamp: bad argument");
-    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16) && (out_dtype == TU_F32 || out_dtype == TU_BF16), "bicubic_add_clamp: bad dtype");
+    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8) && (out_dtype == TU_F32 || out_dtype == TU_BF16 || out_dtype == TU_U8),
+                 "bicubic_add_clamp: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, BS_H), B);
     // source footprint of a 32 x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
-    const int eb = in_dtype == TU_BF16 ? 2 : 4;
+    const int eb = (int)dtype_size(in_dtype);
     BicubicTileGeom g;
     g.xr = (int)((long)(BS_H - 1) * H / outH) + 6;
-    g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 7) & ~7;          // + alignment slack of the first column
+    g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 15) & ~15;        // + alignment slack of the first column
     g.rr = res ? (int)((long)(BS_H - 1) * rH / outH) + 6 : 0;
     g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 6 + 3 + 3) & ~3 : 0;
     const size_t x_bytes = ((size_t)3 * g.xr * g.xc * eb + 127) & ~(size_t)127;
@@ -271,22 +382,34 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
         if (tma) {                                                                                                              \
             static bool attr_done = false;                                                                                      \
             if (!attr_done) {                                                                                                   \
-                cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, true>,                              \
+                cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, 1>,                              \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                  \
+                if (e == cudaSuccess)                                                                                           \
+                    e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, 2>,                                         \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                          \
                 if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                            \
                 attr_done = true;                                                                                               \
             }                                                                                                                   \
-            bicubic_add_clamp_strip_kernel<TI, TO, true><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW, \
-                                                                                          (TO *)out, outH, outW, clamp);        \
+            if (res)                                                                                                            \
+                bicubic_add_clamp_strip_kernel<TI, TO, 1><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, \
+                                                                                               rW, (TO *)out, outH, outW, clamp); \
+            else                                                                                                                \
+                bicubic_add_clamp_strip_kernel<TI, TO, 2><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, \
+                                                                                               rW, (TO *)out, outH, outW, clamp); \
         } else {                                                                                                                \
-            bicubic_add_clamp_strip_kernel<TI, TO, false><<<grid, BS_W, 0, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW,     \
+            bicubic_add_clamp_strip_kernel<TI, TO, 0><<<grid, BS_W, 0, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW,     \
                                                                                   (TO *)out, outH, outW, clamp);                \
         }                                                                                                                       \
     } while (0)
     if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC(float, float);
     else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC(float, bf16);
     else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC(bf16, float);
-    else TU_BIC(bf16, bf16);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC(bf16, bf16);
+    else if (in_dtype == TU_U8 && out_dtype == TU_U8) TU_BIC(uint8_t, uint8_t);
+    else if (in_dtype == TU_U8 && out_dtype == TU_F32) TU_BIC(uint8_t, float);
+    else if (in_dtype == TU_U8 && out_dtype == TU_BF16) TU_BIC(uint8_t, bf16);
+    else if (in_dtype == TU_F32 && out_dtype == TU_U8) TU_BIC(float, uint8_t);
+    else TU_BIC(bf16, uint8_t);
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
     return TU_OK;

@@ -35,6 +35,11 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
+// image element -> float for the bf16 operand (uint8 frames: x * (1/255); the product is rounded to bf16 right after)
+__device__ __forceinline__ float ldx(float v) { return v; }
+__device__ __forceinline__ float ldx(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float ldx(uint8_t v) { return (float)v * 0.00392156862745098f; }
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -118,7 +123,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const int ix = px + kx - 1;
-                        v[c][r][kx] = (rowok && ix >= 0 && ix < p.W) ? to_f(row[ix]) : 0.f;
+                        v[c][r][kx] = (rowok && ix >= 0 && ix < p.W) ? ldx(row[ix]) : 0.f;
                     }
                 }
         };
@@ -229,6 +234,7 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
     if (!g_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem attribute");
         g_attr_set = true;
     }
@@ -261,6 +267,8 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
     const int grid = p.total_tiles < 2 * g_sm_count ? p.total_tiles : 2 * g_sm_count;
     if (in_dtype == TU_F32)
         stem_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const float *)x, p);
+    else if (in_dtype == TU_U8)
+        stem_tc_kernel<uint8_t><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const uint8_t *)x, p);
     else
         stem_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const bf16 *)x, p);
     TU_CHECK_LAUNCH("stem_tc");

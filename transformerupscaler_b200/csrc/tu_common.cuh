@@ -35,9 +35,13 @@ void count_launch();   // every kernel launch of the library is counted (tu_laun
 // ---- scalar load/store with dtype conversion --------------------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+// uint8 frames: ToTensor semantics on the way in (x / 255 in fp32, inference.py:65-70, app_overlay.py:298) and
+// (out * 255).clamp(0, 255).to(uint8) on the way out (truncation, app_overlay.py:383)
+__device__ __forceinline__ float to_f(uint8_t v) { return (float)v / 255.f; }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ uint8_t from_f<uint8_t>(float v) { return (uint8_t)fminf(fmaxf(v * 255.f, 0.f), 255.f); }
 
 // 4 consecutive elements -> float4 (pointer must be aligned to 4 elements)
 __device__ __forceinline__ float4 load4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -62,6 +66,6 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static inline size_t dtype_size(int dtype) { return dtype == TU_BF16 ? 2 : 4; }
+static inline size_t dtype_size(int dtype) { return dtype == TU_BF16 ? 2 : dtype == TU_U8 ? 1 : 4; }
 
 }  // namespace tu

@@ -16,7 +16,8 @@ import torch
 from . import _lib
 from .packing import PackedWeights
 
-_DT = {torch.float32: _lib.TU_F32, torch.bfloat16: _lib.TU_BF16}
+_DT = {torch.float32: _lib.TU_F32, torch.bfloat16: _lib.TU_BF16, torch.uint8: _lib.TU_U8}
+_TORCH_DT = {v: k for k, v in _DT.items()}
 _REGISTRY: Dict[int, PackedWeights] = {}
 _next_handle = [1]
 
@@ -45,12 +46,12 @@ def _require_cuda(*ts: torch.Tensor) -> None:
 
 def _code(dt: torch.dtype) -> int:
     if dt not in _DT:
-        raise TypeError(f"unsupported dtype {dt}; the engine handles float32 and bfloat16")
+        raise TypeError(f"unsupported dtype {dt}; the engine handles float32, bfloat16 and (frames only) uint8")
     return _DT[dt]
 
 
 def _forward_impl(x: torch.Tensor, handle: int, out_h: int, out_w: int, scale: int, compute_bf16: bool,
-                  out_bf16: bool, clamp: bool) -> torch.Tensor:
+                  out_code: int, clamp: bool) -> torch.Tensor:
     lib = _lib.load()
     pw = _REGISTRY[handle]
     _require_cuda(x)
@@ -59,7 +60,7 @@ def _forward_impl(x: torch.Tensor, handle: int, out_h: int, out_w: int, scale: i
     x = x.contiguous()
     B, _, H, W = x.shape
     cdt = _lib.TU_BF16 if compute_bf16 else _lib.TU_F32
-    out = torch.empty((B, 3, out_h, out_w), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    out = torch.empty((B, 3, out_h, out_w), dtype=_TORCH_DT[out_code], device=x.device)
     mid = _lib.MODEL_IDS[pw.model]
     nbytes = lib.tu_forward_workspace_bytes(mid, B, H, W, out_h, out_w, scale, cdt)
     if nbytes == 0:
@@ -74,13 +75,13 @@ def _forward_impl(x: torch.Tensor, handle: int, out_h: int, out_w: int, scale: i
 
 @torch.library.custom_op("tu::forward", mutates_args=(), device_types="cuda")
 def tu_forward(x: torch.Tensor, handle: int, out_h: int, out_w: int, scale: int, compute_bf16: bool,
-               out_bf16: bool, clamp: bool) -> torch.Tensor:
-    return _forward_impl(x, handle, out_h, out_w, scale, compute_bf16, out_bf16, clamp)
+               out_code: int, clamp: bool) -> torch.Tensor:
+    return _forward_impl(x, handle, out_h, out_w, scale, compute_bf16, out_code, clamp)
 
 
 @tu_forward.register_fake
-def _(x, handle, out_h, out_w, scale, compute_bf16, out_bf16, clamp):
-    return x.new_empty((x.shape[0], 3, out_h, out_w), dtype=torch.bfloat16 if out_bf16 else torch.float32)
+def _(x, handle, out_h, out_w, scale, compute_bf16, out_code, clamp):
+    return x.new_empty((x.shape[0], 3, out_h, out_w), dtype=_TORCH_DT[out_code])
 
 
 @torch.library.custom_op("tu::resize_aa", mutates_args=(), device_types="cuda")
@@ -108,9 +109,9 @@ def run_forward(pw_handle: int, model: str, x: torch.Tensor, res_out: Tuple[int,
     if upscale_factor is not None:
         res_out = (H * upscale_factor, W * upscale_factor)
     res_out = (int(res_out[0]), int(res_out[1]))
-    out_bf16 = out_dtype == torch.bfloat16
+    out_code = _code(out_dtype)
     if model != "FastTransformer":
-        return tu_forward(x, pw_handle, res_out[0], res_out[1], 0, compute_bf16, out_bf16, clamp)
+        return tu_forward(x, pw_handle, res_out[0], res_out[1], 0, compute_bf16, out_code, clamp)
     scale = upscale_factor if upscale_factor is not None else math.ceil(max(res_out[0] / H, res_out[1] / W))
     if scale not in (2, 3, 4, 6):
         raise ValueError(f"Requested scale={scale} was not built.")
@@ -119,6 +120,9 @@ def run_forward(pw_handle: int, model: str, x: torch.Tensor, res_out: Tuple[int,
     # output and is the identity when the size already matches
     need_resize = require_ratio and res_out != (oh, oh) and res_out != (oh, ow)
     if not need_resize:
-        return tu_forward(x, pw_handle, oh, ow, scale, compute_bf16, out_bf16, clamp)
-    full = tu_forward(x, pw_handle, oh, ow, scale, compute_bf16, out_bf16, False)
+        return tu_forward(x, pw_handle, oh, ow, scale, compute_bf16, out_code, clamp)
+    if out_dtype == torch.uint8:
+        raise NotImplementedError("uint8 frame output is not available on FastTransformer's antialiased-Resize path "
+                                  "(res_out that is not an integer multiple of the input): request float output")
+    full = tu_forward(x, pw_handle, oh, ow, scale, compute_bf16, out_code, False)
     return tu_resize_aa(full, res_out[0], res_out[1], clamp)

@@ -121,12 +121,17 @@ class EngineModel(nn.Module):
                                "(dropout is treated as identity; there is no backward)")
         if not x.is_cuda:
             raise RuntimeError("transformerupscaler_b200 has no CPU path: move the model and the input to a CUDA device")
-        if x.dtype not in (torch.float32, torch.bfloat16):
+        # uint8 frames in -> uint8 frames out (ToTensor scaling on read, (out*255).clamp(0,255).to(uint8) on write, fused into
+        # the first and last kernels): the video-pipeline entry, an extension of the reference's float-only signature
+        frames_u8 = x.dtype == torch.uint8
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
             x = x.float()
         bf16, out_dt = self._select_precision(x)
+        if frames_u8:
+            out_dt = torch.uint8
         handle = self._packed(bf16, x.device)
         out = engine.run_forward(handle, self.ENGINE_MODEL, x, res_out, upscale_factor, require_ratio, bf16, out_dt)
-        if x.is_cuda and torch.is_autocast_enabled("cuda") and not self.AUTOCAST_OUT_FP32:
+        if not frames_u8 and x.is_cuda and torch.is_autocast_enabled("cuda") and not self.AUTOCAST_OUT_FP32:
             want = torch.get_autocast_dtype("cuda")
             if out.dtype != want:
                 out = out.to(want)
