@@ -172,6 +172,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons are sampled every 100 ms from before the warm-up until after the end-to-end loops (the
+    # device-timed region alone lasts tens of milliseconds -- shorter than nvidia-smi's start-up)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+
     # ---------------- device-resident throughput (`value`)
     with torch.no_grad():
         for i in range(warmup):
@@ -179,7 +183,6 @@ def main():
         barrier()
         lib.tu_profile_enable(1)
         n0 = lib.tu_launch_count()
-        clocks = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -199,7 +202,6 @@ def main():
             name, tot, cnt = ln.split()
             breakdown[name] = round(float(tot) / max(int(cnt), 1), 5)      # mean ms per launch, live CUDA events
         lib.tu_profile_reset()
-        clk = clocks.stop() if clocks else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -236,6 +238,7 @@ def main():
     hin = [xs[i].cpu().pin_memory() for i in range(2)]
     hout = [torch.empty((FRAMES_PER_GPU, 3, OH, OW), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
     e2e_bf16_fps, checksum = run_e2e(hin, hout)
+    clk = clocks.stop() if clocks else None
 
     if rank == 0:
         tf_peak, hbm_peak, peak_src = peaks()

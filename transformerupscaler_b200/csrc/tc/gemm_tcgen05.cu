@@ -213,6 +213,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 // instruction; instead the warp transposes through shared memory so that 8 lanes cover one pixel (128
                 // contiguous bytes) and an instruction touches 4 lines.  The skip-connection loads do not depend on the
                 // accumulator, so all 8 are issued before waiting for the MMAs (one DRAM latency per tile, overlapped).
+                {   // L2 prefetch of the skip pixel this thread's token row needs in the CTA's NEXT tile (every 128-byte line of
+                    // the skip tensor is used exactly once, so this only moves its DRAM fetch one tile earlier)
+                    const int t2 = t + gridDim.x;
+                    if (t2 < p.total_tiles) {
+                        const int m2 = (t2 / p.tiles_n) * BM + i;
+                        int b2, ty2, tx2;
+                        if (p.window) {
+                            const int wi = m2 >> 6, tk = m2 & 63;
+                            const int wx = wi % p.nWx, rest = wi / p.nWx;
+                            b2 = rest / p.nWy;
+                            ty2 = (rest % p.nWy) * 8 + (tk >> 3);
+                            tx2 = wx * 8 + (tk & 7);
+                        } else {
+                            tx2 = m2 % p.Wt;
+                            const int rest = m2 / p.Wt;
+                            ty2 = rest % p.Ht;
+                            b2 = rest / p.Ht;
+                        }
+                        const int pix2 = ((t2 % p.tiles_n) * p.BN + cbeg) >> 6;
+                        const int gy2 = ty2 * 8 + (pix2 >> 3), gx2 = tx2 * 8 + (pix2 & 7);
+                        if (m2 < p.M && ty2 < p.Ht && tx2 < p.Wt && gy2 < p.Hc && gx2 < p.Wc) {
+                            const bf16 *a = p.skip + (((long)b2 * p.skipH + gy2) * p.skipW + gx2) * 64;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+                        }
+                    }
+                }
                 float *stg = stage_f32 + (warp - 4) * (32 * UE_PITCH);
                 const uint32_t geo = valid ? ((uint32_t)b << 20) | ((uint32_t)ty << 10) | (uint32_t)tx : 0xFFFFFFFFu;
                 const int sub = lane >> 3, chunk = lane & 7;

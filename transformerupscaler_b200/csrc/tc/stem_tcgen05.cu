@@ -40,6 +40,13 @@ __device__ __forceinline__ float ldx(float v) { return v; }
 __device__ __forceinline__ float ldx(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float ldx(uint8_t v) { return (float)v * 0.00392156862745098f; }
 
+// (lo, hi) -> bf16x2 with ReLU in the same instruction
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -58,7 +65,6 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES + 256);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
-    if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
     if (threadIdx.x == 0) {
         ptx::mbar_init(ptx::smem_u32(&bars->a_full), 128);
         ptx::mbar_init(ptx::smem_u32(&bars->a_empty), 1);
@@ -87,6 +93,18 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
         __syncwarp();
         ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
+        // fold the bias into the contraction: operand columns k = 27, 28 are constant 1, filter columns 27, 28 hold the
+        // bias split into bf16 hi + lo parts (fp32 accuracy), so the epilogue is a single convert-with-ReLU per pair
+#pragma unroll
+        for (int co = lane; co < 64; co += 32) {
+            const float bv = p.bias[co];
+            const bf16 hi = __float2bfloat16_rn(bv), lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+            bf16 *row = reinterpret_cast<bf16 *>(smem_al + ROWS * A_BYTES + co * 128 + ((3 ^ (co & 7)) << 4));
+            row[3] = hi;      // k = 27
+            row[4] = lo;      // k = 28
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
         const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
         const uint32_t a_lo = ptx::sdesc_lo(a_sm), w_lo = ptx::sdesc_lo(w_sm);
         uint32_t ph = 0;
@@ -127,8 +145,21 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     }
                 }
         };
+        // one L2 prefetch per thread and tile, two tiles ahead: thread i touches row segment i % 18 = (channel, input row) at
+        // pixel 18 * (i / 18), so every 128-byte line of the tile's footprint is requested; the register loads of the next
+        // iteration then pay L2 latency instead of DRAM latency
+        auto prefetch_tile = [&](int t) {
+            const int tx = t % p.tiles_x;
+            int rem = t / p.tiles_x;
+            const int ty = rem % p.tiles_y, b = rem / p.tiles_y;
+            const int seg = i % 18, c = seg / 6, r = seg % 6;
+            const int iy = min(max(ty * ROWS + r - 1, 0), p.H - 1), ix = min(tx * 128 + (i / 18) * 18, p.W - 1);
+            const TI *a = x + (((long)b * 3 + c) * p.H + iy) * p.W + ix;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        };
         uint32_t ph = 0;
         if (blockIdx.x < p.total_tiles) load_tile(blockIdx.x);
+        if (blockIdx.x + gridDim.x < p.total_tiles) prefetch_tile(blockIdx.x + gridDim.x);
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
             ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), ph ^ 1);
 #pragma unroll
@@ -142,7 +173,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
                         for (int c = 0; c < 3; ++c) k[(ky * 3 + kx) * 3 + c] = v[c][r + ky][kx];
 #pragma unroll
-                for (int z = 27; z < 32; ++z) k[z] = 0.f;
+                for (int z = 27; z < 32; ++z) k[z] = z < 29 ? 1.f : 0.f;       // k = 27, 28 multiply the bias columns
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     uint4 u;
@@ -156,6 +187,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             ptx::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(ptx::smem_u32(&bars->a_full));
             if (t + gridDim.x < p.total_tiles) load_tile(t + gridDim.x);   // next tile's pixels fly while this one is consumed
+            if (t + 2 * gridDim.x < p.total_tiles) prefetch_tile(t + 2 * gridDim.x);
         }
     } else {
         // ================================ epilogue ================================
@@ -191,13 +223,12 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 uint8_t *rowp = stg_w + buf * 4096 + lane * 128;
 #pragma unroll
                 for (int c = 0; c < 64; c += 8) {
-                    const float4 ba = *reinterpret_cast<const float4 *>(bias_s + c), bb = *reinterpret_cast<const float4 *>(bias_s + c + 4);
                     const uint32_t *v = c < 32 ? &v0[c] : &v1[c - 32];
                     uint4 u;
-                    u.x = pack2(fmaxf(__uint_as_float(v[0]) + ba.x, 0.f), fmaxf(__uint_as_float(v[1]) + ba.y, 0.f));
-                    u.y = pack2(fmaxf(__uint_as_float(v[2]) + ba.z, 0.f), fmaxf(__uint_as_float(v[3]) + ba.w, 0.f));
-                    u.z = pack2(fmaxf(__uint_as_float(v[4]) + bb.x, 0.f), fmaxf(__uint_as_float(v[5]) + bb.y, 0.f));
-                    u.w = pack2(fmaxf(__uint_as_float(v[6]) + bb.z, 0.f), fmaxf(__uint_as_float(v[7]) + bb.w, 0.f));
+                    u.x = pack2_relu(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                    u.y = pack2_relu(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                    u.z = pack2_relu(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                    u.w = pack2_relu(__uint_as_float(v[6]), __uint_as_float(v[7]));
                     *reinterpret_cast<uint4 *>(rowp + (((c >> 3) ^ (lane & 7)) << 4)) = u;      // 128-byte swizzle: chunk ^= row % 8
                 }
                 ptx::fence_proxy_async();

@@ -17,7 +17,7 @@
 //                          (24 slabs = 384 KB per block, pre-packed on the host).
 // Roles: warps 0-15 "math" (LN, epilogues, attention; thread = token row x column quarter: warp w may only touch TMEM
 // lanes 32*(w%4).., so the four warps of a lane quadrant split the columns), warp 16 TMA producer, warp 17 MMA issuer
-// + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc_ready (MMA -> math).
+// + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc[] (MMA -> math, one per commit point).
 #include <cuda.h>
 
 #include "ptx.cuh"
@@ -41,7 +41,7 @@ constexpr int OFF_RING = OFF_STG + STG_BYTES;
 constexpr int OFF_PAR = OFF_RING + NRING * SLAB;
 constexpr int PAR_FLOATS = 1664;                // c0 | ln1w | ln1b | qkvb(384) | c1 | ln2w | ln2b | fc1b(512)
 constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
-constexpr int OFF_BAR = OFF_STAT + 128 * 4 * 4;
+constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4 * 8;      // two (sum, sumsq) tables: LN1 and LN2 alternate, so no barrier guards reuse
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int P_C0 = 0, P_LN1W = 128, P_LN1B = 256, P_QKVB = 384, P_C1 = 768, P_LN2W = 896, P_LN2B = 1024, P_FC1B = 1152;
 
@@ -53,9 +53,14 @@ struct StackParams {
     int n_tiles, n_blocks;
 };
 
+// commit points of one block, in issue order: qkv column thirds, proj, fc1 (first half) column halves, fc1 (second half)
+// column halves, fc2 (second half).  A part's epilogue starts while the MMAs of the next part are still running.
+enum { ACC_QKV0 = 0, ACC_QKV1, ACC_QKV2, ACC_PROJ, ACC_FC1A0, ACC_FC1A1, ACC_FC1B0, ACC_FC1B1, ACC_FC2B, NACC };
+
 struct Barriers {
     uint64_t full[NRING], empty[NRING];
-    uint64_t a_ready, acc_ready;
+    uint64_t a_ready;
+    uint64_t acc[NACC];          // MMA -> math, one barrier per commit point of a block (each completes once per block)
     uint32_t tmem_base;
 };
 
@@ -98,25 +103,20 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// LayerNorm of this thread's 32 columns of row i (x already includes the folded bias offset), two-pass statistics
-// shared with the three partner threads holding the rest of the row; result -> A32 slab part/2, swizzled.
-__device__ __forceinline__ void layernorm_to_a32(float (&x)[32], const float *gam, const float *bet, float *stat, uint8_t *a32,
+// LayerNorm of this thread's 32 columns of row i (x already includes the folded bias offset); statistics are shared
+// with the three partner threads holding the rest of the row; result -> A32 slab part/2, swizzled.
+__device__ __forceinline__ void layernorm_to_a32(float (&x)[32], const float *gam, const float *bet, float2 *stat, uint8_t *a32,
                                                  int i, int part) {
-    float s = 0.f;
+    // one exchange: every thread publishes (sum, sum of squares) of its 32 columns; var = E[x^2] - mean^2 in fp32
+    float s = 0.f, ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s += x[j];
-    stat[i * 4 + part] = s;
+    for (int j = 0; j < 32; ++j) { s += x[j]; ss = fmaf(x[j], x[j], ss); }
+    stat[i * 4 + part] = make_float2(s, ss);
     math_barrier();
-    const float4 s4 = *reinterpret_cast<const float4 *>(stat + i * 4);
-    const float mean = ((s4.x + s4.y) + (s4.z + s4.w)) * (1.0f / DIM);
-    math_barrier();
-    float qv = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { const float d = x[j] - mean; qv = fmaf(d, d, qv); }
-    stat[i * 4 + part] = qv;
-    math_barrier();
-    const float4 q4 = *reinterpret_cast<const float4 *>(stat + i * 4);
-    const float rstd = rsqrtf(((q4.x + q4.y) + (q4.z + q4.w)) * (1.0f / DIM) + 1e-5f);
+    const float4 p01 = *reinterpret_cast<const float4 *>(stat + i * 4), p23 = *reinterpret_cast<const float4 *>(stat + i * 4 + 2);
+    const float mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.0f / DIM);
+    const float ex2 = ((p01.y + p01.w) + (p23.y + p23.w)) * (1.0f / DIM);
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
     uint8_t *rowp = a32 + (part >> 1) * SLAB + i * 128;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -136,7 +136,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     uint8_t *sm = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
     Barriers *bars = reinterpret_cast<Barriers *>(sm + OFF_BAR);
     float *par = reinterpret_cast<float *>(sm + OFF_PAR);
-    float *stat = reinterpret_cast<float *>(sm + OFF_STAT);
+    float2 *stat = reinterpret_cast<float2 *>(sm + OFF_STAT);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x == 0) {
@@ -144,8 +144,8 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
         }
-        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH * 32);
-        ptx::mbar_init(ptx::smem_u32(&bars->acc_ready), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH);
+        for (int i = 0; i < NACC; ++i) ptx::mbar_init(ptx::smem_u32(&bars->acc[i]), 1);
         ptx::fence_barrier_init();
     }
     if (warp == NMATH + 1) {
@@ -201,24 +201,27 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
             for (int bk = 0; bk < p.n_blocks; ++bk) {
                 wait_a();                                       // LN1 output in A32
-                for (int nc = 0; nc < 3; ++nc)
+                for (int nc = 0; nc < 3; ++nc) {
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_QKV0 + nc]), leader);
+                }
                 wait_a();                                       // attention output in A32
                 for (int ks = 0; ks < 2; ++ks) slab_mma(TX, a32 + ks * SL, false);            // x += att Wp^T
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_PROJ]), leader);
                 wait_a();                                       // LN2 output in A32
-                for (int nc = 0; nc < 2; ++nc)
+                for (int nc = 0; nc < 2; ++nc) {
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 0
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1A0 + nc]), leader);
+                }
                 wait_a();                                       // GELU(half 0) in HID, ACC drained
                 for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);            // x += h0 W2[:, h0]^T
-                for (int nc = 0; nc < 2; ++nc)
+                for (int nc = 0; nc < 2; ++nc) {
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 1
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1B0 + nc]), leader);
+                }
                 wait_a();                                       // GELU(half 1) in HID
                 for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_ready), leader);
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2B]), leader);
             }
     } else {
         // ================================ math warps ================================
@@ -227,16 +230,16 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int mt = threadIdx.x;                          // 0..511
         uint8_t *a32 = sm + OFF_A32, *stg = sm + OFF_STG;
-        uint32_t cph = 0;
-        auto wait_acc = [&]() {
-            ptx::mbar_wait(ptx::smem_u32(&bars->acc_ready), cph);
-            cph ^= 1;
+        uint32_t cph = 0;             // every acc barrier completes exactly once per block: one shared phase bit
+        auto wait_acc = [&](int which) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc[which]), cph);
             ptx::tc_fence_after();
         };
-        auto signal_a = [&]() {
+        auto signal_a = [&]() {       // every thread orders its own writes, one lane per warp arrives
             ptx::fence_proxy_async();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
         };
         // x row quarter (+ offset vector) -> registers
         auto load_x = [&](float (&x)[32], const float *cvec) {
@@ -278,12 +281,12 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     layernorm_to_a32(x, par + P_LN1W + part * 32, par + P_LN1B + part * 32, stat, a32, i, part);
                 }
                 signal_a();
-                // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows
-                wait_acc();
+                // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows, one column third at a time as its MMAs retire
                 {
                     uint8_t *rowp = stg + i * STG_PITCH;
 #pragma unroll
                     for (int nc = 0; nc < 3; ++nc) {
+                        wait_acc(ACC_QKV0 + nc);
                         uint32_t v[32];
                         const int col = nc * 128 + part * 32;
                         ptx::tmem_ld_x32(TACC + lane_base + col, v);
@@ -310,6 +313,15 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                         const int win = task >> 5, h = (task >> 2) & 7, rg = task & 3;
                         const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
                         const int r0 = rg * 16 + g;
+                        // relative-position bias of this thread's 2 rows x 16 columns: issued first, the L2 latency hides
+                        // behind the Q/K fragment loads and the QK^T MMAs
+                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+                        float2 ba[8], bb[8];
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
+                            bb[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                        }
                         uint32_t qa[4];
                         qa[0] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (h * 16 + tq * 2) * 2);
                         qa[1] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (h * 16 + tq * 2) * 2);
@@ -323,13 +335,10 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                             s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
                             mma16816(s[n], qa, b0, b1);
                         }
-                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
                         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
-                            const float2 ba = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
-                            const float2 bb = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
-                            s[n][0] += ba.x; s[n][1] += ba.y; s[n][2] += bb.x; s[n][3] += bb.y;
+                            s[n][0] += ba[n].x; s[n][1] += ba[n].y; s[n][2] += bb[n].x; s[n][3] += bb[n].y;
                             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
@@ -378,19 +387,19 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 }
                 signal_a();
                 // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
-                wait_acc();
+                wait_acc(ACC_PROJ);
                 {
                     float x[32];
                     load_x(x, par + P_C1);
-                    layernorm_to_a32(x, par + P_LN2W + part * 32, par + P_LN2B + part * 32, stat, a32, i, part);
+                    layernorm_to_a32(x, par + P_LN2W + part * 32, par + P_LN2B + part * 32, stat + 128 * 4, a32, i, part);
                 }
                 signal_a();
                 // ---- MLP: two halves of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
-                    wait_acc();
 #pragma unroll
                     for (int nc = 0; nc < 2; ++nc) {
+                        wait_acc((half ? ACC_FC1B0 : ACC_FC1A0) + nc);
                         const int col = nc * 128 + part * 32;                       // column of this 256-wide half
                         uint8_t *rowp = stg + (col >> 6) * SLAB + i * 128;          // HID K-slab = hidden column / 64
                         uint32_t v[32];
@@ -410,7 +419,8 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     }
                     signal_a();
                 }
-                wait_acc();      // fc2 of the second half accumulated: X holds the block output (minus folded biases)
+                wait_acc(ACC_FC2B);      // fc2 of the second half accumulated: X holds the block output (minus folded biases)
+                cph ^= 1;
             }
             // ---- X (+ final offset) -> global
             {
