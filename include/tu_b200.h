@@ -108,12 +108,12 @@ typedef struct TuModelWeights {
     const float *dec1_b;
     const float *dec2_w;        /* fp32 (9, 64 ci, 3 co)                                          */
     const float *dec2_b;        /* (3)                                                            */
-    const void *dec2_w16;       /* bf16 (9, 16 co [3 real + 13 zero], 64 ci) for the tensor-core head, or NULL */
+    const void *dec2_w16;       /* bf16 (3 ky, 16 rows n = kx*4 + co [co < 3, rest zero], 64 ci) for the tensor-core head, or NULL */
     /* FastTransformer only */
     TuUpsamplerStage up1[4][2];     /* indexed by scale slot {2,3,4,6} -> 0..3, stage 0/1         */
     TuUpsamplerStage fin[4][2];
     const float *up1conv_w;     /* fp32 (9, 64, 3), no bias                                       */
-    const void *up1conv_w16;    /* bf16 (9, 16, 64) or NULL                                        */
+    const void *up1conv_w16;    /* bf16 (3, 16, 64), same layout, or NULL                          */
     const float *finconv_w;     /* fp32 (27, 3)                                                   */
     const float *finconv_b;     /* (3)                                                            */
 } TuModelWeights;
@@ -140,7 +140,7 @@ int tu_stem_conv(const void *x, int in_dtype, const float *w27x64, const void *w
  * (then nchunk = r*r and chunk p holds phase (i,j) = (p/r, p%r) for all 64 channels). */
 int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int dtype,
                    int B, int H, int W, int stride, int relu, int nchunk, int ps_r, void *stream);
-/* 64->3 3x3 p1 conv, NHWC in -> planar fp32 (B,3,H,W) out.  w16 (optional, bf16 (9,16,64)) enables the
+/* 64->3 3x3 p1 conv, NHWC in -> planar fp32 (B,3,H,W) out.  w16 (optional, bf16 (3 ky, 16 n = kx*4+co, 64 ci)) enables the
  * tensor-core kernel for dtype TU_BF16; w (fp32 (9,64,3)) is always required. */
 int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const void *w16, const float *b, float *out,
                        int B, int H, int W, int relu, void *stream);

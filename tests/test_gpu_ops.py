@@ -98,8 +98,9 @@ def test_conv64to3(dev, dt, bias, relu):
     out = G.conv64to3(x.to(dev), wp, None if b is None else b.to(dev), relu=relu)
     assert _maxerr(out, ref) < TOL32 * 4
     if dt == BF16:      # tensor-core head: bf16 weights (3 of 16 output channels real)
-        w16 = torch.zeros(9, 16, 64)
-        w16[:, :3] = w.permute(2, 3, 0, 1).reshape(9, 3, 64)
+        w16 = torch.zeros(3, 4, 4, 64)                       # (ky, kx, co, ci) -> rows n = kx*4 + co
+        w16[:, :3, :3] = w.permute(2, 3, 0, 1)
+        w16 = w16.reshape(3, 16, 64)
         ref16 = orc.conv3x3_nhwc(x.float(), w.to(BF16).float(), b, relu=bool(relu)).permute(0, 3, 1, 2)
         out16 = G.conv64to3(x.to(dev), wp, None if b is None else b.to(dev), relu=relu, w16=w16.to(dev, BF16))
         assert _maxerr(out16, ref16) < 1e-3

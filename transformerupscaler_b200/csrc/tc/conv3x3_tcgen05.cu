@@ -57,6 +57,7 @@ struct Barriers {
     uint64_t w_full;
     uint64_t w_free;
     uint32_t tmem_base;
+    float xchg[64];          // NOUT == 16 epilogue: seam values between the four epilogue warps, two row parities
 };
 
 template <int NOUT, int S>
@@ -65,7 +66,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                   const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    constexpr int W_TAP = NOUT * 128, W_BYTES = 9 * W_TAP;
+    // NOUT == 64: nine (co 64 x ci 64) filter taps.  NOUT == 16 (the 64 -> 3 heads): three ky blocks of 16 rows n = kx*4 + co, so
+    // the tensor core sums over ky and ci on the UNSHIFTED pixel rows and the epilogue adds the three kx-shifted columns
+    // (3 x fewer MMAs than nine N = 16 taps, whose cost is the 4 KB shared-memory read of the A operand, not the math).
+    constexpr int NTAPS = NOUT == 64 ? 9 : 3;
+    constexpr int W_TAP = NOUT * 128, W_BYTES = NTAPS * W_TAP;
+    constexpr int TILE_W = NOUT == 64 ? TILE_M : TILE_M - 2;      // output pixels per tile (the head needs a 1-pixel halo of rows)
     const uint32_t w_sm = smem0;
     const uint32_t ring_sm = smem0 + W_BYTES_MAX;
     const uint32_t stg_sm = ring_sm + RING_UNITS * UNIT_BYTES;      // 1024-byte aligned (UNIT_BYTES = 17 * 1024)
@@ -123,11 +129,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                     wphase ^= 1;
                 }
                 ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
-                for (int tap = 0; tap < 9; ++tap)
-                    ptx::tma_load_2d(w_sm + tap * W_TAP, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * 9 + tap) * NOUT);
+                for (int tap = 0; tap < NTAPS; ++tap)
+                    ptx::tma_load_2d(w_sm + tap * W_TAP, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * NTAPS + tap) * NOUT);
                 cur_chunk = chunk;
             }
-            const int x0 = tx * TILE_M, y0 = ty * TILE_R;
+            const int x0 = tx * TILE_W, y0 = ty * TILE_R;
             for (int j = 0; j < nsteps; ++j) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), phase ^ 1);
                 const uint32_t dst = ring_sm + slot * units_per_step * UNIT_BYTES;
@@ -172,7 +178,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                 ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), tphase ^ ((j / nslots) & 1));
                 ptx::tc_fence_after();
                 const uint32_t a0 = ring_lo + ((slot * units_per_step * UNIT_BYTES) >> 4);
-                if (S == 1) {
+                if (S == 1 && NOUT == 16) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int r = j - ky;
+                        if (r < 0 || r >= TILE_R) continue;
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint32_t ad = a0 + ((k4 * 32) >> 4);                       // slot pixel 0 = image pixel x0 - 1
+                            const uint32_t bd = w_lo + ((ky * W_TAP + k4 * 32) >> 4);
+                            if ((ky | k4) != 0) ptx::umma_bf16_lo<1>(acc0 + r * 64, ad, bd, idesc, leader);
+                            else ptx::umma_bf16_lo<0>(acc0 + r * 64, ad, bd, idesc, leader);
+                        }
+                    }
+                } else if (S == 1) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
                         const int r = j - ky;
@@ -224,6 +243,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         const int q = warp - 4;                     // TMEM lane quadrant of this warp
         int it = 0;
         uint32_t nstore = 0;
+        float *xchg = bars->xchg;
         uint8_t *stg_w = smem_al + W_BYTES_MAX + RING_UNITS * UNIT_BYTES + q * 8192;
         const uint32_t stg_w_sm = stg_sm + q * 8192;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -237,13 +257,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
             ptx::tc_fence_after();
-            const int px0 = tx * TILE_M + q * 32, px = px0 + lane;
+            const int px0 = tx * TILE_W + q * 32, px = px0 + lane;
             const float *bias = p.bias ? p.bias + chunk * 64 : nullptr;
 #pragma unroll 1
             for (int r = 0; r < TILE_R; ++r) {
                 const int y = ty * TILE_R + r;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * (TILE_R * 64) + r * 64;
                 if (NOUT == 16) {
+                    // lane i holds D[q][kx*4 + co] for input pixel q = x0 - 1 + i; out[x] = D[x-1][kx 0] + D[x][kx 1] + D[x+1][kx 2]
                     uint32_t v[32];
                     ptx::tmem_ld_x32(taddr, v);       // columns 16..31 belong to nobody (row stride is 64 columns)
                     ptx::tmem_ld_wait();
@@ -252,12 +273,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
                     }
-                    if (y < p.Ho && px < p.Wo) {
+                    float lft[3], rgt[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        lft[c] = __shfl_up_sync(0xffffffffu, __uint_as_float(v[c]), 1);
+                        rgt[c] = __shfl_down_sync(0xffffffffu, __uint_as_float(v[8 + c]), 1);
+                    }
+                    // warp seams go through shared memory (double-buffered by row parity; one named barrier per row)
+                    float *xs = xchg + (r & 1) * 32;
+                    if (lane == 31) { xs[q * 8 + 0] = __uint_as_float(v[0]); xs[q * 8 + 1] = __uint_as_float(v[1]); xs[q * 8 + 2] = __uint_as_float(v[2]); }
+                    if (lane == 0) { xs[q * 8 + 4] = __uint_as_float(v[8]); xs[q * 8 + 5] = __uint_as_float(v[9]); xs[q * 8 + 6] = __uint_as_float(v[10]); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (lane == 0 && q > 0) { lft[0] = xs[(q - 1) * 8 + 0]; lft[1] = xs[(q - 1) * 8 + 1]; lft[2] = xs[(q - 1) * 8 + 2]; }
+                    if (lane == 31 && q < 3) { rgt[0] = xs[(q + 1) * 8 + 4]; rgt[1] = xs[(q + 1) * 8 + 5]; rgt[2] = xs[(q + 1) * 8 + 6]; }
+                    const int i = q * 32 + lane, xo = tx * TILE_W + i - 1;
+                    if (i >= 1 && i <= TILE_W && y < p.Ho && xo < p.Wo) {
                         const long plane = (long)p.Ho * p.Wo;
-                        float *o = p.out3 + (long)b * 3 * plane + (long)y * p.Wo + px;
+                        float *o = p.out3 + (long)b * 3 * plane + (long)y * p.Wo + xo;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            float a = __uint_as_float(v[c]) + (bias ? __ldg(bias + c) : 0.f);
+                            float a = (lft[c] + __uint_as_float(v[4 + c])) + rgt[c] + (bias ? __ldg(bias + c) : 0.f);
                             o[c * plane] = p.relu ? fmaxf(a, 0.f) : a;
                         }
                     }
@@ -376,7 +411,7 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
             set_error("tu: cuTensorMapEncodeTiled(activations) failed with code " + std::to_string((int)r));
             return TU_ERR_CUDA;
         }
-        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * 9 * nout}, ws[1] = {128};
+        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * (nout == 64 ? 9 : 3) * nout}, ws[1] = {128};
         cuuint32_t wb[2] = {64, (cuuint32_t)nout}, we[2] = {1, 1};
         r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -409,7 +444,7 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
     p.B = B; p.H = H; p.W = W;
     p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
     p.stride = stride; p.relu = relu; p.nchunk = nchunk; p.ps_r = ps_r;
-    p.tiles_x = ceil_div(p.Wo, TILE_M); p.tiles_y = ceil_div(p.Ho, TILE_R);
+    p.tiles_x = ceil_div(p.Wo, nout == 64 ? TILE_M : TILE_M - 2); p.tiles_y = ceil_div(p.Ho, TILE_R);
     p.tiles_per_chunk = p.tiles_x * p.tiles_y * B;
     p.total_tiles = p.tiles_per_chunk * nchunk;
     p.bias = bias; p.out = out; p.out3 = out3;

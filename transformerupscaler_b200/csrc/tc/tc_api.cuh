@@ -39,7 +39,7 @@ int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, 
 // conv1 3 -> 64 + ReLU, NCHW (fp32|bf16) -> NHWC bf16 (stem_tcgen05.cu)
 int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st);
 
-// 64 -> 3 head (decoder_conv2 / up1_conv): w16 = bf16 [9 taps][16 co (3 real, 13 zero)][64 ci]; planar fp32 (B,3,H,W) out
+// 64 -> 3 head (decoder_conv2 / up1_conv): w16 = bf16 [3 ky][16 rows n = kx*4 + co (co < 3)][64 ci]; planar fp32 (B,3,H,W) out
 int tc_conv3x3_c64_to3(const bf16 *in, const bf16 *w16, const float *bias, float *out, int B, int H, int W, int relu,
                        cudaStream_t st);
 

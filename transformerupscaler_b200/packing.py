@@ -48,10 +48,10 @@ class PackedWeights:
         def conv_to3(w):        # (3, 64, 3, 3) -> (9, 64, 3)
             return dev(w.float().permute(2, 3, 1, 0).reshape(9, 64, 3), f32)
 
-        def conv_to3_tc(w):     # (3, 64, 3, 3) -> bf16 (9 taps, 16 co [3 real], 64 ci) for the tensor-core head
-            t = torch.zeros(9, 16, 64, dtype=torch.float32, device=w.device)
-            t[:, :3] = w.float().permute(2, 3, 0, 1).reshape(9, 3, 64)
-            return dev(t, torch.bfloat16)
+        def conv_to3_tc(w):     # (3, 64, 3, 3) -> bf16 (3 ky, 16 rows n = kx*4 + co [co < 3], 64 ci) for the tensor-core head
+            t = torch.zeros(3, 4, 4, 64, dtype=torch.float32, device=w.device)       # (ky, kx, co, ci)
+            t[:, :3, :3] = w.float().permute(2, 3, 0, 1)                             # (ky, kx, co, ci)
+            return dev(t.reshape(3, 16, 64), torch.bfloat16)
 
         mw = _lib.TuModelWeights()
         mw.model = _lib.MODEL_IDS[model]
