@@ -9,6 +9,7 @@
 // (+bias, ReLU, bf16) into full 128-byte pixel stores.  Tiles are row segments of 128 pixels; the CTA is
 // persistent and double-buffers both the operand tile and the accumulator.
 #include <cuda.h>
+#include <string.h>
 
 #include "ptx.cuh"
 #include "tc_api.cuh"
@@ -21,8 +22,20 @@ constexpr int NUM_THREADS = 288;      // warps 0-3 epilogue, 4-7 builders, 8 MMA
 constexpr int ROWS = 4;               // image rows per tile (halo rows are loaded once for all four)
 constexpr int A_BYTES = 128 * 128;    // one operand tile: 128 pixels x 128-byte rows
 constexpr int W_BYTES = 64 * 128;     // 64 output channels x (64 k, 27 real)
-constexpr int STG_BYTES = 4 * 2 * 4096;   // epilogue staging: 4 warps x 2 buffers x (32 pixels x 128 B), source of the TMA stores
-constexpr int SMEM_BYTES = ROWS * A_BYTES + W_BYTES + STG_BYTES + 256 + 256 + 1024;
+constexpr int STG_BYTES = 4 * 4096;       // epilogue staging: 4 warps x (32 pixels x 128 B), source of the TMA stores
+constexpr int NRAW_MAX = 3;               // raw input tiles in flight (TMA variant)
+constexpr int RAW_BUDGET = 20 * 1024;     // bytes reserved for them
+constexpr int SMEM_BYTES = ROWS * A_BYTES + W_BYTES + STG_BYTES + RAW_BUDGET + 256 + 256 + 1024;
+// raw input tile of the TMA variant: (3 channels, ROWS + 2 rows, RW columns) of the image element type; the box starts
+// PADL = 16 / sizeof(element) pixels left of the tile (the innermost TMA start coordinate must be 16-byte aligned), so image
+// pixel x0 + d sits in column PADL + d
+template <typename TI> struct RawGeom {
+    static constexpr int PADL = 16 / (int)sizeof(TI);
+    static constexpr int RW = 128 + 2 * PADL;
+    static constexpr int BYTES = ((3 * (ROWS + 2) * RW * (int)sizeof(TI)) + 127) & ~127;
+    static constexpr int NRAW = (NRAW_MAX * BYTES <= RAW_BUDGET) ? NRAW_MAX : 2;
+    static_assert(NRAW * BYTES <= RAW_BUDGET, "raw tiles exceed their shared-memory budget");
+};
 
 struct StemParams {
     int B, H, W, tiles_x, tiles_y, total_tiles;
@@ -31,7 +44,7 @@ struct StemParams {
 };
 
 struct Barriers {
-    uint64_t a_full, a_empty, acc_full[ROWS], acc_empty[ROWS], w_full;
+    uint64_t a_full, a_empty, acc_full[ROWS], acc_empty[ROWS], w_full, raw_full[NRAW_MAX];
     uint32_t tmem_base;
 };
 
@@ -52,17 +65,21 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&h);
 }
 
-template <typename TI>
+// RAWTMA: the image footprint of a tile arrives by TMA (zero-filled outside the image = the convolution's padding), NRAW tiles
+// ahead, so the builders never wait on global-memory latency; otherwise (row pitch not a multiple of 16 bytes) they load
+// their pixels through registers one tile ahead.
+template <typename TI, bool RAWTMA>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
-stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, const TI *__restrict__ x,
-               const StemParams p) {
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+               const __grid_constant__ CUtensorMap tmap_x, const TI *__restrict__ x, const StemParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
     const uint32_t a_sm = smem0, w_sm = smem0 + ROWS * A_BYTES;
     const uint32_t stg_sm = w_sm + W_BYTES;        // 1024-byte aligned
-    float *bias_s = reinterpret_cast<float *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES);
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES + 256);
+    uint8_t *raw_al = smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES;      // 1024-byte aligned
+    const uint32_t raw_sm = stg_sm + STG_BYTES;
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + ROWS * A_BYTES + W_BYTES + STG_BYTES + RAW_BUDGET + 256);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x == 0) {
@@ -73,6 +90,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
         }
         ptx::mbar_init(ptx::smem_u32(&bars->w_full), 1);
+        for (int i = 0; i < NRAW_MAX; ++i) ptx::mbar_init(ptx::smem_u32(&bars->raw_full[i]), 1);
         ptx::fence_barrier_init();
     }
     if (warp == 8) {
@@ -157,11 +175,8 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const TI *a = x + (((long)b * 3 + c) * p.H + iy) * p.W + ix;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         };
-        uint32_t ph = 0;
-        if (blockIdx.x < p.total_tiles) load_tile(blockIdx.x);
-        if (blockIdx.x + gridDim.x < p.total_tiles) prefetch_tile(blockIdx.x + gridDim.x);
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
-            ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), ph ^ 1);
+        // im2col rows of the four image rows of a tile -> swizzled operand tiles (k = (ky*3+kx)*3 + c; k = 27, 28 = 1 for the bias)
+        auto build = [&]() {
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 uint8_t *rowp = smem_al + r * A_BYTES + i * 128;
@@ -186,17 +201,56 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             }
             ptx::fence_proxy_async();        // generic-proxy writes -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(ptx::smem_u32(&bars->a_full));
-            if (t + gridDim.x < p.total_tiles) load_tile(t + gridDim.x);   // next tile's pixels fly while this one is consumed
-            if (t + 2 * gridDim.x < p.total_tiles) prefetch_tile(t + 2 * gridDim.x);
+        };
+        uint32_t ph = 0;
+        if (RAWTMA) {
+            using G = RawGeom<TI>;
+            auto issue = [&](int t, int stage) {          // one thread: TMA of tile t's footprint into raw stage `stage`
+                const int tx = t % p.tiles_x;
+                int rem = t / p.tiles_x;
+                const int ty = rem % p.tiles_y, b = rem / p.tiles_y;
+                const uint32_t fb = ptx::smem_u32(&bars->raw_full[stage]);
+                ptx::mbar_expect_tx(fb, 3 * (ROWS + 2) * G::RW * (int)sizeof(TI));
+                ptx::tma_load_4d(raw_sm + stage * G::BYTES, &tmap_x, fb, tx * 128 - G::PADL, ty * ROWS - 1, 0, b);
+            };
+            if (i == 0)
+                for (int s = 0; s < G::NRAW; ++s)
+                    if (blockIdx.x + s * gridDim.x < p.total_tiles) issue(blockIdx.x + s * gridDim.x, s);
+            int stage = 0;
+            uint32_t rph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->raw_full[stage]), rph);
+                const TI *raw = reinterpret_cast<const TI *>(raw_al + stage * G::BYTES) + (G::PADL - 1 + i);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int r = 0; r < ROWS + 2; ++r)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) v[c][r][kx] = ldx(raw[(c * (ROWS + 2) + r) * G::RW + kx]);
+                asm volatile("bar.sync 2, 128;" ::: "memory");          // all builders have read the stage: refill it
+                if (i == 0 && t + G::NRAW * gridDim.x < p.total_tiles) issue(t + G::NRAW * gridDim.x, stage);
+                if (++stage == G::NRAW) { stage = 0; rph ^= 1; }
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), ph ^ 1);
+                build();
+            }
+        } else {
+            if (blockIdx.x < p.total_tiles) load_tile(blockIdx.x);
+            if (blockIdx.x + gridDim.x < p.total_tiles) prefetch_tile(blockIdx.x + gridDim.x);
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), ph ^ 1);
+                build();
+                if (t + gridDim.x < p.total_tiles) load_tile(t + gridDim.x);   // next tile's pixels fly while this one is consumed
+                if (t + 2 * gridDim.x < p.total_tiles) prefetch_tile(t + 2 * gridDim.x);
+            }
         }
     } else {
         // ================================ epilogue ================================
         // TMEM -> (+bias, ReLU, bf16) -> the pixel's 128 bytes into a swizzled staging buffer -> one TMA store per 32-pixel
         // row segment and warp (a thread storing its own pixel would touch 32 different cache lines per instruction).
         const int q = warp;
-        uint32_t ph = 0, nstore = 0;
-        uint8_t *stg_w = smem_al + ROWS * A_BYTES + W_BYTES + q * 8192;
-        const uint32_t stg_w_sm = stg_sm + q * 8192;
+        uint32_t ph = 0;
+        uint8_t *stg_w = smem_al + ROWS * A_BYTES + W_BYTES + q * 4096;
+        const uint32_t stg_w_sm = stg_sm + q * 4096;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ph ^= 1) {
             const int tx = t % p.tiles_x;
             int rem = t / p.tiles_x;
@@ -216,11 +270,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 __syncwarp();
                 if (lane == 0) {
                     ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[r]));   // values are in registers now
-                    ptx::bulk_wait_read<1>();                               // the store that last used this buffer has read it
+                    ptx::bulk_wait_read<0>();                               // the previous row's store has read the staging buffer
                 }
                 __syncwarp();
-                const uint32_t buf = nstore & 1;
-                uint8_t *rowp = stg_w + buf * 4096 + lane * 128;
+                uint8_t *rowp = stg_w + lane * 128;
 #pragma unroll
                 for (int c = 0; c < 64; c += 8) {
                     const uint32_t *v = c < 32 ? &v0[c] : &v1[c - 32];
@@ -234,10 +287,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 ptx::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (y < p.H && px0 < p.W) ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, y, b);
+                    if (y < p.H && px0 < p.W) ptx::tma_store_4d(&tmap_out, stg_w_sm, 0, px0, y, b);
                     ptx::bulk_commit();
                 }
-                ++nstore;
             }
         }
         if (lane == 0) ptx::bulk_wait<0>();
@@ -263,9 +315,13 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
     if (!g_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaSuccess;
+#define TU_STEM_ATTR(TI, R) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<TI, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
+        TU_STEM_ATTR(float, false); TU_STEM_ATTR(float, true);
+        TU_STEM_ATTR(bf16, false); TU_STEM_ATTR(bf16, true);
+        TU_STEM_ATTR(uint8_t, false); TU_STEM_ATTR(uint8_t, true);
+#undef TU_STEM_ATTR
         if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem attribute");
         g_attr_set = true;
     }
@@ -296,12 +352,31 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
     p.total_tiles = p.tiles_x * p.tiles_y * B;
     p.bias = bias; p.out = out;
     const int grid = p.total_tiles < 2 * g_sm_count ? p.total_tiles : 2 * g_sm_count;
-    if (in_dtype == TU_F32)
-        stem_tc_kernel<float><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const float *)x, p);
-    else if (in_dtype == TU_U8)
-        stem_tc_kernel<uint8_t><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const uint8_t *)x, p);
-    else
-        stem_tc_kernel<bf16><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, (const bf16 *)x, p);
+    // raw image tiles by TMA when the row pitch allows it: (W, H, 3, B) view, box (RW, ROWS + 2, 3, 1)
+    const int eb = in_dtype == TU_F32 ? 4 : in_dtype == TU_BF16 ? 2 : 1;
+    const int rw = 128 + 2 * (16 / eb);
+    CUtensorMap tx;
+    memset(&tx, 0, sizeof(tx));
+    bool raw_tma = ((size_t)W * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (raw_tma) {
+        cuuint64_t xd[4] = {(cuuint64_t)W, (cuuint64_t)H, 3, (cuuint64_t)B};
+        cuuint64_t xs[3] = {(cuuint64_t)W * eb, (cuuint64_t)H * W * eb, (cuuint64_t)3 * H * W * eb};
+        cuuint32_t xb[4] = {(cuuint32_t)rw, ROWS + 2, 3, 1}, xe[4] = {1, 1, 1, 1};
+        raw_tma = enc(&tx, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : eb == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                      4, const_cast<void *>(x), xd, xs, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+#define TU_STEM_LAUNCH(TI)                                                                                         \
+    do {                                                                                                           \
+        if (raw_tma)                                                                                               \
+            stem_tc_kernel<TI, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, tx, (const TI *)x, p);         \
+        else                                                                                                       \
+            stem_tc_kernel<TI, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, tx, (const TI *)x, p);        \
+    } while (0)
+    if (in_dtype == TU_F32) TU_STEM_LAUNCH(float);
+    else if (in_dtype == TU_U8) TU_STEM_LAUNCH(uint8_t);
+    else TU_STEM_LAUNCH(bf16);
+#undef TU_STEM_LAUNCH
     TU_CHECK_LAUNCH("stem_tc");
     return TU_OK;
 }
