@@ -31,8 +31,9 @@ constexpr int BM = 128, BK = 64, NSTAGE = 4, NUM_THREADS = 384;   // warps 0-3: 
 constexpr int A_STAGE = BM * BK * 2;   // 16384
 constexpr int UE_PITCH = 68;           // floats per staged row of the unembed epilogue (64 + 4: conflict-free 16-byte accesses)
 constexpr int UE_BYTES = 8 * 32 * UE_PITCH * 4;
+constexpr int UT_BYTES = 8 * 2 * 4096;     // UNEMBED_TMA: per epilogue warp two 4 KB boxes (32 pixels x 64 channels), skip in / result out
 
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_EMBED = 2, EPI_UNEMBED = 3 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_EMBED = 2, EPI_UNEMBED = 3, EPI_UNEMBED_TMA = 4 };
 
 struct GemmParams {
     int M, N, K, BN;
@@ -59,6 +60,7 @@ struct Barriers {
     uint64_t empty[NSTAGE];
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
+    uint64_t skip_full[8][2];   // UNEMBED_TMA: private to each epilogue warp
     uint32_t tmem_base;
 };
 
@@ -79,14 +81,17 @@ __device__ __forceinline__ float gelu_f(float x) {
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_skip, const __grid_constant__ CUtensorMap tmap_o5, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int w_stage = p.BN * 128;
     const int stage_bytes = A_STAGE + w_stage;
     uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
-    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + NSTAGE * stage_bytes);
-    float *stage_f32 = reinterpret_cast<float *>(smem_al + NSTAGE * stage_bytes + 256);   // UNEMBED only: 8 warps x 32 rows x 68 floats
+    // UNEMBED_TMA keeps its 1024-byte aligned pixel boxes right after the operand stages; barriers follow
+    const int bar_off = NSTAGE * stage_bytes + (p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0);
+    Barriers *bars = reinterpret_cast<Barriers *>(smem_al + bar_off);
+    float *stage_f32 = reinterpret_cast<float *>(smem_al + bar_off + 256);   // UNEMBED only: 8 warps x 32 rows x 68 floats
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int nk = p.K / BK;
 
@@ -99,6 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_init(ptx::smem_u32(&bars->acc_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 8);
         }
+        for (int i = 0; i < 16; ++i) ptx::mbar_init(ptx::smem_u32(&bars->skip_full[i >> 1][i & 1]), 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -108,6 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_w);
+        if (p.epi == EPI_UNEMBED_TMA) { ptx::prefetch_tmap(&tmap_skip); ptx::prefetch_tmap(&tmap_o5); }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -168,6 +175,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
         const int cbeg = half * (p.BN >> 1), cend = cbeg + (p.BN >> 1);
         const int i = q * 32 + lane;                  // row of the tile owned by this thread
+        if (p.epi == EPI_UNEMBED_TMA) {
+            // Window-ordered tokens, BN = 128 (two pixels of every token), no crop inside a patch.  This warp's 32 token rows are
+            // half a window: 4 token rows x 8 token columns, and it owns pixel (dy, dx) of each.  Those 32 pixels are a strided
+            // box (c 64, dx 1, tx 8, y 4 rows at stride 8, b 1) of the NHWC tensor: the skip connection arrives by TMA (the box of
+            // the NEXT tile is requested before this tile is processed), the sum is written over it in shared memory and
+            // leaves by a TMA store.  Rows / columns outside the image are clipped by the TMA engine in both directions, so pad
+            // tokens need no special case and no thread computes a global address.
+            const int w8 = warp - 4;
+            uint8_t *box = smem_al + NSTAGE * stage_bytes + w8 * 8192;
+            const uint32_t box_sm = smem0 + NSTAGE * stage_bytes + w8 * 8192;
+            auto coords = [&](int t, int &dx, int &tx0, int &y0, int &b) -> bool {
+                const int tn = t % p.tiles_n, tm = t / p.tiles_n;
+                const int wi = tm * 2 + (q >> 1);                 // window of this warp's rows
+                const int wx = wi % p.nWx, rest = wi / p.nWx;
+                const int wy = rest % p.nWy;
+                b = rest / p.nWy;
+                const int pix = ((tn * p.BN) >> 6) + half;
+                dx = pix & 7;
+                tx0 = wx * 8;
+                y0 = (wy * 8 + (q & 1) * 4) * 8 + (pix >> 3);
+                return b < p.B;
+            };
+            auto request = [&](int t, int buf) {                  // lane 0: skip box of tile t -> buffer buf
+                int dx, tx0, y0, b;
+                if (!coords(t, dx, tx0, y0, b)) return;
+                const uint32_t fb = ptx::smem_u32(&bars->skip_full[w8][buf]);
+                ptx::mbar_expect_tx(fb, 4096);
+                ptx::tma_load_5d(box_sm + buf * 4096, &tmap_skip, fb, 0, dx, tx0, y0, b);
+            };
+            const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias);
+            if (lane == 0 && blockIdx.x < p.total_tiles) request(blockIdx.x, 0);
+            int it = 0;
+            uint32_t sph[2] = {0u, 0u};
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int set = it & 1, buf = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                int dx, tx0, y0, b;
+                const bool live = coords(t, dx, tx0, y0, b);
+                if (lane == 0 && t + gridDim.x < p.total_tiles) request(t + gridDim.x, buf ^ 1);   // that buffer's store has been read (below)
+                ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
+                ptx::tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256 + cbeg;
+                uint32_t v0[32], v1[32];
+                ptx::tmem_ld_x32(tbase, v0);
+                ptx::tmem_ld_x32(tbase + 32, v1);
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
+                if (!live) continue;                              // warp-uniform
+                ptx::mbar_wait(ptx::smem_u32(&bars->skip_full[w8][buf]), sph[buf]);
+                sph[buf] ^= 1;
+                uint8_t *rowp = box + buf * 4096 + lane * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 *sp = reinterpret_cast<uint4 *>(rowp + ((c ^ (lane & 7)) << 4));
+                    const uint4 su = *sp;
+                    const __nv_bfloat162 *sh = reinterpret_cast<const __nv_bfloat162 *>(&su);
+                    const float2 s0 = __bfloat1622float2(sh[0]), s1 = __bfloat1622float2(sh[1]), s2 = __bfloat1622float2(sh[2]), s3 = __bfloat1622float2(sh[3]);
+                    const float4 ba = __ldg(bias4 + c * 2), bb = __ldg(bias4 + c * 2 + 1);
+                    const uint32_t *v = c < 4 ? &v0[c * 8] : &v1[(c - 4) * 8];
+                    uint4 u;
+                    __nv_bfloat162 h;
+                    h = __floats2bfloat162_rn(__uint_as_float(v[0]) + ba.x + s0.x, __uint_as_float(v[1]) + ba.y + s0.y); u.x = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(__uint_as_float(v[2]) + ba.z + s1.x, __uint_as_float(v[3]) + ba.w + s1.y); u.y = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(__uint_as_float(v[4]) + bb.x + s2.x, __uint_as_float(v[5]) + bb.y + s2.y); u.z = *reinterpret_cast<uint32_t *>(&h);
+                    h = __floats2bfloat162_rn(__uint_as_float(v[6]) + bb.z + s3.x, __uint_as_float(v[7]) + bb.w + s3.y); u.w = *reinterpret_cast<uint32_t *>(&h);
+                    *sp = u;
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_5d(&tmap_o5, box_sm + buf * 4096, 0, dx, tx0, y0, b);
+                    ptx::bulk_commit();
+                    ptx::bulk_wait_read<0>();                     // the box may be refilled by the request two tiles ahead
+                }
+                __syncwarp();
+            }
+            if (lane == 0) ptx::bulk_wait<0>();
+            __syncwarp();
+        } else {
         int it = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int tn = t % p.tiles_n, tm = t / p.tiles_n;
@@ -358,6 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[set]));
         }
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -387,13 +476,14 @@ int encode_2d(CUtensorMap *tm, const void *ptr, uint64_t rows, uint64_t cols, ui
     return TU_OK;
 }
 
-int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStream_t st) {
+int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStream_t st, const CUtensorMap *tskip = nullptr,
+           const CUtensorMap *to5 = nullptr) {
     if (!g_sm_count) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + (p.epi == EPI_UNEMBED ? UE_BYTES : 0) + 1024;
+    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + (p.epi == EPI_UNEMBED ? UE_BYTES : p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0) + 1024;
     if (smem > g_smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "gemm_tc smem attribute");
@@ -402,7 +492,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStre
     p.tiles_n = p.N / p.BN;
     p.total_tiles = p.tiles_m * p.tiles_n;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ta, tw, p);
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ta, tw, tskip ? *tskip : ta, to5 ? *to5 : ta, p);
     TU_CHECK_LAUNCH("gemm_tc");
     return TU_OK;
 }
@@ -482,6 +572,23 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
     p.epi = EPI_UNEMBED;
     p.bias = bias; p.out = out; p.skip = skip; p.skipH = skipH; p.skipW = skipW; p.Hc = Hc; p.Wc = Wc;
     p.B = B; p.Ht = Ht; p.Wt = Wt; p.nWy = nWy; p.nWx = nWx; p.window = window; p.dim = dim;
+    // strided-box TMA epilogue when a patch is never cropped horizontally: (c 64, dx 8, tx, y, b) views of skip and out
+    if (window && Wc == 8 * Wt && (reinterpret_cast<uintptr_t>(skip) & 127) == 0 && (reinterpret_cast<uintptr_t>(out) & 127) == 0) {
+        CUtensorMap ts, to;
+        cuuint64_t sd[5] = {64, 8, (cuuint64_t)Wt, (cuuint64_t)Hc, (cuuint64_t)B};
+        cuuint64_t ss[4] = {128, 1024, (cuuint64_t)skipW * 128, (cuuint64_t)skipH * skipW * 128};
+        cuuint64_t os[4] = {128, 1024, (cuuint64_t)Wc * 128, (cuuint64_t)Hc * Wc * 128};
+        cuuint32_t box[5] = {64, 1, 8, 32, 1}, es[5] = {1, 1, 1, 8, 1};
+        TcEncodeFn enc = tc_encode_fn();
+        const bool ok = enc(&ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)skip, sd, ss, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                        enc(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void *)out, sd, os, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        if (ok) {
+            p.epi = EPI_UNEMBED_TMA;
+            return launch(ta, tw, p, st, &ts, &to);
+        }
+    }
     return launch(ta, tw, p, st);
 }
 
