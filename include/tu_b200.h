@@ -58,7 +58,8 @@ void tu_profile_enable(int on);
 int tu_profile_collect(const char *name, double *total_ms, int *launches);
 int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
-/* bring-up switches (not part of the stable interface): key "tc_base_off_mode" in {0,1} */
+/* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
+ * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution vs single-CTA) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 60 tools/probes/tma_probe
-for k in bicubic; do
+for k in conv3x3_c64; do
   timeout 300 python -m pytest tests/test_gpu_ops.py -q -m gpu -x --timeout 120 -p no:cacheprovider -k "$k" > gpurun_out/dbg_$k.log 2>&1
-  echo "$k rc=$? $(tail -1 gpurun_out/dbg_$k.log)"
+  echo "$k rc=$? $(tail -1 gpurun_out/dbg_$k.log)"; grep -E "^E  " gpurun_out/dbg_$k.log | head -5
 done

@@ -36,6 +36,11 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
 int tc_conv3x3_c64(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
                    int nchunk, int ps_r, cudaStream_t st);
 
+// the same convolution on a CTA pair (tcgen05 cta_group::2, conv3x3_2cta_tcgen05.cu): plain 64 -> 64 only
+int tc_conv3x3_c64_pair(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int stride, int relu,
+                        cudaStream_t st);
+void tc_set_conv_2cta(int on);
+
 // conv1 3 -> 64 + ReLU, NCHW (fp32|bf16) -> NHWC bf16 (stem_tcgen05.cu)
 int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st);
 
