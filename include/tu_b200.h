@@ -59,7 +59,7 @@ int tu_profile_collect(const char *name, double *total_ms, int *launches);
 int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
- * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution vs single-CTA) */
+ * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------

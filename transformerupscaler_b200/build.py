@@ -19,6 +19,7 @@ SOURCES = [
     "resample.cu",
     "tc/conv3x3_tcgen05.cu",
     "tc/conv3x3_2cta_tcgen05.cu",
+    "tc/conv3x3_stream_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",
