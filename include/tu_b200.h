@@ -47,8 +47,9 @@ int tu_bf16_uses_tcgen05(void);
 void tu_set_bf16_tcgen05(int enable);
 /* number of kernels this library has launched in the calling process (monotonic) */
 long long tu_launch_count(void);
-/* Measurement hook for bench.py: when enabled, tu_forward brackets every kernel it launches with CUDA events on
- * the caller's stream, tagged with the reference op it implements ("conv1", "conv2", "downsample", "patch_embed",
+/* Measurement hook for bench.py: tu_profile_enable(1) brackets the dominant kernel ("conv2") of every tu_forward with CUDA
+ * events on the caller's stream (two event records per forward: cheap enough for the timed region); tu_profile_enable(2)
+ * brackets EVERY kernel, tagged with the reference op it implements ("conv1", "conv2", "downsample", "patch_embed",
  * "transformer_blocks", "patch_unembed", "decoder_conv1", "decoder_conv2", "bicubic_add_clamp", "up1", "up1_conv",
  * "final_upscale", "final_conv_add").  tu_profile_collect / tu_profile_report synchronise those events (the only
  * calls in the library that wait on the device): collect sums the milliseconds and launches recorded under `name`
@@ -165,6 +166,9 @@ int tu_patch_unembed(const float *tokens, const void *w, const float *b, const v
 size_t tu_block_workspace_bytes(int M, int dim, int dtype);
 int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                          int dtype, void *workspace, size_t workspace_bytes, void *stream);
+/* window attention alone: softmax(q k^T + rel_bias) v per 8x8 window and head (head_dim 16) on qkv rows (nWin*64, 3*dim) with q
+ * pre-scaled; rel_bias dense (heads,64,64) fp32; out (nWin*64, dim).  WindowTransformer/model.py:104-127 between qkv and proj. */
+int tu_window_attention(const void *qkv, const float *rel_bias, void *out, int nWin, int dim, int heads, int dtype, void *stream);
 /* out = clamp?(bicubic(x -> outH,outW) + bicubic(res -> outH,outW)); res may be NULL */
 int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW,
                          void *out, int out_dtype, int B, int outH, int outW, int clamp, void *stream);

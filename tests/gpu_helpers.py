@@ -110,3 +110,11 @@ def resize_aa(x, outH, outW, clamp):
     out = torch.empty(B, 3, outH, outW, dtype=x.dtype, device=x.device)
     chk(lib.tu_resize_bilinear_aa(p(x), DT[x.dtype], p(out), B, H, W, outH, outW, int(clamp), stream()))
     return out
+
+
+def window_attention(qkv, rel_bias, dim, heads):
+    lib = _lib.load()
+    M = qkv.shape[0]
+    out = torch.empty(M, dim, dtype=qkv.dtype, device=qkv.device)
+    chk(lib.tu_window_attention(p(qkv), p(rel_bias), p(out), M // 64, dim, heads, DT[qkv.dtype], stream()))
+    return out

@@ -187,6 +187,22 @@ def test_transformer_block(dev, dt, model):
     assert _maxerr(out, ref) < tol
 
 
+@pytest.mark.parametrize("dt", [F32, BF16])
+@pytest.mark.parametrize("dim,heads", [(128, 8), (192, 12)])
+def test_window_attention(dev, dt, dim, heads):
+    """softmax(q k^T + bias) v per window and head vs a direct restatement (WindowTransformer/model.py:104-127)."""
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(12)
+    nW = 7
+    qkv = torch.from_numpy(rs.standard_normal((nW * 64, 3 * dim)).astype(np.float32)).to(dt)
+    bias = torch.from_numpy((0.5 * rs.standard_normal((heads, 64, 64))).astype(np.float32))
+    q, k, v = qkv.float().reshape(nW, 64, 3, heads, 16).permute(2, 0, 3, 1, 4)      # (nW, h, 64, 16) each
+    att = torch.softmax(q @ k.transpose(-1, -2) + bias[None], dim=-1) @ v            # q is taken as already scaled
+    ref = att.permute(0, 2, 1, 3).reshape(nW * 64, dim)
+    out = G.window_attention(qkv.to(dev), bias.to(dev), dim, heads)
+    assert _maxerr(out, ref) < (2e-5 if dt == F32 else 3e-2)
+
+
 @pytest.mark.parametrize("in_dt,out_dt", [(F32, F32), (BF16, BF16), (F32, BF16)])
 @pytest.mark.parametrize("geom", [((72, 104), (36, 52), (108, 156)), ((64, 80), (32, 40), (128, 160)), ((45, 37), (20, 16), (200, 111))])
 def test_bicubic_add_clamp(dev, in_dt, out_dt, geom):

@@ -11,6 +11,7 @@
 
 namespace tu {
 
+int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
 static thread_local std::string g_err;
 static int g_use_tc = 1;
 static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
@@ -25,15 +26,17 @@ static std::mutex g_prof_mu;
 struct ProfRec { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_events;
 static cudaEvent_t g_prof_open = nullptr;
+static const char *g_prof_name = nullptr;      // the op about to be launched (set by TU_STEP)
+static inline bool prof_wanted() { return g_prof_on >= 2 || (g_prof_on == 1 && g_prof_name && !strcmp(g_prof_name, "conv2")); }
 static void prof_begin(cudaStream_t st) {
-    if (!g_prof_on) return;
+    if (!prof_wanted()) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, st);
     g_prof_open = e;
 }
 static void prof_end(cudaStream_t st, const char *name) {
-    if (!g_prof_on || !g_prof_open) return;
+    if (!g_prof_open) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, st);
@@ -44,6 +47,7 @@ static void prof_end(cudaStream_t st, const char *name) {
 // run one launcher call, bracketed when profiling is on
 #define TU_STEP(name, call)            \
     do {                               \
+        g_prof_name = name;            \
         prof_begin(st);                \
         rc = (call);                   \
         prof_end(st, name);            \
@@ -190,6 +194,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         TU_STEP("patch_embed", tu_patch_embed(fd, dt, w->embed_w, w->embed_b, w->pos_embed, tok, B, Hd, Wd, Ht, Wt, dim, window ? 1 : 0,
                                               fast ? 1 : 0, stv));
         const bool tc = tc_on(dt);
+        g_prof_name = "transformer_blocks";
         prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
         if (tc && window && dim == 128 && w->stack_w && g_use_stack)
@@ -201,6 +206,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
                                            (tc && i == w->n_blocks - 1) ? tok16 : nullptr, st)))
                 return rc;
         prof_end(st, "transformer_blocks");
+        g_prof_name = "patch_unembed";
         prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
         if (tc)
@@ -256,6 +262,10 @@ extern "C" void tu_set_bf16_tcgen05(int enable) { g_use_tc = enable; }
 extern "C" int tu_debug_set(const char *key, int value) {
     if (key && !strcmp(key, "tc_base_off_mode")) {
         tc_set_base_off_mode(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "pdl")) {
+        g_use_pdl = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "conv_stream")) {

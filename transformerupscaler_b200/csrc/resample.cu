@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
                                                                        const BicubicTileGeom g, const TI *__restrict__ x, int H, int W,
                                                                        const float *__restrict__ res, int rH, int rW,
                                                                        TO *__restrict__ out, int oH, int oW, int clamp) {
+    pdl_trigger();
+    pdl_wait();          // the residual image is written by the previous kernel of the stream
     __shared__ float yw[2][BS_H][4];
     __shared__ int ybase[2][BS_H];
     __shared__ __align__(8) uint64_t bar;
@@ -391,11 +393,11 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
                 attr_done = true;                                                                                               \
             }                                                                                                                   \
             if (res)                                                                                                            \
-                bicubic_add_clamp_strip_kernel<TI, TO, 1><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, \
-                                                                                               rW, (TO *)out, outH, outW, clamp); \
+                launch_pdl(bicubic_add_clamp_strip_kernel<TI, TO, 1>, grid, dim3(BS_W), tile_bytes + 128, st, tx, tr, g, (const TI *)x, H, W, \
+                           res, rH, rW, (TO *)out, outH, outW, clamp);                                                      \
             else                                                                                                                \
-                bicubic_add_clamp_strip_kernel<TI, TO, 2><<<grid, BS_W, tile_bytes + 128, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, \
-                                                                                               rW, (TO *)out, outH, outW, clamp); \
+                launch_pdl(bicubic_add_clamp_strip_kernel<TI, TO, 2>, grid, dim3(BS_W), tile_bytes + 128, st, tx, tr, g, (const TI *)x, H, W, \
+                           res, rH, rW, (TO *)out, outH, outW, clamp);                                                      \
         } else {                                                                                                                \
             bicubic_add_clamp_strip_kernel<TI, TO, 0><<<grid, BS_W, 0, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW,     \
                                                                                   (TO *)out, outH, outW, clamp);                \

@@ -57,6 +57,7 @@ static_assert(sizeof(StreamBarriers) <= 512, "barrier block too large");
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_out, const StreamParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_sm = smem0, ring_sm = smem0 + W_BYTES, stg_sm = ring_sm + RING * UNIT_BYTES;
@@ -89,6 +90,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
 
     // work item -> (frame b, first output row y0, rows in the item, first pixel x0)
     auto item_geom = [&](int it, int &b, int &y0, int &rows, int &x0) {
@@ -308,7 +310,7 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
     p.total_items = p.tiles_x * p.chunks_y * B;
     p.bias = bias;
     const int grid = p.total_items < g_sm_count_s ? p.total_items : g_sm_count_s;
-    conv3x3_stream_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
+    launch_pdl(conv3x3_stream_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     TU_CHECK_LAUNCH("conv3x3_stream");
     return TU_OK;
 }

@@ -64,6 +64,7 @@ template <int NOUT, int S>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     // NOUT == 64: nine (co 64 x ci 64) filter taps.  NOUT == 16 (the 64 -> 3 heads): three ky blocks of 16 rows n = kx*4 + co, so
@@ -109,6 +110,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
 
     if (warp == 0 && lane == 0) {
         // ================================ TMA producer ================================
@@ -450,11 +452,11 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
     p.bias = bias; p.out = out; p.out3 = out3;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
     if (nout == 64 && stride == 1)
-        conv3x3_tc_kernel<64, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
+        launch_pdl(conv3x3_tc_kernel<64, 1>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     else if (nout == 64)
-        conv3x3_tc_kernel<64, 2><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
+        launch_pdl(conv3x3_tc_kernel<64, 2>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     else
-        conv3x3_tc_kernel<16, 1><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tm_act, tm_w, tm_out, p);
+        launch_pdl(conv3x3_tc_kernel<16, 1>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     TU_CHECK_LAUNCH("conv3x3_tc");
     return TU_OK;
 }

@@ -83,6 +83,7 @@ __device__ __forceinline__ float gelu_f(float x) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const __grid_constant__ CUtensorMap tmap_skip, const __grid_constant__ CUtensorMap tmap_o5, const GemmParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const int w_stage = p.BN * 128;
@@ -120,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
 
     if (warp == 0 && lane == 0) {
         // ================================ TMA producer ================================
@@ -492,7 +494,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStre
     p.tiles_n = p.N / p.BN;
     p.total_tiles = p.tiles_m * p.tiles_n;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ta, tw, tskip ? *tskip : ta, to5 ? *to5 : ta, p);
+    launch_pdl(gemm_tc_kernel, dim3(grid), dim3(NUM_THREADS), (size_t)smem, st, ta, tw, tskip ? *tskip : ta, to5 ? *to5 : ta, p);
     TU_CHECK_LAUNCH("gemm_tc");
     return TU_OK;
 }

@@ -72,6 +72,7 @@ template <typename TI, bool RAWTMA>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                const __grid_constant__ CUtensorMap tmap_x, const TI *__restrict__ x, const StemParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem_al = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
@@ -101,6 +102,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    pdl_wait();
 
     if (warp == 8) {
         // ================================ weights + MMA issuer (whole warp converged, elected lane issues) ================================
@@ -369,9 +371,9 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
 #define TU_STEM_LAUNCH(TI)                                                                                         \
     do {                                                                                                           \
         if (raw_tma)                                                                                               \
-            stem_tc_kernel<TI, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, tx, (const TI *)x, p);         \
+            launch_pdl(stem_tc_kernel<TI, true>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, to, tx, (const TI *)x, p);   \
         else                                                                                                       \
-            stem_tc_kernel<TI, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, to, tx, (const TI *)x, p);        \
+            launch_pdl(stem_tc_kernel<TI, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, to, tx, (const TI *)x, p);  \
     } while (0)
     if (in_dtype == TU_F32) TU_STEM_LAUNCH(float);
     else if (in_dtype == TU_U8) TU_STEM_LAUNCH(uint8_t);

@@ -118,6 +118,7 @@ __device__ __forceinline__ void layernorm_to_a32(float (&x)[32], const float *ga
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *sm = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
@@ -145,6 +146,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     const uint32_t TX = tmem_base, TACC = tmem_base + 128;
+    pdl_wait();
 
     if (warp == NMATH) {
         if (lane == 0) {
@@ -476,7 +478,7 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.n_tiles = M / 128; p.n_blocks = n_blocks;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
-    window_stack_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tw, p);
+    launch_pdl(window_stack_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, p);
     TU_CHECK_LAUNCH("window_stack");
     return TU_OK;
 }

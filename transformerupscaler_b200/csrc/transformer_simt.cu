@@ -510,6 +510,27 @@ using namespace tu;
 
 extern "C" size_t tu_block_workspace_bytes(int M, int dim, int dtype) { return block_ws(M, dim, dtype); }
 
+// Stand-alone window attention (softmax(q k^T + bias) v per 8x8 window and head, head_dim 16) on qkv rows (nWin*64, 3*dim):
+// the op inside WindowAttention.forward between `qkv` and `proj` (WindowTransformer/model.py:104-127).  Exported so that the
+// "attention TFLOP/s" of the headline metric can be measured on its own; the forward pass itself runs it fused
+// (window_stack_tcgen05.cu) or, for dim 192, through tu_transformer_block.
+extern "C" int tu_window_attention(const void *qkv, const float *rel_bias, void *out, int nWin, int dim, int heads, int dtype,
+                                   void *stream) {
+    TU_CHECK_ARG(qkv && rel_bias && out && nWin > 0, "window_attention: bad argument");
+    TU_CHECK_ARG(dim == heads * 16 && (dim == 128 || dim == 192), "window_attention: dim must be heads*16 and 128|192");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(nWin, heads);
+    if (dtype == TU_BF16) {
+        window_attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16 *)qkv, rel_bias, (bf16 *)out, dim);
+    } else if (dtype == TU_F32) {
+        window_attn_kernel<float><<<grid, 64, 0, st>>>((const float *)qkv, rel_bias, (float *)out, dim, heads);
+    } else {
+        TU_CHECK_ARG(false, "window_attention: bad dtype");
+    }
+    TU_CHECK_LAUNCH("window_attention");
+    return TU_OK;
+}
+
 extern "C" int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                                     int dtype, void *workspace, size_t workspace_bytes, void *stream) {
     return transformer_block_ex(x, w, M, dim, heads, window, S, dtype, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);

@@ -62,6 +62,30 @@ __device__ __forceinline__ void store4(bf16 *p, float4 v) {
     *reinterpret_cast<uint2 *>(p) = u;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// Every kernel of a forward is launched with programmatic stream serialization: it may become resident (and run its prologue:
+// barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream is draining.  pdl_wait() blocks
+// until that kernel has completed and its writes are visible, so it must precede EVERY access to global memory; kernels call
+// pdl_trigger() first thing so that their own successor can be scheduled early.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_use_pdl;      // api.cu (debug key "pdl")
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
