@@ -154,6 +154,13 @@ def main():
         lib.tu_set_bf16_tcgen05(0)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # keep this rank's host thread and its pinned frame buffers on the NUMA node of its GPU (first touch after binding)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
