@@ -176,3 +176,22 @@ def test_uint8_frames_match_float_path(name, bf16):
     tol = 3 if bf16 else 1          # bf16 module: the float path rounds its output to bf16 (4e-3 near 1.0) before the *255
     assert diff.max().item() <= tol, f"{name}: max grey-level difference {diff.max().item()}"
     assert (diff > 0).float().mean().item() < (0.5 if bf16 else 0.02)
+
+
+@pytest.mark.parametrize("model,kw,shape", [("WindowTransformer", dict(res_out=(108, 156)), (72, 104)),
+                                            ("FastTransformer", dict(upscale_factor=2), (40, 56))])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_frame_sharding_is_bitwise_invariant(model, kw, shape, bf16):
+    """Frames are independent: a frame upscaled inside a batch of 3 equals, bit for bit, the same frame
+    upscaled alone -- which is what makes N-GPU frame sharding reproduce the 1-GPU result exactly."""
+    M, _ = build(model, 3)
+    if bf16:
+        M = M.bfloat16()
+    x = synth_frames(3, shape[0], shape[1], seed=31).cuda()
+    if bf16:
+        x = x.bfloat16()
+    with torch.no_grad():
+        full = M(x, **kw)
+        for i in range(3):
+            one = M(x[i:i + 1].contiguous(), **kw)
+            assert torch.equal(one[0], full[i]), f"frame {i} differs between batch-of-3 and batch-of-1"
