@@ -65,7 +65,7 @@ def main():
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / iters
                 lib.tu_profile_reset()
-                lib.tu_profile_enable(1)
+                lib.tu_profile_enable(2)
                 for _ in range(3):
                     y = M(x, **kw)
                 torch.cuda.synchronize()

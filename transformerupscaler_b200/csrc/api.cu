@@ -344,7 +344,7 @@ extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, voi
     cudaStream_t st = (cudaStream_t)stream;
     if (tc_on(dtype)) {
         int rc = TU_TC_UNSUPPORTED;
-        if (nchunk == 1 && ps_r == 0 && stride == 1) rc = tc_conv3x3_c64_stream((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, relu, st);
+        if (stride == 1) rc = tc_conv3x3_c64_stream((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, relu, nchunk, ps_r, st);
         if (rc == TU_TC_UNSUPPORTED && nchunk == 1 && ps_r == 0)
             rc = tc_conv3x3_c64_pair((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, st);
         if (rc == TU_TC_UNSUPPORTED)

@@ -42,14 +42,15 @@ constexpr int NUM_THREADS = 256;
 struct StreamParams {
     int B, H, W, relu;
     int R;                  // output rows per work item
-    int tiles_x, chunks_y, total_items;
-    const float *bias;
+    int tiles_x, chunks_y, items_per_chunk, total_items;
+    int ps_r;               // PixelShuffle factor (0 = plain): output chunk c holds sub-pixel phase (c / r, c % r)
+    const float *bias;      // nchunk * 64, or nullptr
 };
 
 struct StreamBarriers {
     uint64_t full[RING], empty[RING];
     uint64_t acc_full[NACC], acc_empty[NACC];
-    uint64_t w_full;
+    uint64_t w_full, w_free;
     uint32_t tmem_base;
 };
 static_assert(sizeof(StreamBarriers) <= 512, "barrier block too large");
@@ -75,6 +76,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 4);
         }
         ptx::mbar_init(ptx::smem_u32(&bars->w_full), 1);
+        ptx::mbar_init(ptx::smem_u32(&bars->w_free), 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -92,8 +94,11 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
     const uint32_t tmem_base = bars->tmem_base;
     pdl_wait();
 
-    // work item -> (frame b, first output row y0, rows in the item, first pixel x0)
-    auto item_geom = [&](int it, int &b, int &y0, int &rows, int &x0) {
+    // work item -> (output-channel chunk, frame b, first output row y0, rows in the item, first pixel x0); items are ordered
+    // chunk-major, so a CTA switches filter banks at most nchunk - 1 times
+    auto item_geom = [&](int it, int &b, int &y0, int &rows, int &x0) -> int {
+        const int chunk = it / p.items_per_chunk;
+        it -= chunk * p.items_per_chunk;
         const int tx = it % p.tiles_x;
         int rem = it / p.tiles_x;
         const int cy = rem % p.chunks_y;
@@ -101,20 +106,29 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         y0 = cy * p.R;
         rows = min(p.R, p.H - y0);
         x0 = tx * TILE_M;
+        return chunk;
     };
 
     if (warp == 0 && lane == 0) {
         // ================================ TMA producer ================================
         // filter bank -> smem as [kx][ky = 2, 1, 0][co][ci]: block (kx, j) holds tap (ky = 2 - j, kx)
-        ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
-        for (int kx = 0; kx < 3; ++kx)
-            for (int j = 0; j < 3; ++j)
-                ptx::tma_load_2d(w_sm + kx * W_KX + j * W_BLK, &tmap_w, ptx::smem_u32(&bars->w_full), 0, ((2 - j) * 3 + kx) * 64);
-        int slot = 0;
-        uint32_t phase = 0;
+        int slot = 0, cur_chunk = -1;
+        uint32_t phase = 0, wfree_ph = 0;
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
             int b, y0, rows, x0;
-            item_geom(it, b, y0, rows, x0);
+            const int chunk = item_geom(it, b, y0, rows, x0);
+            if (chunk != cur_chunk) {
+                if (cur_chunk >= 0) {          // all MMAs that read the old bank must have retired
+                    ptx::mbar_wait(ptx::smem_u32(&bars->w_free), wfree_ph);
+                    wfree_ph ^= 1;
+                }
+                ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
+                for (int kx = 0; kx < 3; ++kx)
+                    for (int j = 0; j < 3; ++j)
+                        ptx::tma_load_2d(w_sm + kx * W_KX + j * W_BLK, &tmap_w, ptx::smem_u32(&bars->w_full), 0,
+                                         (chunk * 9 + (2 - j) * 3 + kx) * 64);
+                cur_chunk = chunk;
+            }
             for (int u = 0; u < rows + 2; ++u) {          // input rows y0 - 1 .. y0 + rows
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), phase ^ 1);
                 const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
@@ -127,13 +141,17 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
         const uint32_t leader = ptx::elect_one();
         const uint32_t w_lo = ptx::sdesc_lo(w_sm), ring_lo = ptx::sdesc_lo(ring_sm);
-        ptx::mbar_wait(ptx::smem_u32(&bars->w_full), 0);
-        int slot = 0;
-        uint32_t phase = 0;
+        int slot = 0, cur_chunk = -1;
+        uint32_t phase = 0, wfull_ph = 0;
         uint32_t g0 = 0;                                   // global index (per CTA) of the item's first output row
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
             int b, y0, rows, x0;
-            item_geom(it, b, y0, rows, x0);
+            const int chunk = item_geom(it, b, y0, rows, x0);
+            if (chunk != cur_chunk) {
+                ptx::mbar_wait(ptx::smem_u32(&bars->w_full), wfull_ph);
+                wfull_ph ^= 1;
+                cur_chunk = chunk;
+            }
             for (int u = 0; u < rows + 2; ++u) {
                 // input row u - 1 (relative) feeds output rows lo..hi with ky = u - row; filter block of row m is 2 - (u - m).
                 // Every accumulator slot is zero when a row opens (the epilogue clears it after draining), so all MMAs accumulate.
@@ -171,6 +189,9 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
                 if (++slot == RING) { slot = 0; phase ^= 1; }
             }
             g0 += rows;
+            // does this CTA's next item use another filter bank?
+            const int nx = it + gridDim.x;
+            if (nx < p.total_items && nx / p.items_per_chunk != chunk) ptx::umma_commit_pred(ptx::smem_u32(&bars->w_free), leader);
         }
     } else if (warp >= 4) {
         // ================================ epilogue: one output row at a time ================================
@@ -190,8 +211,9 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         const uint32_t stg_w_sm = stg_sm + q * 8192;
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
             int b, y0, rows, x0;
-            item_geom(it, b, y0, rows, x0);
+            const int chunk = item_geom(it, b, y0, rows, x0);
             const int px0 = x0 + q * 32;
+            const float *bias = p.bias ? p.bias + chunk * 64 : nullptr;
 #pragma unroll 1
             for (int m = 0; m < rows; ++m, ++g) {
                 const int sl = g & (NACC - 1);
@@ -219,7 +241,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        float a = __uint_as_float(c < 32 ? v0[c + e] : v1[c - 32 + e]) + __ldg(p.bias + c + e);
+                        float a = __uint_as_float(c < 32 ? v0[c + e] : v1[c - 32 + e]) + (bias ? __ldg(bias + c + e) : 0.f);
                         f[e] = p.relu ? fmaxf(a, 0.f) : a;
                     }
                     uint4 uu;
@@ -233,7 +255,14 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
                 ptx::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (px0 < p.W) ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, y0 + m, b);
+                    if (px0 < p.W) {
+                        if (p.ps_r) {
+                            const int rr = p.ps_r;
+                            ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, chunk % rr, (b * p.H + y0 + m) * rr + chunk / rr);
+                        } else {
+                            ptx::tma_store_4d(&tmap_out, stg_w_sm + buf * 4096, 0, px0, y0 + m, b);
+                        }
+                    }
                     ptx::bulk_commit();
                 }
                 ++nstore;
@@ -255,9 +284,12 @@ int g_enable_stream = 1;
 
 void tc_set_conv_stream(int on) { g_enable_stream = on; }
 
-// plain 64 -> 64, stride 1 only; w = [9 taps][64 co][64 ci] bf16 (the same bank the tap-by-tap kernel uses)
-int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int relu, cudaStream_t st) {
-    if (!g_enable_stream || !bias) return TU_TC_UNSUPPORTED;
+// stride 1 only; w = [chunk][9 taps][64 co][64 ci] bf16 (the same banks the tap-by-tap kernel uses); nchunk > 1 needs ps_r
+// with ps_r * ps_r == nchunk: chunk c is written as sub-pixel phase (c / r, c % r) of a (B, H r, W r, 64) tensor
+int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int relu, int nchunk,
+                          int ps_r, cudaStream_t st) {
+    if (!g_enable_stream) return TU_TC_UNSUPPORTED;
+    if (nchunk > 1 && (ps_r == 0 || ps_r * ps_r != nchunk)) return TU_TC_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(w) & 127) || (reinterpret_cast<uintptr_t>(out) & 15))
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
@@ -279,14 +311,20 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
         cuuint32_t box[4] = {64, (cuuint32_t)BOXW, 1, 1}, estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        cuuint64_t wd[2] = {64, 9 * 64}, ws[1] = {128};
+        cuuint64_t wd[2] = {64, (cuuint64_t)nchunk * 9 * 64}, ws[1] = {128};
         cuuint32_t wb[2] = {64, 64}, we[2] = {1, 1};
         if (r == CUDA_SUCCESS)
             r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cuuint32_t ob[4] = {64, 32, 1, 1};
+        cuuint64_t od[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t os[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+        if (ps_r) {      // (c, px [stride r pixels], pj, (b*H + y)*r + pi): PixelShuffle addressing done by the TMA engine
+            od[1] = (cuuint64_t)W; od[2] = (cuuint64_t)ps_r; od[3] = (cuuint64_t)B * H * ps_r;
+            os[0] = (cuuint64_t)ps_r * 128; os[1] = 128; os[2] = (cuuint64_t)W * ps_r * 128;
+        }
         if (r == CUDA_SUCCESS)
-            r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, dims, strides, ob, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)out, od, os, ob, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("tu: cuTensorMapEncodeTiled(conv stream) failed with code " + std::to_string((int)r));
@@ -300,14 +338,16 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
     int bestR = H < 8 ? H : 8;
     double best = 1e30;
     for (int R = 8; R <= 64 && R <= (H > 8 ? H : 8); ++R) {
-        const long items = (long)p.tiles_x * ceil_div(H, R) * B;
+        const long items = (long)p.tiles_x * ceil_div(H, R) * B * nchunk;
         const long waves = (items + g_sm_count_s - 1) / g_sm_count_s;
         const double cost = (double)waves * (R + 2);       // steps executed by the busiest SM
         if (cost < best - 1e-9) { best = cost; bestR = R; }
     }
     p.R = bestR;
     p.chunks_y = ceil_div(H, p.R);
-    p.total_items = p.tiles_x * p.chunks_y * B;
+    p.items_per_chunk = p.tiles_x * p.chunks_y * B;
+    p.total_items = p.items_per_chunk * nchunk;
+    p.ps_r = ps_r;
     p.bias = bias;
     const int grid = p.total_items < g_sm_count_s ? p.total_items : g_sm_count_s;
     launch_pdl(conv3x3_stream_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);

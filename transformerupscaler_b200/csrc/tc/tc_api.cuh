@@ -42,7 +42,8 @@ int tc_conv3x3_c64_pair(const bf16 *in, const bf16 *w, const float *bias, bf16 *
 void tc_set_conv_2cta(int on);
 // the same convolution streaming down the image with the three ky taps stacked into N = 192 (conv3x3_stream_tcgen05.cu):
 // plain 64 -> 64, stride 1
-int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int relu, cudaStream_t st);
+int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int relu, int nchunk,
+                          int ps_r, cudaStream_t st);
 void tc_set_conv_stream(int on);
 
 // conv1 3 -> 64 + ReLU, NCHW (fp32|bf16) -> NHWC bf16 (stem_tcgen05.cu)
