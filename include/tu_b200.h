@@ -100,7 +100,7 @@ typedef struct TuModelWeights {
     const float *embed_b;
     const float *pos_embed;     /* fp32 (3600, dim) or NULL                                       */
     const TuBlockWeights *blocks; /* HOST pointer to n_blocks structs                             */
-    /* fused window-transformer stack (dim 128, bf16, tcgen05) or NULL: see packing.py / window_stack_tcgen05.cu */
+    /* fused window-transformer stack (bf16, tcgen05) or NULL: layouts per dim in packing.py / window_stack{,192}_tcgen05.cu */
     const void *stack_w;        /* bf16 (n_blocks*24*128, 64): weight slabs [128 n][64 k] in consumption order   */
     const float *stack_p;       /* fp32 n_blocks*1664 + 128: per block c0|ln1w|ln1b|qkvb|c1|ln2w|ln2b|fc1b, then c_final */
     const float *stack_rel;     /* fp32 (n_blocks, heads, 64, 64) dense relative-position bias            */
@@ -166,6 +166,9 @@ int tu_patch_unembed(const float *tokens, const void *w, const float *b, const v
 size_t tu_block_workspace_bytes(int M, int dim, int dtype);
 int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                          int dtype, void *workspace, size_t workspace_bytes, void *stream);
+/* all window-transformer blocks of a bf16 WindowTransformer / FastTransformer in one fused kernel, in place on the fp32
+ * window-ordered token stream (M, dim), M a multiple of 128 (`for block in self.window_blocks`, W:272-273, F:288-289) */
+int tu_window_stack(float *tokens, const TuModelWeights *w, int M, void *stream);
 /* window attention alone: softmax(q k^T + rel_bias) v per 8x8 window and head (head_dim 16) on qkv rows (nWin*64, 3*dim) with q
  * pre-scaled; rel_bias dense (heads,64,64) fp32; out (nWin*64, dim).  WindowTransformer/model.py:104-127 between qkv and proj. */
 int tu_window_attention(const void *qkv, const float *rel_bias, void *out, int nWin, int dim, int heads, int dtype, void *stream);

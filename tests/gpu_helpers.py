@@ -118,3 +118,9 @@ def window_attention(qkv, rel_bias, dim, heads):
     out = torch.empty(M, dim, dtype=qkv.dtype, device=qkv.device)
     chk(lib.tu_window_attention(p(qkv), p(rel_bias), p(out), M // 64, dim, heads, DT[qkv.dtype], stream()))
     return out
+
+
+def window_stack(tok, pw):
+    lib = _lib.load()
+    chk(lib.tu_window_stack(p(tok), C.byref(pw.struct), tok.shape[0], stream()))
+    return tok

@@ -187,6 +187,27 @@ def test_transformer_block(dev, dt, model):
     assert _maxerr(out, ref) < tol
 
 
+@pytest.mark.parametrize("model,nW", [("WindowTransformer", 6), ("FastTransformer", 6), ("FastTransformer", 2)])
+def test_fused_window_stack(dev, model, nW):
+    """All window blocks in one tcgen05 kernel (bf16 operands, fp32 residual stream in TMEM) vs the oracle's block loop with
+    bf16-rounded weights (WindowTransformer/model.py:272-273, FastTransformer/model.py:288-289)."""
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200.packing import PackedWeights
+    rs = np.random.RandomState(21)
+    sd = synth_state_dict(model, 5)
+    pw = PackedWeights(model, sd, BF16, dev)
+    dim, heads, nb = pw.dim, pw.heads, pw.n_blocks
+    x = torch.from_numpy(rs.standard_normal((nW, 64, dim)).astype(np.float32))
+    sdq = {k: (v.to(BF16).float() if (v.dim() == 2 and "table" not in k) else v) for k, v in sd.items()}
+    ref = x.clone()
+    for blk in range(nb):
+        ref = orc.window_block(ref, sdq, f"window_blocks.{blk}.", heads, F32)
+    out = G.window_stack(x.reshape(nW * 64, dim).to(dev).clone(), pw).reshape(nW, 64, dim)
+    err = _maxerr(out, ref)
+    assert err < 0.15, err          # 6-8 blocks of bf16 activations on an O(1..10) residual stream
+    assert (out.cpu() - ref).abs().mean().item() < 1.5e-2
+
+
 @pytest.mark.parametrize("dt", [F32, BF16])
 @pytest.mark.parametrize("dim,heads", [(128, 8), (192, 12)])
 def test_window_attention(dev, dt, dim, heads):

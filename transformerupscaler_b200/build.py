@@ -23,6 +23,7 @@ SOURCES = [
     "tc/gemm_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",
+    "tc/window_stack192_tcgen05.cu",
 ]
 
 NVCC_FLAGS = [

@@ -199,6 +199,8 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         rc = TU_TC_UNSUPPORTED;
         if (tc && window && dim == 128 && w->stack_w && g_use_stack)
             rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+        else if (tc && window && dim == 192 && w->stack_w && g_use_stack)
+            rc = tc_window_stack192(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
         if (rc != TU_TC_UNSUPPORTED && rc != TU_OK) return rc;
         const bool stack_done = rc == TU_OK;
         for (int i = 0; i < w->n_blocks && !stack_done; ++i)
@@ -356,6 +358,18 @@ extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, voi
     if (dtype == TU_BF16)
         return conv3x3_c64<bf16>((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
     TU_CHECK_ARG(false, "conv3x3_c64: bad dtype");
+}
+
+extern "C" int tu_window_stack(float *tokens, const TuModelWeights *w, int M, void *stream) {
+    TU_CHECK_ARG(tokens && w && M > 0 && M % 64 == 0, "window_stack: bad argument");
+    TU_CHECK_ARG(w->stack_w && w->stack_p && w->stack_rel, "window_stack: the model has no fused-stack weights (bf16 WindowTransformer / FastTransformer only)");
+    TU_CHECK_ARG(tc_enabled(), "window_stack: tcgen05 kernels are unavailable or switched off");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = TU_TC_UNSUPPORTED;
+    if (w->dim == 128) rc = tc_window_stack(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+    else if (w->dim == 192) rc = tc_window_stack192(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+    TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "window_stack: unsupported shape (token count must be a multiple of 128)");
+    return rc;
 }
 
 extern "C" int tu_patch_embed(const void *feat, int dtype, const void *w, const float *b, const float *pos_embed,

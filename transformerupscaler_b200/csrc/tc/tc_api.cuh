@@ -57,6 +57,10 @@ int tc_conv3x3_c64_to3(const bf16 *in, const bf16 *w16, const float *bias, float
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                     const float *rel_bias, cudaStream_t st);
 
+// the same for FastTransformer (dim 192, 12 heads; window_stack192_tcgen05.cu)
+int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
+                       const float *rel_bias, cudaStream_t st);
+
 // one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
 int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
                          void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st);

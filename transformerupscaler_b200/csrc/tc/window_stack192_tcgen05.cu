@@ -1,0 +1,503 @@
+// The whole window-transformer stack of FastTransformer (dim 192, 12 heads, hidden 768) in ONE persistent kernel.
+//
+// Reference: `for block in self.window_blocks: tokens_windows = block(tokens_windows)` (FastTransformer/model.py:288-289) over
+// WindowTransformerBlock (model.py:135-172) with WindowAttention (model.py:65-133).  Same idea as window_stack_tcgen05.cu
+// (dim 128): windows are never shifted, so a CTA takes 128 tokens (two windows) through all blocks on-chip.  With dim 192
+// neither the qkv activations (128 x 576) nor an MLP half fit beside the residual stream, so the block is cut finer:
+//
+//   TMEM columns [0,192)    X: fp32 residual stream (one lane per token); proj and fc2 accumulate straight onto it, their
+//                           biases folded into offset vectors added on read (c0 before LN1, c1 before LN2, c_final at the end)
+//   TMEM columns [192,384)  ACC: one qkv head-group (96 columns) or one MLP hidden quarter (192 columns) at a time
+//   smem A32  (48 KB)       LayerNorm output: three 128 x 64 swizzled K-slabs (A operand of qkv and fc1)
+//   smem AO   (48 KB)       attention output (A operand of proj); later aliased by HID = GELU(fc1 quarter) (A operand of fc2)
+//   smem STG  (27 KB)       q | k | v (32 + 32 + 32 columns, bf16) of the CURRENT group of two heads, 128 token rows
+//   smem ring (3 x 24 KB)   weight slabs streamed by TMA in consumption order (packing.py): per block 18 slabs [96 n x 64 k]
+//                           (qkv: 6 head-groups x 3 K-slabs, rows q|k|v of the group) then 27 slabs [192 n x 64 k]
+//                           (proj 3; fc1 quarter 0: 3; then per quarter p: fc2 p: 3, fc1 p+1: 3)
+// Head-group pipeline: the qkv MMAs of group g+1 run while the math warps do the attention of group g (one (window, head,
+// 16-row) task per warp: mma.sync QK^T, + dense bias, softmax, PV).
+// Roles: warps 0-15 math (thread = token row x column quarter), warp 16 TMA producer, warp 17 MMA issuer + TMEM allocation.
+#include <cuda.h>
+
+#include "ptx.cuh"
+#include "tc_api.cuh"
+
+namespace tu {
+
+namespace {
+
+constexpr int DIM = 192, HEADS = 12, HID = 768;
+constexpr int NGROUP = 6, NPASS = 4;
+constexpr int NMATH = 16;
+constexpr int NUM_THREADS = (NMATH + 2) * 32;     // 576
+constexpr int SLAB_A = 128 * 128;                 // activation K-slab: 128 rows x 64 bf16
+constexpr int SLAB_W = 192 * 128;                 // weight slab slot: up to 192 rows x 64 bf16
+constexpr int NRING = 3;
+constexpr int STG_PITCH = 96 * 2 + 16;            // 208 B per token row (conflict-free fragment loads)
+constexpr int OFF_A32 = 0;
+constexpr int OFF_AO = 3 * SLAB_A;                // 49152
+constexpr int OFF_STG = OFF_AO + 3 * SLAB_A;      // 98304
+constexpr int STG_BYTES = 27 * 1024;              // >= 128 * 208 = 26624
+constexpr int OFF_RING = OFF_STG + STG_BYTES;     // 125952 = 123 * 1024
+constexpr int OFF_PAR = OFF_RING + NRING * SLAB_W;
+constexpr int PAR_FLOATS = 2496;                  // c0 | ln1w | ln1b | qkvb(576, group-major) | c1 | ln2w | ln2b | fc1b(768)
+constexpr int P_C0 = 0, P_LN1W = 192, P_LN1B = 384, P_QKVB = 576, P_C1 = 1152, P_LN2W = 1344, P_LN2B = 1536, P_FC1B = 1728;
+constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
+constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4 * 8;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SLABS96 = NGROUP * 3, SLABS192 = 3 + NPASS * 6;       // 18 + 27 per block
+constexpr int ROWS_PER_BLOCK = SLABS96 * 96 + SLABS192 * 192;       // 6912 rows of 64 bf16
+
+enum { ACC_QKV0 = 0, ACC_PROJ = NGROUP, ACC_FC1_0, ACC_FC2L = ACC_FC1_0 + NPASS, NACC };
+
+struct Stack192Params {
+    float *tok;            // (M, 192) fp32 token stream, window-ordered; updated in place
+    bf16 *tok16;           // optional bf16 copy of the result
+    const float *par;      // nblocks * PAR_FLOATS + 192 (final offset vector)
+    const float *rel_bias; // nblocks x (12, 64, 64) fp32 dense relative-position bias
+    int n_tiles, n_blocks;
+};
+
+struct Barriers {
+    uint64_t full[NRING], empty[NRING];
+    uint64_t a_ready;
+    uint64_t acc[NACC];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Barriers) <= 256, "barrier block too large");
+
+__device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+// same fitted GELU as window_stack_tcgen05.cu (tools/fit_gelu.py)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float x2 = fminf(x * x, 64.f);
+    float q = fmaf(-0.0003515167826820022f, x2, 0.03700564597780192f);
+    q = fmaf(q, x2, 0.7975078843613885f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * q));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 48 consecutive TMEM columns of this thread's lane -> registers (32 + 16)
+__device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t (&v)[48]) {
+    uint32_t a[32], b[16];
+    ptx::tmem_ld_x32(taddr, a);
+    ptx::tmem_ld_x16(taddr + 32, b);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = a[j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[32 + j] = b[j];
+}
+
+// byte offset of the 16-byte chunk holding columns [col, col+8) of row i inside a stack of swizzled 128 x 64 K-slabs
+__device__ __forceinline__ int slab_chunk_off(int col, int i) { return (col >> 6) * SLAB_A + i * 128 + ((((col & 63) >> 3) ^ (i & 7)) << 4); }
+
+// LayerNorm of this thread's 48 columns of row i (x already includes the folded offset) -> A32, swizzled
+__device__ __forceinline__ void layernorm_to_a32(float (&x)[48], const float *gam, const float *bet, float2 *stat, uint8_t *a32, int i,
+                                                 int part) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 48; ++j) { s += x[j]; ss = fmaf(x[j], x[j], ss); }
+    stat[i * 4 + part] = make_float2(s, ss);
+    math_barrier();
+    const float4 p01 = *reinterpret_cast<const float4 *>(stat + i * 4), p23 = *reinterpret_cast<const float4 *>(stat + i * 4 + 2);
+    const float mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.0f / DIM);
+    const float ex2 = ((p01.y + p01.w) + (p23.y + p23.w)) * (1.0f / DIM);
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int ch = 0; ch < 6; ++ch) {
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (x[ch * 8 + e] - mean) * rstd * gam[ch * 8 + e] + bet[ch * 8 + e];
+        uint4 u;
+        u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+        *reinterpret_cast<uint4 *>(a32 + slab_chunk_off(part * 48 + ch * 8, i)) = u;
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __grid_constant__ CUtensorMap tmap_w192,
+                       const Stack192Params p) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *sm = smem_raw + (smem0 - ptx::smem_u32(smem_raw));
+    Barriers *bars = reinterpret_cast<Barriers *>(sm + OFF_BAR);
+    float *par = reinterpret_cast<float *>(sm + OFF_PAR);
+    float2 *stat = reinterpret_cast<float2 *>(sm + OFF_STAT);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NRING; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+        }
+        ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH);
+        for (int i = 0; i < NACC; ++i) ptx::mbar_init(ptx::smem_u32(&bars->acc[i]), 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == NMATH + 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), 512);
+        ptx::tmem_relinquish();
+    }
+    if (warp == NMATH && lane == 0) {
+        ptx::prefetch_tmap(&tmap_w96);
+        ptx::prefetch_tmap(&tmap_w192);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t TX = tmem_base, TACC = tmem_base + DIM;
+    pdl_wait();
+
+    if (warp == NMATH) {
+        if (lane == 0) {
+            // ================================ TMA producer: weight slabs in consumption order ================================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+                for (int bk = 0; bk < p.n_blocks; ++bk) {
+                    int row = bk * ROWS_PER_BLOCK;
+                    for (int s = 0; s < SLABS96 + SLABS192; ++s) {
+                        const bool small = s < SLABS96;
+                        ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
+                        const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
+                        ptx::mbar_expect_tx(fb, (small ? 96 : 192) * 128);
+                        ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB_W, small ? &tmap_w96 : &tmap_w192, fb, 0, row);
+                        row += small ? 96 : 192;
+                        if (++stage == NRING) { stage = 0; phase ^= 1; }
+                    }
+                }
+        }
+    } else if (warp == NMATH + 1) {
+        // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
+        const uint32_t leader = ptx::elect_one();
+        const uint32_t id96 = ptx::make_idesc_bf16(128, 96), id192 = ptx::make_idesc_bf16(128, 192);
+        const uint32_t ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
+        int stage = 0;
+        uint32_t phase = 0, aph = 0;
+        // one weight slab: D[128 x N] (+)= A_slab[128 x 64] * W_slab[N x 64]^T
+        auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, bool first_clears) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+            ptx::tc_fence_after();
+            const uint32_t w_lo = ring_lo + ((stage * SLAB_W) >> 4);
+            ptx::umma_bf16_lo_rt(d_tmem, a_lo, w_lo, idesc, first_clears ? 0u : 1u, leader);
+#pragma unroll
+            for (int k4 = 1; k4 < 4; ++k4) ptx::umma_bf16_lo<1>(d_tmem, a_lo + k4 * 2, w_lo + k4 * 2, idesc, leader);
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
+            if (++stage == NRING) { stage = 0; phase ^= 1; }
+        };
+        auto wait_a = [&]() {
+            ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), aph);
+            aph ^= 1;
+            ptx::tc_fence_after();
+        };
+        auto commit = [&](int which) { ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[which]), leader); };
+        const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32), ao = ptx::sdesc_lo(smem0 + OFF_AO);
+        constexpr uint32_t SL = SLAB_A >> 4;
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
+            for (int bk = 0; bk < p.n_blocks; ++bk) {
+                for (int g = 0; g < NGROUP; ++g) {
+                    wait_a();                                   // g = 0: LN1 output in A32; g > 0: ACC drained by the previous group
+                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id96, ks == 0);
+                    commit(ACC_QKV0 + g);
+                }
+                wait_a();                                       // attention output of all heads in AO
+                for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, false);          // x += att Wp^T
+                commit(ACC_PROJ);
+                wait_a();                                       // LN2 output in A32
+                for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id192, ks == 0);     // fc1, quarter 0
+                commit(ACC_FC1_0);
+                for (int q4 = 0; q4 < NPASS; ++q4) {
+                    wait_a();                                   // GELU(quarter q4) in HID (= AO region), ACC drained
+                    for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, false);      // x += h W2[:, quarter]^T
+                    if (q4 + 1 < NPASS) {
+                        for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id192, ks == 0);
+                        commit(ACC_FC1_0 + q4 + 1);
+                    } else {
+                        commit(ACC_FC2L);
+                    }
+                }
+            }
+    } else {
+        // ================================ math warps ================================
+        const int q = warp & 3, part = warp >> 2;           // TMEM lane quadrant, column quarter (48 columns)
+        const int i = q * 32 + lane;                        // token row of the tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int mt = threadIdx.x;                          // 0..511
+        uint8_t *a32 = sm + OFF_A32, *aout = sm + OFF_AO, *stg = sm + OFF_STG;
+        uint32_t cph = 0;             // every acc barrier completes exactly once per block: one shared phase bit
+        auto wait_acc = [&](int which) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->acc[which]), cph);
+            ptx::tc_fence_after();
+        };
+        auto signal_a = [&]() {       // every thread orders its own writes, one lane per warp arrives
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
+        };
+        auto load_x = [&](float (&x)[48], const float *cvec) {
+            uint32_t v[48];
+            tmem_ld48(TX + lane_base + part * 48, v);
+#pragma unroll
+            for (int j = 0; j < 48; ++j) x[j] = __uint_as_float(v[j]) + cvec[part * 48 + j];
+        };
+
+        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            // ---- tokens -> TMEM X
+            {
+                const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 48;
+                uint32_t v[32], w[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 f = *reinterpret_cast<const float4 *>(src + j);
+                    v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 f = *reinterpret_cast<const float4 *>(src + 32 + j);
+                    w[j] = __float_as_uint(f.x); w[j + 1] = __float_as_uint(f.y); w[j + 2] = __float_as_uint(f.z); w[j + 3] = __float_as_uint(f.w);
+                }
+                ptx::tmem_st_x32(TX + lane_base + part * 48, v);
+                ptx::tmem_st_x16(TX + lane_base + part * 48 + 32, w);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+            }
+            for (int bk = 0; bk < p.n_blocks; ++bk) {
+                // ---- per-block parameters -> smem
+                math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
+                ptx::tc_fence_after();
+                {
+                    const float4 *g4 = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
+                    float4 *d = reinterpret_cast<float4 *>(par);
+                    for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g4[e];
+                }
+                math_barrier();
+                // ---- LN1(x + c0) -> A32
+                {
+                    float x[48];
+                    load_x(x, par + P_C0);
+                    layernorm_to_a32(x, par + P_LN1W + part * 48, par + P_LN1B + part * 48, stat, a32, i, part);
+                }
+                signal_a();
+                // ---- six groups of two heads: qkv epilogue of group g, then its attention while the MMAs of g+1 run
+                const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
+#pragma unroll 1
+                for (int g = 0; g < NGROUP; ++g) {
+                    wait_acc(ACC_QKV0 + g);
+                    if (g > 0) math_barrier();            // every warp is done reading the previous group's q, k, v
+                    if (part < 3) {                       // 96 columns: q | k | v of the group, 32 columns per part
+                        uint32_t v[32];
+                        ptx::tmem_ld_x32(TACC + lane_base + part * 32, v);
+                        ptx::tmem_ld_wait();
+                        const float *bb = par + P_QKVB + g * 96 + part * 32;
+                        uint8_t *rowp = stg + i * STG_PITCH + part * 64;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 u;
+                            u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
+                            u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
+                            u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
+                            u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
+                            *reinterpret_cast<uint4 *>(rowp + j * 2) = u;
+                        }
+                    }
+                    if (g + 1 < NGROUP) signal_a();       // ACC is drained: the MMAs of the next group may run
+                    math_barrier();                       // q, k, v of the group are staged
+                    // ---- attention: 2 windows x 2 heads x 4 row groups = 16 warp tasks, one per warp
+                    {
+                        const int gq = lane >> 2, tq = lane & 3;
+                        const int win = warp >> 3, hl = (warp >> 2) & 1, rg = warp & 3;
+                        const int h = g * 2 + hl;
+                        const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
+                        const int r0 = rg * 16 + gq;
+                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+                        float2 ba[8], bb2[8];
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
+                            bb2[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                        }
+                        uint32_t qa[4];
+                        qa[0] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (hl * 16 + tq * 2) * 2);
+                        qa[1] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (hl * 16 + tq * 2) * 2);
+                        qa[2] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (hl * 16 + tq * 2 + 8) * 2);
+                        qa[3] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (hl * 16 + tq * 2 + 8) * 2);
+                        float s[8][4];
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            const uint8_t *kp = wbase + (n * 8 + gq) * STG_PITCH + (32 + hl * 16 + tq * 2) * 2;
+                            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kp), b1 = *reinterpret_cast<const uint32_t *>(kp + 16);
+                            s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+                            mma16816(s[n], qa, b0, b1);
+                        }
+                        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            s[n][0] += ba[n].x; s[n][1] += ba[n].y; s[n][2] += bb2[n].x; s[n][3] += bb2[n].y;
+                            m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
+                            m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
+                        }
+                        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+                        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+                        float l0 = 0.f, l1 = 0.f;
+                        const float L2E = 1.4426950408889634f;
+                        const float mm0 = m0 * L2E, mm1 = m1 * L2E;
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            s[n][0] = exp2f(fmaf(s[n][0], L2E, -mm0)); s[n][1] = exp2f(fmaf(s[n][1], L2E, -mm0));
+                            s[n][2] = exp2f(fmaf(s[n][2], L2E, -mm1)); s[n][3] = exp2f(fmaf(s[n][3], L2E, -mm1));
+                            l0 += s[n][0] + s[n][1];
+                            l1 += s[n][2] + s[n][3];
+                        }
+                        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+                        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+                        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                        for (int kt = 0; kt < 4; ++kt) {
+                            uint32_t pa[4];
+                            pa[0] = pk(s[2 * kt][0], s[2 * kt][1]);
+                            pa[1] = pk(s[2 * kt][2], s[2 * kt][3]);
+                            pa[2] = pk(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+                            pa[3] = pk(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+                            uint32_t v0, v1, v2, v3;
+                            const uint32_t addr = ptx::smem_u32(wbase + (kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STG_PITCH +
+                                                                (64 + hl * 16 + (lane >> 4) * 8) * 2);
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                                         : "r"(addr));
+                            mma16816(o[0], pa, v0, v1);
+                            mma16816(o[1], pa, v2, v3);
+                        }
+                        const float i0 = 1.f / l0, i1 = 1.f / l1;
+                        // attention output -> AO (row = token of the tile, column = h*16 + d), swizzled K-slabs
+                        const int row0 = win * 64 + r0, row1 = row0 + 8;
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt) {
+                            const int col = h * 16 + nt * 8 + tq * 2;
+                            const int bo = (col & 7) * 2;
+                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row0) + bo) = pk(o[nt][0] * i0, o[nt][1] * i0);
+                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row1) + bo) = pk(o[nt][2] * i1, o[nt][3] * i1);
+                        }
+                    }
+                }
+                signal_a();                               // attention output of all 12 heads is in AO
+                // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
+                wait_acc(ACC_PROJ);
+                {
+                    float x[48];
+                    load_x(x, par + P_C1);
+                    layernorm_to_a32(x, par + P_LN2W + part * 48, par + P_LN2B + part * 48, stat + 128 * 4, a32, i, part);
+                }
+                signal_a();
+                // ---- MLP: four quarters of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs (AO region)
+#pragma unroll 1
+                for (int q4 = 0; q4 < NPASS; ++q4) {
+                    wait_acc(ACC_FC1_0 + q4);
+                    uint32_t v[48];
+                    tmem_ld48(TACC + lane_base + part * 48, v);
+                    const float *bb = par + P_FC1B + q4 * 192 + part * 48;
+#pragma unroll
+                    for (int j = 0; j < 48; j += 8) {
+                        float y[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) y[e] = gelu_fast(__uint_as_float(v[j + e]) + bb[j + e]);
+                        uint4 u;
+                        u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+                        *reinterpret_cast<uint4 *>(aout + slab_chunk_off(part * 48 + j, i)) = u;
+                    }
+                    signal_a();
+                }
+                wait_acc(ACC_FC2L);      // fc2 of the last quarter accumulated: X holds the block output (minus folded biases)
+                cph ^= 1;
+            }
+            // ---- X (+ final offset) -> global
+            {
+                const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS + part * 48;
+                float *dst = p.tok + ((long)t * 128 + i) * DIM + part * 48;
+                bf16 *dst16 = p.tok16 ? p.tok16 + ((long)t * 128 + i) * DIM + part * 48 : nullptr;
+                uint32_t v[48];
+                tmem_ld48(TX + lane_base + part * 48, v);
+#pragma unroll
+                for (int j = 0; j < 48; j += 4) {
+                    float4 f;
+                    f.x = __uint_as_float(v[j]) + __ldg(cfin + j);
+                    f.y = __uint_as_float(v[j + 1]) + __ldg(cfin + j + 1);
+                    f.z = __uint_as_float(v[j + 2]) + __ldg(cfin + j + 2);
+                    f.w = __uint_as_float(v[j + 3]) + __ldg(cfin + j + 3);
+                    *reinterpret_cast<float4 *>(dst + j) = f;
+                    if (dst16) {
+                        uint2 u;
+                        u.x = pk(f.x, f.y); u.y = pk(f.z, f.w);
+                        *reinterpret_cast<uint2 *>(dst16 + j) = u;
+                    }
+                }
+                ptx::tc_fence_before();
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == NMATH + 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+int g_sm_count = 0;
+bool g_attr_set = false;
+
+}  // namespace
+
+// stack_w: bf16 (n_blocks * 6912, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*2496 + 192;
+// rel_bias: fp32 n_blocks x (12,64,64).  tok: (M,192) fp32 with M % 128 == 0.
+int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
+                       const float *rel_bias, cudaStream_t st) {
+    TcEncodeFn enc = tc_encode_fn();
+    if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
+        (reinterpret_cast<uintptr_t>(tok) & 15))
+        return TU_TC_UNSUPPORTED;
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (!g_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(window_stack192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_fail(e, "window_stack192 smem attribute");
+        g_attr_set = true;
+    }
+    CUtensorMap t96, t192;
+    cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * ROWS_PER_BLOCK}, ws[1] = {128};
+    cuuint32_t b96[2] = {64, 96}, b192[2] = {64, 192}, we[2] = {1, 1};
+    CUresult r = enc(&t96, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, b96, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = enc(&t192, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, b192, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tu: cuTensorMapEncodeTiled(window stack 192 weights) failed with code " + std::to_string((int)r));
+        return TU_ERR_CUDA;
+    }
+    Stack192Params p;
+    p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
+    p.n_tiles = M / 128; p.n_blocks = n_blocks;
+    const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
+    launch_pdl(window_stack192_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, t96, t192, p);
+    TU_CHECK_LAUNCH("window_stack192");
+    return TU_OK;
+}
+
+}  // namespace tu

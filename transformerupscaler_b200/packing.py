@@ -112,6 +112,8 @@ class PackedWeights:
         mw.blocks = C.cast(self.blocks, C.POINTER(_lib.TuBlockWeights))
         if dtype == torch.bfloat16 and not resid and dim == 128:
             self._pack_fused_stack(sd, mw, nb, dim, bprefix, dev, ptr)
+        if dtype == torch.bfloat16 and not resid and dim == 192:
+            self._pack_fused_stack192(sd, mw, nb, bprefix, dev, ptr)
 
         if fast:
             for slot, s in enumerate(SCALES):
@@ -135,6 +137,56 @@ class PackedWeights:
             mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
         self.struct = mw
         self.dim, self.heads, self.n_blocks = dim, heads, nb
+
+    def _pack_fused_stack192(self, sd, mw, nb, bprefix, dev, ptr):
+        """Weights / parameters of all blocks in the order window_stack192_tcgen05.cu consumes them (dim 192, 12 heads).
+
+        Per block 18 slabs [96 n x 64 k]: for each group g of two heads and each K-slab, the rows q | k | v (32 each) of the
+        group (q pre-scaled); then 27 slabs [192 n x 64 k]: proj (3), fc1 rows of hidden quarter 0 (3), then per quarter p:
+        fc2 columns of quarter p (3) and fc1 rows of quarter p+1 (3, p < 3).  Parameters per block: c0 | ln1 w,b | qkv bias in
+        the same group-major order | c1 | ln2 w,b | fc1 bias; proj / fc2 biases folded into the offsets c0, c1, c_final.
+        """
+        f32 = torch.float32
+        dim = 192
+        slabs, pars, rels = [], [], []
+        c = torch.zeros(dim, dtype=torch.float64)
+        for i in range(nb):
+            p = f"{bprefix}{i}."
+            qw, qb = sd[p + "attn.qkv.weight"].float().cpu().clone(), sd[p + "attn.qkv.bias"].float().cpu().clone()
+            qw[:dim] *= 0.25
+            qb[:dim] *= 0.25
+            pw, pb = sd[p + "attn.proj.weight"].float().cpu(), sd[p + "attn.proj.bias"].float().cpu()
+            w1, b1 = sd[p + "mlp.0.weight"].float().cpu(), sd[p + "mlp.0.bias"].float().cpu()
+            w2, b2 = sd[p + "mlp.2.weight"].float().cpu(), sd[p + "mlp.2.bias"].float().cpu()
+            qb_g = []
+            for g in range(6):
+                rows = torch.cat([torch.arange(s * dim + g * 32, s * dim + g * 32 + 32) for s in range(3)])   # q | k | v of the group
+                for ks in range(3):
+                    slabs.append(qw[rows, ks * 64:(ks + 1) * 64])
+                qb_g.append(qb[rows])
+            for ks in range(3):
+                slabs.append(pw[:, ks * 64:(ks + 1) * 64])
+            for ks in range(3):
+                slabs.append(w1[0:192, ks * 64:(ks + 1) * 64])
+            for q4 in range(4):
+                for ks in range(3):
+                    slabs.append(w2[:, q4 * 192 + ks * 64: q4 * 192 + (ks + 1) * 64])
+                if q4 < 3:
+                    for ks in range(3):
+                        slabs.append(w1[(q4 + 1) * 192:(q4 + 2) * 192, ks * 64:(ks + 1) * 64])
+            c0 = c.clone()
+            c1 = c0 + pb.double()
+            c = c1 + b2.double()
+            pars += [c0.float(), sd[p + "norm1.weight"].float().cpu(), sd[p + "norm1.bias"].float().cpu(), torch.cat(qb_g),
+                     c1.float(), sd[p + "norm2.weight"].float().cpu(), sd[p + "norm2.bias"].float().cpu(), b1]
+            rels.append(dense_rel_bias_t(sd[p + "attn.relative_position_bias_table"].cpu(),
+                                         sd[p + "attn.relative_position_index"].cpu()))
+        pars.append(c.float())
+        flat = torch.cat([t.reshape(-1, 64) for t in slabs])
+        assert flat.shape[0] == 6912 * nb
+        mw.stack_w = ptr(dev(flat, torch.bfloat16))
+        mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
+        mw.stack_rel = ptr(dev(torch.stack(rels), f32))
 
     @staticmethod
     def _slabs(w: torch.Tensor, n_chunks: int, k_slabs: int):
