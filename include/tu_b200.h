@@ -60,7 +60,8 @@ int tu_profile_collect(const char *name, double *total_ms, int *launches);
 int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
- * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on) */
+ * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
+ * "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------
@@ -85,6 +86,17 @@ typedef struct TuUpsamplerStage {
     const float *b;     /* same out-channel order as w's last dim(s)                              */
     int r;              /* PixelShuffle factor of this stage                                      */
 } TuUpsamplerStage;
+
+/* the last up1 stage (Conv2d 64 -> 64 r^2 + PixelShuffle(r)) folded with up1_conv (Conv2d 64 -> 3, no bias) into one
+ * 5x5 convolution 64 -> 3 r^2 (packing.py::fold_up1; tc/upfold_stream_tcgen05.cu).  bf16 tensor-core path only. */
+typedef struct TuUpFold {
+    const void *w;          /* bf16 (nchunk, 5 kx, 5 ky-blocks holding ky = 4..0, NO rows, 64 ci); row n of a chunk =      */
+                            /*   ((c*r + i) - chunk*RPC)*r + j; (NO, RPC, nchunk) = (16,6,1) r=2, (32,9,1) r=3, (32,5,4) r=6 */
+    const float *b;         /* fp32 (nchunk*NO), zero in unused rows                                                        */
+    const float *ring_w;    /* fp32 (9 border cases vy*3+vx, 3r^2 outputs o=(c*r+i)*r+j, 25 taps dy*5+dx, 64 ci)             */
+    const float *ring_b;    /* fp32 (9, 3r^2)                                                                               */
+    int r;                  /* PixelShuffle factor of the folded stage; 0 = not packed                                       */
+} TuUpFold;
 
 typedef struct TuModelWeights {
     int model;                  /* TU_MODEL_*                                                     */
@@ -118,6 +130,9 @@ typedef struct TuModelWeights {
     const void *up1conv_w16;    /* bf16 (3, 16, 64), same layout, or NULL                          */
     const float *finconv_w;     /* fp32 (27, 3)                                                   */
     const float *finconv_b;     /* (3)                                                            */
+    TuUpFold upfold[4];         /* per scale slot: folded last up1 stage + up1_conv (r = 0: absent)   */
+    const float *host_finconv_wb; /* HOST pointer: the 81 finconv_w values then the 3 finconv_b values (they ride in the  */
+                                /* parameters of the fused tail kernel, tu_subpixel_conv_add), or NULL                  */
 } TuModelWeights;
 
 /* ---- whole-model forward (what TransformerModel.forward calls) --------------------------------
@@ -152,6 +167,15 @@ int tu_conv3x3_c3_ps(const float *in, const float *w, const float *b, float *out
 /* out = clamp?(conv3x3_3to3(in) + addend) -> NCHW image of out_dtype */
 int tu_final_conv_add(const float *in, const float *w, const float *b, const float *addend, void *out,
                       int out_dtype, int B, int H, int W, int clamp, void *stream);
+/* relu(up1_conv(PixelShuffle_r(up1_stage(in)))) through the folded 5x5 filter: NHWC bf16 (B,H,W,64) -> planar fp32
+ * (B,3,rH,rW).  FastTransformer/model.py:264-265.  Needs the tcgen05 path and (W*r) % 4 == 0. */
+int tu_upfold_conv(const void *in, const TuUpFold *f, float *out, int B, int H, int W, void *stream);
+/* the last sub-pixel stage of final_upscale, final_upscale_conv, the sum with the other branch and the clamp in one kernel:
+ * out = clamp?(conv3x3_3to3(PixelShuffle_r(conv3x3_3to3r^2(in))) + addend); in (B,3,H,W) and addend (B,3,rH,rW) planar fp32,
+ * w_ps fp32 (27, 3r^2), b_ps (3r^2), r in {2,3,6}; host_fin_wb is a HOST pointer to the 3->3 filter, (27,3) then bias (3).
+ * FastTransformer/model.py:316-327. */
+int tu_subpixel_conv_add(const float *in, const float *w_ps, const float *b_ps, int r, const float *host_fin_wb,
+                         const float *addend, void *out, int out_dtype, int B, int H, int W, int clamp, void *stream);
 /* patch embed (Conv2d k8 s8) as GEMM; reflect-pads feat to x8 when reflect != 0; writes fp32 tokens
  * window-ordered into zero-initialised (B*nWy*nWx*64, dim) (window != 0) or row-major + pos_embed. */
 int tu_patch_embed(const void *feat, int dtype, const void *w, const float *b, const float *pos_embed,

@@ -64,6 +64,35 @@ def final_conv_add(x, w, b, addend, out_dtype, clamp):
     return out
 
 
+def upfold_conv(x, w1, b1, w2, r):
+    """x NHWC bf16 on the GPU; folds (w1, b1, w2) on the host like packing.PackedWeights does"""
+    from transformerupscaler_b200.packing import fold_up1, pack_fold_bank
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    Wf, bf = fold_up1(w1, b1, w2, r)
+    bank, bias = pack_fold_bank(Wf, bf, r)
+    keep = [bank.to(x.device, torch.bfloat16).contiguous(), bias.to(x.device, torch.float32).contiguous(),
+            Wf.permute(0, 1, 2, 4, 5, 3).reshape(9, 3 * r * r, 25, 64).to(x.device, torch.float32).contiguous(),
+            bf.reshape(9, 3 * r * r).to(x.device, torch.float32).contiguous()]
+    f = _lib.TuUpFold()
+    f.w, f.b, f.ring_w, f.ring_b, f.r = p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), r
+    out = torch.empty(B, 3, H * r, W * r, dtype=torch.float32, device=x.device)
+    chk(lib.tu_upfold_conv(p(x), C.byref(f), p(out), B, H, W, stream()))
+    torch.cuda.synchronize()
+    return out, Wf, bf
+
+
+def subpixel_conv_add(x, w_ps, b_ps, r, fin_wb_host, addend, out_dtype, clamp):
+    """fin_wb_host: CPU float tensor of 84 values ((27,3) filter then bias) -- a HOST pointer in the C ABI"""
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    out = torch.empty(B, 3, H * r, W * r, dtype=out_dtype, device=x.device)
+    host = (C.c_float * 84)(*fin_wb_host.reshape(-1).tolist())
+    chk(lib.tu_subpixel_conv_add(p(x), p(w_ps), p(b_ps), r, C.cast(host, C.c_void_p), p(addend), p(out), DT[out_dtype], B, H, W,
+                                 int(clamp), stream()))
+    return out
+
+
 def patch_embed(feat, w, b, pos, Ht, Wt, dim, window, reflect):
     lib = _lib.load()
     B, H, W, _ = feat.shape

@@ -127,6 +127,64 @@ def test_conv3_ps_and_final(dev, r):
     assert _maxerr(out2, ref2) < TOL32
 
 
+@pytest.mark.parametrize("r", [2, 3, 6])
+@pytest.mark.parametrize("shape", [(1, 13, 20), (2, 40, 300), (1, 3, 132), (1, 1, 4)])
+def test_upfold_conv(dev, r, shape):
+    """folded up1 stage + PixelShuffle + up1_conv + ReLU (tensor cores) vs the op chain of the oracle,
+    FastTransformer/utils.py:43-98, 13-40; model.py:264-265"""
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(30 + r)
+    B, H, W = shape
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)).to(BF16)
+    w1 = torch.from_numpy(rs.uniform(-0.05, 0.05, (64 * r * r, 64, 3, 3)).astype(np.float32))
+    b1 = torch.from_numpy(rs.uniform(-0.1, 0.1, 64 * r * r).astype(np.float32))
+    w2 = torch.from_numpy(rs.uniform(-0.1, 0.1, (3, 64, 3, 3)).astype(np.float32))
+    out, Wf, bf = G.upfold_conv(x.to(dev), w1, b1, w2, r)
+    # (a) the reference op chain in fp32 on the same bf16 input: differs by the bf16 rounding of the folded filter only
+    ref = orc.conv3x3_nhwc(orc.pixel_shuffle_nhwc(orc.conv3x3_nhwc(x.float(), w1, b1), r), w2, None, relu=True).permute(0, 3, 1, 2)
+    assert out.shape == ref.shape
+    assert _maxerr(out, ref) < 2e-2
+    # (b) the same 5x5 convolution with the bf16-rounded folded filter, fp64 accumulation: tight
+    Wi = Wf[1, 1].to(BF16).double()                                   # (o, ci, dy, dx)
+    xp = torch.zeros(B, H + 4, W + 4, 64, dtype=torch.float64)
+    xp[:, 2:H + 2, 2:W + 2] = x.double()
+    acc = torch.zeros(B, H, W, 3 * r * r, dtype=torch.float64)
+    for dy in range(5):
+        for dx in range(5):
+            acc += xp[:, dy:dy + H, dx:dx + W].reshape(-1, 64).matmul(Wi[:, :, dy, dx].t()).reshape(B, H, W, -1)
+    acc = (acc + bf[1, 1]).clamp(min=0).reshape(B, H, W, 3, r, r).permute(0, 3, 1, 4, 2, 5).reshape(B, 3, H * r, W * r)
+    inner = (out.double().cpu() - acc)[:, :, 1:-1, 1:-1]
+    assert inner.abs().max().item() < 2e-4 if inner.numel() else True
+    # (c) the border ring is computed with the fp32 border filters: close to the exact chain
+    ring = (out.cpu() - ref).clone()
+    ring[:, :, 1:-1, 1:-1] = 0
+    assert ring.abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("r", [2, 3, 6])
+@pytest.mark.parametrize("shape", [(2, 11, 70), (1, 31, 29), (1, 1, 1), (1, 40, 61)])
+def test_subpixel_conv_add_fused(dev, r, shape):
+    """fused tail (sub-pixel conv + PixelShuffle + 3->3 conv + sum + clamp) vs the op-by-op restatement, FastTransformer/model.py:316-327"""
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(18)
+    B, H, W = shape
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, 3, H, W)).astype(np.float32))
+    w = torch.from_numpy(rs.uniform(-0.2, 0.2, (3 * r * r, 3, 3, 3)).astype(np.float32))
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 3 * r * r).astype(np.float32))
+    w2 = torch.from_numpy(rs.uniform(-0.2, 0.2, (3, 3, 3, 3)).astype(np.float32))
+    b2 = torch.from_numpy(rs.uniform(-0.1, 0.1, 3).astype(np.float32))
+    add = torch.from_numpy(rs.uniform(0, 1, (B, 3, H * r, W * r)).astype(np.float32))
+    mid = orc.pixel_shuffle_nhwc(orc.conv3x3_nhwc(x.permute(0, 2, 3, 1).contiguous(), w, b), r)
+    pre = orc.conv3x3_nhwc(mid, w2, b2).permute(0, 3, 1, 2) + add
+    wp = w.permute(2, 3, 1, 0).reshape(27, 3 * r * r).contiguous().to(dev)
+    fin = torch.cat([w2.permute(2, 3, 1, 0).reshape(-1), b2])
+    for clamp in (False, True):
+        out = G.subpixel_conv_add(x.to(dev), wp, b.to(dev), r, fin, add.to(dev), F32, clamp)
+        assert _maxerr(out, pre.clamp(0, 1) if clamp else pre) < TOL32
+    out16 = G.subpixel_conv_add(x.to(dev), wp, b.to(dev), r, fin, add.to(dev), BF16, True)
+    assert _maxerr(out16, pre.clamp(0, 1)) < 4e-3
+
+
 @pytest.mark.parametrize("dt", [F32, BF16])
 @pytest.mark.parametrize("model,Hf,Wf", [("WindowTransformer", 36, 52), ("FastTransformer", 36, 52), ("FastTransformer", 64, 80)])
 def test_patch_embed_unembed(dev, dt, model, Hf, Wf):

@@ -118,3 +118,43 @@ def test_two_rank_gloo_sharding_and_timing():
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True]       # every rank reassembles the 1-GPU batch order
     assert [r[2] for r in res] == [11.0, 11.0]       # max over ranks
+
+
+@pytest.mark.parametrize("r", [2, 3, 6])
+def test_fold_up1_matches_the_op_chain(r):
+    """packing.fold_up1: the folded 5x5 filter (with its border cases) reproduces conv -> PixelShuffle -> conv (fp64),
+    FastTransformer/utils.py:43-98 + model.py:264-265"""
+    import numpy as np
+    from oracle import upscaler_oracle as orc
+    from transformerupscaler_b200.packing import fold_up1, pack_fold_bank, FOLD_CFG
+    rs = np.random.RandomState(40 + r)
+    H, W = 5, 7
+    x = torch.from_numpy(rs.uniform(-1, 1, (1, H, W, 64)))
+    w1 = torch.from_numpy(rs.uniform(-0.1, 0.1, (64 * r * r, 64, 3, 3)))
+    b1 = torch.from_numpy(rs.uniform(-0.1, 0.1, 64 * r * r))
+    w2 = torch.from_numpy(rs.uniform(-0.1, 0.1, (3, 64, 3, 3)))
+    ref = orc.conv3x3_nhwc(orc.pixel_shuffle_nhwc(orc.conv3x3_nhwc(x, w1, b1), r), w2, None)[0]      # (rH, rW, 3)
+    Wf, bf = fold_up1(w1, b1, w2, r)
+    xp = torch.zeros(H + 4, W + 4, 64, dtype=torch.float64)
+    xp[2:H + 2, 2:W + 2] = x[0]
+    oH, oW = H * r, W * r
+    got = torch.zeros(oH, oW, 3, dtype=torch.float64)
+    for Y in range(oH):
+        for X in range(oW):
+            vy = 0 if Y == 0 else 2 if Y == oH - 1 else 1
+            vx = 0 if X == 0 else 2 if X == oW - 1 else 1
+            y, i, xx, j = Y // r, Y % r, X // r, X % r
+            patch = xp[y:y + 5, xx:xx + 5]                             # (dy, dx, ci)
+            for c in range(3):
+                o = (c * r + i) * r + j
+                got[Y, X, c] = (Wf[vy, vx, o].permute(1, 2, 0) * patch).sum() + bf[vy, vx, o]
+    assert (got - ref).abs().max().item() < 1e-12
+    # tensor-core bank: row n of chunk ch <-> output ((c r + i) - ch RPC) r + j, block blk <-> dy = 4 - blk, kx <-> dx
+    NO, rpc, nchunk = FOLD_CFG[r]
+    bank, bias = pack_fold_bank(Wf, bf, r)
+    assert bank.shape == (nchunk, 5, 5, NO, 64) and bias.shape == (nchunk * NO,)
+    for o in (0, 3 * r * r - 1, r * r + 1):
+        row, j = o // r, o % r
+        ch, q = row // rpc, row % rpc
+        assert torch.equal(bank[ch, 3, 1, q * r + j], Wf[1, 1, o, :, 3, 3])
+        assert bias[ch * NO + q * r + j] == bf[1, 1, o]

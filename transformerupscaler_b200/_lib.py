@@ -28,6 +28,10 @@ class TuUpsamplerStage(C.Structure):
     _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("r", C.c_int)]
 
 
+class TuUpFold(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("ring_w", C.c_void_p), ("ring_b", C.c_void_p), ("r", C.c_int)]
+
+
 class TuModelWeights(C.Structure):
     _fields_ = [
         ("model", C.c_int), ("dim", C.c_int), ("heads", C.c_int), ("n_blocks", C.c_int),
@@ -45,6 +49,8 @@ class TuModelWeights(C.Structure):
         ("fin", (TuUpsamplerStage * 2) * 4),
         ("up1conv_w", C.c_void_p), ("up1conv_w16", C.c_void_p),
         ("finconv_w", C.c_void_p), ("finconv_b", C.c_void_p),
+        ("upfold", TuUpFold * 4),
+        ("host_finconv_wb", C.c_void_p),
     ]
 
 
@@ -67,6 +73,8 @@ SIGNATURES = {
     "tu_conv3x3_c64_to3": (i32, [vp, i32, fp, vp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c3_ps": (i32, [fp, fp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_final_conv_add": (i32, [fp, fp, fp, fp, vp, i32, i32, i32, i32, i32, vp]),
+    "tu_upfold_conv": (i32, [vp, C.POINTER(TuUpFold), fp, i32, i32, i32, vp]),
+    "tu_subpixel_conv_add": (i32, [fp, fp, fp, i32, vp, fp, vp, i32, i32, i32, i32, i32, vp]),
     "tu_patch_embed": (i32, [vp, i32, vp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_patch_unembed": (i32, [fp, vp, fp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_block_workspace_bytes": (sz, [i32, i32, i32]),

@@ -15,11 +15,13 @@ OBJ = os.path.join(HERE, "build")
 SOURCES = [
     "api.cu",
     "small_convs.cu",
+    "subpixel_tail.cu",
     "transformer_simt.cu",
     "resample.cu",
     "tc/conv3x3_tcgen05.cu",
     "tc/conv3x3_2cta_tcgen05.cu",
     "tc/conv3x3_stream_tcgen05.cu",
+    "tc/upfold_stream_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",

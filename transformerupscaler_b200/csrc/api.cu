@@ -14,6 +14,7 @@ namespace tu {
 int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
 static thread_local std::string g_err;
 static int g_use_tc = 1;
+static int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
 static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
 
 static std::atomic<long long> g_launches{0};
@@ -172,17 +173,28 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         const int nst = scale == 4 ? 2 : 1;
         const T *cur = f2;
         int ch = H, cw = W;
+        const TuUpFold *fold = &w->upfold[slot];
+        // fold the last stage with up1_conv when the folded filter is packed and the output row pitch suits TMA
+        const int last_r = w->up1[slot][nst - 1].r;
+        const int lw = nst == 2 ? W * w->up1[slot][0].r : W;
+        const bool use_fold = g_fold_up1 && tc_on(dt) && fold->r == last_r && fold->w && (lw * last_r) % 4 == 0;
         for (int s = 0; s < nst; ++s) {
             const TuUpsamplerStage &sg = w->up1[slot][s];
             const int r = sg.r;
+            if (use_fold && s == nst - 1) break;
             T *nxt = (T *)a.get((size_t)B * ch * r * cw * r * 64 * sizeof(T));
             if (!dry) TU_STEP("up1", tu_conv3x3_c64(cur, sg.w, sg.b, nxt, dt, B, ch, cw, 1, 0, r * r, r, stv));
             cur = nxt;
             ch *= r;
             cw *= r;
         }
-        upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
-        if (!dry) TU_STEP("up1_conv", tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv));
+        if (use_fold) {
+            upA = (float *)a.get((size_t)B * 3 * ch * last_r * cw * last_r * sizeof(float));
+            if (!dry) TU_STEP("up1_folded", tu_upfold_conv(cur, fold, upA, B, ch, cw, stv));
+        } else {
+            upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
+            if (!dry) TU_STEP("up1_conv", tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv));
+        }
     }
 
     // ---- tokens
@@ -233,9 +245,21 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         const int nst = scale == 4 ? 2 : 1;
         const float *cur = res;
         int ch = H, cw = W;
+        const bool fuse_tail = w->host_finconv_wb != nullptr;     // last sub-pixel stage + 3->3 conv + sum + clamp in one kernel
         for (int s = 0; s < nst; ++s) {
             const TuUpsamplerStage &sg = w->fin[slot][s];
             const int r = sg.r;
+            if (fuse_tail && s == nst - 1) {
+                if (!dry) {
+                    if (ch * r != outH || cw * r != outW) {
+                        set_error("tu: FastTransformer output buffer must be (scale*H, scale*W)");
+                        return TU_ERR_ARG;
+                    }
+                    TU_STEP("final_upscale_conv_add", tu_subpixel_conv_add(cur, (const float *)sg.w, sg.b, r, w->host_finconv_wb, upA, out,
+                                                                           out_dtype, B, ch, cw, clamp, stv));
+                }
+                return TU_OK;
+            }
             float *nxt = (float *)a.get((size_t)B * 3 * ch * r * cw * r * sizeof(float));
             if (!dry) TU_STEP("final_upscale", tu_conv3x3_c3_ps(cur, (const float *)sg.w, sg.b, nxt, B, ch, cw, r, stv));
             cur = nxt;
@@ -276,6 +300,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "conv_2cta")) {
         tc_set_conv_2cta(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "fold_up1")) {
+        g_fold_up1 = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "fused_stack")) {
@@ -358,6 +386,16 @@ extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, voi
     if (dtype == TU_BF16)
         return conv3x3_c64<bf16>((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
     TU_CHECK_ARG(false, "conv3x3_c64: bad dtype");
+}
+
+extern "C" int tu_upfold_conv(const void *in, const TuUpFold *f, float *out, int B, int H, int W, void *stream) {
+    TU_CHECK_ARG(in && f && out && B > 0 && H > 0 && W > 0, "upfold_conv: bad argument");
+    TU_CHECK_ARG(f->w && f->b && f->ring_w && f->ring_b && (f->r == 2 || f->r == 3 || f->r == 6), "upfold_conv: folded filter not packed");
+    TU_CHECK_ARG(tc_enabled(), "upfold_conv: tcgen05 kernels are unavailable or switched off");
+    TU_CHECK_ARG((long)B * 3 * H * f->r * W * f->r < (1L << 31), "upfold_conv: image too large for 32-bit indexing");
+    int rc = tc_upfold((const bf16 *)in, f, out, B, H, W, (cudaStream_t)stream);
+    TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "upfold_conv: unsupported shape or alignment ((W*r) % 4 must be 0)");
+    return rc;
 }
 
 extern "C" int tu_window_stack(float *tokens, const TuModelWeights *w, int M, void *stream) {

@@ -1,0 +1,210 @@
+// FastTransformer's image tail in one kernel: the last sub-pixel stage of `final_upscale` (Conv2d 3 -> 3 r^2 + PixelShuffle(r),
+// FastTransformer/utils.py:43-98 with n_feats = 3; model.py:211,316), `final_upscale_conv` (Conv2d 3 -> 3, model.py:212,317),
+// `out = upscaled_input + residual_up` (model.py:320) and the clamp (model.py:327).
+//
+// Unfused, the three steps move the high-resolution 3-channel image through HBM four times and ran at 4 % of the copy
+// bandwidth (one thread per output pixel, every tap a global load).  Here a CTA owns a 30 x 30r tile of the OUTPUT image:
+//   1. the low-resolution residual under the tile (+ halo) is staged in shared memory (zero outside the image = the first
+//      conv's padding);
+//   2. the sub-pixel conv is evaluated into a shared-memory tile of the intermediate high-resolution image, 32 rows x 32r
+//      columns x 3 channels (zero outside the image = the second conv's padding).  A warp owns one intermediate row (one
+//      sub-pixel row phase i, so its filter rows are warp-uniform and are read as broadcast 128-bit loads), a lane one
+//      low-resolution pixel: 27 inputs in registers, 3r outputs of 27 FMAs each;
+//   3. a thread slides a 3x3x3 register window down a column of the intermediate tile (9 shared loads per pixel) and
+//      applies the 3 -> 3 filter, whose 84 coefficients ride in the kernel parameters (constant-bank operands of the FMAs),
+//      adds the other branch and writes the clamped image in its final dtype.
+// Arithmetic is fp32 FFMA throughout (this kernel also serves the 1e-4 fp32 path).
+#include "tu_common.cuh"
+
+namespace tu {
+
+namespace {
+
+constexpr int TH = 30;          // output rows per tile (a multiple of every r in {1,2,3,6}: tiles start on a low-res row)
+constexpr int TLX = 30;         // low-res columns per tile -> 30 r output columns; + 2 halo columns = 32 lanes
+constexpr int IR = TH + 2;      // intermediate rows held
+constexpr int NT = 256;
+
+struct FinFilter { float w[81]; float b[3]; };      // [(ky*3+kx)*3+ci][co], bias
+
+template <int R, typename TO>
+__global__ void __launch_bounds__(NT, 2)
+subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps, const float *__restrict__ bps,
+                     const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, const FinFilter fin) {
+    constexpr int NCO = 3 * R * R;
+    constexpr int NLR = TH / R + 4;            // low-res rows staged: ly0 - 2 .. ly0 + TH/R + 1
+    constexpr int LRW = TLX + 4;               // low-res columns staged: lx0 - 2 .. lx0 + 31
+    constexpr int IW = 32 * R;                 // intermediate columns held: (lx0 - 1) r .. (lx0 + 31) r - 1
+    extern __shared__ float sm[];
+    float *w_s = sm;                           // [NCO][28] (27 taps, padded for 128-bit reads)
+    float *b_s = w_s + NCO * 28;               // [NCO] (+ pad to 4)
+    float *lr_s = b_s + ((NCO + 3) & ~3);      // [3][NLR][LRW]
+    float *im_s = lr_s + 3 * NLR * LRW;        // [3][IR][IW]
+    pdl_trigger();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int oy0 = blockIdx.y * TH, lx0 = blockIdx.x * TLX;
+    const int ly0 = oy0 / R;
+    const int oH = H * R, oW = W * R;
+    pdl_wait();
+
+    for (int i = tid; i < NCO * 27; i += NT) {
+        const int t = i / NCO, o = i - t * NCO;
+        w_s[o * 28 + t] = wps[i];
+    }
+    for (int i = tid; i < NCO; i += NT) {
+        b_s[i] = bps[i];
+        w_s[i * 28 + 27] = 0.f;
+    }
+    for (int i = tid; i < 3 * NLR * LRW; i += NT) {
+        const int c = i / (NLR * LRW), rem = i - c * (NLR * LRW);
+        const int ry = rem / LRW, rx = rem - ry * LRW;
+        const int y = ly0 - 2 + ry, x = lx0 - 2 + rx;
+        lr_s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? in[(((long)b * 3 + c) * H + y) * W + x] : 0.f;
+    }
+    __syncthreads();
+
+    // ---- step 2: intermediate rows hy = oy0 - 1 + hr; lane = low-res column lx0 - 1 + lane
+    for (int hr = warp; hr < IR; hr += NT / 32) {
+        const int hy = oy0 - 1 + hr;
+        float *dst = im_s + hr * IW + lane * R;
+        const int lx = lx0 - 1 + lane;
+        if (hy < 0 || hy >= oH || lx < 0 || lx >= W) {          // outside the image: the 3 -> 3 conv's zero padding
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < R; ++j) dst[c * IR * IW + j] = 0.f;
+            continue;
+        }
+        const int ly = hy / R, i = hy - ly * R;
+        const float *src = lr_s + (ly - ly0 + 1) * LRW + lane;       // tap (ky, kx) -> row ly - 1 + ky, column lx - 1 + kx
+        float v[27];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = src[c * NLR * LRW + ky * LRW + kx];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int o = c * R * R + i * R + j;
+                const float4 *wr = reinterpret_cast<const float4 *>(w_s + o * 28);
+                float acc = b_s[o];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    const float4 ww = wr[q];
+                    acc = fmaf(v[q * 4 + 0], ww.x, acc);
+                    acc = fmaf(v[q * 4 + 1], ww.y, acc);
+                    acc = fmaf(v[q * 4 + 2], ww.z, acc);
+                    if (q < 6) acc = fmaf(v[q * 4 + 3], ww.w, acc);
+                }
+                dst[c * IR * IW + j] = acc;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- step 3: 3 -> 3 conv + addend (+ clamp); a thread walks down one output column of the tile
+    constexpr int TW = TLX * R;
+    constexpr int G = NT / TW >= 1 ? NT / TW : 1;      // row groups
+    constexpr int RPG = (TH + G - 1) / G;
+    const int cx = tid % TW, g = tid / TW;
+    if (g >= G) return;
+    const int ox = lx0 * R + cx;
+    if (ox >= oW) return;
+    const int r0 = g * RPG, r1 = min(min(r0 + RPG, TH), oH - oy0);
+    if (r0 >= r1) return;
+    // output row oy0 + ry reads intermediate rows ry .. ry + 2, columns cx + R - 1 .. cx + R + 1
+    const float *col = im_s + cx + R - 1;
+    float win[3][3][3];                                 // [row][kx][ci]
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) win[rr + 1][kx][c] = col[c * IR * IW + (r0 + rr) * IW + kx];
+    const long plane = (long)oH * oW;
+    long o = (long)b * 3 * plane + (long)(oy0 + r0) * oW + ox;
+#pragma unroll 1
+    for (int ry = r0; ry < r1; ++ry, o += oW) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                win[0][kx][c] = win[1][kx][c];
+                win[1][kx][c] = win[2][kx][c];
+                win[2][kx][c] = col[c * IR * IW + (ry + 2) * IW + kx];
+            }
+        float a[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) a[co] = fmaf(win[ky][kx][c], fin.w[((ky * 3 + kx) * 3 + c) * 3 + co], a[co]);
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            // reference: out = upscaled_input + (conv + bias)   (FastTransformer/model.py:320)
+            float r = addend[o + co * plane] + (a[co] + fin.b[co]);
+            if (clamp) r = fminf(fmaxf(r, 0.f), 1.f);
+            out[o + co * plane] = from_f<TO>(r);
+        }
+    }
+}
+
+template <int R>
+constexpr size_t tail_smem() {
+    return sizeof(float) * (3 * R * R * 28 + ((3 * R * R + 3) & ~3) + 3 * (TH / R + 4) * (TLX + 4) + 3 * IR * 32 * R);
+}
+
+template <int R, typename TO>
+int launch_tail(const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp,
+                const FinFilter &fin, cudaStream_t st) {
+    static bool attr = false;
+    constexpr size_t smem = tail_smem<R>();
+    if (!attr && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(subpixel_tail_kernel<R, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "subpixel_tail smem attribute");
+        attr = true;
+    }
+    dim3 grid(ceil_div(W, TLX), ceil_div(H * R, TH), B);
+    launch_pdl(subpixel_tail_kernel<R, TO>, grid, dim3(NT), smem, st, in, wps, bps, addend, out, H, W, clamp, fin);
+    TU_CHECK_LAUNCH("subpixel_tail");
+    return TU_OK;
+}
+
+template <typename TO>
+int tail_by_r(int r, const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp,
+              const FinFilter &fin, cudaStream_t st) {
+    switch (r) {
+        case 2: return launch_tail<2, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
+        case 3: return launch_tail<3, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
+        case 6: return launch_tail<6, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
+    }
+    set_error("tu: subpixel_conv_add: r must be 2, 3 or 6");
+    return TU_ERR_ARG;
+}
+
+}  // namespace
+
+}  // namespace tu
+
+using namespace tu;
+
+extern "C" int tu_subpixel_conv_add(const float *in, const float *w_ps, const float *b_ps, int r, const float *host_fin_wb,
+                                    const float *addend, void *out, int out_dtype, int B, int H, int W, int clamp, void *stream) {
+    TU_CHECK_ARG(in && w_ps && b_ps && host_fin_wb && addend && out && B > 0 && H > 0 && W > 0, "subpixel_conv_add: bad argument");
+    TU_CHECK_ARG((long)B * 3 * H * r * W * r < (1L << 31), "subpixel_conv_add: image too large for 32-bit pixel indexing");
+    cudaStream_t st = (cudaStream_t)stream;
+    FinFilter fin;
+    for (int i = 0; i < 81; ++i) fin.w[i] = host_fin_wb[i];
+    for (int i = 0; i < 3; ++i) fin.b[i] = host_fin_wb[81 + i];
+    if (out_dtype == TU_F32) return tail_by_r<float>(r, in, w_ps, b_ps, addend, (float *)out, B, H, W, clamp, fin, st);
+    if (out_dtype == TU_BF16) return tail_by_r<bf16>(r, in, w_ps, b_ps, addend, (bf16 *)out, B, H, W, clamp, fin, st);
+    if (out_dtype == TU_U8) return tail_by_r<uint8_t>(r, in, w_ps, b_ps, addend, (uint8_t *)out, B, H, W, clamp, fin, st);
+    TU_CHECK_ARG(false, "subpixel_conv_add: bad dtype");
+}

@@ -23,6 +23,62 @@ def dense_rel_bias_t(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return b.permute(2, 0, 1).contiguous()                               # (h, i, j)
 
 
+FOLD_CFG = {2: (16, 6, 1), 3: (32, 9, 1), 6: (32, 5, 4)}      # r -> (NO, (c,i) rows per chunk, chunks); tc/upfold_stream_tcgen05.cu
+
+
+def fold_up1(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, r: int):
+    """Compose the last up1 stage with up1_conv (FastTransformer/utils.py:43-98, 13-40; model.py:264-265).
+
+    w1 (64 r^2, 64, 3, 3), b1 (64 r^2): Conv2d before nn.PixelShuffle(r); w2 (3, 64, 3, 3): up1_conv (no bias).
+    High-res pixel (y r + i, x r + j), channel c:
+        out = sum_{m,ky,kx} w2[c,m,ky,kx] * U[m, y r + i + ky - 1, x r + j + kx - 1],   U = PixelShuffle(conv(F; w1, b1)),
+    and U[m, y' r + i', x' r + j'] = b1[m r^2 + i' r + j'] + sum_{ci,ay,ax} w1[m r^2 + i' r + j', ci, ay, ax] F[ci, y'+ay-1, x'+ax-1],
+    so out is a 5x5 convolution of F.  Returns (Wf, bf) in fp64 for the nine border cases (vy, vx) in {first, interior, last}^2
+    of the HIGH-RES row / column: the reference zero-pads U, so on the first (last) row the ky = 0 (2) taps are absent.
+    Wf: (3, 3, 3 r^2, 64, 5, 5) indexed [vy, vx, (c r + i) r + j, ci, dy + 2, dx + 2]; bf: (3, 3, 3 r^2).
+    """
+    w1 = w1.detach().double().cpu().reshape(64, r, r, 64, 3, 3)       # (m, i', j', ci, ay, ax)
+    b1 = b1.detach().double().cpu().reshape(64, r, r)
+    w2 = w2.detach().double().cpu()                                   # (c, m, ky, kx)
+    Wf = torch.zeros(3, 3, 3, r, r, 64, 5, 5, dtype=torch.float64)     # (vy, vx, c, i, j, ci, dy, dx)
+    bf = torch.zeros(3, 3, 3, r, r, dtype=torch.float64)
+    for i in range(r):
+        for ky in range(3):
+            t = i + ky - 1
+            Dy, ip = t // r, t % r
+            for j in range(r):
+                for kx in range(3):
+                    u = j + kx - 1
+                    Dx, jp = u // r, u % r
+                    contrib = torch.einsum("cm,mkab->ckab", w2[:, :, ky, kx], w1[:, ip, jp])      # (c, ci, ay, ax)
+                    cb = w2[:, :, ky, kx] @ b1[:, ip, jp]                                          # (c)
+                    for vy in range(3):
+                        if (vy == 0 and ky == 0) or (vy == 2 and ky == 2):
+                            continue
+                        for vx in range(3):
+                            if (vx == 0 and kx == 0) or (vx == 2 and kx == 2):
+                                continue
+                            Wf[vy, vx, :, i, j, :, Dy + 1:Dy + 4, Dx + 1:Dx + 4] += contrib
+                            bf[vy, vx, :, i, j] += cb
+    return Wf.reshape(3, 3, 3 * r * r, 64, 5, 5), bf.reshape(3, 3, 3 * r * r)
+
+
+def pack_fold_bank(Wf: torch.Tensor, bf: torch.Tensor, r: int):
+    """Interior folded filter -> the tensor-core bank (nchunk, 5 kx, 5 blocks ky = 4..0, NO, 64) and the padded bias (nchunk*NO)."""
+    NO, rpc, nchunk = FOLD_CFG[r]
+    W = Wf[1, 1].reshape(3 * r, r, 64, 5, 5)              # ((c, i) row, j, ci, dy, dx)
+    B = bf[1, 1].reshape(3 * r, r)
+    bank = torch.zeros(nchunk, 5, 5, NO, 64, dtype=torch.float64)
+    bias = torch.zeros(nchunk, NO, dtype=torch.float64)
+    for ch in range(nchunk):
+        rows = W[ch * rpc:(ch + 1) * rpc]                 # (q, j, ci, dy, dx)
+        n = rows.shape[0] * r
+        # bank[ch, kx, blk, q*r + j, ci] = W[q, j, ci, dy = 4 - blk, dx = kx]
+        bank[ch, :, :, :n] = rows.flip(3).permute(4, 3, 0, 1, 2).reshape(5, 5, n, 64)
+        bias[ch, :n] = B[ch * rpc:(ch + 1) * rpc].reshape(-1)
+    return bank, bias.reshape(-1)
+
+
 class PackedWeights:
     """Keeps the packed tensors alive and exposes the TuModelWeights struct."""
 
@@ -130,11 +186,26 @@ class PackedWeights:
                     mw.fin[slot][si].w = ptr(conv_small_in(sd[f"final_upscale.upsamplers.{s}.{idx}.weight"]))
                     mw.fin[slot][si].b = ptr(dev(sd[f"final_upscale.upsamplers.{s}.{idx}.bias"], f32))
                     mw.fin[slot][si].r = r
+                if dtype == torch.bfloat16:     # folded last up1 stage + up1_conv (tensor-core path only)
+                    idx, r = stages[-1]
+                    Wf, bf = fold_up1(sd[f"up1.upsamplers.{s}.{idx}.weight"], sd[f"up1.upsamplers.{s}.{idx}.bias"],
+                                      sd["up1_conv.conv.weight"], r)
+                    bank, bias = pack_fold_bank(Wf, bf, r)
+                    uf = mw.upfold[slot]
+                    uf.w, uf.b = ptr(dev(bank, torch.bfloat16)), ptr(dev(bias, f32))
+                    uf.ring_w = ptr(dev(Wf.permute(0, 1, 2, 4, 5, 3).reshape(9, 3 * r * r, 25, 64), f32))
+                    uf.ring_b = ptr(dev(bf.reshape(9, 3 * r * r), f32))
+                    uf.r = r
             mw.up1conv_w = ptr(conv_to3(sd["up1_conv.conv.weight"]))
             if dtype == torch.bfloat16:
                 mw.up1conv_w16 = ptr(conv_to3_tc(sd["up1_conv.conv.weight"]))
             mw.finconv_w = ptr(conv_small_in(sd["final_upscale_conv.weight"]))
             mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
+            # host copy of the 3 -> 3 filter: its 84 values travel in the parameters of the fused tail kernel
+            wb = torch.cat([sd["final_upscale_conv.weight"].float().permute(2, 3, 1, 0).reshape(-1),
+                            sd["final_upscale_conv.bias"].float().reshape(-1)]).cpu().tolist()
+            self.host_finconv = (C.c_float * 84)(*wb)
+            mw.host_finconv_wb = C.cast(self.host_finconv, C.c_void_p)
         self.struct = mw
         self.dim, self.heads, self.n_blocks = dim, heads, nb
 
