@@ -3,10 +3,10 @@
 // `out = upscaled_input + residual_up` (model.py:320) and the clamp (model.py:327).
 //
 // Unfused, the three steps move the high-resolution 3-channel image through HBM four times and ran at 4 % of the copy
-// bandwidth (one thread per output pixel, every tap a global load).  Here a CTA owns a 30 x 30r tile of the OUTPUT image:
+// bandwidth (one thread per output pixel, every tap a global load).  Here a CTA owns a 36 x 30r tile of the OUTPUT image:
 //   1. the low-resolution residual under the tile (+ halo) is staged in shared memory (zero outside the image = the first
 //      conv's padding);
-//   2. the sub-pixel conv is evaluated into a shared-memory tile of the intermediate high-resolution image, 32 rows x 32r
+//   2. the sub-pixel conv is evaluated into a shared-memory tile of the intermediate high-resolution image, 38 rows x 32r
 //      columns x 3 channels (zero outside the image = the second conv's padding).  A warp owns one intermediate row (one
 //      sub-pixel row phase i, so its filter rows are warp-uniform and are read as broadcast 128-bit loads), a lane one
 //      low-resolution pixel: 27 inputs in registers, 3r outputs of 27 FMAs each;
@@ -20,7 +20,7 @@ namespace tu {
 
 namespace {
 
-constexpr int TH = 30;          // output rows per tile (a multiple of every r in {1,2,3,6}: tiles start on a low-res row)
+constexpr int TH = 36;          // output rows per tile (a multiple of every r in {2,3,6}: tiles start on a low-res row)
 constexpr int TLX = 30;         // low-res columns per tile -> 30 r output columns; + 2 halo columns = 32 lanes
 constexpr int IR = TH + 2;      // intermediate rows held
 constexpr int NT = 256;
@@ -127,8 +127,15 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
             for (int c = 0; c < 3; ++c) win[rr + 1][kx][c] = col[c * IR * IW + (r0 + rr) * IW + kx];
     const long plane = (long)oH * oW;
     long o = (long)b * 3 * plane + (long)(oy0 + r0) * oW + ox;
+    float ad[3];                                        // the other branch, fetched one row ahead of its use
+#pragma unroll
+    for (int co = 0; co < 3; ++co) ad[co] = addend[o + co * plane];
 #pragma unroll 1
     for (int ry = r0; ry < r1; ++ry, o += oW) {
+        float adn[3];
+        const long on = ry + 1 < r1 ? o + oW : o;
+#pragma unroll
+        for (int co = 0; co < 3; ++co) adn[co] = addend[on + co * plane];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -149,9 +156,10 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
 #pragma unroll
         for (int co = 0; co < 3; ++co) {
             // reference: out = upscaled_input + (conv + bias)   (FastTransformer/model.py:320)
-            float r = addend[o + co * plane] + (a[co] + fin.b[co]);
+            float r = ad[co] + (a[co] + fin.b[co]);
             if (clamp) r = fminf(fmaxf(r, 0.f), 1.f);
             out[o + co * plane] = from_f<TO>(r);
+            ad[co] = adn[co];
         }
     }
 }

@@ -298,20 +298,27 @@ upfold_ring_kernel(const bf16 *__restrict__ in, const float *__restrict__ ring_w
     const int y = Y / r, i = Y - y * r, x = X / r, j = X - x * r;
     const int nco = 3 * r * r;
     float acc[3] = {0.f, 0.f, 0.f};
+    const float *wv = ring_w + ((long)(vy * 3 + vx) * nco) * 25 * 64 + lane * 2;
+    const int o0 = i * r + j;                        // output o = c*r*r + o0
     for (int dy = 0; dy < 5; ++dy) {
         const int iy = y + dy - 2;
         if (iy < 0 || iy >= H) continue;
+        const bf16 *row = in + ((long)b * H + iy) * W * 64 + lane * 2;
+        // the five taps of a row are independent: all their loads are in flight together (the kernel is latency bound)
+        float2 fv[5];
+#pragma unroll
         for (int dx = 0; dx < 5; ++dx) {
             const int ix = x + dx - 2;
-            if (ix < 0 || ix >= W) continue;
-            const __nv_bfloat162 f2 = *reinterpret_cast<const __nv_bfloat162 *>(in + (((long)b * H + iy) * W + ix) * 64 + lane * 2);
-            const float2 f = __bfloat1622float2(f2);
+            fv[dx] = (ix >= 0 && ix < W) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(row + (long)ix * 64)) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const int o = (c * r + i) * r + j;
-                const float2 w2 = *reinterpret_cast<const float2 *>(ring_w + ((((long)(vy * 3 + vx) * nco + o) * 25 + dy * 5 + dx) * 64) + lane * 2);
-                acc[c] = fmaf(f.x, w2.x, fmaf(f.y, w2.y, acc[c]));
-            }
+        for (int c = 0; c < 3; ++c) {
+            float2 w2[5];
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx)
+                w2[dx] = *reinterpret_cast<const float2 *>(wv + ((long)(c * r * r + o0) * 25 + dy * 5 + dx) * 64);
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) acc[c] = fmaf(fv[dx].x, w2[dx].x, fmaf(fv[dx].y, w2[dx].y, acc[c]));
         }
     }
 #pragma unroll
