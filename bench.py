@@ -8,7 +8,7 @@ One "step" = one TransformerModel.forward over a batch of 8 synthetic 720p frame
 independent, so every rank upscales its own 8 frames; NCCL only carries the barrier and the max-over-ranks of the
 timings).  Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same metric
 through the public API with pinned HOST buffers (H2D + forward + D2H inside the timed region, overlapped on three
-streams); `roofline` = the dominant kernel (conv2, 64->64 3x3 at 720p) timed live with CUDA events; `cpu_baseline` =
+streams); `roofline` = the dominant kernel (conv1 fused into conv2, 64->64 3x3 at 720p) timed live with CUDA events; `cpu_baseline` =
 the reference's own modules timed on this box's host cores (rank 0, N=1 only).
 
 --impl reference: times the reference's CPU implementation (baseline/_ref, unmodified; else the oracle port) on one
@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 FRAMES_PER_GPU = 8
 H, W, OH, OW = 720, 1280, 1080, 1920
 CONV2_FLOP_PER_FRAME = 2.0 * 576 * 64 * H * W          # 67.95 GFLOP: 2*Cin*9*Cout*H*W
+CONV1_FLOP_PER_FRAME = 2.0 * 27 * 64 * H * W           # 3.19 GFLOP (conv1 runs inside the same kernel when fused)
 WORKLOAD = "WindowTransformer 720p->1080p, batch 8 frames per GPU, bf16 (BASELINE.json configs[1])"
 
 
@@ -200,7 +201,10 @@ def main():
         ms_total = e0.elapsed_time(e1)
         lib.tu_profile_enable(0)
         kms, kn = C.c_double(0), C.c_int(0)
-        lib.tu_profile_collect(b"conv2", C.byref(kms), C.byref(kn))
+        lib.tu_profile_collect(b"conv1_conv2", C.byref(kms), C.byref(kn))      # conv1 fused into conv2 (the default path)
+        fused12 = kn.value > 0
+        if not fused12:
+            lib.tu_profile_collect(b"conv2", C.byref(kms), C.byref(kn))
         lib.tu_profile_reset()
         # per-kernel breakdown: a separate, untimed pass with every launch bracketed (the extra event records would perturb
         # the timed region: they sit between kernels that otherwise chain through programmatic dependent launch)
@@ -281,10 +285,11 @@ def main():
     if rank == 0:
         tf_peak, hbm_peak, peak_src = peaks()
         achieved = None
+        kflop = (CONV2_FLOP_PER_FRAME + (CONV1_FLOP_PER_FRAME if fused12 else 0.0)) * FRAMES_PER_GPU
         if kn.value > 0 and kms.value > 0:
-            achieved = CONV2_FLOP_PER_FRAME * FRAMES_PER_GPU / (kms.value / kn.value * 1e-3) / 1e12
+            achieved = kflop / (kms.value / kn.value * 1e-3) / 1e12
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "conv2_traffic_bytes.json")
+        tp = os.path.join(ROOT, "profiles", "conv12_traffic_bytes.json" if fused12 else "conv2_traffic_bytes.json")
         if os.path.exists(tp):
             try:
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
@@ -297,7 +302,11 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_gpu": FRAMES_PER_GPU, "parallelism": f"frame-sharded x{world}, no collective",
                        "l2": "per-step working set ~2.5 GB (inputs + NHWC intermediates) >> 126 MB L2; two input buffers alternate",
                        "tcgen05": bool(lib.tu_bf16_uses_tcgen05()), "output_mean": checksum},
-            "roofline": {"bound": "tensor", "kernel": "conv2 64->64 3x3 @720p (implicit GEMM, M=B*H*W, N=64, K=576)",
+            "roofline": {"bound": "tensor",
+                         "kernel": ("conv1 3->64 fused into conv2 64->64 3x3 @720p (conv12_fused_kernel: implicit GEMMs K=27 and K=576, "
+                                    "M=B*H*W, N=64; conv1's output stays on chip)") if fused12 else
+                                   "conv2 64->64 3x3 @720p (implicit GEMM, M=B*H*W, N=64, K=576)",
+                         "flop_per_launch": kflop,
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": (kms.value / kn.value) if kn.value else None,

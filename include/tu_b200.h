@@ -49,7 +49,7 @@ void tu_set_bf16_tcgen05(int enable);
 long long tu_launch_count(void);
 /* Measurement hook for bench.py: tu_profile_enable(1) brackets the dominant kernel ("conv2") of every tu_forward with CUDA
  * events on the caller's stream (two event records per forward: cheap enough for the timed region); tu_profile_enable(2)
- * brackets EVERY kernel, tagged with the reference op it implements ("conv1", "conv2", "downsample", "patch_embed",
+ * brackets EVERY kernel, tagged with the reference op it implements ("conv1", "conv2" (or "conv1_conv2" when fused), "downsample", "patch_embed",
  * "transformer_blocks", "patch_unembed", "decoder_conv1", "decoder_conv2", "bicubic_add_clamp", "up1", "up1_conv",
  * "final_upscale", "final_conv_add").  tu_profile_collect / tu_profile_report synchronise those events (the only
  * calls in the library that wait on the device): collect sums the milliseconds and launches recorded under `name`
@@ -61,7 +61,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
+ * "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------
@@ -167,6 +167,11 @@ int tu_conv3x3_c3_ps(const float *in, const float *w, const float *b, float *out
 /* out = clamp?(conv3x3_3to3(in) + addend) -> NCHW image of out_dtype */
 int tu_final_conv_add(const float *in, const float *w, const float *b, const float *addend, void *out,
                       int out_dtype, int B, int H, int W, int clamp, void *stream);
+/* relu(conv2(relu(conv1(x)))) in one kernel (bf16 tensor-core path): NCHW image (in_dtype) -> NHWC bf16 (B,H,W,64); w64 = conv1
+ * filter bf16 (64 co, 64 k), w2 = conv2 filter bf16 (9, 64 co, 64 ci).  conv1's output never reaches HBM.  W:244-245, F:251-252,
+ * R:128-129.  Needs an image row pitch that is a multiple of 16 bytes. */
+int tu_conv12_fused(const void *x, int in_dtype, const void *w64, const float *b1, const void *w2, const float *b2, void *out,
+                    int B, int H, int W, void *stream);
 /* relu(up1_conv(PixelShuffle_r(up1_stage(in)))) through the folded 5x5 filter: NHWC bf16 (B,H,W,64) -> planar fp32
  * (B,3,rH,rW).  FastTransformer/model.py:264-265.  Needs the tcgen05 path and (W*r) % 4 == 0. */
 int tu_upfold_conv(const void *in, const TuUpFold *f, float *out, int B, int H, int W, void *stream);

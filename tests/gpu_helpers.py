@@ -64,6 +64,15 @@ def final_conv_add(x, w, b, addend, out_dtype, clamp):
     return out
 
 
+def conv12_fused(x, w64, b1, w2, b2):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    dt = 2 if x.dtype == torch.uint8 else DT[x.dtype]
+    out = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=x.device)
+    chk(lib.tu_conv12_fused(p(x), dt, p(w64), p(b1), p(w2), p(b2), p(out), B, H, W, stream()))
+    return out
+
+
 def upfold_conv(x, w1, b1, w2, r):
     """x NHWC bf16 on the GPU; folds (w1, b1, w2) on the host like packing.PackedWeights does"""
     from transformerupscaler_b200.packing import fold_up1, pack_fold_bank

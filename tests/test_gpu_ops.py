@@ -52,6 +52,40 @@ def test_stem_conv(dev, in_dt, dt):
             assert _maxerr(out16, ref16) < 1e-2
 
 
+@pytest.mark.parametrize("in_dt", [F32, BF16, torch.uint8])
+@pytest.mark.parametrize("shape", [(2, 19, 48), (1, 5, 304), (1, 1, 16), (1, 70, 136), (3, 33, 256)])
+def test_conv12_fused(dev, in_dt, shape):
+    """conv1 fused into conv2 (one kernel, conv1's output stays on chip) vs the two convolutions of the oracle on bf16-rounded
+    operands (W:244-245, F:251-252, R:128-129)"""
+    from tests import gpu_helpers as G
+    sd = synth_state_dict("WindowTransformer", 2)
+    B, H, W = shape
+    if (W * torch.empty(0, dtype=in_dt).element_size()) % 16:
+        pytest.skip("raw rows arrive by TMA: the image row pitch must be a multiple of 16 bytes (the forward then runs the two kernels)")
+    x = synth_frames(B, H, W, seed=21)
+    if in_dt == torch.uint8:
+        xin = (x * 255).round().clamp(0, 255).to(torch.uint8)
+        xf = xin.float() * (1.0 / 255.0)
+    else:
+        xin = x.to(in_dt)
+        xf = xin.float()
+    w1, b1, w2, b2 = sd["conv1.weight"], sd["conv1.bias"], sd["conv2.weight"], sd["conv2.bias"]
+    # what the kernel computes: bf16 operands, fp32 accumulation, conv1's output rounded to bf16
+    f1 = orc.conv3x3_nhwc(xf.to(BF16).float().permute(0, 2, 3, 1).contiguous(), w1.to(BF16).float(), b1, relu=True).to(BF16).float()
+    ref = orc.conv3x3_nhwc(f1, w2.to(BF16).float(), b2, relu=True)
+    w64 = torch.zeros(64, 64)
+    w64[:, :27] = w1.permute(0, 2, 3, 1).reshape(64, 27)
+    w2p = w2.permute(2, 3, 0, 1).reshape(9, 64, 64).contiguous()
+    out = G.conv12_fused(xin.to(dev), w64.to(dev, BF16), b1.to(dev), w2p.to(dev, BF16), b2.to(dev))
+    assert out.shape == ref.shape
+    assert _maxerr(out, ref) < 2e-2 * max(ref.abs().max().item(), 1.0)
+    # and against the two-kernel path of the engine (same operands; only summation order and 1-ulp bf16 flips differ)
+    wst = w1.permute(2, 3, 1, 0).reshape(27, 64).contiguous().to(dev)
+    two = G.conv3x3_c64(G.stem_conv(xin.to(dev), wst, b1.to(dev), BF16, w64=w64.to(dev, BF16)) if in_dt != torch.uint8 else
+                        G.stem_conv(xf.to(dev), wst, b1.to(dev), BF16, w64=w64.to(dev, BF16)), w2p.to(dev, BF16), b2.to(dev), relu=1)
+    assert _maxerr(out, two) < 2e-2 * max(ref.abs().max().item(), 1.0)
+
+
 @pytest.mark.parametrize("dt", [F32, BF16])
 @pytest.mark.parametrize("stride,relu,shape", [(1, 1, (2, 19, 45)), (2, 0, (1, 33, 41)), (2, 0, (1, 32, 48)), (1, 0, (1, 8, 130))])
 def test_conv3x3_c64(dev, dt, stride, relu, shape):

@@ -28,7 +28,9 @@ struct ProfRec { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_events;
 static cudaEvent_t g_prof_open = nullptr;
 static const char *g_prof_name = nullptr;      // the op about to be launched (set by TU_STEP)
-static inline bool prof_wanted() { return g_prof_on >= 2 || (g_prof_on == 1 && g_prof_name && !strcmp(g_prof_name, "conv2")); }
+static inline bool prof_wanted() {
+    return g_prof_on >= 2 || (g_prof_on == 1 && g_prof_name && (!strcmp(g_prof_name, "conv2") || !strcmp(g_prof_name, "conv1_conv2")));
+}
 static void prof_begin(cudaStream_t st) {
     if (!prof_wanted()) return;
     cudaEvent_t e;
@@ -161,8 +163,20 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
 
     // ---- encoder
     if (!dry) {
-        TU_STEP("conv1", tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv));
-        TU_STEP("conv2", tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv));
+        // conv1 fused into conv2 (its 64-channel output never reaches HBM) when the tensor-core path and the image pitch allow it
+        rc = TU_TC_UNSUPPORTED;
+        if (tc_on(dt) && w->conv1_w64) {
+            g_prof_name = "conv1_conv2";
+            prof_begin(st);
+            rc = tc_conv12_fused(x, in_dtype, (const bf16 *)w->conv1_w64, w->conv1_b, (const bf16 *)w->conv2_w, w->conv2_b, (bf16 *)f2, B, H, W, st);
+            if (rc == TU_OK) prof_end(st, "conv1_conv2");
+            else if (g_prof_open) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; }
+            if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+        }
+        if (rc == TU_TC_UNSUPPORTED) {
+            TU_STEP("conv1", tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv));
+            TU_STEP("conv2", tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv));
+        }
         if (!fast) TU_STEP("downsample", tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv));
     }
 
@@ -302,6 +316,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
         tc_set_conv_2cta(value);
         return TU_OK;
     }
+    if (key && !strcmp(key, "fuse_conv12")) {
+        tc_set_conv12_fused(value);
+        return TU_OK;
+    }
     if (key && !strcmp(key, "fold_up1")) {
         g_fold_up1 = value;
         return TU_OK;
@@ -386,6 +404,16 @@ extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, voi
     if (dtype == TU_BF16)
         return conv3x3_c64<bf16>((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
     TU_CHECK_ARG(false, "conv3x3_c64: bad dtype");
+}
+
+extern "C" int tu_conv12_fused(const void *x, int in_dtype, const void *w64, const float *b1, const void *w2, const float *b2, void *out,
+                               int B, int H, int W, void *stream) {
+    TU_CHECK_ARG(x && w64 && b1 && w2 && out && B > 0 && H > 0 && W > 0, "conv12_fused: bad argument");
+    TU_CHECK_ARG(in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8, "conv12_fused: bad input dtype");
+    TU_CHECK_ARG(tc_enabled(), "conv12_fused: tcgen05 kernels are unavailable or switched off");
+    int rc = tc_conv12_fused(x, in_dtype, (const bf16 *)w64, b1, (const bf16 *)w2, b2, (bf16 *)out, B, H, W, (cudaStream_t)stream);
+    TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "conv12_fused: unsupported alignment (image row pitch must be a multiple of 16 bytes) or switched off");
+    return rc;
 }
 
 extern "C" int tu_upfold_conv(const void *in, const TuUpFold *f, float *out, int B, int H, int W, void *stream) {

@@ -46,6 +46,11 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
                           int ps_r, cudaStream_t st);
 void tc_set_conv_stream(int on);
 
+// relu(conv2(relu(conv1(x)))) in one kernel (conv12_fused_tcgen05.cu): NCHW image -> NHWC bf16; conv1's output stays on chip
+int tc_conv12_fused(const void *x, int in_dtype, const bf16 *w64, const float *bias1, const bf16 *w2, const float *bias2, bf16 *out,
+                    int B, int H, int W, cudaStream_t st);
+void tc_set_conv12_fused(int on);
+
 // conv1 3 -> 64 + ReLU, NCHW (fp32|bf16) -> NHWC bf16 (stem_tcgen05.cu)
 int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st);
 
