@@ -11,7 +11,7 @@
 //               padding) per step into a 4-stage ring; also loads both filter banks once
 //   warps 12-15 builders: a thread owns pixel x0 + i, keeps a 3x3x3 register window sliding down the strip and writes its
 //               im2col row (27 taps + the two bias columns, bf16) into the swizzled operand tile
-//   warp 1      MMA issuer: per step two 128x64x16 stem MMAs (two rows AHEAD of the conv2 row they feed) into one of two
+//   warp 1      MMA issuer: per step two 128x64x16 stem MMAs (three rows AHEAD of the conv2 row they feed) into one of two
 //               stem accumulators, then conv2's 12 (or 24) ky-stacked MMAs of the current row
 //   warps 8-11  stem epilogue: accumulator -> ReLU -> bf16 -> rows 1..128 of the conv2 input slot (zero outside the image =
 //               conv2's padding), exactly the bytes TMA would have put there
@@ -39,6 +39,7 @@ constexpr int W1_BYTES = 64 * 128;
 constexpr int A1_BYTES = 128 * 128;
 constexpr int STG_BYTES = 4 * 2 * 4096;
 constexpr int NRAW = 4;
+constexpr int STEM_LEAD = 3;                   // conv1 rows the stem MMAs run ahead of the conv2 row they feed (ring of 4 slots)
 constexpr int RAW_STAGE = 1664;               // >= 3 * (128 + 2 PADL) * sizeof(TI) for every TI, multiple of 128
 constexpr int OFF_RING = W2_BYTES;
 constexpr int OFF_A1 = OFF_RING + RING * UNIT_BYTES;
@@ -189,7 +190,7 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const uint32_t w2_lo = ptx::sdesc_lo(smem0), ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
         const uint32_t a1_lo = ptx::sdesc_lo(smem0 + OFF_A1), w1_lo = ptx::sdesc_lo(smem0 + OFF_W1);
         const uint32_t idesc1 = ptx::make_idesc_bf16(128, 64);
-        // the stem runs over the flat sequence of conv1 rows of all this CTA's items, two rows ahead of conv2
+        // the stem runs over the flat sequence of conv1 rows of all this CTA's items, STEM_LEAD rows ahead of conv2
         long stem_total = 0;
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
             int b, y0, rows, x0;
@@ -211,7 +212,7 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             aph ^= 1;
             ++stem_issued;
         };
-        if (stem_total > 0) { issue_stem(); issue_stem(); }
+        for (int k = 0; k < STEM_LEAD && stem_issued < stem_total; ++k) issue_stem();
         uint32_t rs = 0;                                   // conv2 input rows consumed so far (ring slot = rs % RING)
         uint32_t g0 = 0;                                   // running index of the item's first output row
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {

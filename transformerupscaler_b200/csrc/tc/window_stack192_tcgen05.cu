@@ -297,6 +297,19 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 signal_a();
                 // ---- six groups of two heads: qkv epilogue of group g, then its attention while the MMAs of g+1 run
                 const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
+                // relative-position bias of this thread's 2 rows x 16 columns of head (2g + hl): fetched one group ahead of its
+                // use (the 17 KB of L1 left beside the shared memory cannot hold it, so every fetch is an L2 round trip)
+                float2 ba[8], bb2[8];
+                auto load_bias = [&](int g) {
+                    const int gq = lane >> 2, tq = lane & 3, hl = (warp >> 2) & 1, rg = warp & 3;
+                    const float *bp0 = relb + ((long)(g * 2 + hl) * 64 + rg * 16 + gq) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
+                        bb2[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                    }
+                };
+                load_bias(0);
 #pragma unroll 1
                 for (int g = 0; g < NGROUP; ++g) {
                     wait_acc(ACC_QKV0 + g);
@@ -326,13 +339,6 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         const int h = g * 2 + hl;
                         const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
                         const int r0 = rg * 16 + gq;
-                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
-                        float2 ba[8], bb2[8];
-#pragma unroll
-                        for (int n = 0; n < 8; ++n) {
-                            ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
-                            bb2[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
-                        }
                         uint32_t qa[4];
                         qa[0] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (hl * 16 + tq * 2) * 2);
                         qa[1] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (hl * 16 + tq * 2) * 2);
@@ -353,6 +359,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
+                        if (g + 1 < NGROUP) load_bias(g + 1);         // in flight during softmax, PV and the next group's epilogue
                         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
                         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
                         float l0 = 0.f, l1 = 0.f;

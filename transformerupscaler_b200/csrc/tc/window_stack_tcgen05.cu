@@ -270,6 +270,20 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     layernorm_to_a32(x, par + P_LN1W + part * 32, par + P_LN1B + part * 32, stat, a32, i, part);
                 }
                 signal_a();
+                // relative-position bias of this thread's 2 rows x 16 columns: a warp's four attention tasks are (head hw, window 0),
+                // (hw, window 1), (hw + 4, window 0), (hw + 4, window 1) with the same 16-row group, so two fetches serve four tasks;
+                // the first is issued here and flies during the qkv epilogue, the second right after the first's last use
+                const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
+                float2 ba[8], bb[8];
+                auto load_bias = [&](int h) {
+                    const float *bp0 = relb + ((long)h * 64 + (warp & 3) * 16 + (lane >> 2)) * 64 + (lane & 3) * 2, *bp1 = bp0 + 8 * 64;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
+                        bb[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                    }
+                };
+                load_bias(warp >> 2);
                 // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows, one column third at a time as its MMAs retire
                 {
                     uint8_t *rowp = stg + i * STG_PITCH;
@@ -280,14 +294,14 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                         const int col = nc * 128 + part * 32;
                         ptx::tmem_ld_x32(TACC + lane_base + col, v);
                         ptx::tmem_ld_wait();
-                        const float *bb = par + P_QKVB + col;
+                        const float *qb = par + P_QKVB + col;
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 u;
-                            u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
-                            u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
-                            u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
-                            u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
+                            u.x = pk(__uint_as_float(v[j + 0]) + qb[j + 0], __uint_as_float(v[j + 1]) + qb[j + 1]);
+                            u.y = pk(__uint_as_float(v[j + 2]) + qb[j + 2], __uint_as_float(v[j + 3]) + qb[j + 3]);
+                            u.z = pk(__uint_as_float(v[j + 4]) + qb[j + 4], __uint_as_float(v[j + 5]) + qb[j + 5]);
+                            u.w = pk(__uint_as_float(v[j + 6]) + qb[j + 6], __uint_as_float(v[j + 7]) + qb[j + 7]);
                             *reinterpret_cast<uint4 *>(rowp + (col + j) * 2) = u;
                         }
                     }
@@ -296,21 +310,11 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 // ---- window attention: 2 windows x 8 heads x 4 row groups = 64 warp tasks, 4 per warp
                 {
                     const int g = lane >> 2, tq = lane & 3;
-                    const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
 #pragma unroll 1
-                    for (int task = warp; task < 64; task += NMATH) {
-                        const int win = task >> 5, h = (task >> 2) & 7, rg = task & 3;
+                    for (int tk = 0; tk < 4; ++tk) {
+                        const int win = tk & 1, h = (warp >> 2) + 4 * (tk >> 1), rg = warp & 3;
                         const uint8_t *wbase = stg + (win * 64) * STG_PITCH;
                         const int r0 = rg * 16 + g;
-                        // relative-position bias of this thread's 2 rows x 16 columns: issued first, the L2 latency hides
-                        // behind the Q/K fragment loads and the QK^T MMAs
-                        const float *bp0 = relb + ((long)h * 64 + r0) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
-                        float2 ba[8], bb[8];
-#pragma unroll
-                        for (int n = 0; n < 8; ++n) {
-                            ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
-                            bb[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
-                        }
                         uint32_t qa[4];
                         qa[0] = *reinterpret_cast<const uint32_t *>(wbase + r0 * STG_PITCH + (h * 16 + tq * 2) * 2);
                         qa[1] = *reinterpret_cast<const uint32_t *>(wbase + (r0 + 8) * STG_PITCH + (h * 16 + tq * 2) * 2);
@@ -331,6 +335,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
+                        if (tk == 1) load_bias((warp >> 2) + 4);       // the second head's bias flies during this task's softmax and PV
                         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
                         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
                         float l0 = 0.f, l1 = 0.f;
