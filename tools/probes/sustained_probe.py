@@ -10,7 +10,10 @@ from transformerupscaler_b200 import _lib
 from transformerupscaler_b200.models.WindowTransformer.model import TransformerModel
 
 lib = _lib.load()
+U8 = "u8" in sys.argv[1:]
 for kv in sys.argv[1:]:
+    if "=" not in kv:
+        continue
     k, v = kv.split("=")
     lib.tu_debug_set(k.encode(), int(v))
 dev = torch.device("cuda:0")
@@ -18,6 +21,8 @@ m = TransformerModel().eval()
 m.load_state_dict(synth_state_dict("WindowTransformer", 0), strict=True)
 m = m.to(dev).bfloat16()
 xs = [synth_frames(8, 720, 1280, seed=123 + i).to(dev).bfloat16() for i in range(2)]
+if U8:      # uint8 frames in and out (the end-to-end path of bench.py)
+    xs = [(x.float() * 255).round().clamp(0, 255).to(torch.uint8) for x in xs]
 import pynvml
 pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)

@@ -56,7 +56,7 @@ constexpr int BS_W = 128, BS_H = 32;
 // element as stored -> float, and the factor applied once per 4-tap sum (uint8 frames: 1/255, ToTensor)
 __device__ __forceinline__ float raw_f(float v) { return v; }
 __device__ __forceinline__ float raw_f(bf16 v) { return __bfloat162float(v); }
-__device__ __forceinline__ float raw_f(uint8_t v) { return (float)v; }
+__device__ __forceinline__ float raw_f(uint8_t v) { return u8_to_float(v); }
 template <typename TS> __device__ __forceinline__ float src_scale(float t) { return t; }
 template <> __device__ __forceinline__ float src_scale<uint8_t>(float t) { return t * 0.00392156862745098f; }
 
@@ -143,7 +143,7 @@ template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, bf16) {
 template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, uint8_t) {
     unsigned short h;
     asm("ld.shared.u8 %0, [%1+%2];" : "=h"(h) : "r"(a), "n"(OFF));
-    return (float)h;
+    return u8_to_float(h);
 }
 // 4-tap horizontal sum of one source row of the replicate-padded tile (ATen's left-to-right order)
 template <typename TS>

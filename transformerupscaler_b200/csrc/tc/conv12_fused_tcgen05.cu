@@ -78,7 +78,7 @@ static_assert(sizeof(FusedBarriers) <= 512, "barrier block too large");
 
 __device__ __forceinline__ float ldx(float v) { return v; }
 __device__ __forceinline__ float ldx(bf16 v) { return __bfloat162float(v); }
-__device__ __forceinline__ float ldx(uint8_t v) { return (float)v * 0.00392156862745098f; }
+__device__ __forceinline__ float ldx(uint8_t v) { return u8_to_float(v) * 0.00392156862745098f; }
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));

@@ -202,6 +202,18 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs -----------------------------------------------------------------------------
+// sm_100 executes two IEEE fp32 operations per FFMA2 / FMUL2 / FADD2 instruction (one issue slot); results are
+// bit-identical to the scalar operations.  The window-stack kernels are issue bound on their CUDA-core math.
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void up2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 ld2(const float *p) { return *reinterpret_cast<const f32x2 *>(p); }     // 8-byte aligned pair
+
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major operand stored as rows of 128 bytes (64 bf16) with the
 // 128-byte swizzle (what TMA SWIZZLE_128B writes): 8-row atoms of 1024 B, stride-byte-offset 1024 between atoms.

@@ -51,7 +51,7 @@ struct Barriers {
 // image element -> float for the bf16 operand (uint8 frames: x * (1/255); the product is rounded to bf16 right after)
 __device__ __forceinline__ float ldx(float v) { return v; }
 __device__ __forceinline__ float ldx(bf16 v) { return __bfloat162float(v); }
-__device__ __forceinline__ float ldx(uint8_t v) { return (float)v * 0.00392156862745098f; }
+__device__ __forceinline__ float ldx(uint8_t v) { return u8_to_float(v) * 0.00392156862745098f; }
 
 // (lo, hi) -> bf16x2 with ReLU in the same instruction
 __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {

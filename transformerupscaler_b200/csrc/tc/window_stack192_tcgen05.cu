@@ -84,6 +84,27 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return fmaf(h, t, h);
 }
 
+// ---- packed-fp32 (FFMA2 / FMUL2 / FADD2) forms of the element-wise math: same IEEE operations, half the issue slots
+using ptx::f32x2;
+__device__ __forceinline__ uint32_t pk_pair(f32x2 v) {          // (lo, hi) -> bf16x2
+    float lo, hi;
+    ptx::up2(v, lo, hi);
+    return pk(lo, hi);
+}
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+    float a, b;
+    ptx::up2(ptx::mul2(x, x), a, b);
+    const f32x2 x2 = ptx::pk2(fminf(a, 64.f), fminf(b, 64.f));
+    f32x2 q = ptx::fma2(ptx::pk2(-0.0003515167826820022f, -0.0003515167826820022f), x2, ptx::pk2(0.03700564597780192f, 0.03700564597780192f));
+    q = ptx::fma2(q, x2, ptx::pk2(0.7975078843613885f, 0.7975078843613885f));
+    float u0, u1, t0, t1;
+    ptx::up2(ptx::mul2(x, q), u0, u1);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+    const f32x2 h = ptx::mul2(x, ptx::pk2(0.5f, 0.5f));
+    return ptx::fma2(h, ptx::pk2(t0, t1), h);
+}
+
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -106,24 +127,30 @@ __device__ __forceinline__ void tmem_ld48(uint32_t taddr, uint32_t (&v)[48]) {
 __device__ __forceinline__ int slab_chunk_off(int col, int i) { return (col >> 6) * SLAB_A + i * 128 + ((((col & 63) >> 3) ^ (i & 7)) << 4); }
 
 // LayerNorm of this thread's 48 columns of row i (x already includes the folded offset) -> A32, swizzled
-__device__ __forceinline__ void layernorm_to_a32(float (&x)[48], const float *gam, const float *bet, float2 *stat, uint8_t *a32, int i,
+__device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[24], const float *gam, const float *bet, float2 *stat, uint8_t *a32, int i,
                                                  int part) {
-    float s = 0.f, ss = 0.f;
+    // one exchange: every thread publishes (sum, sum of squares) of its columns; var = E[x^2] - mean^2 in fp32
+    f32x2 s2 = ptx::pk2(0.f, 0.f), q2 = ptx::pk2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 48; ++j) { s += x[j]; ss = fmaf(x[j], x[j], ss); }
-    stat[i * 4 + part] = make_float2(s, ss);
+    for (int j = 0; j < 24; ++j) { s2 = ptx::add2(s2, x[j]); q2 = ptx::fma2(x[j], x[j], q2); }
+    float s_lo, s_hi, q_lo, q_hi;
+    ptx::up2(s2, s_lo, s_hi);
+    ptx::up2(q2, q_lo, q_hi);
+    stat[i * 4 + part] = make_float2(s_lo + s_hi, q_lo + q_hi);
     math_barrier();
     const float4 p01 = *reinterpret_cast<const float4 *>(stat + i * 4), p23 = *reinterpret_cast<const float4 *>(stat + i * 4 + 2);
     const float mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.0f / DIM);
     const float ex2 = ((p01.y + p01.w) + (p23.y + p23.w)) * (1.0f / DIM);
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+    const f32x2 nmean = ptx::pk2(-mean, -mean), rs = ptx::pk2(rstd, rstd);
 #pragma unroll
     for (int ch = 0; ch < 6; ++ch) {
-        float y[8];
+        uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (x[ch * 8 + e] - mean) * rstd * gam[ch * 8 + e] + bet[ch * 8 + e];
+        for (int e = 0; e < 4; ++e)      // ((x - mean) * rstd) * gamma + beta, two columns per instruction
+            w[e] = pk_pair(ptx::fma2(ptx::mul2(ptx::add2(x[ch * 4 + e], nmean), rs), ptx::ld2(gam + ch * 8 + 2 * e), ptx::ld2(bet + ch * 8 + 2 * e)));
         uint4 u;
-        u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+        u.x = w[0]; u.y = w[1]; u.z = w[2]; u.w = w[3];
         *reinterpret_cast<uint4 *>(a32 + slab_chunk_off(part * 48 + ch * 8, i)) = u;
     }
 }
@@ -251,11 +278,11 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready));
         };
-        auto load_x = [&](float (&x)[48], const float *cvec) {
+        auto load_x = [&](f32x2 (&x)[24], const float *cvec) {
             uint32_t v[48];
             tmem_ld48(TX + lane_base + part * 48, v);
 #pragma unroll
-            for (int j = 0; j < 48; ++j) x[j] = __uint_as_float(v[j]) + cvec[part * 48 + j];
+            for (int j = 0; j < 24; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 48 + 2 * j));
         };
 
         for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -290,7 +317,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 math_barrier();
                 // ---- LN1(x + c0) -> A32
                 {
-                    float x[48];
+                    f32x2 x[24];
                     load_x(x, par + P_C0);
                     layernorm_to_a32(x, par + P_LN1W + part * 48, par + P_LN1B + part * 48, stat, a32, i, part);
                 }
@@ -299,14 +326,14 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
                 // relative-position bias of this thread's 2 rows x 16 columns of head (2g + hl): fetched one group ahead of its
                 // use (the 17 KB of L1 left beside the shared memory cannot hold it, so every fetch is an L2 round trip)
-                float2 ba[8], bb2[8];
+                f32x2 ba[8], bb2[8];
                 auto load_bias = [&](int g) {
                     const int gq = lane >> 2, tq = lane & 3, hl = (warp >> 2) & 1, rg = warp & 3;
                     const float *bp0 = relb + ((long)(g * 2 + hl) * 64 + rg * 16 + gq) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
-                        ba[n] = __ldg(reinterpret_cast<const float2 *>(bp0 + n * 8));
-                        bb2[n] = __ldg(reinterpret_cast<const float2 *>(bp1 + n * 8));
+                        ba[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp0 + n * 8));
+                        bb2[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp1 + n * 8));
                     }
                 };
                 load_bias(0);
@@ -323,10 +350,10 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 u;
-                            u.x = pk(__uint_as_float(v[j + 0]) + bb[j + 0], __uint_as_float(v[j + 1]) + bb[j + 1]);
-                            u.y = pk(__uint_as_float(v[j + 2]) + bb[j + 2], __uint_as_float(v[j + 3]) + bb[j + 3]);
-                            u.z = pk(__uint_as_float(v[j + 4]) + bb[j + 4], __uint_as_float(v[j + 5]) + bb[j + 5]);
-                            u.w = pk(__uint_as_float(v[j + 6]) + bb[j + 6], __uint_as_float(v[j + 7]) + bb[j + 7]);
+                            u.x = pk_pair(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(bb + j + 0)));
+                            u.y = pk_pair(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(bb + j + 2)));
+                            u.z = pk_pair(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(bb + j + 4)));
+                            u.w = pk_pair(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(bb + j + 6)));
                             *reinterpret_cast<uint4 *>(rowp + j * 2) = u;
                         }
                     }
@@ -353,9 +380,13 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                             mma16816(s[n], qa, b0, b1);
                         }
                         float m0 = -INFINITY, m1 = -INFINITY;
+                        f32x2 sa[8], sb[8];                       // (row r0: columns c, c+1), (row r0 + 8: columns c, c+1)
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
-                            s[n][0] += ba[n].x; s[n][1] += ba[n].y; s[n][2] += bb2[n].x; s[n][3] += bb2[n].y;
+                            sa[n] = ptx::add2(ptx::pk2(s[n][0], s[n][1]), ba[n]);
+                            sb[n] = ptx::add2(ptx::pk2(s[n][2], s[n][3]), bb2[n]);
+                            ptx::up2(sa[n], s[n][0], s[n][1]);
+                            ptx::up2(sb[n], s[n][2], s[n][3]);
                             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
@@ -365,10 +396,14 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         float l0 = 0.f, l1 = 0.f;
                         const float L2E = 1.4426950408889634f;
                         const float mm0 = m0 * L2E, mm1 = m1 * L2E;
+                        const f32x2 l2e2 = ptx::pk2(L2E, L2E), nm0 = ptx::pk2(-mm0, -mm0), nm1 = ptx::pk2(-mm1, -mm1);
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
-                            s[n][0] = exp2f(fmaf(s[n][0], L2E, -mm0)); s[n][1] = exp2f(fmaf(s[n][1], L2E, -mm0));
-                            s[n][2] = exp2f(fmaf(s[n][2], L2E, -mm1)); s[n][3] = exp2f(fmaf(s[n][3], L2E, -mm1));
+                            float e0, e1, e2, e3;
+                            ptx::up2(ptx::fma2(sa[n], l2e2, nm0), e0, e1);
+                            ptx::up2(ptx::fma2(sb[n], l2e2, nm1), e2, e3);
+                            s[n][0] = exp2f(e0); s[n][1] = exp2f(e1);
+                            s[n][2] = exp2f(e2); s[n][3] = exp2f(e3);
                             l0 += s[n][0] + s[n][1];
                             l1 += s[n][2] + s[n][3];
                         }
@@ -398,8 +433,8 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         for (int nt = 0; nt < 2; ++nt) {
                             const int col = h * 16 + nt * 8 + tq * 2;
                             const int bo = (col & 7) * 2;
-                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row0) + bo) = pk(o[nt][0] * i0, o[nt][1] * i0);
-                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row1) + bo) = pk(o[nt][2] * i1, o[nt][3] * i1);
+                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row0) + bo) = pk_pair(ptx::mul2(ptx::pk2(o[nt][0], o[nt][1]), ptx::pk2(i0, i0)));
+                            *reinterpret_cast<uint32_t *>(aout + slab_chunk_off(col, row1) + bo) = pk_pair(ptx::mul2(ptx::pk2(o[nt][2], o[nt][3]), ptx::pk2(i1, i1)));
                         }
                     }
                 }
@@ -407,7 +442,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
                 wait_acc(ACC_PROJ);
                 {
-                    float x[48];
+                    f32x2 x[24];
                     load_x(x, par + P_C1);
                     layernorm_to_a32(x, par + P_LN2W + part * 48, par + P_LN2B + part * 48, stat + 128 * 4, a32, i, part);
                 }
@@ -421,11 +456,11 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     const float *bb = par + P_FC1B + q4 * 192 + part * 48;
 #pragma unroll
                     for (int j = 0; j < 48; j += 8) {
-                        float y[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) y[e] = gelu_fast(__uint_as_float(v[j + e]) + bb[j + e]);
                         uint4 u;
-                        u.x = pk(y[0], y[1]); u.y = pk(y[2], y[3]); u.z = pk(y[4], y[5]); u.w = pk(y[6], y[7]);
+                        u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(bb + j + 0))));
+                        u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(bb + j + 2))));
+                        u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(bb + j + 4))));
+                        u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(bb + j + 6))));
                         *reinterpret_cast<uint4 *>(aout + slab_chunk_off(part * 48 + j, i)) = u;
                     }
                     signal_a();

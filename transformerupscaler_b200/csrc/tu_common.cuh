@@ -37,11 +37,16 @@ __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 // uint8 frames: ToTensor semantics on the way in (x / 255 in fp32, inference.py:65-70, app_overlay.py:298) and
 // (out * 255).clamp(0, 255).to(uint8) on the way out (truncation, app_overlay.py:383)
-__device__ __forceinline__ float to_f(uint8_t v) { return (float)v / 255.f; }
+// exact uint8 -> float without the conversion pipe: 2^23 + v has v in its low mantissa bits
+__device__ __forceinline__ float u8_to_float(uint32_t v) { return __uint_as_float(0x4B000000u | v) - 8388608.f; }
+__device__ __forceinline__ float to_f(uint8_t v) { return u8_to_float(v) / 255.f; }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
-template <> __device__ __forceinline__ uint8_t from_f<uint8_t>(float v) { return (uint8_t)fminf(fmaxf(v * 255.f, 0.f), 255.f); }
+// trunc(clamp(v * 255, 0, 255)): adding 2^23 with round-down leaves floor(t) in the low mantissa bits (t >= 0)
+template <> __device__ __forceinline__ uint8_t from_f<uint8_t>(float v) {
+    return (uint8_t)(__float_as_uint(__fadd_rd(fminf(fmaxf(v * 255.f, 0.f), 255.f), 8388608.f)) & 0xFFu);
+}
 
 // 4 consecutive elements -> float4 (pointer must be aligned to 4 elements)
 __device__ __forceinline__ float4 load4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
