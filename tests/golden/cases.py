@@ -23,3 +23,9 @@ CASES = {
     "residual_720p_1080p": dict(model="ResidualTransformer", shape=(1, 3, 720, 1280), wseed=8, xseed=20,
                                 kw=dict(res_out=(1080, 1920)), stride=8),
 }
+
+# natural-image fixtures (tests/golden/make_natural.py): uint8 LR frame, uint8 HR target, the reference's fp32 output as fp16
+NATURAL = {
+    "natural_window_96x176_r1p5": dict(model="WindowTransformer", wseed=31, kw=dict(res_out=(144, 264))),
+    "natural_fast_96x176_x2": dict(model="FastTransformer", wseed=32, kw=dict(upscale_factor=2)),
+}

@@ -17,10 +17,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 from oracle.weights import synth_state_dict, synth_frames      # noqa: E402
 from tests.golden.cases import CASES                             # noqa: E402
+from tests.golden._refload import ref_model                      # noqa: E402
 
 
 def run_ref(model, sd, x, kw):
-    M = importlib.import_module(f"models.{model}.model").TransformerModel().eval()
+    M = ref_model(model)
     M.load_state_dict(sd, strict=True)
     with torch.no_grad():
         out = M(x, **kw)

@@ -195,3 +195,32 @@ def test_frame_sharding_is_bitwise_invariant(model, kw, shape, bf16):
         for i in range(3):
             one = M(x[i:i + 1].contiguous(), **kw)
             assert torch.equal(one[0], full[i]), f"frame {i} differs between batch-of-3 and batch-of-1"
+
+
+@pytest.mark.parametrize("name", ["natural_window_96x176_r1p5", "natural_fast_96x176_x2"])
+def test_natural_image_psnr_delta(name):
+    """BASELINE.json north_star: bf16 within max-abs 2e-2 of the reference on [0,1] outputs with PSNR delta <= 0.05 dB.
+    LR/HR pair cut from one of the reference's training images; delta = PSNR(ours, HR) - PSNR(reference, HR)."""
+    from tests.golden.cases import NATURAL
+    c = NATURAL[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    M, sd = build(c["model"], c["wseed"])
+    hr = torch.from_numpy(g["hr_u8"]).float() / 255.0
+    ref = torch.from_numpy(g["ref"].astype(np.float32))
+    lr_u8 = torch.from_numpy(g["lr_u8"]).unsqueeze(0).cuda()
+    x = lr_u8.float() / 255.0
+    with torch.no_grad():
+        o32 = M(x, **c["kw"])[0].cpu()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o16 = M(x, **c["kw"])[0].float().cpu()
+        ou8 = M.bfloat16()(lr_u8, **c["kw"])[0].cpu()            # uint8 frame in -> uint8 frame out
+    assert (o32 - ref).abs().max().item() < 6e-4                # reference stored as fp16
+    assert (o16 - ref).abs().max().item() < TOL_BF16
+    p_ref = psnr(ref, hr)
+    for o in (o32, o16):
+        assert abs(psnr(o, hr) - p_ref) <= 0.05, f"{name}: PSNR delta {psnr(o, hr) - p_ref:+.4f} dB"
+    # uint8 frames: against the reference's output put through the reference's own glue, (out * 255).clamp(0, 255).to(uint8)
+    # (app_overlay.py:383; truncation)
+    ref_u8 = (ref * 255.0).clamp(0, 255).to(torch.uint8)
+    assert (ou8.int() - ref_u8.int()).abs().max().item() <= 6           # 2e-2 * 255, + 1 for truncation at a boundary
+    assert abs(psnr(ou8.float() / 255.0, hr) - psnr(ref_u8.float() / 255.0, hr)) <= 0.05

@@ -48,3 +48,17 @@ def test_oracle_error_behaviour():
     sdr = synth_state_dict("ResidualTransformer", 0)
     with pytest.raises(RuntimeError, match="must match"):
         orc.residual_forward(sdr, torch.rand(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("name", ["natural_window_96x176_r1p5", "natural_fast_96x176_x2"])
+def test_oracle_matches_reference_on_natural_image(name):
+    """LR/HR pair cut from one of the reference's training images (tests/golden/make_natural.py); the stored reference
+    output is fp16, hence the looser bound"""
+    from tests.golden.cases import NATURAL
+    c = NATURAL[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    x = torch.from_numpy(g["lr_u8"]).float().div(255.0).unsqueeze(0)
+    out = orc.forward(c["model"], synth_state_dict(c["model"], c["wseed"]), x, **c["kw"])[0].numpy()
+    ref = g["ref"].astype(np.float32)
+    assert out.shape == ref.shape == g["hr_u8"].shape
+    assert np.abs(out - ref).max() < 6e-4          # fp16 storage of values in [0, 1]: half-ulp 2.4e-4
