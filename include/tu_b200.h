@@ -61,7 +61,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
+ * "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------
@@ -123,11 +123,15 @@ typedef struct TuModelWeights {
     const float *dec2_w;        /* fp32 (9, 64 ci, 3 co)                                          */
     const float *dec2_b;        /* (3)                                                            */
     const void *dec2_w16;       /* bf16 (3 ky, 16 rows n = kx*4 + co [co < 3, rest zero], 64 ci) for the tensor-core head, or NULL */
+    const void *dec2_wst;       /* bf16 (3 kx, 3 blocks ky = 2..0, 16 rows co [co < 3, rest zero], 64 ci): streaming head, or NULL  */
+    const float *dec2_b16;      /* fp32 (16): bias padded with zeros (streaming head)                                          */
     /* FastTransformer only */
     TuUpsamplerStage up1[4][2];     /* indexed by scale slot {2,3,4,6} -> 0..3, stage 0/1         */
     TuUpsamplerStage fin[4][2];
     const float *up1conv_w;     /* fp32 (9, 64, 3), no bias                                       */
     const void *up1conv_w16;    /* bf16 (3, 16, 64), same layout, or NULL                          */
+    const void *up1conv_wst;    /* bf16 (3, 3, 16, 64) streaming-head layout, or NULL; its bias vector is 16 zeros */
+    const float *up1conv_b16;
     const float *finconv_w;     /* fp32 (27, 3)                                                   */
     const float *finconv_b;     /* (3)                                                            */
     TuUpFold upfold[4];         /* per scale slot: folded last up1 stage + up1_conv (r = 0: absent)   */
@@ -161,6 +165,10 @@ int tu_conv3x3_c64(const void *in, const void *w, const float *b, void *out, int
  * tensor-core kernel for dtype TU_BF16; w (fp32 (9,64,3)) is always required. */
 int tu_conv3x3_c64_to3(const void *in, int dtype, const float *w, const void *w16, const float *b, float *out,
                        int B, int H, int W, int relu, void *stream);
+/* the same 64->3 convolution on the streaming tensor-core kernel (bf16 NHWC in, planar fp32 out): wst = bf16 (3 kx, 3 blocks
+ * ky = 2..0, 16 rows co, 64 ci), b16 = fp32 (16, zero padded).  Needs the tcgen05 path and W % 4 == 0. */
+int tu_conv3x3_c64_to3_stream(const void *in, const void *wst, const float *b16, float *out, int B, int H, int W, int relu,
+                              void *stream);
 /* 3->3r^2 3x3 conv + PixelShuffle(r) on planar fp32 */
 int tu_conv3x3_c3_ps(const float *in, const float *w, const float *b, float *out, int B, int H, int W, int r,
                      void *stream);

@@ -48,6 +48,22 @@ def conv64to3(x, w, b, relu=0, w16=None):
     return out
 
 
+def conv64to3_stream(x, w, b, relu=0):
+    """x NHWC bf16; w (3, 64, 3, 3), b (3) or None: packed here the way packing.PackedWeights does"""
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    t = torch.zeros(3, 3, 16, 64)
+    t[:, :, :3] = w.float().permute(3, 2, 0, 1).flip(1)
+    b16 = torch.zeros(16)
+    if b is not None:
+        b16[:3] = b
+    wst, b16 = t.to(x.device, torch.bfloat16).contiguous(), b16.to(x.device)
+    out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
+    chk(lib.tu_conv3x3_c64_to3_stream(p(x), p(wst), p(b16), p(out), B, H, W, relu, stream()))
+    torch.cuda.synchronize()
+    return out
+
+
 def conv3_ps(x, w, b, r):
     lib = _lib.load()
     B, _, H, W = x.shape

@@ -140,6 +140,22 @@ def test_conv64to3(dev, dt, bias, relu):
         assert _maxerr(out16, ref16) < 1e-3
 
 
+@pytest.mark.parametrize("bias,relu", [(True, 0), (False, 1)])
+@pytest.mark.parametrize("shape", [(2, 17, 152), (1, 1, 4), (1, 70, 640), (3, 9, 260)])
+def test_conv64to3_stream(dev, bias, relu, shape):
+    """64->3 heads (decoder_conv2 / up1_conv) on the streaming tensor-core kernel vs the oracle conv with bf16-rounded weights"""
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(17)
+    B, H, W = shape
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)).to(BF16)
+    w = torch.from_numpy(rs.uniform(-0.05, 0.05, (3, 64, 3, 3)).astype(np.float32))
+    b = torch.from_numpy(rs.uniform(-0.1, 0.1, 3).astype(np.float32)) if bias else None
+    ref16 = orc.conv3x3_nhwc(x.float(), w.to(BF16).float(), b, relu=bool(relu)).permute(0, 3, 1, 2)
+    out = G.conv64to3_stream(x.to(dev), w, b, relu=relu)
+    assert out.shape == ref16.shape
+    assert _maxerr(out, ref16) < 1e-3
+
+
 @pytest.mark.parametrize("r", [2, 3, 6])
 def test_conv3_ps_and_final(dev, r):
     from tests import gpu_helpers as G

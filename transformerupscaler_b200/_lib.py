@@ -45,9 +45,10 @@ class TuModelWeights(C.Structure):
         ("unembed_w", C.c_void_p), ("unembed_b", C.c_void_p),
         ("dec1_w", C.c_void_p), ("dec1_b", C.c_void_p),
         ("dec2_w", C.c_void_p), ("dec2_b", C.c_void_p), ("dec2_w16", C.c_void_p),
+        ("dec2_wst", C.c_void_p), ("dec2_b16", C.c_void_p),
         ("up1", (TuUpsamplerStage * 2) * 4),
         ("fin", (TuUpsamplerStage * 2) * 4),
-        ("up1conv_w", C.c_void_p), ("up1conv_w16", C.c_void_p),
+        ("up1conv_w", C.c_void_p), ("up1conv_w16", C.c_void_p), ("up1conv_wst", C.c_void_p), ("up1conv_b16", C.c_void_p),
         ("finconv_w", C.c_void_p), ("finconv_b", C.c_void_p),
         ("upfold", TuUpFold * 4),
         ("host_finconv_wb", C.c_void_p),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "tu_stem_conv": (i32, [vp, i32, fp, vp, fp, vp, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c64": (i32, [vp, vp, fp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c64_to3": (i32, [vp, i32, fp, vp, fp, fp, i32, i32, i32, i32, vp]),
+    "tu_conv3x3_c64_to3_stream": (i32, [vp, vp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_conv3x3_c3_ps": (i32, [fp, fp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_final_conv_add": (i32, [fp, fp, fp, fp, vp, i32, i32, i32, i32, i32, vp]),
     "tu_conv12_fused": (i32, [vp, i32, vp, fp, vp, fp, vp, i32, i32, i32, vp]),

@@ -14,6 +14,7 @@ namespace tu {
 int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
 static thread_local std::string g_err;
 static int g_use_tc = 1;
+static int g_head_stream = 0; // 64 -> 3 heads on the streaming kernel (debug switch "head_stream"): measured slower than the tile kernel
 static int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
 static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
 
@@ -207,7 +208,15 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             if (!dry) TU_STEP("up1_folded", tu_upfold_conv(cur, fold, upA, B, ch, cw, stv));
         } else {
             upA = (float *)a.get((size_t)B * 3 * ch * cw * sizeof(float));
-            if (!dry) TU_STEP("up1_conv", tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv));
+            if (!dry) {
+                g_prof_name = "up1_conv";
+                prof_begin(st);
+                rc = TU_TC_UNSUPPORTED;
+                if (tc_on(dt) && g_head_stream) rc = tc_conv3x3_c64_to3_stream((const bf16 *)cur, (const bf16 *)w->up1conv_wst, w->up1conv_b16, upA, B, ch, cw, 1, st);
+                if (rc == TU_TC_UNSUPPORTED) rc = tu_conv3x3_c64_to3(cur, dt, w->up1conv_w, w->up1conv_w16, nullptr, upA, B, ch, cw, 1, stv);
+                prof_end(st, "up1_conv");
+                if (rc) return rc;
+            }
         }
     }
 
@@ -246,7 +255,15 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         if (rc) return rc;
         // ---- decoder
         TU_STEP("decoder_conv1", tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv));
-        TU_STEP("decoder_conv2", tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv));
+        {   // 64 -> 3 head: streaming kernel when packed and the row pitch suits its TMA stores, else the tile kernel
+            g_prof_name = "decoder_conv2";
+            prof_begin(st);
+            rc = TU_TC_UNSUPPORTED;
+            if (tc && g_head_stream) rc = tc_conv3x3_c64_to3_stream((const bf16 *)dec, (const bf16 *)w->dec2_wst, w->dec2_b16, res, B, Hc, Wc, 0, st);
+            if (rc == TU_TC_UNSUPPORTED) rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv);
+            prof_end(st, "decoder_conv2");
+            if (rc) return rc;
+        }
     }
 
     if (!fast) {
@@ -314,6 +331,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "conv_2cta")) {
         tc_set_conv_2cta(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "head_stream")) {
+        g_head_stream = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "fuse_conv12")) {
@@ -404,6 +425,15 @@ extern "C" int tu_conv3x3_c64(const void *in, const void *w, const float *b, voi
     if (dtype == TU_BF16)
         return conv3x3_c64<bf16>((const bf16 *)in, (const bf16 *)w, b, (bf16 *)out, B, H, W, stride, relu, nchunk, ps_r, st);
     TU_CHECK_ARG(false, "conv3x3_c64: bad dtype");
+}
+
+extern "C" int tu_conv3x3_c64_to3_stream(const void *in, const void *wst, const float *b16, float *out, int B, int H, int W, int relu,
+                                         void *stream) {
+    TU_CHECK_ARG(in && wst && b16 && out && B > 0 && H > 0 && W > 0, "conv3x3_c64_to3_stream: bad argument");
+    TU_CHECK_ARG(tc_enabled(), "conv3x3_c64_to3_stream: tcgen05 kernels are unavailable or switched off");
+    int rc = tc_conv3x3_c64_to3_stream((const bf16 *)in, (const bf16 *)wst, b16, out, B, H, W, relu, (cudaStream_t)stream);
+    TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "conv3x3_c64_to3_stream: unsupported alignment (W % 4 must be 0)");
+    return rc;
 }
 
 extern "C" int tu_conv12_fused(const void *x, int in_dtype, const void *w64, const float *b1, const void *w2, const float *b2, void *out,

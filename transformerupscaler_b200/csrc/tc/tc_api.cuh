@@ -61,6 +61,10 @@ int tc_conv3x3_c64_to3(const bf16 *in, const bf16 *w16, const float *bias, float
 // folded last up1 stage + up1_conv (upfold_stream_tcgen05.cu): NHWC bf16 -> planar fp32 (B,3,rH,rW), ReLU applied
 int tc_upfold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int W, cudaStream_t st);
 
+// 64 -> 3 head on the streaming kernel (3x3 instance of upfold_stream_tcgen05.cu); wst / bias16 as packed by packing.py
+int tc_conv3x3_c64_to3_stream(const bf16 *in, const bf16 *wst, const float *bias16, float *out, int B, int H, int W, int relu,
+                              cudaStream_t st);
+
 // all window-transformer blocks in one persistent kernel (dim 128; window_stack_tcgen05.cu)
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                     const float *rel_bias, cudaStream_t st);

@@ -32,14 +32,15 @@ constexpr int UNIT_BYTES = BOXW * 128;        // one input row segment (136 pixe
 constexpr int NACC = 16;                      // output-row accumulators in TMEM
 constexpr int NUM_THREADS = 256;
 
-template <int NO, int R>
+// KS = filter size: 5 for the folded up-sampling branch, 3 for the plain 64 -> 3 heads (R = 1: decoder_conv2, up1_conv)
+template <int NO, int R, int KS>
 struct FoldCfg {
-    static constexpr int RPC = R == 2 ? 6 : R == 3 ? 9 : 5;          // (c, i) output rows per chunk
-    static constexpr int NCHUNK = (3 * R + RPC - 1) / RPC;           // 1, 1, 4
+    static constexpr int RPC = R == 1 ? 3 : R == 2 ? 6 : R == 3 ? 9 : 5;   // (c, i) output rows per chunk
+    static constexpr int NCHUNK = (3 * R + RPC - 1) / RPC;           // 1, 1, 1, 4
     static constexpr int RING = NO == 16 ? 6 : 5;                    // input row slots
     static constexpr int W_BLK = NO * 128;                           // one (kx, ky) filter block: NO rows x 64 ci
-    static constexpr int W_KX = 5 * W_BLK;                           // per kx: [ky = 4, 3, 2, 1, 0] stacked
-    static constexpr int W_BYTES = 5 * W_KX;
+    static constexpr int W_KX = KS * W_BLK;                          // per kx: [ky = KS-1 .. 0] stacked
+    static constexpr int W_BYTES = KS * W_KX;
     static constexpr int ROW_BYTES = 32 * R * 4;                     // one staged high-res row segment of a warp
     static constexpr int STG_WARP = RPC * ROW_BYTES;                 // per buffer
     static constexpr int STG_BYTES = 4 * 2 * STG_WARP;
@@ -49,7 +50,7 @@ struct FoldCfg {
 };
 
 struct FoldParams {
-    int B, H, W;
+    int B, H, W, relu;
     int R_rows;             // output (low-res) rows per work item
     int tiles_x, chunks_y, items_per_chunk, total_items;
     const float *bias;      // (NCHUNK * NO), zero in unused columns
@@ -63,11 +64,12 @@ struct FoldBarriers {
 };
 static_assert(sizeof(FoldBarriers) <= 512, "barrier block too large");
 
-template <int NO, int R>
+template <int NO, int R, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_out, const FoldParams p) {
-    using Cfg = FoldCfg<NO, R>;
+    using Cfg = FoldCfg<NO, R, KS>;
+    constexpr int PAD = KS / 2;
     constexpr int RING = Cfg::RING, W_BLK = Cfg::W_BLK, W_KX = Cfg::W_KX, W_BYTES = Cfg::W_BYTES, RPC = Cfg::RPC;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -132,15 +134,15 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                     wfree_ph ^= 1;
                 }
                 ptx::mbar_expect_tx(ptx::smem_u32(&bars->w_full), W_BYTES);
-                for (int kx = 0; kx < 5; ++kx)      // global order = shared order: [chunk][kx][ky = 4..0][NO][64]
-                    ptx::tma_load_2d(w_sm + kx * W_KX, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * 5 + kx) * 5 * NO);
+                for (int kx = 0; kx < KS; ++kx)     // global order = shared order: [chunk][kx][ky = KS-1..0][NO][64]
+                    ptx::tma_load_2d(w_sm + kx * W_KX, &tmap_w, ptx::smem_u32(&bars->w_full), 0, (chunk * KS + kx) * KS * NO);
                 cur_chunk = chunk;
             }
-            for (int u = 0; u < rows + 4; ++u) {          // input rows y0 - 2 .. y0 + rows + 1
+            for (int u = 0; u < rows + 2 * PAD; ++u) {    // input rows y0 - PAD .. y0 + rows + PAD - 1
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[slot]), phase ^ 1);
                 const uint32_t fb = ptx::smem_u32(&bars->full[slot]);
                 ptx::mbar_expect_tx(fb, UNIT_BYTES);
-                ptx::tma_load_4d(ring_sm + slot * UNIT_BYTES, &tmap_act, fb, 0, x0 - 2, y0 - 2 + u, b);
+                ptx::tma_load_4d(ring_sm + slot * UNIT_BYTES, &tmap_act, fb, 0, x0 - PAD, y0 - PAD + u, b);
                 if (++slot == RING) { slot = 0; phase ^= 1; }
             }
         }
@@ -159,10 +161,10 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                 wfull_ph ^= 1;
                 cur_chunk = chunk;
             }
-            for (int u = 0; u < rows + 4; ++u) {
-                // input row y0 - 2 + u feeds output rows m in [lo, hi] with ky = u - m; the stacked block of row m is 4 - (u - m).
+            for (int u = 0; u < rows + 2 * PAD; ++u) {
+                // input row y0 - PAD + u feeds output rows m in [lo, hi] with ky = u - m; the stacked block of row m is KS-1 - (u - m).
                 // A slot is zero when its row opens (the epilogue clears it after draining), so every MMA accumulates.
-                const int lo = max(u - 4, 0), hi = min(u, rows - 1);
+                const int lo = max(u - (KS - 1), 0), hi = min(u, rows - 1);
                 ptx::mbar_wait(ptx::smem_u32(&bars->full[slot]), phase);
                 if (u <= rows - 1) {                       // row u opens: its slot must have been drained and cleared
                     const uint32_t g = g0 + u;
@@ -170,21 +172,21 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                 }
                 ptx::tc_fence_after();
                 const uint32_t a_lo = ring_lo + ((uint32_t)(slot * UNIT_BYTES) >> 4);
-                const int n = hi - lo + 1, blk0 = 4 - (u - lo);
+                const int n = hi - lo + 1, blk0 = KS - 1 - (u - lo);
                 const int s0 = (g0 + lo) & (NACC - 1);
                 const int n1 = min(n, NACC - s0), n2 = n - n1;            // the window of slots may wrap around the ring
                 const uint32_t d1 = tmem_base + s0 * NO, b1 = w_lo + ((uint32_t)(blk0 * W_BLK) >> 4);
                 const uint32_t id1 = ptx::make_idesc_bf16(TILE_M, NO * n1);
                 if (n2 == 0) {
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx)
+                    for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4)
                             ptx::umma_bf16_lo<1>(d1, a_lo + ((kx * 128 + k4 * 32) >> 4), b1 + ((kx * W_KX + k4 * 32) >> 4), id1, leader);
                 } else {
                     const uint32_t b2 = b1 + ((uint32_t)(n1 * W_BLK) >> 4), id2 = ptx::make_idesc_bf16(TILE_M, NO * n2);
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx)
+                    for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
                         for (int k4 = 0; k4 < 4; ++k4) {
                             ptx::umma_bf16_lo<1>(d1, a_lo + ((kx * 128 + k4 * 32) >> 4), b1 + ((kx * W_KX + k4 * 32) >> 4), id1, leader);
@@ -192,7 +194,7 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                         }
                 }
                 ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[slot]), leader);
-                if (u >= 4) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_full[(g0 + u - 4) & (NACC - 1)]), leader);   // row u-4 is complete
+                if (u >= KS - 1) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc_full[(g0 + u - (KS - 1)) & (NACC - 1)]), leader);   // row u-(KS-1) is complete
                 if (++slot == RING) { slot = 0; phase ^= 1; }
             }
             g0 += rows;
@@ -252,7 +254,10 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
                         const int nidx = qq * R + j;
-                        rowp[qq * 32 * R + j] = fmaxf(__uint_as_float(v[nidx]) + __ldg(bias + nidx), 0.f);
+                        {
+                            const float a = __uint_as_float(v[nidx]) + __ldg(bias + nidx);
+                            rowp[qq * 32 * R + j] = p.relu ? fmaxf(a, 0.f) : a;
+                        }
                     }
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -335,9 +340,9 @@ upfold_ring_kernel(const bf16 *__restrict__ in, const float *__restrict__ ring_w
 
 int g_sm_count_f = 0;
 
-template <int NO, int R>
-int launch_fold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int W, cudaStream_t st) {
-    using Cfg = FoldCfg<NO, R>;
+template <int NO, int R, int KS>
+int launch_fold(const bf16 *in, const void *wbank, const float *bias, int relu, float *out, int B, int H, int W, cudaStream_t st) {
+    using Cfg = FoldCfg<NO, R, KS>;
     static bool attr = false;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
@@ -347,7 +352,7 @@ int launch_fold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int
         cudaDeviceGetAttribute(&g_sm_count_f, cudaDevAttrMultiProcessorCount, dev);
     }
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(upfold_stream_kernel<NO, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(upfold_stream_kernel<NO, R, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "upfold_stream smem attribute");
         attr = true;
     }
@@ -358,10 +363,10 @@ int launch_fold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int
         cuuint32_t box[4] = {64, (cuuint32_t)BOXW, 1, 1}, estr[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_act, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        cuuint64_t wd[2] = {64, (cuuint64_t)Cfg::NCHUNK * 25 * NO}, ws[1] = {128};
-        cuuint32_t wb[2] = {64, (cuuint32_t)(5 * NO)}, we[2] = {1, 1};
+        cuuint64_t wd[2] = {64, (cuuint64_t)Cfg::NCHUNK * KS * KS * NO}, ws[1] = {128};
+        cuuint32_t wb[2] = {64, (cuuint32_t)(KS * NO)}, we[2] = {1, 1};
         if (r == CUDA_SUCCESS)
-            r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)f->w, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)wbank, wd, ws, wb, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         // planar fp32 image as (x, plane row): a warp stores one (c, i) row segment of 32 r pixels at a time
         cuuint64_t od[2] = {(cuuint64_t)W * R, (cuuint64_t)B * 3 * H * R}, os[1] = {(cuuint64_t)W * R * 4};
@@ -375,28 +380,25 @@ int launch_fold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int
         }
     }
     FoldParams p;
-    p.B = B; p.H = H; p.W = W;
+    p.B = B; p.H = H; p.W = W; p.relu = relu;
     p.tiles_x = ceil_div(W, TILE_M);
-    // rows per work item: tall items amortise the four halo rows, but the item count should fill whole waves of SMs
+    // rows per work item: tall items amortise the halo rows, but the item count should fill whole waves of SMs
     int bestR = H < 8 ? H : 8;
     double best = 1e30;
     for (int Rr = 8; Rr <= 96 && Rr <= (H > 8 ? H : 8); ++Rr) {
         const long items = (long)p.tiles_x * ceil_div(H, Rr) * B * Cfg::NCHUNK;
         const long waves = (items + g_sm_count_f - 1) / g_sm_count_f;
-        const double cost = (double)waves * (Rr + 4);
+        const double cost = (double)waves * (Rr + KS - 1);
         if (cost < best - 1e-9) { best = cost; bestR = Rr; }
     }
     p.R_rows = bestR;
     p.chunks_y = ceil_div(H, p.R_rows);
     p.items_per_chunk = p.tiles_x * p.chunks_y * B;
     p.total_items = p.items_per_chunk * Cfg::NCHUNK;
-    p.bias = f->b;
+    p.bias = bias;
     const int grid = p.total_items < g_sm_count_f ? p.total_items : g_sm_count_f;
-    launch_pdl(upfold_stream_kernel<NO, R>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
+    launch_pdl(upfold_stream_kernel<NO, R, KS>, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     TU_CHECK_LAUNCH("upfold_stream");
-    const long ring = (long)B * (2L * W * R + 2L * (H * R - 2));
-    launch_pdl(upfold_ring_kernel, dim3((unsigned)((ring + 7) / 8)), dim3(256), 0, st, in, f->ring_w, f->ring_b, out, B, H, W, R);
-    TU_CHECK_LAUNCH("upfold_ring");
     return TU_OK;
 }
 
@@ -407,12 +409,29 @@ int tc_upfold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int W
     if ((reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(f->w) & 127) || (reinterpret_cast<uintptr_t>(out) & 15))
         return TU_TC_UNSUPPORTED;
     if (((long)W * f->r * 4) % 16) return TU_TC_UNSUPPORTED;       // TMA row pitch of the output image
+    int rc;
     switch (f->r) {
-        case 2: return launch_fold<16, 2>(in, f, out, B, H, W, st);
-        case 3: return launch_fold<32, 3>(in, f, out, B, H, W, st);
-        case 6: return launch_fold<32, 6>(in, f, out, B, H, W, st);
+        case 2: rc = launch_fold<16, 2, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
+        case 3: rc = launch_fold<32, 3, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
+        case 6: rc = launch_fold<32, 6, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
+        default: return TU_TC_UNSUPPORTED;
     }
-    return TU_TC_UNSUPPORTED;
+    if (rc) return rc;
+    const int R = f->r;
+    const long ring = (long)B * (2L * W * R + 2L * (H * R - 2));
+    launch_pdl(upfold_ring_kernel, dim3((unsigned)((ring + 7) / 8)), dim3(256), 0, st, in, f->ring_w, f->ring_b, out, B, H, W, R);
+    TU_CHECK_LAUNCH("upfold_ring");
+    return TU_OK;
+}
+
+// 64 -> 3 head (decoder_conv2, up1_conv) on the same streaming kernel with a 3x3 filter and no PixelShuffle: wst = bf16
+// (3 kx, 3 blocks holding ky = 2..0, 16 rows [co < 3, rest zero], 64 ci); bias16 = fp32 (16) or nullptr.  Needs W % 4 == 0.
+int tc_conv3x3_c64_to3_stream(const bf16 *in, const bf16 *wst, const float *bias16, float *out, int B, int H, int W, int relu,
+                              cudaStream_t st) {
+    if (!wst || !bias16 || (reinterpret_cast<uintptr_t>(in) & 127) || (reinterpret_cast<uintptr_t>(wst) & 127) ||
+        (reinterpret_cast<uintptr_t>(out) & 15) || (W & 3))
+        return TU_TC_UNSUPPORTED;
+    return launch_fold<16, 1, 3>(in, wst, bias16, relu, out, B, H, W, st);
 }
 
 }  // namespace tu

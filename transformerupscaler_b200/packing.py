@@ -109,6 +109,17 @@ class PackedWeights:
             t[:, :3, :3] = w.float().permute(2, 3, 0, 1)                             # (ky, kx, co, ci)
             return dev(t.reshape(3, 16, 64), torch.bfloat16)
 
+        def conv_to3_stream(w):  # (3, 64, 3, 3) -> bf16 (3 kx, 3 blocks ky = 2..0, 16 rows co [co < 3], 64 ci): streaming head
+            t = torch.zeros(3, 3, 16, 64, dtype=torch.float32, device=w.device)
+            t[:, :, :3] = w.float().permute(3, 2, 0, 1).flip(1)                      # (kx, ky, co, ci) with ky reversed
+            return dev(t, torch.bfloat16)
+
+        def bias16(b):
+            t = torch.zeros(16, dtype=torch.float32)
+            if b is not None:
+                t[:3] = b.detach().float().cpu()
+            return dev(t, f32)
+
         mw = _lib.TuModelWeights()
         mw.model = _lib.MODEL_IDS[model]
         fast, resid = model == "FastTransformer", model == "ResidualTransformer"
@@ -143,6 +154,8 @@ class PackedWeights:
         mw.dec2_b = ptr(dev(sd["decoder_conv2.bias"], f32))
         if dtype == torch.bfloat16:
             mw.dec2_w16 = ptr(conv_to3_tc(sd["decoder_conv2.weight"]))
+            mw.dec2_wst = ptr(conv_to3_stream(sd["decoder_conv2.weight"]))
+            mw.dec2_b16 = ptr(bias16(sd["decoder_conv2.bias"]))
 
         # transformer blocks (q rows and q bias pre-scaled by head_dim^-0.5 = 0.25: exact in fp32 and bf16)
         self.blocks = (_lib.TuBlockWeights * nb)()
@@ -199,6 +212,8 @@ class PackedWeights:
             mw.up1conv_w = ptr(conv_to3(sd["up1_conv.conv.weight"]))
             if dtype == torch.bfloat16:
                 mw.up1conv_w16 = ptr(conv_to3_tc(sd["up1_conv.conv.weight"]))
+                mw.up1conv_wst = ptr(conv_to3_stream(sd["up1_conv.conv.weight"]))
+                mw.up1conv_b16 = ptr(bias16(None))
             mw.finconv_w = ptr(conv_small_in(sd["final_upscale_conv.weight"]))
             mw.finconv_b = ptr(dev(sd["final_upscale_conv.bias"], f32))
             # host copy of the 3 -> 3 filter: its 84 values travel in the parameters of the fused tail kernel
