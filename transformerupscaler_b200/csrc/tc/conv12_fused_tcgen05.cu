@@ -47,7 +47,7 @@ constexpr int OFF_W1 = OFF_A1 + A1_BYTES;
 constexpr int OFF_STG = OFF_W1 + W1_BYTES;
 constexpr int OFF_RAW = OFF_STG + STG_BYTES;
 constexpr int OFF_BAR = OFF_RAW + NRAW * RAW_STAGE;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 640 + 1024;
 constexpr int NUM_THREADS = 512;
 static_assert(OFF_A1 % 1024 == 0 && OFF_W1 % 1024 == 0 && OFF_STG % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory layout");
 
@@ -74,7 +74,7 @@ struct FusedBarriers {
     uint64_t a_full, a_empty, w_full;
     uint32_t tmem_base;
 };
-static_assert(sizeof(FusedBarriers) <= 512, "barrier block too large");
+static_assert(sizeof(FusedBarriers) <= 384, "barrier block too large (the last 256 bytes of its 640-byte area hold conv2's bias)");
 
 __device__ __forceinline__ float ldx(float v) { return v; }
 __device__ __forceinline__ float ldx(bf16 v) { return __bfloat162float(v); }
@@ -420,10 +420,30 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         // ================================ conv2 epilogue (warps 4-7): one output row at a time ================================
         const int q = warp - 4;
         uint32_t g = 0, nstore = 0;
-        uint32_t zero32[32];
+        // conv2's bias is folded into the accumulators: a row accumulator is "cleared" to the bias vector, so the drain is only
+        // ReLU + convert (it used to issue 64 bias loads per row and thread on a kernel bound by the load/store and
+        // shared-memory pipes).  The vector is staged once in shared memory and re-read (8 x 128 bit) for every clear.
+        float *bias_s = reinterpret_cast<float *>(sm + OFF_BAR + 384);
+        if (q == 0) {
+            bias_s[lane] = p.bias2 ? p.bias2[lane] : 0.f;
+            bias_s[lane + 32] = p.bias2 ? p.bias2[lane + 32] : 0.f;
+        }
+        asm volatile("bar.sync 3, 128;" ::: "memory");
+        auto store_bias = [&](uint32_t taddr) {           // 64 columns of this warp's 32 lanes <- bias
 #pragma unroll
-        for (int c = 0; c < 32; ++c) zero32[c] = 0u;
-        for (int c = 0; c < NACC * 64; c += 32) ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero32);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t t[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint4 u;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                 : "r"(ptx::smem_u32(bias_s + h * 32 + j * 4)));
+                    t[j * 4 + 0] = u.x; t[j * 4 + 1] = u.y; t[j * 4 + 2] = u.z; t[j * 4 + 3] = u.w;
+                }
+                ptx::tmem_st_x32(taddr + h * 32, t);
+            }
+        };
+        for (int sl = 0; sl < NACC; ++sl) store_bias(tmem_base + ((uint32_t)(q * 32) << 16) + sl * 64);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -445,8 +465,7 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 ptx::tmem_ld_x32(taddr, v0);
                 ptx::tmem_ld_x32(taddr + 32, v1);
                 ptx::tmem_ld_wait();
-                ptx::tmem_st_x32(taddr, zero32);
-                ptx::tmem_st_x32(taddr + 32, zero32);
+                store_bias(taddr);                      // "clear" the slot for the row that opens it next
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -459,14 +478,12 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 uint8_t *rowp = stg_w + buf * 4096 + lane * 128;
 #pragma unroll
                 for (int c = 0; c < 64; c += 8) {
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float a = __uint_as_float(c < 32 ? v0[c + e] : v1[c - 32 + e]) + (p.bias2 ? __ldg(p.bias2 + c + e) : 0.f);
-                        f[e] = p.relu ? fmaxf(a, 0.f) : a;
-                    }
-                    uint4 uu;
-                    uu.x = pack2(f[0], f[1]); uu.y = pack2(f[2], f[3]); uu.z = pack2(f[4], f[5]); uu.w = pack2(f[6], f[7]);
+                    const uint32_t *v = c < 32 ? &v0[c] : &v1[c - 32];
+                    uint4 uu;      // conv2 is always followed by ReLU (W:245, F:252, R:129): one convert-with-ReLU per channel pair
+                    uu.x = pack2_relu(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                    uu.y = pack2_relu(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                    uu.z = pack2_relu(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                    uu.w = pack2_relu(__uint_as_float(v[6]), __uint_as_float(v[7]));
                     *reinterpret_cast<uint4 *>(rowp + ((((c >> 3) ^ (lane & 7))) << 4)) = uu;
                 }
                 ptx::fence_proxy_async();

@@ -45,6 +45,7 @@ struct StreamParams {
     int tiles_x, chunks_y, items_per_chunk, total_items;
     int ps_r;               // PixelShuffle factor (0 = plain): output chunk c holds sub-pixel phase (c / r, c % r)
     const float *bias;      // nchunk * 64, or nullptr
+    int acc_bias;           // single bank: the bias vector is folded into the accumulator "clear" instead of being added in the drain
 };
 
 struct StreamBarriers {
@@ -197,11 +198,18 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         // ================================ epilogue: one output row at a time ================================
         const int q = warp - 4;
         uint32_t g = 0, nstore = 0;
-        uint32_t zero32[32];
+        // value a row accumulator is reset to after its drain: zero, or (single filter bank) the bias vector, which then never has
+        // to be added in the drain (64 global loads per row and thread otherwise)
+        uint32_t init0[32], init1[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) zero32[c] = 0u;
-        // all eight accumulator slots start cleared (this warp's 32 TMEM lanes); the first acc_empty phase publishes it
-        for (int c = 0; c < 512; c += 32) ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero32);
+        for (int c = 0; c < 32; ++c) {
+            init0[c] = p.acc_bias ? __float_as_uint(__ldg(p.bias + c)) : 0u;
+            init1[c] = p.acc_bias ? __float_as_uint(__ldg(p.bias + 32 + c)) : 0u;
+        }
+        for (int c = 0; c < 512; c += 64) {
+            ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, init0);
+            ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c + 32, init1);
+        }
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -213,7 +221,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
             int b, y0, rows, x0;
             const int chunk = item_geom(it, b, y0, rows, x0);
             const int px0 = x0 + q * 32;
-            const float *bias = p.bias ? p.bias + chunk * 64 : nullptr;
+            const float *bias = (p.bias && !p.acc_bias) ? p.bias + chunk * 64 : nullptr;
 #pragma unroll 1
             for (int m = 0; m < rows; ++m, ++g) {
                 const int sl = g & (NACC - 1);
@@ -224,8 +232,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
                 ptx::tmem_ld_x32(taddr, v0);
                 ptx::tmem_ld_x32(taddr + 32, v1);
                 ptx::tmem_ld_wait();
-                ptx::tmem_st_x32(taddr, zero32);                                // clear the slot for the row that opens it next
-                ptx::tmem_st_x32(taddr + 32, zero32);
+                ptx::tmem_st_x32(taddr, init0);                                 // reset the slot for the row that opens it next
+                ptx::tmem_st_x32(taddr + 32, init1);
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -349,6 +357,7 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
     p.total_items = p.items_per_chunk * nchunk;
     p.ps_r = ps_r;
     p.bias = bias;
+    p.acc_bias = (bias != nullptr && nchunk == 1) ? 1 : 0;
     const int grid = p.total_items < g_sm_count_s ? p.total_items : g_sm_count_s;
     launch_pdl(conv3x3_stream_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);
     TU_CHECK_LAUNCH("conv3x3_stream");

@@ -205,10 +205,12 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
         // ================================ epilogue: one low-res output row at a time ================================
         const int q = warp - 4;
         uint32_t g = 0, nstore = 0;
+        // value a row accumulator is reset to after its drain: with a single filter bank the bias vector itself, so that the drain
+        // does not add it; zero otherwise
+        constexpr bool ACC_BIAS = Cfg::NCHUNK == 1;
         uint32_t zero[NO];
 #pragma unroll
-        for (int c = 0; c < NO; ++c) zero[c] = 0u;
-        // all accumulator slots start cleared (this warp's 32 TMEM lanes); the first acc_empty phase publishes it
+        for (int c = 0; c < NO; ++c) zero[c] = ACC_BIAS ? __float_as_uint(__ldg(p.bias + c)) : 0u;
         for (int c = 0; c < NACC * NO; c += NO) {
             if constexpr (NO == 16) ptx::tmem_st_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero);
             else ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero);
@@ -255,7 +257,7 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                     for (int j = 0; j < R; ++j) {
                         const int nidx = qq * R + j;
                         {
-                            const float a = __uint_as_float(v[nidx]) + __ldg(bias + nidx);
+                            const float a = ACC_BIAS ? __uint_as_float(v[nidx]) : __uint_as_float(v[nidx]) + __ldg(bias + nidx);
                             rowp[qq * 32 * R + j] = p.relu ? fmaxf(a, 0.f) : a;
                         }
                     }
