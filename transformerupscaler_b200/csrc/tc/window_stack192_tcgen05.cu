@@ -86,6 +86,17 @@ __device__ __forceinline__ float gelu_fast(float x) {
 
 // ---- packed-fp32 (FFMA2 / FMUL2 / FADD2) forms of the element-wise math: same IEEE operations, half the issue slots
 using ptx::f32x2;
+// softmax: single-instruction exp2 / reciprocal (2 ulp; arguments are <= 0 resp. >= 1, the results are rounded to bf16)
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pk_pair(f32x2 v) {          // (lo, hi) -> bf16x2
     float lo, hi;
     ptx::up2(v, lo, hi);
@@ -402,8 +413,8 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                             float e0, e1, e2, e3;
                             ptx::up2(ptx::fma2(sa[n], l2e2, nm0), e0, e1);
                             ptx::up2(ptx::fma2(sb[n], l2e2, nm1), e2, e3);
-                            s[n][0] = exp2f(e0); s[n][1] = exp2f(e1);
-                            s[n][2] = exp2f(e2); s[n][3] = exp2f(e3);
+                            s[n][0] = ex2_fast(e0); s[n][1] = ex2_fast(e1);
+                            s[n][2] = ex2_fast(e2); s[n][3] = ex2_fast(e3);
                             l0 += s[n][0] + s[n][1];
                             l1 += s[n][2] + s[n][3];
                         }
@@ -426,7 +437,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                             mma16816(o[0], pa, v0, v1);
                             mma16816(o[1], pa, v2, v3);
                         }
-                        const float i0 = 1.f / l0, i1 = 1.f / l1;
+                        const float i0 = rcp_fast(l0), i1 = rcp_fast(l1);      // l >= 1: the row maximum contributes exp2(0)
                         // attention output -> AO (row = token of the tile, column = h*16 + d), swizzled K-slabs
                         const int row0 = win * 64 + r0, row1 = row0 + 8;
 #pragma unroll
