@@ -193,7 +193,19 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool vali
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
-__global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
+// packed fp32 pairs and single-instruction exp2 for the attention inner loop (sm_100: FFMA2 / FADD2 are two IEEE fp32
+// operations per issue slot; ex2.approx is 2 ulp, its results are rounded to bf16 for the PV product)
+__device__ __forceinline__ uint64_t ga_pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void ga_up2(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ga_fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t ga_add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ga_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// GA_MT m16 query tiles per warp, GA_WARPS warps per CTA (128 queries per CTA either way).  Measured on cfg5a (2 frames, 8 layers,
+// transformer blocks in total): GA_MT = 1 1.33 ms, 2 1.21 ms, 4 1.33 ms -- one tile per warp doubles the K/V fragment loads per
+// query, four tiles leave too few warps per SM.
+constexpr int GA_MT = 2, GA_WARPS = 128 / (16 * GA_MT);
+__global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
     __shared__ __align__(16) bf16 ks[2][GA_KT][GA_PITCH];
     __shared__ __align__(16) bf16 vs[2][GA_KT][GA_PITCH];
     const int b = blockIdx.z, h = blockIdx.y;
@@ -201,32 +213,34 @@ __global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__rest
     const int g = lane >> 2, tq = lane & 3;
     const long ld = 3L * dim;
     const bf16 *base = qkv + (long)b * S * ld + h * 16;
-    const int q0 = blockIdx.x * 128 + warp * 32;
+    const int q0 = blockIdx.x * 128 + warp * 16 * GA_MT;
     const float L2E = 1.4426950408889634f;
 
     auto stage = [&](int buf, int k0) {
-        const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
-        const int key = k0 + r;
-        const bool ok = key < S;
-        const bf16 *src = base + (long)(ok ? key : 0) * ld + hf * 8;
-        cp_async16(&ks[buf][r][hf * 8], src + dim, ok);
-        cp_async16(&vs[buf][r][hf * 8], src + 2 * dim, ok);
+        for (int e = threadIdx.x; e < 2 * GA_KT; e += GA_WARPS * 32) {
+            const int r = e >> 1, hf = e & 1;
+            const int key = k0 + r;
+            const bool ok = key < S;
+            const bf16 *src = base + (long)(ok ? key : 0) * ld + hf * 8;
+            cp_async16(&ks[buf][r][hf * 8], src + dim, ok);
+            cp_async16(&vs[buf][r][hf * 8], src + 2 * dim, ok);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     // Q fragments of the two m16 tiles (rows beyond S read row S-1; their results are never stored)
-    uint32_t qa[2][4];
+    uint32_t qa[GA_MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < GA_MT; ++mt) {
         const int r0 = min(q0 + mt * 16 + g, S - 1), r1 = min(q0 + mt * 16 + g + 8, S - 1);
         qa[mt][0] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2);
         qa[mt][1] = *reinterpret_cast<const uint32_t *>(base + (long)r1 * ld + tq * 2);
         qa[mt][2] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2 + 8);
         qa[mt][3] = *reinterpret_cast<const uint32_t *>(base + (long)r1 * ld + tq * 2 + 8);
     }
-    float o[2][2][4], m[2][2], l[2][2];
+    float o[GA_MT][2][4], m[GA_MT][2], l[GA_MT][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < GA_MT; ++mt) {
         m[mt][0] = m[mt][1] = -INFINITY;
         l[mt][0] = l[mt][1] = 0.f;
 #pragma unroll
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__rest
                          : "r"(addr));
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+        for (int mt = 0; mt < GA_MT; ++mt) {
             float s[8][4];
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
@@ -284,18 +298,28 @@ __global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__rest
             t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
             t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
             const float n0 = fmaxf(m[mt][0], t0), n1 = fmaxf(m[mt][1], t1);
-            const float c0 = exp2f((m[mt][0] - n0) * L2E), c1 = exp2f((m[mt][1] - n1) * L2E);   // exp2(-inf) = 0 on the first tile
+            const float c0 = ga_ex2((m[mt][0] - n0) * L2E), c1 = ga_ex2((m[mt][1] - n1) * L2E);   // exp2(-inf) = 0 on the first tile
             m[mt][0] = n0; m[mt][1] = n1;
             l[mt][0] *= c0; l[mt][1] *= c1;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) { o[mt][nt][0] *= c0; o[mt][nt][1] *= c0; o[mt][nt][2] *= c1; o[mt][nt][3] *= c1; }
-            const float b0 = n0 * L2E, b1 = n1 * L2E;
+            // exponent arguments on packed fp32 pairs (FFMA2), one MUFU per exponential, row sums on packed pairs
+            const uint64_t l2e2 = ga_pk2(L2E, L2E), nb0 = ga_pk2(-n0 * L2E, -n0 * L2E), nb1 = ga_pk2(-n1 * L2E, -n1 * L2E);
+            uint64_t ls0 = ga_pk2(0.f, 0.f), ls1 = ga_pk2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                s[n][0] = exp2f(fmaf(s[n][0], L2E, -b0)); s[n][1] = exp2f(fmaf(s[n][1], L2E, -b0));
-                s[n][2] = exp2f(fmaf(s[n][2], L2E, -b1)); s[n][3] = exp2f(fmaf(s[n][3], L2E, -b1));
-                l[mt][0] += s[n][0] + s[n][1];
-                l[mt][1] += s[n][2] + s[n][3];
+                float e0, e1, e2, e3;
+                ga_up2(ga_fma2(ga_pk2(s[n][0], s[n][1]), l2e2, nb0), e0, e1);
+                ga_up2(ga_fma2(ga_pk2(s[n][2], s[n][3]), l2e2, nb1), e2, e3);
+                s[n][0] = ga_ex2(e0); s[n][1] = ga_ex2(e1);
+                s[n][2] = ga_ex2(e2); s[n][3] = ga_ex2(e3);
+                ls0 = ga_add2(ls0, ga_pk2(s[n][0], s[n][1]));
+                ls1 = ga_add2(ls1, ga_pk2(s[n][2], s[n][3]));
+            }
+            {
+                float x0, x1;
+                ga_up2(ls0, x0, x1); l[mt][0] += x0 + x1;
+                ga_up2(ls1, x0, x1); l[mt][1] += x0 + x1;
             }
 #pragma unroll
             for (int kt = 0; kt < 4; ++kt) {
@@ -311,7 +335,7 @@ __global__ void __launch_bounds__(128) global_attn_mma_kernel(const bf16 *__rest
         __syncthreads();       // everyone is done with this buffer before the next prefetch overwrites it
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < GA_MT; ++mt) {
         float l0 = l[mt][0], l1 = l[mt][1];
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -466,7 +490,7 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
         TU_CHECK_LAUNCH("window_attn");
     } else if (tc && sizeof(T) == 2) {
         dim3 grid(ceil_div(S, 128), heads, M / S);
-        global_attn_mma_kernel<<<grid, 128, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
+        global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
         TU_CHECK_LAUNCH("global_attn_mma");
     } else {
         dim3 grid(ceil_div(S, 128), heads, M / S);
