@@ -13,7 +13,7 @@ import importlib, json, os, sys, time, copy, math, platform
 os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference" if os.path.isdir("/root/reference/models") else os.path.join(HERE, "_ref")
-sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(HERE))      # repository root: baseline.refload
 
 import torch
 
@@ -24,7 +24,8 @@ OUT = {"ref_path": REF, "torch": torch.__version__, "cuda": torch.version.cuda,
 
 def model(name, seed=0):
     torch.manual_seed(seed)
-    return importlib.import_module(f"models.{name}.model").TransformerModel().eval()
+    from baseline.refload import reference_model_class
+    return reference_model_class(os.path.join(REF, "models"), name)().eval()
 
 
 def psnr(a, b):

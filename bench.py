@@ -87,9 +87,8 @@ def reference_cpu_fps(steps, warmup):
     x = synth_frames(1, H, W, seed=123)
     torch.set_num_threads(os.cpu_count() or 1)
     if os.path.isdir(os.path.join(ref_dir, "models", "WindowTransformer")):
-        sys.path.insert(0, ref_dir)
-        M = importlib.import_module("models.WindowTransformer.model").TransformerModel().eval()
-        sys.path.pop(0)
+        from baseline.refload import reference_model_class      # the reference's class, not this repo's drop-in alias
+        M = reference_model_class(os.path.join(ref_dir, "models"), "WindowTransformer")().eval()
         M.load_state_dict(sd, strict=True)
         kind = "reference"
 

@@ -158,3 +158,27 @@ def test_fold_up1_matches_the_op_chain(r):
         ch, q = row // rpc, row % rpc
         assert torch.equal(bank[ch, 3, 1, q * r + j], Wf[1, 1, o, :, 3, 3])
         assert bias[ch * NO + q * r + j] == bf[1, 1, o]
+
+
+def test_reference_loader_resolves_to_the_reference_not_to_the_drop_in_alias():
+    """bench.py's reference arm / cpu_baseline must time the UNMODIFIED reference modules (baseline/_ref), although this
+    repository ships a `models` package with the same module paths"""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref", "models")
+    if not os.path.isdir(os.path.join(ref, "WindowTransformer")):
+        pytest.skip("baseline/_ref not present")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from baseline.refload import reference_model_class
+    for name in ("WindowTransformer", "FastTransformer", "ResidualTransformer"):
+        cls = reference_model_class(ref, name)
+        assert os.path.abspath(sys.modules[cls.__module__].__file__).startswith(ref)
+        m = cls().eval()
+        assert isinstance(m, torch.nn.Module) and not cls.__module__.startswith("transformerupscaler_b200")
+    # and the reference really runs on CPU (the drop-in alias raises without a CUDA device)
+    m = reference_model_class(ref, "WindowTransformer")().eval()
+    with torch.no_grad():
+        y = m(torch.rand(1, 3, 64, 80), res_out=(96, 120))
+    assert tuple(y.shape) == (1, 3, 96, 120)
