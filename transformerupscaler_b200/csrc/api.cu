@@ -14,6 +14,7 @@ namespace tu {
 int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
 static thread_local std::string g_err;
 static int g_use_tc = 1;
+static int g_unembed_overlap = 1;   // unembed starts on the SMs the window stack's last wave leaves idle (debug switch "unembed_overlap")
 static int g_head_stream = 0; // 64 -> 3 heads on the streaming kernel (debug switch "head_stream"): measured slower than the tile kernel
 static int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
 static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
@@ -161,8 +162,16 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     T *comb = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
     T *dec = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
     float *res = (float *)a.get((size_t)B * 3 * Hc * Wc * sizeof(float));
+    // tile hand-off between the fused window stack and the unembed GEMM: word 0 = tile counter, words 16.. = one flag per 128 tokens
+    const size_t sync_bytes = (size_t)(16 + Mtok / 128 + 1) * sizeof(int);
+    int *sync_words = (int *)a.get(sync_bytes);
+    const bool overlap = g_unembed_overlap && window && tc_on(dt) && w->stack_w && g_use_stack && (Mtok % 128) == 0;
 
     // ---- encoder
+    if (!dry && overlap) {
+        cudaError_t e = cudaMemsetAsync(sync_words, 0, sync_bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "memset tile flags");
+    }
     if (!dry) {
         // conv1 fused into conv2 (its 64-channel output never reaches HBM) when the tensor-core path and the image pitch allow it
         rc = TU_TC_UNSUPPORTED;
@@ -233,9 +242,11 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
         if (tc && window && dim == 128 && w->stack_w && g_use_stack)
-            rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+            rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel,
+                                 overlap ? sync_words + 16 : nullptr, st);
         else if (tc && window && dim == 192 && w->stack_w && g_use_stack)
-            rc = tc_window_stack192(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+            rc = tc_window_stack192(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel,
+                                    overlap ? sync_words + 16 : nullptr, st);
         if (rc != TU_TC_UNSUPPORTED && rc != TU_OK) return rc;
         const bool stack_done = rc == TU_OK;
         for (int i = 0; i < w->n_blocks && !stack_done; ++i)
@@ -246,9 +257,12 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         g_prof_name = "patch_unembed";
         prof_begin(st);
         rc = TU_TC_UNSUPPORTED;
-        if (tc)
+        if (tc && overlap && stack_done && !g_prof_open)       // (the per-kernel profiling events would serialise the two kernels)
             rc = tc_patch_unembed(tok16, (const bf16 *)w->unembed_w, w->unembed_b, (const bf16 *)fd, Hd, Wd, (bf16 *)comb, B, Ht, Wt,
-                                  Hc, Wc, dim, window ? 1 : 0, st);
+                                  Hc, Wc, dim, 1, sync_words, sync_words + 16, st);
+        if (tc && rc == TU_TC_UNSUPPORTED)
+            rc = tc_patch_unembed(tok16, (const bf16 *)w->unembed_w, w->unembed_b, (const bf16 *)fd, Hd, Wd, (bf16 *)comb, B, Ht, Wt,
+                                  Hc, Wc, dim, window ? 1 : 0, nullptr, nullptr, st);
         if (rc == TU_TC_UNSUPPORTED)
             rc = tu_patch_unembed(tok, w->unembed_w, w->unembed_b, fd, Hd, Wd, comb, dt, B, Ht, Wt, Hc, Wc, dim, window ? 1 : 0, stv);
         prof_end(st, "patch_unembed");
@@ -331,6 +345,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "conv_2cta")) {
         tc_set_conv_2cta(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "unembed_overlap")) {
+        g_unembed_overlap = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "head_stream")) {
@@ -462,8 +480,8 @@ extern "C" int tu_window_stack(float *tokens, const TuModelWeights *w, int M, vo
     TU_CHECK_ARG(tc_enabled(), "window_stack: tcgen05 kernels are unavailable or switched off");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = TU_TC_UNSUPPORTED;
-    if (w->dim == 128) rc = tc_window_stack(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
-    else if (w->dim == 192) rc = tc_window_stack192(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, st);
+    if (w->dim == 128) rc = tc_window_stack(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, st);
+    else if (w->dim == 192) rc = tc_window_stack192(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, st);
     TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "window_stack: unsupported shape (token count must be a multiple of 128)");
     return rc;
 }

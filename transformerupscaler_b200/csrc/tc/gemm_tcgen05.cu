@@ -53,7 +53,13 @@ struct GemmParams {
     int tiles_tx;       // embed: x-tiles of 16 tokens
     const bf16 *skip;
     int skipH, skipW, Hc, Wc;
+    // UNEMBED_TMA behind the fused window stack: tiles are handed out through a global counter and an M tile is touched only
+    // after the stack has published it (tile_flags[tm] != 0), so that this kernel can start -- programmatic dependent launch,
+    // no griddepcontrol.wait -- on the SMs the stack's last, partly filled wave leaves idle
+    int *dyn_ctr;
+    const int *tile_flags;
 };
+constexpr int QD = 4;      // depth of the tile-index queue between the scheduler thread and the three roles
 
 struct Barriers {
     uint64_t full[NSTAGE];
@@ -61,8 +67,17 @@ struct Barriers {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t skip_full[8][2];   // UNEMBED_TMA: private to each epilogue warp
+    uint64_t q_full[QD], q_empty[QD];
+    int tq[QD];
     uint32_t tmem_base;
 };
+static_assert(sizeof(Barriers) <= 512, "barrier block too large");
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ long win_row(int b, int ty, int tx, int nWy, int nWx) {
     return (((long)b * nWy + (ty >> 3)) * nWx + (tx >> 3)) * 64 + (ty & 7) * 8 + (tx & 7);
@@ -92,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // UNEMBED_TMA keeps its 1024-byte aligned pixel boxes right after the operand stages; barriers follow
     const int bar_off = NSTAGE * stage_bytes + (p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0);
     Barriers *bars = reinterpret_cast<Barriers *>(smem_al + bar_off);
-    float *stage_f32 = reinterpret_cast<float *>(smem_al + bar_off + 256);   // UNEMBED only: 8 warps x 32 rows x 68 floats
+    float *stage_f32 = reinterpret_cast<float *>(smem_al + bar_off + 512);   // UNEMBED only: 8 warps x 32 rows x 68 floats
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int nk = p.K / BK;
 
@@ -106,6 +121,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 8);
         }
         for (int i = 0; i < 16; ++i) ptx::mbar_init(ptx::smem_u32(&bars->skip_full[i >> 1][i & 1]), 1);
+        for (int i = 0; i < QD; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->q_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->q_empty[i]), 10);       // TMA producer, MMA warp, 8 epilogue warps
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -121,15 +140,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    pdl_wait();
+    const bool dyn = p.dyn_ctr != nullptr;
+    if (!dyn) pdl_wait();       // dynamic mode orders itself behind the window stack tile by tile (tile_flags)
 
-    if (warp == 0 && lane == 0) {
+    // k-th tile of this CTA: static round-robin, or the k-th index the scheduler thread drew from the global counter
+    auto tile_at = [&](int k) -> int {
+        if (!dyn) {
+            const int t = blockIdx.x + k * gridDim.x;
+            return t < p.total_tiles ? t : -1;
+        }
+        ptx::mbar_wait(ptx::smem_u32(&bars->q_full[k % QD]), (k / QD) & 1);
+        return *reinterpret_cast<volatile int *>(&bars->tq[k % QD]);
+    };
+    auto tile_done = [&](int k) {        // one arrival per consumer (the calling thread)
+        if (dyn) ptx::mbar_arrive(ptx::smem_u32(&bars->q_empty[k % QD]));
+    };
+    auto wait_published = [&](int tm) {  // the window stack has written (and fenced) the tokens of M tile tm
+        if (!p.tile_flags) return;
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(p.tile_flags + tm) == 0) {
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: a protocol bug traps instead of hanging the GPU
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy acquire -> the TMA reads that follow
+    };
+
+    if (warp == 3 && lane == 0 && dyn) {
+        // ================================ tile scheduler ================================
+        for (int k = 0;; ++k) {
+            if (k >= QD) ptx::mbar_wait(ptx::smem_u32(&bars->q_empty[k % QD]), ((k / QD) & 1) ^ 1);
+            const int t = atomicAdd(p.dyn_ctr, 1);
+            *reinterpret_cast<volatile int *>(&bars->tq[k % QD]) = t < p.total_tiles ? t : -1;
+            ptx::mbar_arrive(ptx::smem_u32(&bars->q_full[k % QD]));      // release: the index is visible to whoever passes the wait
+            if (t >= p.total_tiles) break;
+        }
+    } else if (warp == 0 && lane == 0) {
         // ================================ TMA producer ================================
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int ready_tm = -1;
+        for (int k = 0;; ++k) {
+            const int t = tile_at(k);
+            if (t < 0) break;
             const int tn = t % p.tiles_n, tm = t / p.tiles_n;
             const int n0 = tn * p.BN;
+            if (tm != ready_tm) { wait_published(tm); ready_tm = tm; }
             for (int s = 0; s < nk; ++s) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                 const uint32_t dst = smem0 + stage * stage_bytes;
@@ -144,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ptx::tma_load_2d(dst + A_STAGE, &tmap_w, fb, s * BK, n0);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            tile_done(k);
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
@@ -152,8 +208,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t smem_lo = ptx::sdesc_lo(smem0);
         int stage = 0;
         uint32_t phase = 0;
-        int it = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        for (int it = 0;; ++it) {
+            if (tile_at(it) < 0) break;
+            __syncwarp();
+            if (lane == 0) tile_done(it);        // the MMA warp needs no tile coordinates, only the count
             const int set = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), aphase ^ 1);
@@ -202,20 +260,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             auto request = [&](int t, int buf) {                  // lane 0: skip box of tile t -> buffer buf
                 int dx, tx0, y0, b;
                 if (!coords(t, dx, tx0, y0, b)) return;
+                wait_published(t / p.tiles_n);                    // (dynamic mode) nothing of a tile is touched before the stack published it
                 const uint32_t fb = ptx::smem_u32(&bars->skip_full[w8][buf]);
                 ptx::mbar_expect_tx(fb, 4096);
                 ptx::tma_load_5d(box_sm + buf * 4096, &tmap_skip, fb, 0, dx, tx0, y0, b);
             };
             const float4 *bias4 = reinterpret_cast<const float4 *>(p.bias);
-            if (lane == 0 && blockIdx.x < p.total_tiles) request(blockIdx.x, 0);
-            int it = 0;
+            int t = tile_at(0);
+            if (lane == 0 && t >= 0) request(t, 0);
             uint32_t sph[2] = {0u, 0u};
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            for (int it = 0; t >= 0; ++it) {
                 const int set = it & 1, buf = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 int dx, tx0, y0, b;
                 const bool live = coords(t, dx, tx0, y0, b);
-                if (lane == 0 && t + gridDim.x < p.total_tiles) request(t + gridDim.x, buf ^ 1);   // that buffer's store has been read (below)
+                const int t_next = tile_at(it + 1);
+                __syncwarp();
+                if (lane == 0) {
+                    tile_done(it);
+                    if (t_next >= 0) request(t_next, buf ^ 1);   // that buffer's store has been read (below)
+                }
+                const int t_cur = t;
+                t = t_next;
+                (void)t_cur;
                 ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
                 ptx::tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256 + cbeg;
@@ -485,7 +552,7 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStre
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 256 + (p.epi == EPI_UNEMBED ? UE_BYTES : p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0) + 1024;
+    const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 512 + (p.epi == EPI_UNEMBED ? UE_BYTES : p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0) + 1024;
     if (smem > g_smem_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "gemm_tc smem attribute");
@@ -556,8 +623,10 @@ int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const flo
     return launch(ta, tw, p, st);
 }
 
+// dyn_ctr / tile_flags (both or neither; zeroed by the caller earlier in the stream): the launch follows the fused window stack,
+// which publishes every 128-token tile in tile_flags; used only with the strided-box TMA epilogue
 int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, const bf16 *skip, int skipH, int skipW, bf16 *out,
-                     int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, cudaStream_t st) {
+                     int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, int *dyn_ctr, const int *tile_flags, cudaStream_t st) {
     if (!tc_encode_fn() || dim % 64 || (reinterpret_cast<uintptr_t>(tok_bf16) & 127) || (reinterpret_cast<uintptr_t>(W) & 127) ||
         (reinterpret_cast<uintptr_t>(skip) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || B >= 2048 || Ht >= 1024 || Wt >= 1024)
         return TU_TC_UNSUPPORTED;
@@ -588,9 +657,11 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         if (ok) {
             p.epi = EPI_UNEMBED_TMA;
+            if (dyn_ctr && tile_flags) { p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; }
             return launch(ta, tw, p, st, &ts, &to);
         }
     }
+    if (tile_flags) return TU_TC_UNSUPPORTED;      // the caller relaunches without the overlap (this path waits for the whole stack)
     return launch(ta, tw, p, st);
 }
 

@@ -56,6 +56,7 @@ struct Stack192Params {
     const float *par;      // nblocks * PAR_FLOATS + 192 (final offset vector)
     const float *rel_bias; // nblocks x (12, 64, 64) fp32 dense relative-position bias
     int n_tiles, n_blocks;
+    int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
 };
 
 struct Barriers {
@@ -501,6 +502,11 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     }
                 }
                 ptx::tc_fence_before();
+                if (p.tile_flags) {       // publish the tile: every thread fences its own stores, then one thread raises the flag
+                    __threadfence();
+                    math_barrier();
+                    if (mt == 0) atomicExch(p.tile_flags + t, 1);
+                }
             }
         }
     }
@@ -517,7 +523,7 @@ bool g_attr_set = false;
 // stack_w: bf16 (n_blocks * 6912, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*2496 + 192;
 // rel_bias: fp32 n_blocks x (12,64,64).  tok: (M,192) fp32 with M % 128 == 0.
 int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
-                       const float *rel_bias, cudaStream_t st) {
+                       const float *rel_bias, int *tile_flags, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
         (reinterpret_cast<uintptr_t>(tok) & 15))
@@ -546,7 +552,7 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     }
     Stack192Params p;
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
-    p.n_tiles = M / 128; p.n_blocks = n_blocks;
+    p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     launch_pdl(window_stack192_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, t96, t192, p);
     TU_CHECK_LAUNCH("window_stack192");
