@@ -224,3 +224,26 @@ def test_natural_image_psnr_delta(name):
     ref_u8 = (ref * 255.0).clamp(0, 255).to(torch.uint8)
     assert (ou8.int() - ref_u8.int()).abs().max().item() <= 6           # 2e-2 * 255, + 1 for truncation at a boundary
     assert abs(psnr(ou8.float() / 255.0, hr) - psnr(ref_u8.float() / 255.0, hr)) <= 0.05
+
+
+@pytest.mark.parametrize("model,kw,shape", [("WindowTransformer", dict(res_out=(540, 960)), (3, 3, 360, 640)),
+                                            ("FastTransformer", dict(upscale_factor=2), (2, 3, 184, 328))])
+def test_unembed_overlap_is_bitwise_neutral(model, kw, shape):
+    """The unembed GEMM starts behind the fused window stack tile by tile (publish flags + dynamic tile scheduler, no
+    griddepcontrol.wait).  It must compute exactly what the plainly ordered launch computes, every time."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    M, sd = build(model, 41)
+    Mb = M.bfloat16()
+    x = synth_frames(shape[0], shape[2], shape[3], seed=91).cuda().bfloat16()
+    try:
+        lib.tu_debug_set(b"unembed_overlap", 0)
+        with torch.no_grad():
+            ref = Mb(x, **kw).clone()
+        lib.tu_debug_set(b"unembed_overlap", 1)
+        for _ in range(8):
+            with torch.no_grad():
+                out = Mb(x, **kw)
+            assert torch.equal(out, ref)
+    finally:
+        lib.tu_debug_set(b"unembed_overlap", 1)
