@@ -204,7 +204,7 @@ __device__ __forceinline__ float ga_ex2(float x) { float y; asm("ex2.approx.ftz.
 // GA_MT m16 query tiles per warp, GA_WARPS warps per CTA (128 queries per CTA either way).  Measured on cfg5a (2 frames, 8 layers,
 // transformer blocks in total): GA_MT = 1 1.33 ms, 2 1.21 ms, 4 1.33 ms -- one tile per warp doubles the K/V fragment loads per
 // query, four tiles leave too few warps per SM.
-constexpr int GA_MT = 2, GA_WARPS = 128 / (16 * GA_MT);
+constexpr int GA_MT = 2, GA_WARPS = 4, GA_QPB = GA_WARPS * 16 * GA_MT;      // queries per CTA
 __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
     __shared__ __align__(16) bf16 ks[2][GA_KT][GA_PITCH];
     __shared__ __align__(16) bf16 vs[2][GA_KT][GA_PITCH];
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
     const int g = lane >> 2, tq = lane & 3;
     const long ld = 3L * dim;
     const bf16 *base = qkv + (long)b * S * ld + h * 16;
-    const int q0 = blockIdx.x * 128 + warp * 16 * GA_MT;
+    const int q0 = blockIdx.x * GA_QPB + warp * 16 * GA_MT;
     const float L2E = 1.4426950408889634f;
 
     auto stage = [&](int buf, int k0) {
@@ -489,7 +489,7 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
         window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
         TU_CHECK_LAUNCH("window_attn");
     } else if (tc && sizeof(T) == 2) {
-        dim3 grid(ceil_div(S, 128), heads, M / S);
+        dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
         global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
         TU_CHECK_LAUNCH("global_attn_mma");
     } else {
