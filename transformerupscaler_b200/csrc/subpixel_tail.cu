@@ -20,18 +20,20 @@ namespace tu {
 
 namespace {
 
-constexpr int TH = 36;          // output rows per tile (a multiple of every r in {2,3,6}: tiles start on a low-res row)
+// output rows per tile (a multiple of r: tiles start on a low-res row).  36 rows, but 18 at r = 6, where the 36-row intermediate
+// tile (87 KB) allowed only two CTAs per SM (ncu: 20 % warps active, issue slots 49 % busy)
+template <int R> constexpr int tile_rows() { return R == 6 ? 18 : 36; }
 constexpr int TLX = 30;         // low-res columns per tile -> 30 r output columns; + 2 halo columns = 32 lanes
-constexpr int IR = TH + 2;      // intermediate rows held
 constexpr int NT = 256;
 
 struct FinFilter { float w[81]; float b[3]; };      // [(ky*3+kx)*3+ci][co], bias
 
 template <int R, typename TO>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 4)
 subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps, const float *__restrict__ bps,
                      const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, const FinFilter fin) {
     constexpr int NCO = 3 * R * R;
+    constexpr int TH = tile_rows<R>(), IR = TH + 2;     // IR = intermediate rows held
     constexpr int NLR = TH / R + 4;            // low-res rows staged: ly0 - 2 .. ly0 + TH/R + 1
     constexpr int LRW = TLX + 4;               // low-res columns staged: lx0 - 2 .. lx0 + 31
     constexpr int IW = 32 * R;                 // intermediate columns held: (lx0 - 1) r .. (lx0 + 31) r - 1
@@ -190,6 +192,7 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
 
 template <int R>
 constexpr size_t tail_smem() {
+    constexpr int TH = tile_rows<R>(), IR = TH + 2;
     return sizeof(float) * (3 * R * R * 28 + ((3 * R * R + 3) & ~3) + 3 * (TH / R + 4) * (TLX + 4) + 3 * IR * 32 * R);
 }
 
@@ -203,7 +206,7 @@ int launch_tail(const float *in, const float *wps, const float *bps, const float
         if (e != cudaSuccess) return cuda_fail(e, "subpixel_tail smem attribute");
         attr = true;
     }
-    dim3 grid(ceil_div(W, TLX), ceil_div(H * R, TH), B);
+    dim3 grid(ceil_div(W, TLX), ceil_div(H * R, tile_rows<R>()), B);
     launch_pdl(subpixel_tail_kernel<R, TO>, grid, dim3(NT), smem, st, in, wps, bps, addend, out, H, W, clamp, fin);
     TU_CHECK_LAUNCH("subpixel_tail");
     return TU_OK;
