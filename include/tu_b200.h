@@ -91,7 +91,7 @@ typedef struct TuUpsamplerStage {
  * 5x5 convolution 64 -> 3 r^2 (packing.py::fold_up1; tc/upfold_stream_tcgen05.cu).  bf16 tensor-core path only. */
 typedef struct TuUpFold {
     const void *w;          /* bf16 (nchunk, 5 kx, 5 ky-blocks holding ky = 4..0, NO rows, 64 ci); row n of a chunk =      */
-                            /*   ((c*r + i) - chunk*RPC)*r + j; (NO, RPC, nchunk) = (16,6,1) r=2, (32,9,1) r=3, (32,5,4) r=6 */
+                            /*   ((c*r + i) - chunk*RPC)*r + j; (NO, RPC, nchunk) = (16,6,1) r=2, (32,9,1) r=3, (48,6,3) r=6 */
     const float *b;         /* fp32 (nchunk*NO), zero in unused rows                                                        */
     const float *ring_w;    /* fp32 (9 border cases vy*3+vx, 3r^2 outputs o=(c*r+i)*r+j, 25 taps dy*5+dx, 64 ci)             */
     const float *ring_b;    /* fp32 (9, 3r^2)                                                                               */

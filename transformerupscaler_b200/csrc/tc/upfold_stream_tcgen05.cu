@@ -14,7 +14,8 @@
 //     ky = 4..0 with the SAME operand view, so one 128 x (5 NO) x 16 MMA against the stacked filter [W(ky=4);..;W(ky=0)]
 //     accumulates into five consecutive row accumulators (a ring of sixteen NO-column slots in TMEM); five kx shifts of
 //     the operand view x four k-steps = 20 MMAs per input row;
-//   * NO = 16 (r = 2: 12 outputs), 32 (r = 3: 27 outputs; r = 6: four chunks of five (c, i) output rows = 30 outputs);
+//   * NO = 16 (r = 2: 12 outputs), 32 (r = 3: 27 outputs), 48 (r = 6: three chunks, one colour = 36 outputs each; eight row
+//     accumulators, three input-row slots and one staging buffer per epilogue warp to fit 227 KB);
 //   * epilogue: row accumulator -> +bias, ReLU -> fp32 staging laid out as the high-resolution row segments
 //     [(c, i)][32 pixels x r] -> one TMA store per (c, i) into the planar (B, 3, rH, rW) image: PixelShuffle is address math.
 #include <cuda.h>
@@ -29,21 +30,23 @@ namespace {
 
 constexpr int TILE_M = 128, BOXW = 136;
 constexpr int UNIT_BYTES = BOXW * 128;        // one input row segment (136 pixels from x0 - 2)
-constexpr int NACC = 16;                      // output-row accumulators in TMEM
+constexpr int NACC_MAX = 16;                  // output-row accumulators in TMEM (8 when a row needs 48 columns)
 constexpr int NUM_THREADS = 256;
 
 // KS = filter size: 5 for the folded up-sampling branch, 3 for the plain 64 -> 3 heads (R = 1: decoder_conv2, up1_conv)
 template <int NO, int R, int KS>
 struct FoldCfg {
-    static constexpr int RPC = R == 1 ? 3 : R == 2 ? 6 : R == 3 ? 9 : 5;   // (c, i) output rows per chunk
-    static constexpr int NCHUNK = (3 * R + RPC - 1) / RPC;           // 1, 1, 1, 4
-    static constexpr int RING = NO == 16 ? 6 : 5;                    // input row slots
+    static constexpr int RPC = R == 1 ? 3 : R == 2 ? 6 : R == 3 ? 9 : NO == 48 ? 6 : 5;   // (c, i) output rows per chunk
+    static constexpr int NCHUNK = (3 * R + RPC - 1) / RPC;           // 1, 1, 1; r = 6: 3 (one colour per chunk, NO = 48) or 4
+    static constexpr int RING = NO == 16 ? 6 : NO == 32 ? 5 : 3;     // input row slots
+    static constexpr int NACC = NO == 48 ? 8 : 16;                   // row accumulators: NACC * NO <= 512 TMEM columns
+    static constexpr int NBUF = NO == 48 ? 1 : 2;                    // staging buffers per epilogue warp
     static constexpr int W_BLK = NO * 128;                           // one (kx, ky) filter block: NO rows x 64 ci
     static constexpr int W_KX = KS * W_BLK;                          // per kx: [ky = KS-1 .. 0] stacked
     static constexpr int W_BYTES = KS * W_KX;
     static constexpr int ROW_BYTES = 32 * R * 4;                     // one staged high-res row segment of a warp
     static constexpr int STG_WARP = RPC * ROW_BYTES;                 // per buffer
-    static constexpr int STG_BYTES = 4 * 2 * STG_WARP;
+    static constexpr int STG_BYTES = 4 * NBUF * STG_WARP;
     static constexpr int SMEM_BYTES = W_BYTES + RING * UNIT_BYTES + STG_BYTES + 512 + 1024;
     static_assert(RPC * R <= NO, "chunk does not fit its accumulator");
     static_assert(W_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory layout");
@@ -58,11 +61,44 @@ struct FoldParams {
 
 struct FoldBarriers {
     uint64_t full[6], empty[6];
-    uint64_t acc_full[NACC], acc_empty[NACC];
+    uint64_t acc_full[NACC_MAX], acc_empty[NACC_MAX];
     uint64_t w_full, w_free;
     uint32_t tmem_base;
 };
 static_assert(sizeof(FoldBarriers) <= 512, "barrier block too large");
+
+// NO consecutive TMEM columns of this warp's 32 lanes <-> registers
+template <int NO> __device__ __forceinline__ void tm_ld(uint32_t taddr, uint32_t (&v)[NO]) {
+    if constexpr (NO == 16) {
+        ptx::tmem_ld_x16(taddr, v);
+    } else if constexpr (NO == 32) {
+        ptx::tmem_ld_x32(taddr, v);
+    } else {
+        uint32_t a[32], b[16];
+        ptx::tmem_ld_x32(taddr, a);
+        ptx::tmem_ld_x16(taddr + 32, b);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = a[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[32 + j] = b[j];
+    }
+}
+template <int NO> __device__ __forceinline__ void tm_st(uint32_t taddr, const uint32_t (&v)[NO]) {
+    if constexpr (NO == 16) {
+        ptx::tmem_st_x16(taddr, v);
+    } else if constexpr (NO == 32) {
+        ptx::tmem_st_x32(taddr, v);
+    } else {
+        uint32_t a[32], b[16];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = v[j];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = v[32 + j];
+        ptx::tmem_st_x32(taddr, a);
+        ptx::tmem_st_x16(taddr + 32, b);
+    }
+}
 
 template <int NO, int R, int KS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -70,6 +106,7 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                      const __grid_constant__ CUtensorMap tmap_out, const FoldParams p) {
     using Cfg = FoldCfg<NO, R, KS>;
     constexpr int PAD = KS / 2;
+    constexpr int NACC = Cfg::NACC, NBUF = Cfg::NBUF;
     constexpr int RING = Cfg::RING, W_BLK = Cfg::W_BLK, W_KX = Cfg::W_KX, W_BYTES = Cfg::W_BYTES, RPC = Cfg::RPC;
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -211,23 +248,26 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
         uint32_t zero[NO];
 #pragma unroll
         for (int c = 0; c < NO; ++c) zero[c] = ACC_BIAS ? __float_as_uint(__ldg(p.bias + c)) : 0u;
-        for (int c = 0; c < NACC * NO; c += NO) {
-            if constexpr (NO == 16) ptx::tmem_st_x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero);
-            else ptx::tmem_st_x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero);
-        }
+        for (int c = 0; c < NACC * NO; c += NO) tm_st<NO>(tmem_base + ((uint32_t)(q * 32) << 16) + c, zero);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0)
             for (int sl = 0; sl < NACC; ++sl) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[sl]));
-        uint8_t *stg_w = smem_al + W_BYTES + RING * UNIT_BYTES + q * 2 * Cfg::STG_WARP;
-        const uint32_t stg_w_sm = stg_sm + q * 2 * Cfg::STG_WARP;
+        uint8_t *stg_w = smem_al + W_BYTES + RING * UNIT_BYTES + q * NBUF * Cfg::STG_WARP;
+        const uint32_t stg_w_sm = stg_sm + q * NBUF * Cfg::STG_WARP;
+        float bch[RPC * R];                          // bias of the current chunk (several chunks: added in the drain, from registers)
+        int bch_chunk = -1;
         const int oH = p.H * R;
         for (int it = blockIdx.x; it < p.total_items; it += gridDim.x) {
             int b, y0, rows, x0;
             const int chunk = item_geom(it, b, y0, rows, x0);
             const int px0 = x0 + q * 32;
-            const float *bias = p.bias + chunk * NO;
+            if (!ACC_BIAS && chunk != bch_chunk) {
+#pragma unroll
+                for (int e = 0; e < RPC * R; ++e) bch[e] = __ldg(p.bias + chunk * NO + e);
+                bch_chunk = chunk;
+            }
             const int nrow = min(RPC, 3 * R - chunk * RPC);          // (c, i) rows this chunk really has
 #pragma unroll 1
             for (int m = 0; m < rows; ++m, ++g) {
@@ -236,20 +276,19 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                 ptx::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + sl * NO;
                 uint32_t v[NO];
-                if constexpr (NO == 16) ptx::tmem_ld_x16(taddr, v);
-                else ptx::tmem_ld_x32(taddr, v);
+                tm_ld<NO>(taddr, v);
                 ptx::tmem_ld_wait();
-                if constexpr (NO == 16) ptx::tmem_st_x16(taddr, zero);      // clear the slot for the row that opens it next
-                else ptx::tmem_st_x32(taddr, zero);
+                tm_st<NO>(taddr, zero);                                         // reset the slot for the row that opens it next
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[sl]));      // the row is in registers, the slot is zero
-                    ptx::bulk_wait_read<1>();                                   // the stores that last used this buffer have read it
+                    if constexpr (NBUF == 2) ptx::bulk_wait_read<1>();          // the stores that last used this buffer have read it
+                    else ptx::bulk_wait_read<0>();
                 }
                 __syncwarp();
-                const uint32_t buf = nstore & 1;
+                const uint32_t buf = NBUF == 2 ? (nstore & 1) : 0;
                 float *rowp = reinterpret_cast<float *>(stg_w + buf * Cfg::STG_WARP) + lane * R;
 #pragma unroll
                 for (int qq = 0; qq < RPC; ++qq)
@@ -257,7 +296,7 @@ upfold_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
                     for (int j = 0; j < R; ++j) {
                         const int nidx = qq * R + j;
                         {
-                            const float a = ACC_BIAS ? __uint_as_float(v[nidx]) : __uint_as_float(v[nidx]) + __ldg(bias + nidx);
+                            const float a = ACC_BIAS ? __uint_as_float(v[nidx]) : __uint_as_float(v[nidx]) + bch[nidx];
                             rowp[qq * 32 * R + j] = p.relu ? fmaxf(a, 0.f) : a;
                         }
                     }
@@ -415,7 +454,7 @@ int tc_upfold(const bf16 *in, const TuUpFold *f, float *out, int B, int H, int W
     switch (f->r) {
         case 2: rc = launch_fold<16, 2, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
         case 3: rc = launch_fold<32, 3, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
-        case 6: rc = launch_fold<32, 6, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
+        case 6: rc = launch_fold<48, 6, 5>(in, f->w, f->b, 1, out, B, H, W, st); break;
         default: return TU_TC_UNSUPPORTED;
     }
     if (rc) return rc;

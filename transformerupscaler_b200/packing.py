@@ -23,7 +23,7 @@ def dense_rel_bias_t(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return b.permute(2, 0, 1).contiguous()                               # (h, i, j)
 
 
-FOLD_CFG = {2: (16, 6, 1), 3: (32, 9, 1), 6: (32, 5, 4)}      # r -> (NO, (c,i) rows per chunk, chunks); tc/upfold_stream_tcgen05.cu
+FOLD_CFG = {2: (16, 6, 1), 3: (32, 9, 1), 6: (48, 6, 3)}      # r -> (NO, (c,i) rows per chunk, chunks); tc/upfold_stream_tcgen05.cu
 
 
 def fold_up1(w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, r: int):
