@@ -247,3 +247,38 @@ def test_unembed_overlap_is_bitwise_neutral(model, kw, shape):
             assert torch.equal(out, ref)
     finally:
         lib.tu_debug_set(b"unembed_overlap", 1)
+
+
+def _ragged_cases():
+    """seeded sweep of awkward shapes: odd sizes (ceil stride-2 downsample, floor patch grid, crops, reflect pad), widths that do and
+    do not give a 16-byte image row pitch (fused conv1+conv2 vs the two kernels; TMA vs direct resampling), single windows, batches"""
+    rs = np.random.RandomState(2024)
+    cases = []
+    for k in range(6):
+        B = int(rs.choice([1, 2, 3]))
+        H, W = int(rs.randint(33, 150)), int(rs.randint(33, 200))
+        f = float(rs.choice([1.5, 2.0, 1.25, 3.0]))
+        cases.append(("WindowTransformer", (B, H, W), dict(res_out=(int(H * f), int(W * f))), 50 + k))
+    for k in range(6):
+        B = int(rs.choice([1, 2]))
+        H, W = int(rs.randint(17, 90)), int(rs.randint(17, 120))
+        s = int(rs.choice([2, 3, 4, 6]))
+        cases.append(("FastTransformer", (B, H, W), dict(upscale_factor=s), 60 + k))
+    return cases
+
+
+@pytest.mark.parametrize("model,shape,kw,seed", _ragged_cases())
+def test_ragged_shapes_vs_oracle(model, shape, kw, seed):
+    B, H, W = shape
+    M, sd = build(model, seed)
+    x = synth_frames(B, H, W, seed=seed + 100)
+    ref = orc.forward(model, sd, x, **kw)
+    with torch.no_grad():
+        o32 = M(x.cuda(), **kw)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o16 = M(x.cuda(), **kw)
+        ob = M.bfloat16()(x.cuda().bfloat16(), **kw)
+    assert tuple(o32.shape) == tuple(ref.shape)
+    assert (o32.cpu() - ref).abs().max().item() < TOL_FP32, (model, shape, kw)
+    assert (o16.float().cpu() - ref).abs().max().item() < TOL_BF16, (model, shape, kw)
+    assert (ob.float().cpu() - ref).abs().max().item() < TOL_BF16, (model, shape, kw)

@@ -62,3 +62,32 @@ def test_oracle_matches_reference_on_natural_image(name):
     ref = g["ref"].astype(np.float32)
     assert out.shape == ref.shape == g["hr_u8"].shape
     assert np.abs(out - ref).max() < 6e-4          # fp16 storage of values in [0, 1]: half-ulp 2.4e-4
+
+
+def _ragged_cases():
+    from tests.test_gpu_models import _ragged_cases as rc
+    return rc()
+
+
+@pytest.mark.parametrize("model,shape,kw,seed", _ragged_cases())
+def test_oracle_matches_live_reference_on_ragged_shapes(model, shape, kw, seed):
+    """the same seeded sweep of awkward shapes the GPU suite runs, here oracle vs the UNMODIFIED reference modules executed live
+    (baseline/_ref, a verbatim copy of the reference's models/ made in the build container)"""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_dir = os.path.join(root, "baseline", "_ref", "models")
+    if not os.path.isdir(os.path.join(ref_dir, model)):
+        pytest.skip("baseline/_ref not present")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from baseline.refload import reference_model_class
+    B, H, W = shape
+    sd = synth_state_dict(model, seed)
+    x = synth_frames(B, H, W, seed=seed + 100)
+    M = reference_model_class(ref_dir, model)().eval()
+    M.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        ref = M(x, **kw)
+    out = orc.forward(model, sd, x, **kw)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert (out - ref).abs().max().item() < TOL_FP32, (model, shape, kw)
