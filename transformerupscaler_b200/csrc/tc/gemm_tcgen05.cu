@@ -280,9 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     tile_done(it);
                     if (t_next >= 0) request(t_next, buf ^ 1);   // that buffer's store has been read (below)
                 }
-                const int t_cur = t;
-                t = t_next;
-                (void)t_cur;
+                t = t_next;                                       // (everything below uses the coordinates computed above)
                 ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[set]), aphase);
                 ptx::tc_fence_after();
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256 + cbeg;
