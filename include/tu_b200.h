@@ -61,7 +61,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph) */
+ * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral) */
 int tu_debug_set(const char *key, int value);
 
 /* ---- packed weights -------------------------------------------------------------------------
@@ -180,6 +180,13 @@ int tu_final_conv_add(const float *in, const float *w, const float *b, const flo
  * R:128-129.  Needs an image row pitch that is a multiple of 16 bytes. */
 int tu_conv12_fused(const void *x, int in_dtype, const void *w64, const float *b1, const void *w2, const float *b2, void *out,
                     int B, int H, int W, void *stream);
+/* decoder_conv2(relu(decoder_conv1(in))) in one kernel (bf16 tensor-core path): NHWC bf16 (B,H,W,64) -> planar fp32 (B,3,H,W);
+ * w1 = decoder_conv1 filter bf16 (9, 64 co, 64 ci), w16 = decoder_conv2 filter bf16 (3 ky, 16 rows n = kx*4 + co, 64 ci), b1 (64)
+ * and b2 (3) fp32.  The 64-channel map between the two convolutions never reaches HBM.  W:297-298, F:312-313, R:156-157.
+ * out is written with plain stores except for the columns two 128-pixel strips share (atomicAdd onto zeros: the op zeroes
+ * them itself, on the same stream). */
+int tu_dec12_fused(const void *in, const void *w1, const float *b1, const void *w16, const float *b2, float *out, int B, int H,
+                   int W, void *stream);
 /* relu(up1_conv(PixelShuffle_r(up1_stage(in)))) through the folded 5x5 filter: NHWC bf16 (B,H,W,64) -> planar fp32
  * (B,3,rH,rW).  FastTransformer/model.py:264-265.  Needs the tcgen05 path and (W*r) % 4 == 0. */
 int tu_upfold_conv(const void *in, const TuUpFold *f, float *out, int B, int H, int W, void *stream);

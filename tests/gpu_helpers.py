@@ -89,6 +89,16 @@ def conv12_fused(x, w64, b1, w2, b2):
     return out
 
 
+def dec12_fused(x, w1p, b1, w16, b2):
+    """x NHWC bf16; w1p (9, 64, 64) bf16 tap-major; w16 (3, 16, 64) bf16 head bank; planar fp32 (B, 3, H, W) out"""
+    lib = _lib.load()
+    B, H, W, _ = x.shape
+    out = torch.full((B, 3, H, W), float("nan"), dtype=torch.float32, device=x.device)      # the op must write / zero every pixel
+    chk(lib.tu_dec12_fused(p(x), p(w1p), p(b1), p(w16), p(b2), p(out), B, H, W, stream()))
+    torch.cuda.synchronize()
+    return out
+
+
 def upfold_conv(x, w1, b1, w2, r):
     """x NHWC bf16 on the GPU; folds (w1, b1, w2) on the host like packing.PackedWeights does"""
     from transformerupscaler_b200.packing import fold_up1, pack_fold_bank

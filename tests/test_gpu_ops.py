@@ -156,6 +156,33 @@ def test_conv64to3_stream(dev, bias, relu, shape):
     assert _maxerr(out, ref16) < 1e-3
 
 
+@pytest.mark.parametrize("shape", [(2, 17, 152), (1, 1, 4), (1, 2, 128), (1, 70, 640), (3, 9, 260), (1, 131, 256), (2, 64, 384), (1, 3, 129)])
+def test_dec12_fused(dev, shape):
+    """decoder_conv1 + ReLU + decoder_conv2 in one kernel (the 64-channel map stays on chip) vs the two convolutions of the
+    oracle on bf16-rounded operands, decoder_conv1's output rounded to bf16 (W:297-298, F:312-313, R:156-157); shapes cover
+    one / several 128-pixel strips (seam pixels), partial strips, single rows and more rows than one work item holds"""
+    from tests import gpu_helpers as G
+    rs = np.random.RandomState(23)
+    B, H, W = shape
+    x = torch.from_numpy(rs.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)).to(BF16)
+    w1 = torch.from_numpy(rs.uniform(-0.05, 0.05, (64, 64, 3, 3)).astype(np.float32)).to(BF16)
+    b1 = torch.from_numpy(rs.uniform(-0.1, 0.1, 64).astype(np.float32))
+    w2 = torch.from_numpy(rs.uniform(-0.05, 0.05, (3, 64, 3, 3)).astype(np.float32)).to(BF16)
+    b2 = torch.from_numpy(rs.uniform(-0.1, 0.1, 3).astype(np.float32))
+    mid = orc.conv3x3_nhwc(x.float(), w1.float(), b1, relu=True).to(BF16).float()
+    ref = orc.conv3x3_nhwc(mid, w2.float(), b2).permute(0, 3, 1, 2)
+    w1p = w1.float().permute(2, 3, 0, 1).reshape(9, 64, 64).contiguous().to(dev, BF16)
+    w16 = torch.zeros(3, 4, 4, 64)                       # (ky, kx, co, ci) -> rows n = kx*4 + co
+    w16[:, :3, :3] = w2.float().permute(2, 3, 0, 1)
+    w16 = w16.reshape(3, 16, 64).to(dev, BF16)
+    out = G.dec12_fused(x.to(dev), w1p, b1.to(dev), w16, b2.to(dev))
+    assert out.shape == ref.shape
+    assert not torch.isnan(out).any()
+    assert _maxerr(out, ref) < 3e-3          # 1-ulp bf16 flips of the intermediate map (summation order differs from the oracle's)
+    out2 = G.dec12_fused(x.to(dev), w1p, b1.to(dev), w16, b2.to(dev))
+    assert torch.equal(out, out2)            # the seam atomics add two terms onto zero: order independent
+
+
 @pytest.mark.parametrize("r", [2, 3, 6])
 def test_conv3_ps_and_final(dev, r):
     from tests import gpu_helpers as G

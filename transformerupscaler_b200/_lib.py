@@ -76,6 +76,7 @@ SIGNATURES = {
     "tu_conv3x3_c3_ps": (i32, [fp, fp, fp, fp, i32, i32, i32, i32, vp]),
     "tu_final_conv_add": (i32, [fp, fp, fp, fp, vp, i32, i32, i32, i32, i32, vp]),
     "tu_conv12_fused": (i32, [vp, i32, vp, fp, vp, fp, vp, i32, i32, i32, vp]),
+    "tu_dec12_fused": (i32, [vp, vp, fp, vp, fp, fp, i32, i32, i32, vp]),
     "tu_upfold_conv": (i32, [vp, C.POINTER(TuUpFold), fp, i32, i32, i32, vp]),
     "tu_subpixel_conv_add": (i32, [fp, fp, fp, i32, vp, fp, vp, i32, i32, i32, i32, i32, vp]),
     "tu_patch_embed": (i32, [vp, i32, vp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

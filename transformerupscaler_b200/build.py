@@ -23,6 +23,7 @@ SOURCES = [
     "tc/conv3x3_stream_tcgen05.cu",
     "tc/upfold_stream_tcgen05.cu",
     "tc/conv12_fused_tcgen05.cu",
+    "tc/dec12_fused_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",

@@ -167,6 +167,11 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     int *sync_words = (int *)a.get(sync_bytes);
     const bool overlap = g_unembed_overlap && window && tc_on(dt) && w->stack_w && g_use_stack && (Mtok % 128) == 0;
 
+    // decoder_conv1 + decoder_conv2 in one kernel: the pixels two of its strips share are accumulated atomically and are
+    // zeroed here, ahead of the whole forward, so that no memset sits between two kernels chained by programmatic launch
+    const bool fuse_dec = tc_on(dt) && w->dec2_w16 && w->dec1_b && w->dec2_b && tc_dec12_fused_enabled();
+    if (!dry && fuse_dec && (rc = tc_dec12_zero_seams(res, B, Hc, Wc, st))) return rc;
+
     // ---- encoder
     if (!dry && overlap) {
         cudaError_t e = cudaMemsetAsync(sync_words, 0, sync_bytes, st);
@@ -268,6 +273,16 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         prof_end(st, "patch_unembed");
         if (rc) return rc;
         // ---- decoder
+        rc = TU_TC_UNSUPPORTED;
+        if (fuse_dec) {
+            g_prof_name = "decoder_fused";
+            prof_begin(st);
+            rc = tc_dec12_fused((const bf16 *)comb, (const bf16 *)w->dec1_w, w->dec1_b, (const bf16 *)w->dec2_w16, w->dec2_b, res, B, Hc, Wc, st);
+            if (rc == TU_OK) prof_end(st, "decoder_fused");
+            else if (g_prof_open) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; }
+            if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+        }
+        if (rc == TU_TC_UNSUPPORTED) {
         TU_STEP("decoder_conv1", tu_conv3x3_c64(comb, w->dec1_w, w->dec1_b, dec, dt, B, Hc, Wc, 1, 1, 1, 0, stv));
         {   // 64 -> 3 head: streaming kernel when packed and the row pitch suits its TMA stores, else the tile kernel
             g_prof_name = "decoder_conv2";
@@ -277,6 +292,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
             if (rc == TU_TC_UNSUPPORTED) rc = tu_conv3x3_c64_to3(dec, dt, w->dec2_w, w->dec2_w16, w->dec2_b, res, B, Hc, Wc, 0, stv);
             prof_end(st, "decoder_conv2");
             if (rc) return rc;
+        }
         }
     }
 
@@ -361,6 +377,14 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "fold_up1")) {
         g_fold_up1 = value;
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "fuse_dec12")) {
+        tc_set_dec12_fused(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "snake")) {
+        tc_set_snake(value);
         return TU_OK;
     }
     if (key && !strcmp(key, "fused_stack")) {
@@ -451,6 +475,17 @@ extern "C" int tu_conv3x3_c64_to3_stream(const void *in, const void *wst, const 
     TU_CHECK_ARG(tc_enabled(), "conv3x3_c64_to3_stream: tcgen05 kernels are unavailable or switched off");
     int rc = tc_conv3x3_c64_to3_stream((const bf16 *)in, (const bf16 *)wst, b16, out, B, H, W, relu, (cudaStream_t)stream);
     TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "conv3x3_c64_to3_stream: unsupported alignment (W % 4 must be 0)");
+    return rc;
+}
+
+extern "C" int tu_dec12_fused(const void *in, const void *w1, const float *b1, const void *w16, const float *b2, float *out, int B, int H,
+                              int W, void *stream) {
+    TU_CHECK_ARG(in && w1 && b1 && w16 && b2 && out && B > 0 && H > 0 && W > 0, "dec12_fused: bad argument");
+    TU_CHECK_ARG(tc_enabled(), "dec12_fused: tcgen05 kernels are unavailable or switched off");
+    int rc = tc_dec12_zero_seams(out, B, H, W, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = tc_dec12_fused((const bf16 *)in, (const bf16 *)w1, b1, (const bf16 *)w16, b2, out, B, H, W, (cudaStream_t)stream);
+    TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "dec12_fused: unsupported alignment or switched off");
     return rc;
 }
 

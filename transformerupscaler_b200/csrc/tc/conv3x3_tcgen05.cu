@@ -44,6 +44,7 @@ struct ConvParams {
     int B, H, W, Ho, Wo;
     int stride, relu, nchunk, ps_r;
     int tiles_x, tiles_y, tiles_per_chunk, total_tiles;
+    int rev;            // tiles of a chunk are walked last to first: the tail of the producer kernel's output is still in L2
     const float *bias;
     bf16 *out;
     float *out3;        // NOUT == 16: planar fp32 (B,3,Ho,Wo)
@@ -121,6 +122,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const int chunk = t / p.tiles_per_chunk;
             int rem = t - chunk * p.tiles_per_chunk;
+            if (p.rev) rem = p.tiles_per_chunk - 1 - rem;
             const int tx = rem % p.tiles_x;
             rem /= p.tiles_x;
             const int ty = rem % p.tiles_y;
@@ -251,6 +253,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int chunk = t / p.tiles_per_chunk;
             int rem = t - chunk * p.tiles_per_chunk;
+            if (p.rev) rem = p.tiles_per_chunk - 1 - rem;
             const int tx = rem % p.tiles_x;
             rem /= p.tiles_x;
             const int ty = rem % p.tiles_y;
@@ -361,6 +364,11 @@ bool g_attr_set = false;
 
 }  // namespace
 
+// debug key "snake": bit k set = kernel k walks its work items last to first, so that it starts on the part of its input the
+// previous kernel wrote last (still in L2).  bit 0 downsample, 1 the 64 -> 3 head, 2 window stack + unembed, 3 tile conv 64 -> 64
+int g_snake_mask = 0;
+void tc_set_snake(int mask) { g_snake_mask = mask; }
+
 TcEncodeFn tc_encode_fn() {
     static TcEncodeFn fn = nullptr;
     static std::once_flag once;
@@ -450,6 +458,7 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
     p.tiles_per_chunk = p.tiles_x * p.tiles_y * B;
     p.total_tiles = p.tiles_per_chunk * nchunk;
     p.bias = bias; p.out = out; p.out3 = out3;
+    p.rev = (g_snake_mask >> (nout == 64 ? (stride == 2 ? 0 : 3) : 1)) & 1;
     const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
     if (nout == 64 && stride == 1)
         launch_pdl(conv3x3_tc_kernel<64, 1>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tm_act, tm_w, tm_out, p);

@@ -58,6 +58,7 @@ struct GemmParams {
     // no griddepcontrol.wait -- on the SMs the stack's last, partly filled wave leaves idle
     int *dyn_ctr;
     const int *tile_flags;
+    int rev;            // tiles are walked last to first (debug key "snake", bit 2: unembed behind a reversed window stack)
 };
 constexpr int QD = 4;      // depth of the tile-index queue between the scheduler thread and the three roles
 
@@ -147,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto tile_at = [&](int k) -> int {
         if (!dyn) {
             const int t = blockIdx.x + k * gridDim.x;
-            return t < p.total_tiles ? t : -1;
+            return t < p.total_tiles ? (p.rev ? p.total_tiles - 1 - t : t) : -1;
         }
         ptx::mbar_wait(ptx::smem_u32(&bars->q_full[k % QD]), (k / QD) & 1);
         return *reinterpret_cast<volatile int *>(&bars->tq[k % QD]);
@@ -170,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int k = 0;; ++k) {
             if (k >= QD) ptx::mbar_wait(ptx::smem_u32(&bars->q_empty[k % QD]), ((k / QD) & 1) ^ 1);
             const int t = atomicAdd(p.dyn_ctr, 1);
-            *reinterpret_cast<volatile int *>(&bars->tq[k % QD]) = t < p.total_tiles ? t : -1;
+            *reinterpret_cast<volatile int *>(&bars->tq[k % QD]) = t < p.total_tiles ? (p.rev ? p.total_tiles - 1 - t : t) : -1;
             ptx::mbar_arrive(ptx::smem_u32(&bars->q_full[k % QD]));      // release: the index is visible to whoever passes the wait
             if (t >= p.total_tiles) break;
         }
@@ -655,6 +656,7 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         if (ok) {
             p.epi = EPI_UNEMBED_TMA;
+            p.rev = ((g_snake_mask >> 2) & 1) && dim == 128;      // the dim-128 stack publishes its tiles in the same order
             if (dyn_ctr && tile_flags) { p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; }
             return launch(ta, tw, p, st, &ts, &to);
         }

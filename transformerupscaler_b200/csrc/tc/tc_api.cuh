@@ -14,6 +14,9 @@ int tc_available();
 bool tc_enabled();
 // debug: 0 = UMMA descriptor base_offset 0, 1 = base_offset (addr>>7)&7 for row-shifted operand views
 void tc_set_base_off_mode(int m);
+// debug: reversed work-item order per kernel (bit mask, see conv3x3_tcgen05.cu)
+extern int g_snake_mask;
+void tc_set_snake(int mask);
 
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda); nullptr without a driver
 typedef CUresult (*TcEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -45,6 +48,15 @@ void tc_set_conv_2cta(int on);
 int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16 *out, int B, int H, int W, int relu, int nchunk,
                           int ps_r, cudaStream_t st);
 void tc_set_conv_stream(int on);
+
+// decoder_conv2(relu(decoder_conv1(x))) in one kernel (dec12_fused_tcgen05.cu): NHWC bf16 -> planar fp32 (B, 3, H, W); w1 = the
+// 64 -> 64 bank of tc_conv3x3_c64, w16 = the head bank of tc_conv3x3_c64_to3.  The pixels shared by two 128-pixel strips are
+// accumulated with atomicAdd: tc_dec12_zero_seams must run on the same stream beforehand (anywhere before the launch)
+int tc_dec12_fused(const bf16 *in, const bf16 *w1, const float *bias1, const bf16 *w16, const float *bias2, float *out3, int B, int H,
+                   int W, cudaStream_t st);
+int tc_dec12_zero_seams(float *out3, int B, int H, int W, cudaStream_t st);
+void tc_set_dec12_fused(int on);
+bool tc_dec12_fused_enabled();
 
 // relu(conv2(relu(conv1(x)))) in one kernel (conv12_fused_tcgen05.cu): NCHW image -> NHWC bf16; conv1's output stays on chip
 int tc_conv12_fused(const void *x, int in_dtype, const bf16 *w64, const float *bias1, const bf16 *w2, const float *bias2, bf16 *out,

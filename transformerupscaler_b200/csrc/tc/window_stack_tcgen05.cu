@@ -51,6 +51,7 @@ struct StackParams {
     const float *par;      // nblocks * PAR_FLOATS + 128 (final offset vector)
     const float *rel_bias; // nblocks x (8, 64, 64) fp32 dense relative-position bias
     int n_tiles, n_blocks;
+    int rev;               // token tiles are walked last to first (debug key "snake", bit 2)
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
 };
 
@@ -277,7 +278,8 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             for (int j = 0; j < 16; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 32 + 2 * j));
         };
 
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x) {
+            const int t = p.rev ? p.n_tiles - 1 - t0 : t0;
             // ---- tokens -> TMEM X
             {
                 const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 32;
@@ -533,6 +535,7 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     StackParams p;
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
+    p.rev = (g_snake_mask >> 2) & 1;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     launch_pdl(window_stack_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, p);
     TU_CHECK_LAUNCH("window_stack");
