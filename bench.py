@@ -255,7 +255,7 @@ def main():
     # around the model); the ToTensor scaling and the (out*255).clamp().to(uint8) are fused into the first / last kernel.
     # The same pipeline with bf16 host tensors (the float signature of the reference) is reported beside it.
     def run_e2e(hin, hout):
-        pipe = FramePipeline(model, depth=3, device=dev, res_out=(OH, OW))
+        pipe = FramePipeline(model, depth=3, device=dev, compute_streams=int(os.environ.get("TU_COMPUTE_STREAMS", "1")), res_out=(OH, OW))
         for i in range(warmup):
             pipe.submit(hin[i & 1], hout[i & 1])
         pipe.drain()

@@ -249,6 +249,30 @@ def test_unembed_overlap_is_bitwise_neutral(model, kw, shape):
         lib.tu_debug_set(b"unembed_overlap", 1)
 
 
+@pytest.mark.parametrize("model,frames,kw", [("WindowTransformer", 5, {}), ("WindowTransformer", 8, {}),
+                                             ("FastTransformer", 2, dict(upscale_factor=2))])
+def test_stack_split_is_bitwise_neutral(model, frames, kw):
+    """When the 128-token tiles do not fill whole waves of SMs (150 / 240 tiles on 148 SMs; FastTransformer: 240 tiles of dim 192) the window stack hands tiles from one
+    CTA to the next at block boundaries (the fp32 residual stream travels through the token buffer, guarded by a flag per tile).
+    The arithmetic per tile is unchanged, so the forward must be bitwise what the whole-tile schedule computes, every time."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    M, sd = build(model, 43)
+    Mb = M.bfloat16()
+    x = synth_frames(frames, 720, 1280, seed=93).cuda().bfloat16()
+    try:
+        lib.tu_debug_set(b"stack_split", 0)
+        with torch.no_grad():
+            ref = Mb(x, **kw).clone()
+        lib.tu_debug_set(b"stack_split", 1)
+        for _ in range(6):
+            with torch.no_grad():
+                out = Mb(x, **kw)
+            assert torch.equal(out, ref)
+    finally:
+        lib.tu_debug_set(b"stack_split", 1)
+
+
 def _ragged_cases():
     """seeded sweep of awkward shapes: odd sizes (ceil stride-2 downsample, floor patch grid, crops, reflect pad), widths that do and
     do not give a 16-byte image row pitch (fused conv1+conv2 vs the two kernels; TMA vs direct resampling), single windows, batches"""

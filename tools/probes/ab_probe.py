@@ -3,7 +3,7 @@
 per-kernel breakdown (tu_profile mode 2) for each setting, interleaved over several rounds so that clock / power drift
 hits every setting alike.
 usage: python tools/probes/ab_probe.py key=v0,v1,... [model=WindowTransformer] [frames=8] [n=40] [rounds=3]"""
-import os, sys, ctypes as C
+import os, sys, time, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
@@ -16,6 +16,7 @@ model_name = opts.pop("model", "WindowTransformer")
 frames = int(opts.pop("frames", 8))
 N = int(opts.pop("n", 40))
 rounds = int(opts.pop("rounds", 3))
+cool = float(opts.pop("cool", 0))      # seconds of idle before every measurement (and no long warm-up): the regime of a short bench.py run
 kw = {}
 if "scale" in opts:
     kw["upscale_factor"] = int(opts.pop("scale"))
@@ -58,12 +59,14 @@ with torch.no_grad():
             ref = y
         else:
             print(f"{key}={v}: max-abs vs {key}={vals[0]}: {(y - ref).abs().max().item():.3e}")
-    for i in range(int(os.environ.get("AB_WARM", "150"))):      # reach the board's steady state (power cap) before comparing
+    for i in range(0 if cool else int(os.environ.get("AB_WARM", "150"))):      # reach the board's steady state (power cap) before comparing
         m(xs[i & 1], **kw)
     torch.cuda.synchronize()
     for r in range(rounds):
         for v in vals:
             lib.tu_debug_set(key.encode(), v)
+            if cool:
+                time.sleep(cool)
             for i in range(3):
                 m(xs[i & 1], **kw)
             torch.cuda.synchronize()

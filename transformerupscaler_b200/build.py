@@ -25,6 +25,7 @@ SOURCES = [
     "tc/conv12_fused_tcgen05.cu",
     "tc/dec12_fused_tcgen05.cu",
     "tc/gemm_tcgen05.cu",
+    "tc/embed_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",
     "tc/window_stack192_tcgen05.cu",

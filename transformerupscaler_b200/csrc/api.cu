@@ -163,9 +163,12 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     T *dec = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
     float *res = (float *)a.get((size_t)B * 3 * Hc * Wc * sizeof(float));
     // tile hand-off between the fused window stack and the unembed GEMM: word 0 = tile counter, words 16.. = one flag per 128 tokens
-    const size_t sync_bytes = (size_t)(16 + Mtok / 128 + 1) * sizeof(int);
+    // ... and, behind them, one flag per tile for the hand-over of a tile between two CTAs of the stack kernel (block-level split)
+    const int n_tok_tiles = Mtok / 128 + 1;
+    const size_t sync_bytes = (size_t)(16 + 2 * n_tok_tiles) * sizeof(int);
     int *sync_words = (int *)a.get(sync_bytes);
     const bool overlap = g_unembed_overlap && window && tc_on(dt) && w->stack_w && g_use_stack && (Mtok % 128) == 0;
+    const bool stack_flags = window && tc_on(dt) && w->stack_w && g_use_stack && (Mtok % 128) == 0;
 
     // decoder_conv1 + decoder_conv2 in one kernel: the pixels two of its strips share are accumulated atomically and are
     // zeroed here, ahead of the whole forward, so that no memset sits between two kernels chained by programmatic launch
@@ -173,7 +176,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     if (!dry && fuse_dec && (rc = tc_dec12_zero_seams(res, B, Hc, Wc, st))) return rc;
 
     // ---- encoder
-    if (!dry && overlap) {
+    if (!dry && (overlap || stack_flags)) {
         cudaError_t e = cudaMemsetAsync(sync_words, 0, sync_bytes, st);
         if (e != cudaSuccess) return cuda_fail(e, "memset tile flags");
     }
@@ -248,10 +251,10 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         rc = TU_TC_UNSUPPORTED;
         if (tc && window && dim == 128 && w->stack_w && g_use_stack)
             rc = tc_window_stack(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel,
-                                 overlap ? sync_words + 16 : nullptr, st);
+                                 overlap ? sync_words + 16 : nullptr, stack_flags ? sync_words + 16 + n_tok_tiles : nullptr, st);
         else if (tc && window && dim == 192 && w->stack_w && g_use_stack)
             rc = tc_window_stack192(tok, tok16, Mtok, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel,
-                                    overlap ? sync_words + 16 : nullptr, st);
+                                    overlap ? sync_words + 16 : nullptr, stack_flags ? sync_words + 16 + n_tok_tiles : nullptr, st);
         if (rc != TU_TC_UNSUPPORTED && rc != TU_OK) return rc;
         const bool stack_done = rc == TU_OK;
         for (int i = 0; i < w->n_blocks && !stack_done; ++i)
@@ -377,6 +380,18 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "fold_up1")) {
         g_fold_up1 = value;
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "stack_split")) {
+        tc_set_stack_split(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "embed_pair")) {
+        tc_set_embed_pair(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "bicubic_pair")) {
+        g_bicubic_pair = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "fuse_dec12")) {
@@ -515,8 +530,8 @@ extern "C" int tu_window_stack(float *tokens, const TuModelWeights *w, int M, vo
     TU_CHECK_ARG(tc_enabled(), "window_stack: tcgen05 kernels are unavailable or switched off");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = TU_TC_UNSUPPORTED;
-    if (w->dim == 128) rc = tc_window_stack(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, st);
-    else if (w->dim == 192) rc = tc_window_stack192(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, st);
+    if (w->dim == 128) rc = tc_window_stack(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, nullptr, st);
+    else if (w->dim == 192) rc = tc_window_stack192(tokens, nullptr, M, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, w->stack_rel, nullptr, nullptr, st);
     TU_CHECK_ARG(rc != TU_TC_UNSUPPORTED, "window_stack: unsupported shape (token count must be a multiple of 128)");
     return rc;
 }
@@ -530,7 +545,9 @@ extern "C" int tu_patch_embed(const void *feat, int dtype, const void *w, const 
     TU_CHECK_ARG(!reflect || ((8 * Ht - H) < H && (8 * Wt - W) < W), "patch_embed: reflect pad larger than the input");
     cudaStream_t st = (cudaStream_t)stream;
     if (tc_on(dtype) && (!reflect || (H % 8 == 0 && W % 8 == 0))) {
-        int rc = tc_patch_embed((const bf16 *)feat, (const bf16 *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, st);
+        int rc = tc_patch_embed_pair((const bf16 *)feat, (const bf16 *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, st);
+        if (rc == TU_TC_UNSUPPORTED)
+            rc = tc_patch_embed((const bf16 *)feat, (const bf16 *)w, b, pos_embed, tokens, B, H, W, Ht, Wt, dim, window, st);
         if (rc != TU_TC_UNSUPPORTED) return rc;
     }
     if (dtype == TU_F32)

@@ -103,7 +103,7 @@ __device__ __forceinline__ void replicate_pad(TS *s, int r0, int c0, int nr, int
     const int padL = max(0, -c0), padR = max(0, c0 + nc - W), padT = max(0, -r0), padB = max(0, r0 + nr - H);
     if ((padL | padR | padT | padB) == 0) return;           // interior tile (uniform across the CTA)
     if (padL | padR) {
-        for (int e = threadIdx.x; e < 3 * nr; e += BS_W) {
+        for (int e = threadIdx.x; e < 3 * nr; e += blockDim.x) {
             TS *p = s + e * nc;
             const TS l = p[min(padL, nc - 1)], r = p[max(nc - 1 - padR, 0)];
             for (int c = 0; c < padL; ++c) p[c] = l;
@@ -112,7 +112,7 @@ __device__ __forceinline__ void replicate_pad(TS *s, int r0, int c0, int nr, int
         __syncthreads();
     }
     if (padT | padB) {
-        for (int e = threadIdx.x; e < 3 * nc; e += BS_W) {
+        for (int e = threadIdx.x; e < 3 * nc; e += blockDim.x) {
             TS *p = s + (e / nc) * nr * nc + (e % nc);
             const TS tp = p[min(padT, nr - 1) * nc], bt = p[max(nr - 1 - padB, 0) * nc];
             for (int r = 0; r < padT; ++r) p[r * nc] = tp;
@@ -301,6 +301,144 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
     }
 }
 
+// ---- two output columns per thread -----------------------------------------------------------------------------------
+// The strip kernel above is bound by instruction issue (145 instructions per output pixel, 81 % issue slots, 29 % of the HBM
+// bandwidth).  Here a thread owns TWO adjacent output columns: the horizontal and vertical 4-tap sums of the pair run on packed
+// fp32 pairs (FFMA2: one issue slot for both columns, bit-identical to the scalar FMAs in the same order), the per-row vertical
+// weights, row bookkeeping and window shifts are shared by the pair, and the pair leaves as one 4-byte (bf16) / 8-byte (fp32) /
+// 2-byte (uint8) store.  TMA-staged tiles only (PAIR_H x 128 outputs per 64-thread CTA), even output width.
+constexpr int PAIR_H = 36;
+
+template <typename TS>
+__device__ __forceinline__ ptx::f32x2 hrow_pair(uint32_t aA, uint32_t aB, const ptx::f32x2 (&w)[4]) {
+    ptx::f32x2 t = ptx::mul2(ptx::pk2(lds_raw<0>(aA, TS()), lds_raw<0>(aB, TS())), w[0]);
+    t = ptx::fma2(ptx::pk2(lds_raw<1>(aA, TS()), lds_raw<1>(aB, TS())), w[1], t);
+    t = ptx::fma2(ptx::pk2(lds_raw<2>(aA, TS()), lds_raw<2>(aB, TS())), w[2], t);
+    t = ptx::fma2(ptx::pk2(lds_raw<3>(aA, TS()), lds_raw<3>(aB, TS())), w[3], t);
+    if (sizeof(TS) == 1) t = ptx::mul2(t, ptx::pk2(0.00392156862745098f, 0.00392156862745098f));
+    return t;
+}
+template <typename TS>
+__device__ __forceinline__ void slide_pair(ptx::f32x2 (&win)[3][4], int &cur, int base, const uint32_t (&caA)[3], const uint32_t (&caB)[3],
+                                           int trow0, uint32_t pitchB, const ptx::f32x2 (&w)[4]) {
+    if (base == cur) return;
+    if (base == cur + 1) {                  // the only step an up-scaling strip ever takes after its first row
+        const uint32_t ro = (uint32_t)(base + 2 + trow0) * pitchB;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            win[c][0] = win[c][1]; win[c][1] = win[c][2]; win[c][2] = win[c][3];
+            win[c][3] = hrow_pair<TS>(caA[c] + ro, caB[c] + ro, w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ro = (uint32_t)(base - 1 + i + trow0) * pitchB;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) win[c][i] = hrow_pair<TS>(caA[c] + ro, caB[c] + ro, w);
+        }
+    }
+    cur = base;
+}
+__device__ __forceinline__ void store_pair(float *o, float a, float b) { *reinterpret_cast<float2 *>(o) = make_float2(a, b); }
+__device__ __forceinline__ void store_pair(bf16 *o, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void store_pair(uint8_t *o, float a, float b) {
+    *reinterpret_cast<unsigned short *>(o) = (unsigned short)((unsigned)from_f<uint8_t>(a) | ((unsigned)from_f<uint8_t>(b) << 8));
+}
+
+template <typename TI, typename TO, bool RES>
+__global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                          const __grid_constant__ CUtensorMap tmap_r,
+                                                                          const BicubicTileGeom g, int H, int W, int rH, int rW,
+                                                                          TO *__restrict__ out, int oH, int oW, int clamp) {
+    pdl_trigger();
+    pdl_wait();          // the residual image is written by the previous kernel of the stream
+    __shared__ __align__(16) float yw[2][PAIR_H][4];
+    __shared__ int ybase[2][PAIR_H];
+    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ uint8_t tile_dyn[];
+    uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
+    const int t = threadIdx.x;
+    const int ox0 = blockIdx.x * BS_W, ox = ox0 + 2 * t, oy0 = blockIdx.y * PAIR_H, b = blockIdx.z;
+    const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
+    const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
+    constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
+    const int xr0 = src_floor(oy0, H, oH) - 1, xc0 = (src_floor(ox0, W, oW) - 1) & ~(XA - 1);
+    int rr0 = 0, rc0 = 0;
+    if (RES) { rr0 = src_floor(oy0, rH, oH) - 1; rc0 = (src_floor(ox0, rW, oW) - 1) & ~3; }
+    if (t == 0) {
+        const uint32_t bar_a = ptx::smem_u32(&bar);
+        ptx::mbar_init(bar_a, 1);
+        ptx::fence_barrier_init();
+        ptx::mbar_expect_tx(bar_a, x_bytes + (RES ? 3u * g.rr * g.rc * 4u : 0u));
+        ptx::tma_load_4d(ptx::smem_u32(tile_raw), &tmap_x, bar_a, xc0, xr0, 0, b);
+        if (RES) ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
+    }
+    for (int i = t; i < 2 * PAIR_H; i += BS_W / 2) {
+        const int s = i / PAIR_H, r = i % PAIR_H;
+        const int in_size = s ? rH : H;
+        const float scale = (float)in_size / (float)oH;
+        const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        const float A = -0.75f;
+        ybase[s][r] = i0;
+        yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
+    }
+    __syncthreads();
+    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    replicate_pad(reinterpret_cast<TI *>(tile_raw), xr0, xc0, g.xr, g.xc, H, W);
+    if (RES) replicate_pad(reinterpret_cast<float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc, rH, rW);
+    if (ox >= oW) return;           // oW is even: a pair is inside or outside as a whole
+    const Cubic cA = cubic_taps(ox, W, oW), cB = cubic_taps(ox + 1, W, oW);
+    ptx::f32x2 wxp[4], wrp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wxp[j] = ptx::pk2(cA.w[j], cB.w[j]);
+    const uint32_t xpitch = g.xc * sizeof(TI), rpitch = g.rc * 4u;
+    const uint32_t tile_a = ptx::smem_u32(tile_raw);
+    const uint32_t xsA = tile_a + (uint32_t)(src_floor(ox, W, oW) - 1 - xc0) * (uint32_t)sizeof(TI);
+    const uint32_t xsB = tile_a + (uint32_t)(src_floor(ox + 1, W, oW) - 1 - xc0) * (uint32_t)sizeof(TI);
+    const uint32_t xaA[3] = {xsA, xsA + g.xr * xpitch, xsA + 2u * g.xr * xpitch};
+    const uint32_t xaB[3] = {xsB, xsB + g.xr * xpitch, xsB + 2u * g.xr * xpitch};
+    uint32_t raA[3] = {0u, 0u, 0u}, raB[3] = {0u, 0u, 0u};
+    if (RES) {
+        const Cubic rA = cubic_taps(ox, rW, oW), rB = cubic_taps(ox + 1, rW, oW);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wrp[j] = ptx::pk2(rA.w[j], rB.w[j]);
+        const uint32_t rsA = tile_a + x_bytes_al + (uint32_t)(src_floor(ox, rW, oW) - 1 - rc0) * 4u;
+        const uint32_t rsB = tile_a + x_bytes_al + (uint32_t)(src_floor(ox + 1, rW, oW) - 1 - rc0) * 4u;
+        raA[0] = rsA; raA[1] = rsA + g.rr * rpitch; raA[2] = rsA + 2u * g.rr * rpitch;
+        raB[0] = rsB; raB[1] = rsB + g.rr * rpitch; raB[2] = rsB + 2u * g.rr * rpitch;
+    }
+    const long oplane = (long)oH * oW;
+    TO *o0 = out + (long)b * 3 * oplane + (long)oy0 * oW + ox, *o1 = o0 + oplane, *o2 = o1 + oplane;
+    ptx::f32x2 wx[3][4], wr[3][4];
+    int curx = -1000000, curr = -1000000;
+    const int nrows = min(PAIR_H, oH - oy0);
+    for (int r = 0; r < nrows; ++r) {
+        slide_pair<TI>(wx, curx, ybase[0][r], xaA, xaB, -xr0, xpitch, wxp);
+        if (RES) slide_pair<float>(wr, curr, ybase[1][r], raA, raB, -rr0, rpitch, wrp);
+        const float4 a = *reinterpret_cast<const float4 *>(yw[0][r]);
+        const float4 gg = *reinterpret_cast<const float4 *>(yw[1][r]);
+        const ptx::f32x2 a0 = ptx::pk2(a.x, a.x), a1 = ptx::pk2(a.y, a.y), a2 = ptx::pk2(a.z, a.z), a3 = ptx::pk2(a.w, a.w);
+        float lo[3], hi[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            ptx::f32x2 v = ptx::mul2(wx[c][0], a0);
+            v = ptx::fma2(wx[c][1], a1, v); v = ptx::fma2(wx[c][2], a2, v); v = ptx::fma2(wx[c][3], a3, v);
+            if (RES) {
+                ptx::f32x2 u = ptx::mul2(wr[c][0], ptx::pk2(gg.x, gg.x));
+                u = ptx::fma2(wr[c][1], ptx::pk2(gg.y, gg.y), u); u = ptx::fma2(wr[c][2], ptx::pk2(gg.z, gg.z), u);
+                u = ptx::fma2(wr[c][3], ptx::pk2(gg.w, gg.w), u);
+                v = ptx::add2(v, u);
+            }
+            ptx::up2(v, lo[c], hi[c]);
+            if (clamp) { lo[c] = fminf(fmaxf(lo[c], 0.f), 1.f); hi[c] = fminf(fmaxf(hi[c], 0.f), 1.f); }
+        }
+        store_pair(o0, lo[0], hi[0]); store_pair(o1, lo[1], hi[1]); store_pair(o2, lo[2], hi[2]);
+        o0 += oW; o1 += oW; o2 += oW;
+    }
+}
+
 // triangle-filter taps for one output index: [lo, lo+n) and the normalisation 1/sum
 __device__ __forceinline__ void aa_range(int dst, int in_size, int out_size, int &lo, int &n, float &center, float &inv,
                                          float &norm) {
@@ -345,6 +483,8 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const T *__restrict__ in
 
 using namespace tu;
 
+int tu::g_bicubic_pair = 1;      // debug key "bicubic_pair": two output columns per thread (default) / the one-column strip kernel
+
 // (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
 static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, int B, int H, int W, int box_rows, int box_cols) {
     TcEncodeFn enc = tc_encode_fn();
@@ -363,22 +503,47 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8) && (out_dtype == TU_F32 || out_dtype == TU_BF16 || out_dtype == TU_U8),
                  "bicubic_add_clamp: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, BS_H), B);
-    // source footprint of a 32 x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
-    const int eb = (int)dtype_size(in_dtype);
+    const int eb = (int)dtype_size(in_dtype), ob = (int)dtype_size(out_dtype);
     BicubicTileGeom g;
-    g.xr = (int)((long)(BS_H - 1) * H / outH) + 6;
-    g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 15) & ~15;        // + alignment slack of the first column
-    g.rr = res ? (int)((long)(BS_H - 1) * rH / outH) + 6 : 0;
-    g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 6 + 3 + 3) & ~3 : 0;
-    const size_t x_bytes = ((size_t)3 * g.xr * g.xc * eb + 127) & ~(size_t)127;
-    const size_t tile_bytes = x_bytes + (size_t)3 * g.rr * g.rc * 4;
+    size_t tile_bytes = 0;
     CUtensorMap tx, tr;
-    memset(&tx, 0, sizeof(tx));
-    memset(&tr, 0, sizeof(tr));
-    bool tma = tile_bytes <= 96 * 1024 && ((size_t)W * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-               (!res || (((size_t)rW * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0));
-    tma = tma && encode_image_map(&tx, x, eb, B, H, W, g.xr, g.xc) && (!res || encode_image_map(&tr, res, 4, B, rH, rW, g.rr, g.rc));
+    // source footprint of a bh x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
+    auto plan = [&](int bh) -> bool {
+        g.xr = (int)((long)(bh - 1) * H / outH) + 6;
+        g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 15) & ~15;        // + alignment slack of the first column
+        g.rr = res ? (int)((long)(bh - 1) * rH / outH) + 6 : 0;
+        g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 6 + 3 + 3) & ~3 : 0;
+        const size_t x_bytes = ((size_t)3 * g.xr * g.xc * eb + 127) & ~(size_t)127;
+        tile_bytes = x_bytes + (size_t)3 * g.rr * g.rc * 4;
+        memset(&tx, 0, sizeof(tx));
+        memset(&tr, 0, sizeof(tr));
+        bool ok = tile_bytes <= 96 * 1024 && ((size_t)W * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (!res || (((size_t)rW * 4) % 16 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0));
+        return ok && encode_image_map(&tx, x, eb, B, H, W, g.xr, g.xc) && (!res || encode_image_map(&tr, res, 4, B, rH, rW, g.rr, g.rc));
+    };
+    // two output columns per thread: TMA tiles, even output width, pair stores aligned
+    const bool pair = g_bicubic_pair && (outW % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % (2 * ob)) == 0 && plan(PAIR_H);
+    const bool tma = pair || plan(BS_H);
+    dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
+#define TU_BIC_PAIR(TI, TO)                                                                                                     \
+    do {                                                                                                                        \
+        static bool attr_done = false;                                                                                          \
+        if (!attr_done) {                                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_pair_kernel<TI, TO, true>,                                  \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                      \
+            if (e == cudaSuccess)                                                                                               \
+                e = cudaFuncSetAttribute(bicubic_add_clamp_pair_kernel<TI, TO, false>,                                         \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                              \
+            if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
+            attr_done = true;                                                                                                   \
+        }                                                                                                                       \
+        if (res)                                                                                                                \
+            launch_pdl(bicubic_add_clamp_pair_kernel<TI, TO, true>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
+                       (TO *)out, outH, outW, clamp);                                                                          \
+        else                                                                                                                    \
+            launch_pdl(bicubic_add_clamp_pair_kernel<TI, TO, false>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
+                       (TO *)out, outH, outW, clamp);                                                                          \
+    } while (0)
 #define TU_BIC(TI, TO)                                                                                                          \
     do {                                                                                                                        \
         if (tma) {                                                                                                              \
@@ -403,15 +568,22 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
                                                                                   (TO *)out, outH, outW, clamp);                \
         }                                                                                                                       \
     } while (0)
-    if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC(float, float);
-    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC(float, bf16);
-    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC(bf16, float);
-    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC(bf16, bf16);
-    else if (in_dtype == TU_U8 && out_dtype == TU_U8) TU_BIC(uint8_t, uint8_t);
-    else if (in_dtype == TU_U8 && out_dtype == TU_F32) TU_BIC(uint8_t, float);
-    else if (in_dtype == TU_U8 && out_dtype == TU_BF16) TU_BIC(uint8_t, bf16);
-    else if (in_dtype == TU_F32 && out_dtype == TU_U8) TU_BIC(float, uint8_t);
-    else TU_BIC(bf16, uint8_t);
+#define TU_BIC2(TI, TO)          \
+    do {                         \
+        if (pair) TU_BIC_PAIR(TI, TO); \
+        else TU_BIC(TI, TO);     \
+    } while (0)
+    if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC2(float, float);
+    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC2(float, bf16);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC2(bf16, float);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC2(bf16, bf16);
+    else if (in_dtype == TU_U8 && out_dtype == TU_U8) TU_BIC2(uint8_t, uint8_t);
+    else if (in_dtype == TU_U8 && out_dtype == TU_F32) TU_BIC2(uint8_t, float);
+    else if (in_dtype == TU_U8 && out_dtype == TU_BF16) TU_BIC2(uint8_t, bf16);
+    else if (in_dtype == TU_F32 && out_dtype == TU_U8) TU_BIC2(float, uint8_t);
+    else TU_BIC2(bf16, uint8_t);
+#undef TU_BIC2
+#undef TU_BIC_PAIR
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
     return TU_OK;

@@ -31,6 +31,10 @@ int tc_linear(const bf16 *A, const bf16 *W, const float *bias, int M, int N, int
               bf16 *resid_bf16, cudaStream_t st);
 int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
                    int Ht, int Wt, int dim, int window, cudaStream_t st);
+// patch embed at dim 128 with one tile per CTA and two CTAs per SM (embed_tcgen05.cu): same contract as tc_patch_embed
+int tc_patch_embed_pair(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
+                        int Ht, int Wt, int dim, int window, cudaStream_t st);
+void tc_set_embed_pair(int on);
 int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, const bf16 *skip, int skipH, int skipW, bf16 *out,
                      int B, int Ht, int Wt, int Hc, int Wc, int dim, int window, int *dyn_ctr, const int *tile_flags, cudaStream_t st);
 
@@ -79,12 +83,16 @@ int tc_conv3x3_c64_to3_stream(const bf16 *in, const bf16 *wst, const float *bias
 
 // all window-transformer blocks in one persistent kernel (dim 128; window_stack_tcgen05.cu)
 // tile_flags (optional, zeroed by the caller): tile_flags[t] is set once the 128 tokens of tile t are final and fenced
+// seg_flags (optional, zeroed by the caller, one int per tile): allows a tile to be handed from one CTA to the next at a block
+// boundary, so that the (tile, block) units are dealt out evenly when the tiles do not fill whole waves of SMs
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
-                    const float *rel_bias, int *tile_flags, cudaStream_t st);
+                    const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st);
+void tc_set_stack_split(int on);
+bool tc_stack_split_enabled();
 
 // the same for FastTransformer (dim 192, 12 heads; window_stack192_tcgen05.cu)
 int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
-                       const float *rel_bias, int *tile_flags, cudaStream_t st);
+                       const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st);
 
 // one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
 int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,

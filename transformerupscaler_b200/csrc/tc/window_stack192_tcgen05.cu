@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "ptx.cuh"
+#include "stack_split.cuh"
 #include "tc_api.cuh"
 
 namespace tu {
@@ -57,6 +58,8 @@ struct Stack192Params {
     const float *rel_bias; // nblocks x (12, 64, 64) fp32 dense relative-position bias
     int n_tiles, n_blocks;
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
+    int *seg_flags;        // optional: block-level work split (stack_split.cuh); seg_flags[t] = 1 once the first part of tile t is stored
+    int units_per_cta;
 };
 
 struct Barriers {
@@ -208,8 +211,9 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             // ================================ TMA producer: weight slabs in consumption order ================================
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-                for (int bk = 0; bk < p.n_blocks; ++bk) {
+            Seg sg;
+            for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
+                for (int bk = sg.lo; bk < sg.hi; ++bk) {
                     int row = bk * ROWS_PER_BLOCK;
                     for (int s = 0; s < SLABS96 + SLABS192; ++s) {
                         const bool small = s < SLABS96;
@@ -248,8 +252,9 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
         auto commit = [&](int which) { ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[which]), leader); };
         const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32), ao = ptx::sdesc_lo(smem0 + OFF_AO);
         constexpr uint32_t SL = SLAB_A >> 4;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-            for (int bk = 0; bk < p.n_blocks; ++bk) {
+        Seg sg;
+        for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
+            for (int bk = sg.lo; bk < sg.hi; ++bk) {
                 for (int g = 0; g < NGROUP; ++g) {
                     wait_a();                                   // g = 0: LN1 output in A32; g > 0: ACC drained by the previous group
                     for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id96, ks == 0);
@@ -297,19 +302,25 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             for (int j = 0; j < 24; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 48 + 2 * j));
         };
 
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-            // ---- tokens -> TMEM X
+        Seg sg;
+        for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k) {
+            const int t = sg.tile;
+            if (sg.lo > 0) {          // the CTA that ran blocks [0, lo) of this tile has stored and fenced the raw residual stream
+                if (mt == 0) wait_flag_acquire(p.seg_flags + t);
+                math_barrier();
+            }
+            // ---- tokens (or the raw residual stream of a tile in progress) -> TMEM X
             {
                 const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 48;
                 uint32_t v[32], w[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 f = *reinterpret_cast<const float4 *>(src + j);
+                    const float4 f = __ldcg(reinterpret_cast<const float4 *>(src + j));
                     v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 f = *reinterpret_cast<const float4 *>(src + 32 + j);
+                    const float4 f = __ldcg(reinterpret_cast<const float4 *>(src + 32 + j));
                     w[j] = __float_as_uint(f.x); w[j + 1] = __float_as_uint(f.y); w[j + 2] = __float_as_uint(f.z); w[j + 3] = __float_as_uint(f.w);
                 }
                 ptx::tmem_st_x32(TX + lane_base + part * 48, v);
@@ -317,7 +328,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
             }
-            for (int bk = 0; bk < p.n_blocks; ++bk) {
+            for (int bk = sg.lo; bk < sg.hi; ++bk) {
                 // ---- per-block parameters -> smem
                 math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
                 ptx::tc_fence_after();
@@ -480,6 +491,20 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 wait_acc(ACC_FC2L);      // fc2 of the last quarter accumulated: X holds the block output (minus folded biases)
                 cph ^= 1;
             }
+            if (sg.hi < p.n_blocks) {
+                // ---- tile in progress: raw X -> global (the folded bias offsets are NOT applied: the next CTA continues exactly here)
+                float *dst = p.tok + ((long)t * 128 + i) * DIM + part * 48;
+                uint32_t v[48];
+                tmem_ld48(TX + lane_base + part * 48, v);
+#pragma unroll
+                for (int j = 0; j < 48; j += 4)
+                    *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                ptx::tc_fence_before();
+                __threadfence();
+                math_barrier();
+                if (mt == 0) atomicExch(p.seg_flags + t, 1);
+                continue;
+            }
             // ---- X (+ final offset) -> global
             {
                 const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS + part * 48;
@@ -523,7 +548,7 @@ bool g_attr_set = false;
 // stack_w: bf16 (n_blocks * 6912, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*2496 + 192;
 // rel_bias: fp32 n_blocks x (12,64,64).  tok: (M,192) fp32 with M % 128 == 0.
 int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
-                       const float *rel_bias, int *tile_flags, cudaStream_t st) {
+                       const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
         (reinterpret_cast<uintptr_t>(tok) & 15))
@@ -554,6 +579,8 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
+    p.seg_flags = (seg_flags && tc_stack_split_enabled() && p.n_tiles % grid != 0) ? seg_flags : nullptr;
+    p.units_per_cta = ceil_div(p.n_tiles * n_blocks, grid);
     launch_pdl(window_stack192_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, t96, t192, p);
     TU_CHECK_LAUNCH("window_stack192");
     return TU_OK;

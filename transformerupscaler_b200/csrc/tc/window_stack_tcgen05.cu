@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include "ptx.cuh"
+#include "stack_split.cuh"
 #include "tc_api.cuh"
 
 namespace tu {
@@ -53,7 +54,14 @@ struct StackParams {
     int n_tiles, n_blocks;
     int rev;               // token tiles are walked last to first (debug key "snake", bit 2)
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
+    // Block-level work split (seg_flags != nullptr, zeroed by the caller): the n_tiles * n_blocks (tile, block) units are dealt out in
+    // equal contiguous shares, so a CTA may take a tile through its first blocks only and hand the residual stream (raw TMEM X, fp32,
+    // through the token buffer) to the next CTA, which continues it: 240 tiles x 8 blocks on 148 SMs = 13 units per SM instead of
+    // two whole tiles (16).  seg_flags[t] = 1 once the first part of tile t is stored and fenced.
+    int *seg_flags;
+    int units_per_cta;
 };
+
 
 // commit points of one block, in issue order: qkv column thirds, proj, fc1 (first half) column halves, fc1 (second half)
 // column halves, fc2 (second half).  A part's epilogue starts while the MMAs of the next part are still running.
@@ -192,8 +200,9 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             // ================================ TMA producer: weight slabs in consumption order ================================
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-                for (int s = 0; s < p.n_blocks * SLABS_PER_BLOCK; ++s) {
+            Seg sg;
+            for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
+                for (int s = sg.lo * SLABS_PER_BLOCK; s < sg.hi * SLABS_PER_BLOCK; ++s) {
                     ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                     const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
                     ptx::mbar_expect_tx(fb, SLAB);
@@ -226,8 +235,9 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
         };
         const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32), hid = ptx::sdesc_lo(smem0 + OFF_STG);
         constexpr uint32_t SL = SLAB >> 4;
-        for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x)
-            for (int bk = 0; bk < p.n_blocks; ++bk) {
+        Seg sg;
+        for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
+            for (int bk = sg.lo; bk < sg.hi; ++bk) {
                 wait_a();                                       // LN1 output in A32
                 for (int nc = 0; nc < 3; ++nc) {
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);
@@ -278,22 +288,27 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             for (int j = 0; j < 16; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 32 + 2 * j));
         };
 
-        for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x) {
-            const int t = p.rev ? p.n_tiles - 1 - t0 : t0;
-            // ---- tokens -> TMEM X
+        Seg sg;
+        for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k) {
+            const int t = p.rev ? p.n_tiles - 1 - sg.tile : sg.tile;
+            if (sg.lo > 0) {          // the CTA that ran blocks [0, lo) of this tile has stored and fenced the raw residual stream
+                if (mt == 0) wait_flag_acquire(p.seg_flags + t);
+                math_barrier();
+            }
+            // ---- tokens (or the raw residual stream of a tile in progress) -> TMEM X
             {
                 const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 32;
                 uint32_t v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 f = *reinterpret_cast<const float4 *>(src + j);
+                    const float4 f = __ldcg(reinterpret_cast<const float4 *>(src + j));
                     v[j] = __float_as_uint(f.x); v[j + 1] = __float_as_uint(f.y); v[j + 2] = __float_as_uint(f.z); v[j + 3] = __float_as_uint(f.w);
                 }
                 ptx::tmem_st_x32(TX + lane_base + part * 32, v);
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
             }
-            for (int bk = 0; bk < p.n_blocks; ++bk) {
+            for (int bk = sg.lo; bk < sg.hi; ++bk) {
                 // ---- per-block parameters -> smem
                 math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
                 ptx::tc_fence_after();
@@ -464,6 +479,21 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 wait_acc(ACC_FC2B);      // fc2 of the second half accumulated: X holds the block output (minus folded biases)
                 cph ^= 1;
             }
+            if (sg.hi < p.n_blocks) {
+                // ---- tile in progress: raw X -> global (the folded bias offsets are NOT applied: the next CTA continues exactly here)
+                float *dst = p.tok + ((long)t * 128 + i) * DIM + part * 32;
+                uint32_t v[32];
+                ptx::tmem_ld_x32(TX + lane_base + part * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                ptx::tc_fence_before();
+                __threadfence();
+                math_barrier();
+                if (mt == 0) atomicExch(p.seg_flags + t, 1);
+                continue;
+            }
             // ---- X (+ final offset) -> global
             {
                 const float *cfin = p.par + (long)p.n_blocks * PAR_FLOATS + part * 32;
@@ -502,13 +532,17 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
 
 int g_sm_count = 0;
 bool g_attr_set = false;
+int g_stack_split = 1;
 
 }  // namespace
+
+void tc_set_stack_split(int on) { g_stack_split = on; }
+bool tc_stack_split_enabled() { return g_stack_split != 0; }
 
 // stack_w: bf16 (n_blocks * 24 * 128, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*1664 + 128;
 // rel_bias: fp32 n_blocks x (8,64,64).  tok: (M,128) fp32 with M % 128 == 0.
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
-                    const float *rel_bias, int *tile_flags, cudaStream_t st) {
+                    const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
         (reinterpret_cast<uintptr_t>(tok) & 15))
@@ -537,6 +571,9 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     p.rev = (g_snake_mask >> 2) & 1;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
+    // split tiles between CTAs at block boundaries only when whole tiles do not divide evenly (and the caller provided flags)
+    p.seg_flags = (seg_flags && g_stack_split && p.n_tiles % grid != 0) ? seg_flags : nullptr;
+    p.units_per_cta = ceil_div(p.n_tiles * n_blocks, grid);
     launch_pdl(window_stack_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, tw, p);
     TU_CHECK_LAUNCH("window_stack");
     return TU_OK;

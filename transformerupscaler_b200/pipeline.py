@@ -12,10 +12,13 @@ import torch
 
 
 class FramePipeline:
-    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, **forward_kw):
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, compute_streams: int = 1, **forward_kw):
+        """compute_streams > 1: consecutive batches run their forwards on alternating streams, so the kernels of one batch
+        can fill the SMs the other batch's partly filled waves leave idle (needs depth >= compute_streams)"""
         self.model, self.kw, self.depth = model, forward_kw, depth
         self.device = device or next(model.parameters()).device
-        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self.s_in, self.s_out = (torch.cuda.Stream(self.device) for _ in range(2))
+        self.s_comps = [torch.cuda.Stream(self.device) for _ in range(max(1, min(compute_streams, depth)))]
         self.dev_in: List[Optional[torch.Tensor]] = [None] * depth
         self.dev_out: List[Optional[torch.Tensor]] = [None] * depth
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
@@ -34,10 +37,11 @@ class FramePipeline:
         with torch.cuda.stream(self.s_in):
             self.dev_in[slot].copy_(host_in, non_blocking=True)
             self.ev_in[slot].record(self.s_in)
-        with torch.cuda.stream(self.s_comp):
-            self.s_comp.wait_event(self.ev_in[slot])
+        s_comp = self.s_comps[self.n % len(self.s_comps)]
+        with torch.cuda.stream(s_comp):
+            s_comp.wait_event(self.ev_in[slot])
             out = self.model(self.dev_in[slot], **self.kw)
-            self.ev_comp[slot].record(self.s_comp)
+            self.ev_comp[slot].record(s_comp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[slot])
             host_out.copy_(out, non_blocking=True)
@@ -47,5 +51,5 @@ class FramePipeline:
         self.n += 1
 
     def drain(self) -> None:
-        for s in (self.s_in, self.s_comp, self.s_out):
+        for s in (self.s_in, *self.s_comps, self.s_out):
             s.synchronize()
