@@ -295,6 +295,37 @@ def test_patch_embed_unembed(dev, dt, model, Hf, Wf):
     assert _maxerr(out, ref) < _tol(dt, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("model,B,Hf,Wf", [("WindowTransformer", 2, 64, 80), ("WindowTransformer", 3, 40, 136), ("FastTransformer", 2, 64, 80),
+                                            ("FastTransformer", 1, 24, 264), ("WindowTransformer", 5, 360, 640)])
+def test_patch_embed_variants(dev, model, B, Hf, Wf):
+    """patch embed on the tensor cores: the general persistent GEMM kernel, one tile per CTA with two CTAs per SM, and the same with the
+    filter stages multicast inside clusters of two CTAs accumulate the same k-blocks in the same order: bitwise identical tokens, and
+    equal to the oracle's patch_embed on bf16-rounded operands (W:251-254; F:268-270)"""
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(19)
+    sd = synth_state_dict(model, 3)
+    dim = sd["patch_embed.weight"].shape[0]
+    feat = torch.from_numpy(rs.uniform(-1, 1, (B, Hf, Wf, 64)).astype(np.float32)).to(BF16)
+    Ht, Wt = Hf // 8, Wf // 8
+    we = sd["patch_embed.weight"].to(BF16).float()
+    wp = we.permute(0, 2, 3, 1).reshape(dim, 4096).contiguous().to(dev, BF16)
+    outs = []
+    try:
+        for variant in (0, 1 + 4, 2 + 4, 1 + 4 + 8):      # bit mask: 1 two CTAs per SM, 2 cluster multicast, 4 also at dim 192, 8 L2 prefetch
+            lib.tu_debug_set(b"embed_pair", variant)
+            outs.append(G.patch_embed(feat.to(dev), wp, sd["patch_embed.bias"].to(dev), None, Ht, Wt, dim, True, False).clone())
+    finally:
+        lib.tu_debug_set(b"embed_pair", 1)
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    if Hf * Wf <= 64 * 264:
+        tok_ref = orc.patch_embed_nhwc(feat.float()[:, :Ht * 8, :Wt * 8], we, sd["patch_embed.bias"])
+        nWy, nWx = (Ht + 7) // 8, (Wt + 7) // 8
+        grid = outs[1].reshape(B, nWy, nWx, 8, 8, dim).permute(0, 1, 3, 2, 4, 5).reshape(B, nWy * 8, nWx * 8, dim)
+        assert _maxerr(grid[:, :Ht, :Wt], tok_ref) < _tol(BF16, tok_ref.abs().max().item())
+
+
 @pytest.mark.parametrize("dt", [F32, BF16])
 @pytest.mark.parametrize("model", ["WindowTransformer", "FastTransformer", "ResidualTransformer"])
 def test_transformer_block(dev, dt, model):

@@ -532,7 +532,8 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
 
 int g_sm_count = 0;
 bool g_attr_set = false;
-int g_stack_split = 1;
+int g_stack_split = 0;       // measured (profiles/r05c_ab.log): 342 -> 290 us serialised, but inside a forward the unembed overlap already uses
+                             // the SMs the whole-tile schedule leaves idle: 1.2605 -> 1.2637 ms (dim 128), 2.0515 -> 2.0694 ms (dim 192)
 
 }  // namespace
 
