@@ -179,7 +179,8 @@ embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
 // debug key "embed_pair" (bit mask): 0 general GEMM kernel; 1 one tile per CTA, two CTAs per SM (default); 2 the same with the filter
 // stages multicast inside clusters of two CTAs; +4 also at dim 192; +8 L2 prefetch of whole patch rows one ky ahead.
-// Measured (profiles/r05e_ab.log): dim 128: 69.1 -> 62.1 us (1), 63.5 us (2); dim 192 (two 40 KB stages per CTA): 134 -> 140 / 145 us, left off
+// Measured (profiles/r05e_ab.log, r05f_ab.log): dim 128: 69.1 -> 62.1 us (1), 63.5 us (2), 75.3 us (1 + 8); dim 192 (two 40 KB stages per
+// CTA): 134 -> 140 (1 + 4) / 145 (2 + 4) / 171 us (1 + 4 + 8): only the plain dim-128 variant is on
 int g_embed_pair = 1;
 
 template <typename... KArgs, typename... Args>
