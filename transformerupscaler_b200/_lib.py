@@ -62,6 +62,7 @@ SIGNATURES = {
     "tu_bf16_uses_tcgen05": (i32, []),
     "tu_set_bf16_tcgen05": (None, [i32]),
     "tu_debug_set": (i32, [C.c_char_p, i32]),
+    "tu_debug_trace": (i32, [vp, C.c_uint]),
     "tu_launch_count": (C.c_longlong, []),
     "tu_profile_enable": (None, [i32]),
     "tu_profile_collect": (i32, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -409,6 +409,13 @@ extern "C" int tu_debug_set(const char *key, int value) {
     set_error("tu: unknown debug key");
     return TU_ERR_ARG;
 }
+unsigned long long *tu::g_trace_buf = nullptr;
+unsigned int tu::g_trace_cap = 0;
+extern "C" int tu_debug_trace(void *device_buffer, unsigned int capacity_events) {
+    tu::g_trace_buf = (unsigned long long *)device_buffer;
+    tu::g_trace_cap = device_buffer ? capacity_events : 0;
+    return TU_OK;
+}
 extern "C" long long tu_launch_count(void) { return g_launches.load(); }
 extern "C" void tu_profile_enable(int on) { g_prof_on = on; }
 // waits for the recorded events (the only calls in the library that wait on the device)

@@ -58,6 +58,8 @@ struct GemmParams {
     // no griddepcontrol.wait -- on the SMs the stack's last, partly filled wave leaves idle
     int *dyn_ctr;
     const int *tile_flags;
+    unsigned long long *trace;      // debug (tu_debug_trace)
+    unsigned int trace_cap;
     int rev;            // tiles are walked last to first (debug key "snake", bit 2: unembed behind a reversed window stack)
 };
 constexpr int QD = 4;      // depth of the tile-index queue between the scheduler thread and the three roles
@@ -166,14 +168,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy acquire -> the TMA reads that follow
     };
 
+    // the scheduler thread has seen the flag of a tile before it hands the tile out; a role that is about to read the tile through the
+    // async proxy (TMA) only needs the proxy fence (generic-proxy acquire, passed on through the queue's mbarrier -> TMA reads)
+    auto proxy_fence = [&]() {
+        if (p.tile_flags) asm volatile("fence.proxy.async.global;" ::: "memory");
+    };
+
     if (warp == 3 && lane == 0 && dyn) {
         // ================================ tile scheduler ================================
-        for (int k = 0;; ++k) {
-            if (k >= QD) ptx::mbar_wait(ptx::smem_u32(&bars->q_empty[k % QD]), ((k / QD) & 1) ^ 1);
-            const int t = atomicAdd(p.dyn_ctr, 1);
-            *reinterpret_cast<volatile int *>(&bars->tq[k % QD]) = t < p.total_tiles ? (p.rev ? p.total_tiles - 1 - t : t) : -1;
-            ptx::mbar_arrive(ptx::smem_u32(&bars->q_full[k % QD]));      // release: the index is visible to whoever passes the wait
-            if (t >= p.total_tiles) break;
+        // Tiles are drawn DRAW at a time (one atomic and one flag check per draw: the DRAW n-tiles of a draw belong to one M tile, whose
+        // tokens then also stay in L2 for the draw), and the wait for the window stack's flag happens HERE, up to QD tiles ahead of
+        // the roles: a global acquire load is ~0.8 us, which the TMA producer and the eight skip-box prefetches used to pay per tile
+        constexpr int DRAW = 4;
+        int last_tm = -1;
+        for (int k = 0;;) {
+            const int base = (p.tiles_n % DRAW == 0) ? atomicAdd(p.dyn_ctr, DRAW) : atomicAdd(p.dyn_ctr, 1);
+            const int cnt = (p.tiles_n % DRAW == 0) ? DRAW : 1;
+            bool last = false;
+            for (int j = 0; j < cnt && !last; ++j, ++k) {
+                const int t0 = base + j;
+                last = t0 >= p.total_tiles;
+                const int t = last ? -1 : (p.rev ? p.total_tiles - 1 - t0 : t0);
+                if (!last) {
+                    trace_event(p.trace, p.trace_cap, 3, (unsigned)t);          // tile drawn by this CTA's scheduler
+                    const int tm = t / p.tiles_n;
+                    if (tm != last_tm) { wait_published(tm); last_tm = tm; trace_event(p.trace, p.trace_cap, 5, (unsigned)tm); }
+                }
+                if (k >= QD) ptx::mbar_wait(ptx::smem_u32(&bars->q_empty[k % QD]), ((k / QD) & 1) ^ 1);
+                *reinterpret_cast<volatile int *>(&bars->tq[k % QD]) = t;
+                ptx::mbar_arrive(ptx::smem_u32(&bars->q_full[k % QD]));      // release: the index is visible to whoever passes the wait
+            }
+            if (last) break;
         }
     } else if (warp == 0 && lane == 0) {
         // ================================ TMA producer ================================
@@ -185,7 +210,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (t < 0) break;
             const int tn = t % p.tiles_n, tm = t / p.tiles_n;
             const int n0 = tn * p.BN;
-            if (tm != ready_tm) { wait_published(tm); ready_tm = tm; }
+            if (tm != ready_tm) {
+                if (dyn) proxy_fence(); else wait_published(tm);
+                ready_tm = tm;
+            }
             for (int s = 0; s < nk; ++s) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                 const uint32_t dst = smem0 + stage * stage_bytes;
@@ -261,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             auto request = [&](int t, int buf) {                  // lane 0: skip box of tile t -> buffer buf
                 int dx, tx0, y0, b;
                 if (!coords(t, dx, tx0, y0, b)) return;
-                wait_published(t / p.tiles_n);                    // (dynamic mode) nothing of a tile is touched before the stack published it
+                proxy_fence();                                    // (dynamic mode) the scheduler handed the tile out after the stack published it
                 const uint32_t fb = ptx::smem_u32(&bars->skip_full[w8][buf]);
                 ptx::mbar_expect_tx(fb, 4096);
                 ptx::tma_load_5d(box_sm + buf * 4096, &tmap_skip, fb, 0, dx, tx0, y0, b);
@@ -657,7 +685,7 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
         if (ok) {
             p.epi = EPI_UNEMBED_TMA;
             p.rev = ((g_snake_mask >> 2) & 1) && dim == 128;      // the dim-128 stack publishes its tiles in the same order
-            if (dyn_ctr && tile_flags) { p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; }
+            if (dyn_ctr && tile_flags) { p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; p.trace = g_trace_buf; p.trace_cap = g_trace_cap; }
             return launch(ta, tw, p, st, &ts, &to);
         }
     }

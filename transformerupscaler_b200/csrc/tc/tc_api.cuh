@@ -18,6 +18,22 @@ void tc_set_base_off_mode(int m);
 extern int g_snake_mask;
 void tc_set_snake(int mask);
 
+// debug: device buffer of (time, tag) event pairs written by the window stack and the unembed GEMM (tu_debug_trace); word 0 = count
+extern unsigned long long *g_trace_buf;
+extern unsigned int g_trace_cap;
+__device__ __forceinline__ void trace_event(unsigned long long *buf, unsigned int cap, unsigned int kind, unsigned int value) {
+    if (!buf) return;
+    unsigned long long t;
+    unsigned int sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    const unsigned long long i = atomicAdd(buf, 1ULL);
+    if (i < cap) {
+        buf[1 + 2 * i] = t;
+        buf[2 + 2 * i] = ((unsigned long long)kind << 48) | ((unsigned long long)sm << 32) | value;
+    }
+}
+
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda); nullptr without a driver
 typedef CUresult (*TcEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

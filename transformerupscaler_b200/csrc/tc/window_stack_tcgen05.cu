@@ -60,6 +60,8 @@ struct StackParams {
     // two whole tiles (16).  seg_flags[t] = 1 once the first part of tile t is stored and fenced.
     int *seg_flags;
     int units_per_cta;
+    unsigned long long *trace;      // debug (tu_debug_trace)
+    unsigned int trace_cap;
 };
 
 
@@ -295,6 +297,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 if (mt == 0) wait_flag_acquire(p.seg_flags + t);
                 math_barrier();
             }
+            if (mt == 0) trace_event(p.trace, p.trace_cap, 1, (unsigned)t);          // tile begins
             // ---- tokens (or the raw residual stream of a tile in progress) -> TMEM X
             {
                 const float *src = p.tok + ((long)t * 128 + i) * DIM + part * 32;
@@ -522,6 +525,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     math_barrier();
                     if (mt == 0) atomicExch(p.tile_flags + t, 1);
                 }
+                if (mt == 0) trace_event(p.trace, p.trace_cap, 2, (unsigned)t);      // tile stored (and published)
             }
         }
     }
@@ -571,6 +575,7 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     p.rev = (g_snake_mask >> 2) & 1;
+    p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     // split tiles between CTAs at block boundaries only when whole tiles do not divide evenly (and the caller provided flags)
     p.seg_flags = (seg_flags && g_stack_split && p.n_tiles % grid != 0) ? seg_flags : nullptr;
