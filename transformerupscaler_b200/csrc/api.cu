@@ -382,6 +382,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
         g_fold_up1 = value;
         return TU_OK;
     }
+    if (key && !strcmp(key, "unembed_areuse")) {
+        tc_set_unembed_areuse(value);
+        return TU_OK;
+    }
     if (key && !strcmp(key, "stack_split")) {
         tc_set_stack_split(value);
         return TU_OK;

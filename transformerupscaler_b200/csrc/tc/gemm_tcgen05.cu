@@ -60,8 +60,12 @@ struct GemmParams {
     const int *tile_flags;
     unsigned long long *trace;      // debug (tu_debug_trace)
     unsigned int trace_cap;
+    int a_reuse;        // UNEMBED_TMA behind the stack, K = 128: the A tile (128 tokens) is loaded once per M tile into one of two buffers
+                        // (the A halves of the four stage slots) and only the filter streams through the ring: a draw of four n-tiles
+                        // moves 104 KB through the TMA engine instead of 128 KB per tile
     int rev;            // tiles are walked last to first (debug key "snake", bit 2: unembed behind a reversed window stack)
 };
+int g_unembed_areuse = 0;  // debug key "unembed_areuse"
 constexpr int QD = 4;      // depth of the tile-index queue between the scheduler thread and the three roles
 
 struct Barriers {
@@ -70,6 +74,7 @@ struct Barriers {
     uint64_t acc_full[2];
     uint64_t acc_empty[2];
     uint64_t skip_full[8][2];   // UNEMBED_TMA: private to each epilogue warp
+    uint64_t a_full[2], a_empty[2];   // a_reuse: the two A-tile buffers
     uint64_t q_full[QD], q_empty[QD];
     int tq[QD];
     uint32_t tmem_base;
@@ -124,6 +129,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[i]), 8);
         }
         for (int i = 0; i < 16; ++i) ptx::mbar_init(ptx::smem_u32(&bars->skip_full[i >> 1][i & 1]), 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
+        }
         for (int i = 0; i < QD; ++i) {
             ptx::mbar_init(ptx::smem_u32(&bars->q_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->q_empty[i]), 10);       // TMA producer, MMA warp, 8 epilogue warps
@@ -204,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ================================ TMA producer ================================
         int stage = 0;
         uint32_t phase = 0;
-        int ready_tm = -1;
+        int ready_tm = -1, na = 0;
         for (int k = 0;; ++k) {
             const int t = tile_at(k);
             if (t < 0) break;
@@ -213,6 +222,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (tm != ready_tm) {
                 if (dyn) proxy_fence(); else wait_published(tm);
                 ready_tm = tm;
+                if (p.a_reuse) {          // the M tile's tokens -> A buffer na & 1 (free once the MMAs of the M tile before last have retired)
+                    const int ab = na & 1;
+                    ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[ab]), ((na >> 1) & 1) ^ 1);
+                    const uint32_t fa = ptx::smem_u32(&bars->a_full[ab]);
+                    ptx::mbar_expect_tx(fa, nk * A_STAGE);
+                    for (int s = 0; s < nk; ++s) ptx::tma_load_2d(smem0 + (2 * ab + s) * stage_bytes, &tmap_a, fa, s * BK, tm * BM);
+                    ++na;
+                }
+            }
+            if (p.a_reuse) {
+                for (int s = 0; s < nk; ++s) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
+                    const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
+                    ptx::mbar_expect_tx(fb, w_stage);
+                    ptx::tma_load_2d(smem0 + stage * stage_bytes + A_STAGE, &tmap_w, fb, s * BK, n0);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tile_done(k);
+                continue;
             }
             for (int s = 0; s < nk; ++s) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
@@ -237,10 +265,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t smem_lo = ptx::sdesc_lo(smem0);
         int stage = 0;
         uint32_t phase = 0;
+        int cur_tm = -1, na = 0, ab = 0;
         for (int it = 0;; ++it) {
-            if (tile_at(it) < 0) break;
+            const int t = tile_at(it);
+            if (t < 0) break;
             __syncwarp();
-            if (lane == 0) tile_done(it);        // the MMA warp needs no tile coordinates, only the count
+            if (lane == 0) tile_done(it);
+            if (p.a_reuse && t / p.tiles_n != cur_tm) {
+                // every MMA that reads the previous M tile's A buffer has been issued: it is free once they retire
+                if (cur_tm >= 0) ptx::umma_commit_pred(ptx::smem_u32(&bars->a_empty[ab]), leader);
+                ab = na & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_full[ab]), (na >> 1) & 1);
+                ++na;
+                cur_tm = t / p.tiles_n;
+            }
             const int set = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[set]), aphase ^ 1);
@@ -249,7 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int s = 0; s < nk; ++s) {
                 ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
                 ptx::tc_fence_after();
-                const uint32_t a_lo = smem_lo + ((stage * stage_bytes) >> 4), w_lo = a_lo + (A_STAGE >> 4);
+                const uint32_t w_lo = smem_lo + ((stage * stage_bytes + A_STAGE) >> 4);
+                const uint32_t a_lo = p.a_reuse ? smem_lo + (((2 * ab + s) * stage_bytes) >> 4) : smem_lo + ((stage * stage_bytes) >> 4);
                 ptx::umma_bf16_lo_rt(acc, a_lo, w_lo, idesc, s != 0, leader);
 #pragma unroll
                 for (int k4 = 1; k4 < 4; ++k4) ptx::umma_bf16_lo<1>(acc, a_lo + k4 * 2, w_lo + k4 * 2, idesc, leader);
@@ -595,6 +634,8 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStre
 
 }  // namespace
 
+void tc_set_unembed_areuse(int on) { g_unembed_areuse = on; }
+
 int tc_linear(const bf16 *A, const bf16 *W, const float *bias, int M, int N, int K, int act, bf16 *out, float *resid_x,
               bf16 *resid_bf16, cudaStream_t st) {
     const int BN = pick_bn(N);
@@ -685,7 +726,10 @@ int tc_patch_unembed(const bf16 *tok_bf16, const bf16 *W, const float *bias, con
         if (ok) {
             p.epi = EPI_UNEMBED_TMA;
             p.rev = ((g_snake_mask >> 2) & 1) && dim == 128;      // the dim-128 stack publishes its tiles in the same order
-            if (dyn_ctr && tile_flags) { p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; p.trace = g_trace_buf; p.trace_cap = g_trace_cap; }
+            if (dyn_ctr && tile_flags) {
+                p.dyn_ctr = dyn_ctr; p.tile_flags = tile_flags; p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
+                p.a_reuse = (g_unembed_areuse && dim == 2 * BK) ? 1 : 0;
+            }
             return launch(ta, tw, p, st, &ts, &to);
         }
     }

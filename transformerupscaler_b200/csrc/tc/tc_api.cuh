@@ -47,6 +47,7 @@ int tc_linear(const bf16 *A, const bf16 *W, const float *bias, int M, int N, int
               bf16 *resid_bf16, cudaStream_t st);
 int tc_patch_embed(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
                    int Ht, int Wt, int dim, int window, cudaStream_t st);
+void tc_set_unembed_areuse(int on);
 // patch embed at dim 128 with one tile per CTA and two CTAs per SM (embed_tcgen05.cu): same contract as tc_patch_embed
 int tc_patch_embed_pair(const bf16 *feat, const bf16 *W, const float *bias, const float *pos, float *tok, int B, int H, int Wd,
                         int Ht, int Wt, int dim, int window, cudaStream_t st);
