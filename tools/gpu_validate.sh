@@ -1,5 +1,5 @@
 #!/bin/bash
-# round r05i: full GPU parity suite, smoke, bench (+ reference arm), all BASELINE configs, ncu launch list
+# usage: tools/gpu_validate.sh  (tag r05i): full GPU parity suite, smoke, bench (+ reference arm), all BASELINE configs, ncu launch list
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider > gpurun_out/pytest_gpu_r05i.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu_r05i.log
