@@ -182,3 +182,19 @@ def test_reference_loader_resolves_to_the_reference_not_to_the_drop_in_alias():
     with torch.no_grad():
         y = m(torch.rand(1, 3, 64, 80), res_out=(96, 120))
     assert tuple(y.shape) == (1, 3, 96, 120)
+
+
+def test_stack_split_enumeration(tmp_path):
+    """The block-level work split of the window-stack kernels (csrc/tc/stack_split.cuh, plain C++ for the host): every
+    (tile, block) unit exactly once, a tile cut at most once, its leading blocks the first segment of a CTA and the rest the last
+    segment of the next one (tests/host/stack_split_check.cpp states the rules)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "stack_split_check")
+    subprocess.run([gxx, "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "host", "stack_split_check.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
