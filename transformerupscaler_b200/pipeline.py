@@ -12,7 +12,7 @@ import torch
 
 
 class FramePipeline:
-    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, compute_streams: int = 1, **forward_kw):
+    def __init__(self, model, depth: int = 2, device: Optional[torch.device] = None, compute_streams: int = 2, **forward_kw):
         """compute_streams > 1: consecutive batches run their forwards on alternating streams, so the kernels of one batch
         can fill the SMs the other batch's partly filled waves leave idle (needs depth >= compute_streams)"""
         self.model, self.kw, self.depth = model, forward_kw, depth
