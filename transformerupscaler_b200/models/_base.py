@@ -91,6 +91,10 @@ class EngineModel(nn.Module):
             if old is not None:
                 engine.release_weights(old)
             pw = PackedWeights(self.ENGINE_MODEL, sd, torch.bfloat16 if compute_bf16 else torch.float32, device)
+            # The repacking kernels run on the caller's current stream.  Forwards may follow on OTHER streams (FramePipeline alternates
+            # compute streams), so the packed tensors are complete before anyone can use them: one host wait per state_dict version.
+            if torch.device(device).type == "cuda":
+                torch.cuda.current_stream(device).synchronize()
             self._tu_cache = {"key": key, "handle": engine.register_weights(pw)}
         return self._tu_cache["handle"]
 
