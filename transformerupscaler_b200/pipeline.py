@@ -32,9 +32,10 @@ class FramePipeline:
         slot = self.n % self.depth
         if self.n >= self.depth:
             self.ev_out[slot].synchronize()          # slot's previous result has left the device
-        if self.dev_in[slot] is None or self.dev_in[slot].shape != host_in.shape or self.dev_in[slot].dtype != host_in.dtype:
-            self.dev_in[slot] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.device)
         with torch.cuda.stream(self.s_in):
+            if self.dev_in[slot] is None or self.dev_in[slot].shape != host_in.shape or self.dev_in[slot].dtype != host_in.dtype:
+                # allocated on the stream that fills it (the caching allocator orders reuse per stream)
+                self.dev_in[slot] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.device)
             self.dev_in[slot].copy_(host_in, non_blocking=True)
             self.ev_in[slot].record(self.s_in)
         s_comp = self.s_comps[self.n % len(self.s_comps)]
