@@ -31,7 +31,39 @@ NATURAL = {
 }
 
 
+# whole 720p frames: LR = the 4K training image resized to 720p exactly as data_class.py:61-64 does, HR = the
+# same image resized to the model's output size.  The LR frame is stored whole (uint8); HR and the reference output are stored on
+# a stride-3 lattice of the output (1/9 of the pixels: the PSNRs of the test are taken over that lattice for both sides).
+NATURAL_FULL = {
+    "natural_window_720p_1080p": ("WindowTransformer", 33, "image_103.png", (720, 1280), (1080, 1920), dict(res_out=(1080, 1920))),
+    "natural_fast_720p_x2": ("FastTransformer", 34, "image_104.png", (720, 1280), (1440, 2560), dict(upscale_factor=2)),
+    "natural_residual_720p_1080p": ("ResidualTransformer", 35, "image_109.png", (720, 1280), (1080, 1920), dict(res_out=(1080, 1920))),
+}
+
+
+def main_full():
+    torch.set_num_threads(os.cpu_count())
+    for name, (model, wseed, img, lr_size, hr_size, kw) in NATURAL_FULL.items():
+        im = Image.open(os.path.join("/root/reference/images/training_set", img)).convert("RGB")
+        lr = transforms.Compose([transforms.Resize(lr_size), transforms.ToTensor()])(im)
+        hr = transforms.Compose([transforms.Resize(hr_size), transforms.ToTensor()])(im)
+        lr_u8 = (lr * 255).round().clamp(0, 255).to(torch.uint8)
+        hr_u8 = (hr * 255).round().clamp(0, 255).to(torch.uint8)
+        x = (lr_u8.float() / 255.0).unsqueeze(0)
+        M = ref_model(model)
+        M.load_state_dict(synth_state_dict(model, wseed), strict=True)
+        with torch.no_grad():
+            ref = M(x, **kw)
+        assert tuple(ref.shape[2:]) == hr_size
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), lr_u8=lr_u8.numpy(), hr_u8=hr_u8.numpy()[:, ::3, ::3],
+                            ref=ref[0].numpy()[:, ::3, ::3].astype(np.float16), shape=np.array(ref.shape))
+        mse = ((ref[0] - hr_u8.float() / 255) ** 2).mean().item()
+        print(name, tuple(ref.shape), "PSNR(reference, HR) %.3f dB" % (10 * np.log10(1.0 / mse)), "mean", ref.mean().item(), flush=True)
+
+
 def main():
+    if "--full" in sys.argv:
+        return main_full()
     torch.set_num_threads(os.cpu_count())
     for name, (model, wseed, img, box, lr_size, hr_size, kw) in NATURAL.items():
         im = Image.open(os.path.join("/root/reference/images/training_set", img)).convert("RGB").crop(box)

@@ -7,7 +7,7 @@ import torch
 
 from oracle import upscaler_oracle as orc
 from oracle.weights import synth_state_dict, synth_frames
-from tests.golden.cases import CASES
+from tests.golden.cases import CASES, FULLSIZE, sample_fullsize
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 # fp32 oracle vs fp32 reference: both are fp32 evaluations of the same graph with different
@@ -91,3 +91,25 @@ def test_oracle_matches_live_reference_on_ragged_shapes(model, shape, kw, seed):
     out = orc.forward(model, sd, x, **kw)
     assert tuple(out.shape) == tuple(ref.shape)
     assert (out - ref).abs().max().item() < TOL_FP32, (model, shape, kw)
+
+
+_FULL_DEFAULT = ("window_720p_1080p_b8", "fast_720p_x2", "residual_720p_4k", "fast_720p_res1080p")
+
+
+@pytest.mark.parametrize("name", list(FULLSIZE))
+def test_oracle_matches_reference_at_baseline_sizes(name):
+    """BASELINE.json's configurations at their real sizes (first stored frame): the oracle against the unmodified reference's
+    pre-clamp output on the stride-13 lattice and the corner crops.  The x3 / x4 / x6 / 1080p cases take 15-60 s and up to 20 GB
+    each on CPU and run with TU_FULLSIZE_ORACLE=1 (they passed in the build container when the fixtures were made)."""
+    if name not in _FULL_DEFAULT and not os.environ.get("TU_FULLSIZE_ORACLE"):
+        pytest.skip("set TU_FULLSIZE_ORACLE=1 to run the large oracle cases")
+    c = dict(FULLSIZE[name])
+    B, _, H, W = c["shape"]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd = synth_state_dict(c["model"], c["wseed"])
+    x = synth_frames(B, H, W, seed=c["xseed"])[:1]
+    pre = orc.forward(c["model"], sd, x, pre_clamp=True, **c["kw"]).numpy()
+    c["frames"] = (0,)
+    lat, crops = sample_fullsize(pre, c)
+    err = max([np.abs(lat - g["pre"][:1]).max()] + [np.abs(cr - g[f"crop{i}"][:1]).max() for i, cr in enumerate(crops)])
+    assert err < TOL_FP32, f"{name}: max-abs {err}"
