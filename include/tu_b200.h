@@ -29,6 +29,15 @@ extern "C" {
 #define TU_U8 2   /* image I/O only (in_dtype / out_dtype of tu_forward, tu_stem_conv, tu_bicubic_add_clamp,        */
                   /* tu_final_conv_add): uint8 frames, x/255 on read (ToTensor), trunc(clamp(v*255,0,255)) on write  */
 
+/* uint8 frame layouts (OR-ed into TU_U8 for the image input / output of tu_forward, and for the output of tu_bicubic_add_clamp,
+ * tu_subpixel_conv_add and tu_resize_bilinear_aa_to): planar CHW is the default (the reference's tensors); HWC is what PIL /
+ * OpenCV frames are (inference.py:65-70: ToTensor reads HWC RGB); HWC_BGR reverses the channel order on the way
+ * (app_overlay.py:382-386: permute(1,2,0) then [..., [2,1,0]]).  (B,H,W,3) uint8 either way. */
+#define TU_LAYOUT_HWC 0x100
+#define TU_LAYOUT_HWC_BGR 0x200
+#define TU_U8_HWC (TU_U8 | TU_LAYOUT_HWC)
+#define TU_U8_HWC_BGR (TU_U8 | TU_LAYOUT_HWC_BGR)
+
 #define TU_OK 0
 #define TU_ERR_ARG (-1)      /* bad argument (shape / dtype / null pointer)              */
 #define TU_ERR_SCALE (-2)    /* FastTransformer scale not in {2,3,4,6} (utils.py:96-97)   */
@@ -151,6 +160,8 @@ typedef struct TuModelWeights {
  *      tu_resize_bilinear_aa.
  */
 size_t tu_forward_workspace_bytes(int model, int B, int H, int W, int outH, int outW, int scale, int compute_dtype);
+/* the same, sized from the packed weights actually used (non-default dim / heads / n_blocks; which fused kernels are packed) */
+size_t tu_forward_workspace_bytes_for(const TuModelWeights *w, int B, int H, int W, int outH, int outW, int scale, int compute_dtype);
 int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, void *out, int out_dtype,
                int B, int H, int W, int outH, int outW, int scale, int compute_dtype, int clamp,
                void *workspace, size_t workspace_bytes, void *stream);
@@ -225,6 +236,13 @@ int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float 
 /* antialiased bilinear resize (torchvision Resize on a tensor) of an NCHW image, then optional clamp */
 int tu_resize_bilinear_aa(const void *in, int dtype, void *out, int B, int H, int W, int outH, int outW,
                           int clamp, void *stream);
+/* the same with an output dtype of its own (TU_F32 / TU_BF16 / TU_U8 [| layout]): FastTransformer's Resize as the LAST op of a
+ * uint8-frame forward (FastTransformer/model.py:323-327 followed by app_overlay.py:382-386) */
+int tu_resize_bilinear_aa_to(const void *in, int in_dtype, void *out, int out_dtype, int B, int H, int W, int outH, int outW,
+                             int clamp, void *stream);
+/* uint8 frames (B,H,W,3) interleaved (layout TU_LAYOUT_HWC or TU_LAYOUT_HWC_BGR) -> planar RGB (B,3,H,W) uint8; tu_forward does
+ * this itself for an in_dtype that carries a layout (into its workspace) */
+int tu_frames_to_planar(const void *in, int layout, void *out, int B, int H, int W, void *stream);
 
 #ifdef __cplusplus
 }

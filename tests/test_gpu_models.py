@@ -390,3 +390,84 @@ def test_natural_720p_frame_psnr_delta(name):
     ref_u8 = (ref * 255.0).clamp(0, 255).to(torch.uint8)
     assert (ou8.int() - ref_u8.int()).abs().max().item() <= 6
     assert abs(psnr(ou8.float() / 255.0, hr) - psnr(ref_u8.float() / 255.0, hr)) <= 0.05
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interleaved uint8 frames (inference.py:65-70 reads HWC RGB through ToTensor, app_overlay.py:382-386 writes HWC BGR)
+@pytest.mark.parametrize("model,shape,kw", [("WindowTransformer", (2, 72, 104), dict(res_out=(108, 156))),
+                                            ("WindowTransformer", (1, 131, 189), dict(res_out=(200, 281))),       # odd width: direct kernel
+                                            ("ResidualTransformer", (1, 720, 1280), dict(res_out=(1080, 1920))),
+                                            ("FastTransformer", (2, 40, 56), dict(upscale_factor=2)),
+                                            ("FastTransformer", (1, 40, 56), dict(upscale_factor=4)),
+                                            ("FastTransformer", (1, 40, 56), dict(res_out=(60, 84)))])           # Resize is the last op
+@pytest.mark.parametrize("bf16", [False, True])
+def test_interleaved_uint8_frames(model, shape, kw, bf16):
+    """HWC RGB frames in / HWC BGR frames out are the planar uint8 path with the permutes done by the engine: bitwise the same
+    bytes as permute(0,2,3,1)[..., [2,1,0]] of the planar result (app_overlay.py:384-386)."""
+    B, H, W = shape
+    M, sd = build(model, 5)
+    if bf16:
+        M = M.bfloat16()
+    g = torch.Generator().manual_seed(7)
+    xu = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda()
+    with torch.no_grad():
+        planar = M(xu, **kw)
+        assert planar.dtype == torch.uint8
+        x_hwc = xu.permute(0, 2, 3, 1).contiguous()
+        out_hwc = M(x_hwc, in_layout="hwc", out_layout="hwc", **kw)
+        out_bgr = M(x_hwc[..., [2, 1, 0]].contiguous(), in_layout="hwc_bgr", out_layout="hwc_bgr", **kw)
+        mixed = M(xu, out_layout="hwc_bgr", **kw)
+    want = planar.permute(0, 2, 3, 1)
+    assert out_hwc.shape == want.shape and torch.equal(out_hwc, want)
+    assert torch.equal(out_bgr, want[..., [2, 1, 0]])
+    assert torch.equal(mixed, want[..., [2, 1, 0]])
+    with pytest.raises(ValueError):
+        M(xu.float() / 255, out_layout="hwc", **kw)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_uint8_frames_on_fast_resize_path(bf16):
+    """FastTransformer with a res_out that is not an integer multiple (F:323-325): uint8 frames out = the reference's glue
+    (out * 255).clamp(0, 255).to(uint8) applied to the float result, fused into the Resize kernel's store."""
+    M, sd = build("FastTransformer", 9)
+    if bf16:
+        M = M.bfloat16()
+    g = torch.Generator().manual_seed(8)
+    xu = torch.randint(0, 256, (2, 3, 48, 64), generator=g, dtype=torch.uint8).cuda()
+    with torch.no_grad():
+        yu = M(xu, res_out=(72, 96))
+        xf = xu.float() / 255.0
+        yf = M(xf.bfloat16() if bf16 else xf, res_out=(72, 96))
+    assert yu.dtype == torch.uint8 and tuple(yu.shape) == (2, 3, 72, 96)
+    want = (yf.float() * 255).clamp(0, 255).to(torch.uint8)
+    diff = (yu.int() - want.int()).abs()
+    assert diff.max().item() <= (3 if bf16 else 1)
+
+
+def test_non_default_transformer_dim_and_copies():
+    """(a) the workspace is sized from the packed weights actually used, so WindowTransformer(transformer_dim=192,
+    num_heads=12) runs; (b) copy.deepcopy / pickle of a model that has already run does not share or release the original's
+    packed weights."""
+    import copy
+    import pickle
+    from transformerupscaler_b200.models.WindowTransformer.model import TransformerModel as WM
+    torch.manual_seed(0)
+    M = WM(transformer_dim=192, num_heads=12).eval().to("cuda:0")
+    x = synth_frames(1, 72, 104, seed=5).cuda()
+    sd = {k: v.detach().cpu() for k, v in M.state_dict().items()}
+    ref = orc.forward("WindowTransformer", sd, x.cpu(), res_out=(108, 156))
+    with torch.no_grad():
+        o32 = M(x, res_out=(108, 156))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            o16 = M(x, res_out=(108, 156))
+    assert (o32.cpu() - ref).abs().max().item() < TOL_FP32
+    assert (o16.float().cpu() - ref).abs().max().item() < TOL_BF16
+    M2, _ = build("WindowTransformer", 3)
+    with torch.no_grad():
+        a = M2(x, res_out=(108, 156))
+        C1 = copy.deepcopy(M2)
+        C2 = pickle.loads(pickle.dumps(M2))
+        b, c = C1(x, res_out=(108, 156)), C2(x, res_out=(108, 156))
+        del C1, C2
+        a2 = M2(x, res_out=(108, 156))
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, a2)

@@ -417,3 +417,18 @@ def test_resize_aa(dev, geom):
     ref = orc.aa_bilinear_resize_nchw(x, (oH, oW))
     out = G.resize_aa(x.to(dev), oH, oW, False)
     assert _maxerr(out, ref) < 5e-6      # fp32, different summation order / weight normalisation order
+
+
+@pytest.mark.parametrize("shape", [(2, 36, 52), (1, 33, 47), (3, 720, 1280)])
+@pytest.mark.parametrize("bgr", [False, True])
+def test_frames_to_planar(shape, bgr):
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    B, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).cuda()
+    out = torch.empty(B, 3, H, W, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.tu_frames_to_planar(x.data_ptr(), _lib.TU_LAYOUT_HWC_BGR if bgr else _lib.TU_LAYOUT_HWC, out.data_ptr(), B, H, W,
+                                       torch.cuda.current_stream().cuda_stream))
+    want = (x[..., [2, 1, 0]] if bgr else x).permute(0, 3, 1, 2)
+    assert torch.equal(out, want)

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from oracle.weights import synth_state_dict, synth_frames  # noqa: E402
+from transformerupscaler_b200.synth import synth_state_dict, synth_frames  # noqa: E402
 from transformerupscaler_b200 import _lib  # noqa: E402
 
 # GFLOP per frame of the reference op graph

@@ -7,7 +7,7 @@ import os, sys, time, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
-from oracle.weights import synth_state_dict, synth_frames
+from transformerupscaler_b200.synth import synth_state_dict, synth_frames
 from transformerupscaler_b200 import _lib
 
 lib = _lib.load()

@@ -11,25 +11,25 @@
 
 namespace tu {
 
-int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
+thread_local int g_use_pdl = 1;            // programmatic dependent launch of the forward's kernels (debug key "pdl")
 static thread_local std::string g_err;
-static int g_use_tc = 1;
-static int g_unembed_overlap = 1;   // unembed starts on the SMs the window stack's last wave leaves idle (debug switch "unembed_overlap")
-static int g_head_stream = 0; // 64 -> 3 heads on the streaming kernel (debug switch "head_stream"): measured slower than the tile kernel
-static int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
-static int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
+static thread_local int g_use_tc = 1;
+static thread_local int g_unembed_overlap = 1;   // unembed starts on the SMs the window stack's last wave leaves idle (debug switch "unembed_overlap")
+static thread_local int g_head_stream = 0; // 64 -> 3 heads on the streaming kernel (debug switch "head_stream"): measured slower than the tile kernel
+static thread_local int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
+static thread_local int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // bench-only kernel timing hook (see tu_profile_enable in tu_b200.h): every launch of tu_forward is bracketed by a
 // pair of CUDA events on the caller's stream and tagged with the name of the reference op it implements
-static int g_prof_on = 0;
+static thread_local int g_prof_on = 0;
 static std::mutex g_prof_mu;
 struct ProfRec { const char *name; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_events;
-static cudaEvent_t g_prof_open = nullptr;
-static const char *g_prof_name = nullptr;      // the op about to be launched (set by TU_STEP)
+static thread_local cudaEvent_t g_prof_open = nullptr;
+static thread_local const char *g_prof_name = nullptr;      // the op about to be launched (set by TU_STEP)
 static inline bool prof_wanted() {
     return g_prof_on >= 2 || (g_prof_on == 1 && g_prof_name && (!strcmp(g_prof_name, "conv2") || !strcmp(g_prof_name, "conv1_conv2")));
 }
@@ -151,6 +151,13 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     const int Mtok = window ? B * nWy * nWx * 64 : B * Ht * Wt;
     const int Hc = fast ? H : min(Hd, 8 * Ht), Wc = fast ? W : min(Wd, 8 * Wt);
 
+    // interleaved uint8 frames (HWC RGB / BGR) are made planar once; the stem and the final bicubic both read the planar copy
+    uint8_t *xplanar = (uint8_t *)a.get((size_t)B * 3 * H * W);
+    if (!dry && dtype_layout(in_dtype)) {
+        if ((rc = tu_frames_to_planar(x, dtype_layout(in_dtype) << 8, xplanar, B, H, W, stv))) return rc;
+        x = xplanar;
+        in_dtype = TU_U8;
+    }
     const size_t full = (size_t)B * H * W * 64 * sizeof(T);
     T *f1 = (T *)a.get(full);
     T *f2 = (T *)a.get(full);
@@ -413,8 +420,8 @@ extern "C" int tu_debug_set(const char *key, int value) {
     set_error("tu: unknown debug key");
     return TU_ERR_ARG;
 }
-unsigned long long *tu::g_trace_buf = nullptr;
-unsigned int tu::g_trace_cap = 0;
+thread_local unsigned long long *tu::g_trace_buf = nullptr;
+thread_local unsigned int tu::g_trace_cap = 0;
 extern "C" int tu_debug_trace(void *device_buffer, unsigned int capacity_events) {
     tu::g_trace_buf = (unsigned long long *)device_buffer;
     tu::g_trace_cap = device_buffer ? capacity_events : 0;
@@ -611,14 +618,28 @@ extern "C" size_t tu_forward_workspace_bytes(int model, int B, int H, int W, int
     return rc == TU_OK ? a.off : 0;
 }
 
+extern "C" size_t tu_forward_workspace_bytes_for(const TuModelWeights *w, int B, int H, int W, int outH, int outW, int scale,
+                                                 int compute_dtype) {
+    if (check_forward_args(w, B, H, W, outH, outW, compute_dtype)) return 0;
+    Arena a{nullptr, 0, 0, true};
+    int rc = compute_dtype == TU_F32
+                 ? forward_impl<float>(w, nullptr, TU_F32, nullptr, TU_F32, B, H, W, outH, outW, scale, 1, a, 0)
+                 : forward_impl<bf16>(w, nullptr, TU_F32, nullptr, TU_F32, B, H, W, outH, outW, scale, 1, a, 0);
+    return rc == TU_OK ? a.off : 0;
+}
+
 extern "C" int tu_forward(const TuModelWeights *w, const void *x, int in_dtype, void *out, int out_dtype, int B, int H,
                           int W, int outH, int outW, int scale, int compute_dtype, int clamp, void *workspace,
                           size_t workspace_bytes, void *stream) {
     int rc = check_forward_args(w, B, H, W, outH, outW, compute_dtype);
     if (rc) return rc;
     TU_CHECK_ARG(x && out && workspace, "forward: null buffer");
-    TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8) && (out_dtype == TU_F32 || out_dtype == TU_BF16 || out_dtype == TU_U8),
-                 "forward: bad i/o dtype");
+    {
+        const int ib = dtype_base(in_dtype), ob = dtype_base(out_dtype), il = dtype_layout(in_dtype), ol = dtype_layout(out_dtype);
+        TU_CHECK_ARG((ib == TU_F32 || ib == TU_BF16 || ib == TU_U8) && (ob == TU_F32 || ob == TU_BF16 || ob == TU_U8), "forward: bad i/o dtype");
+        TU_CHECK_ARG((il == 0 || (ib == TU_U8 && il <= 2)) && (ol == 0 || (ob == TU_U8 && ol <= 2)),
+                     "forward: interleaved layouts (TU_LAYOUT_HWC / TU_LAYOUT_HWC_BGR) are for uint8 frames");
+    }
     TU_CHECK_ARG(w->blocks && w->n_blocks > 0 && w->dim == w->heads * 16, "forward: bad transformer configuration");
     // size pass, then the real pass
     Arena dry{nullptr, 0, 0, true};

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
                                                                        const __grid_constant__ CUtensorMap tmap_r,
                                                                        const BicubicTileGeom g, const TI *__restrict__ x, int H, int W,
                                                                        const float *__restrict__ res, int rH, int rW,
-                                                                       TO *__restrict__ out, int oH, int oW, int clamp) {
+                                                                       TO *__restrict__ out, int oH, int oW, int clamp, int layout) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
     __shared__ float yw[2][BS_H][4];
@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
             const float4 a = *reinterpret_cast<const float4 *>(yw[0][r]);
             const float4 gg = *reinterpret_cast<const float4 *>(yw[1][r]);
 #pragma unroll
+            float v3[3];
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 float v = 0.f;
                 v += wx[c][0] * a.x; v += wx[c][1] * a.y; v += wx[c][2] * a.z; v += wx[c][3] * a.w;
@@ -258,8 +260,9 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
                     v += u;
                 }
                 if (clamp) v = fminf(fmaxf(v, 0.f), 1.f);
-                ob[c * oplane + (long)(oy0 + r) * oW] = from_f<TO>(v);
+                v3[c] = v;
             }
+            store_rgb<TO>(out, b, oplane, (long)(oy0 + r) * oW + ox, layout, v3[0], v3[1], v3[2]);
         }
     };
     if (TMA) {
@@ -291,8 +294,12 @@ __global__ void __launch_bounds__(BS_W) bicubic_add_clamp_strip_kernel(const __g
                 }
                 if (clamp) v[c] = fminf(fmaxf(v[c], 0.f), 1.f);
             }
-            *o0 = from_f<TO>(v[0]); *o1 = from_f<TO>(v[1]); *o2 = from_f<TO>(v[2]);
-            o0 += oW; o1 += oW; o2 += oW;
+            if (layout == 0) {
+                *o0 = from_f<TO>(v[0]); *o1 = from_f<TO>(v[1]); *o2 = from_f<TO>(v[2]);
+                o0 += oW; o1 += oW; o2 += oW;
+            } else {
+                store_rgb<TO>(out, b, oplane, (long)(oy0 + r) * oW + ox, layout, v[0], v[1], v[2]);
+            }
         }
     } else {
         const GlobalSrc<TI> sx{x + (long)b * 3 * xplane, xplane, H, W};
@@ -349,7 +356,7 @@ template <typename TI, typename TO, bool RES>
 __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                           const __grid_constant__ CUtensorMap tmap_r,
                                                                           const BicubicTileGeom g, int H, int W, int rH, int rW,
-                                                                          TO *__restrict__ out, int oH, int oW, int clamp) {
+                                                                          TO *__restrict__ out, int oH, int oW, int clamp, int layout) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
     __shared__ __align__(16) float yw[2][PAIR_H][4];
@@ -434,8 +441,15 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const 
             ptx::up2(v, lo[c], hi[c]);
             if (clamp) { lo[c] = fminf(fmaxf(lo[c], 0.f), 1.f); hi[c] = fminf(fmaxf(hi[c], 0.f), 1.f); }
         }
-        store_pair(o0, lo[0], hi[0]); store_pair(o1, lo[1], hi[1]); store_pair(o2, lo[2], hi[2]);
-        o0 += oW; o1 += oW; o2 += oW;
+        if (layout == 0) {
+            store_pair(o0, lo[0], hi[0]); store_pair(o1, lo[1], hi[1]); store_pair(o2, lo[2], hi[2]);
+            o0 += oW; o1 += oW; o2 += oW;
+        } else {
+            // interleaved frames: the pair's two pixels are six consecutive elements (ox is even: 2-element aligned)
+            const int c0 = layout == 2 ? 2 : 0, c2 = 2 - c0;
+            TO *o = out + (((long)b * oH + oy0 + r) * oW + ox) * 3;
+            store_pair(o, lo[c0], lo[1]); store_pair(o + 2, lo[c2], hi[c0]); store_pair(o + 4, hi[1], hi[c2]);
+        }
     }
 }
 
@@ -453,9 +467,9 @@ __device__ __forceinline__ void aa_range(int dst, int in_size, int out_size, int
     norm = tot != 0.f ? 1.f / tot : 0.f;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) resize_aa_kernel(const T *__restrict__ in, T *__restrict__ out, int H, int W, int oH,
-                                                        int oW, int clamp) {
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) resize_aa_kernel(const T *__restrict__ in, TO *__restrict__ out, int H, int W, int oH,
+                                                        int oW, int clamp, int layout) {
     const int ox = blockIdx.x * 64 + (threadIdx.x & 63);
     const int oy = blockIdx.y * 4 + (threadIdx.x >> 6);
     const long plane = blockIdx.z;
@@ -476,14 +490,50 @@ __global__ void __launch_bounds__(256) resize_aa_kernel(const T *__restrict__ in
         acc = fmaf(wy, t, acc);
     }
     if (clamp) acc = fminf(fmaxf(acc, 0.f), 1.f);
-    out[(plane * oH + oy) * oW + ox] = from_f<T>(acc);
+    if (layout == 0) {
+        out[(plane * oH + oy) * oW + ox] = from_f<TO>(acc);
+    } else {
+        const long b = plane / 3;
+        const int c = (int)(plane - 3 * b);
+        out[((b * oH + oy) * oW + ox) * 3 + (layout == 2 ? 2 - c : c)] = from_f<TO>(acc);
+    }
+}
+
+// interleaved uint8 frames (B,H,W,3) -> planar RGB (B,3,H,W): four pixels per thread, 12 bytes in, 3 x 4 bytes out
+__global__ void __launch_bounds__(256) frames_to_planar_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, long plane,
+                                                               int swap) {
+    pdl_trigger();
+    pdl_wait();
+    const long b = blockIdx.y;
+    const long q = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q >= plane) return;
+    const uint8_t *src = in + (b * plane + q) * 3;
+    uint8_t *dst = out + b * 3 * plane + q;
+    const int c0 = swap ? 2 : 0, c2 = 2 - c0;
+    if (q + 4 <= plane && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)plane) & 3) == 0) {
+        const uint32_t w0 = reinterpret_cast<const uint32_t *>(src)[0], w1 = reinterpret_cast<const uint32_t *>(src)[1],
+                       w2 = reinterpret_cast<const uint32_t *>(src)[2];
+        // bytes: w0 = p0c0 p0c1 p0c2 p1c0 | w1 = p1c1 p1c2 p2c0 p2c1 | w2 = p2c2 p3c0 p3c1 p3c2
+        const uint32_t ch0 = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);      // p0c0 p1c0 p2c0 p3c0
+        const uint32_t ch1 = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);      // p0c1 p1c1 p2c1 p3c1
+        const uint32_t ch2 = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);      // p0c2 p1c2 p2c2 p3c2
+        reinterpret_cast<uint32_t *>(dst + c0 * plane)[0] = ch0;
+        reinterpret_cast<uint32_t *>(dst + plane)[0] = ch1;
+        reinterpret_cast<uint32_t *>(dst + c2 * plane)[0] = ch2;
+    } else {
+        for (int i = 0; i < 4 && q + i < plane; ++i) {
+            dst[c0 * plane + i] = src[3 * i];
+            dst[plane + i] = src[3 * i + 1];
+            dst[c2 * plane + i] = src[3 * i + 2];
+        }
+    }
 }
 
 }  // namespace tu
 
 using namespace tu;
 
-int tu::g_bicubic_pair = 1;      // debug key "bicubic_pair": two output columns per thread (default) / the one-column strip kernel
+thread_local int tu::g_bicubic_pair = 1;      // debug key "bicubic_pair": two output columns per thread (default) / the one-column strip kernel
 
 // (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
 static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, int B, int H, int W, int box_rows, int box_cols) {
@@ -500,8 +550,11 @@ static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, i
 extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW, void *out,
                                     int out_dtype, int B, int outH, int outW, int clamp, void *stream) {
     TU_CHECK_ARG(x && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "bicubic_add_clamp: bad argument");
+    const int layout = dtype_layout(out_dtype);
+    out_dtype = dtype_base(out_dtype);
     TU_CHECK_ARG((in_dtype == TU_F32 || in_dtype == TU_BF16 || in_dtype == TU_U8) && (out_dtype == TU_F32 || out_dtype == TU_BF16 || out_dtype == TU_U8),
                  "bicubic_add_clamp: bad dtype");
+    TU_CHECK_ARG(layout == 0 || (out_dtype == TU_U8 && layout <= 2), "bicubic_add_clamp: interleaved layouts are for uint8 frames");
     cudaStream_t st = (cudaStream_t)stream;
     const int eb = (int)dtype_size(in_dtype), ob = (int)dtype_size(out_dtype);
     BicubicTileGeom g;
@@ -527,45 +580,45 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
 #define TU_BIC_PAIR(TI, TO)                                                                                                     \
     do {                                                                                                                        \
-        static bool attr_done = false;                                                                                          \
-        if (!attr_done) {                                                                                                       \
+        static PerDeviceFlag attr_done;                                                                                          \
+        if (!attr_done.is_set()) {                                                                                                       \
             cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_pair_kernel<TI, TO, true>,                                  \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                      \
             if (e == cudaSuccess)                                                                                               \
                 e = cudaFuncSetAttribute(bicubic_add_clamp_pair_kernel<TI, TO, false>,                                         \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                              \
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
-            attr_done = true;                                                                                                   \
+            attr_done.set();                                                                                                   \
         }                                                                                                                       \
         if (res)                                                                                                                \
             launch_pdl(bicubic_add_clamp_pair_kernel<TI, TO, true>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
-                       (TO *)out, outH, outW, clamp);                                                                          \
+                       (TO *)out, outH, outW, clamp, layout);                                                                  \
         else                                                                                                                    \
             launch_pdl(bicubic_add_clamp_pair_kernel<TI, TO, false>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
-                       (TO *)out, outH, outW, clamp);                                                                          \
+                       (TO *)out, outH, outW, clamp, layout);                                                                  \
     } while (0)
 #define TU_BIC(TI, TO)                                                                                                          \
     do {                                                                                                                        \
         if (tma) {                                                                                                              \
-            static bool attr_done = false;                                                                                      \
-            if (!attr_done) {                                                                                                   \
+            static PerDeviceFlag attr_done;                                                                                      \
+            if (!attr_done.is_set()) {                                                                                                   \
                 cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, 1>,                              \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                  \
                 if (e == cudaSuccess)                                                                                           \
                     e = cudaFuncSetAttribute(bicubic_add_clamp_strip_kernel<TI, TO, 2>,                                         \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                          \
                 if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                            \
-                attr_done = true;                                                                                               \
+                attr_done.set();                                                                                               \
             }                                                                                                                   \
             if (res)                                                                                                            \
                 launch_pdl(bicubic_add_clamp_strip_kernel<TI, TO, 1>, grid, dim3(BS_W), tile_bytes + 128, st, tx, tr, g, (const TI *)x, H, W, \
-                           res, rH, rW, (TO *)out, outH, outW, clamp);                                                      \
+                           res, rH, rW, (TO *)out, outH, outW, clamp, layout);                                              \
             else                                                                                                                \
                 launch_pdl(bicubic_add_clamp_strip_kernel<TI, TO, 2>, grid, dim3(BS_W), tile_bytes + 128, st, tx, tr, g, (const TI *)x, H, W, \
-                           res, rH, rW, (TO *)out, outH, outW, clamp);                                                      \
+                           res, rH, rW, (TO *)out, outH, outW, clamp, layout);                                              \
         } else {                                                                                                                \
             bicubic_add_clamp_strip_kernel<TI, TO, 0><<<grid, BS_W, 0, st>>>(tx, tr, g, (const TI *)x, H, W, res, rH, rW,     \
-                                                                                  (TO *)out, outH, outW, clamp);                \
+                                                                                  (TO *)out, outH, outW, clamp, layout);        \
         }                                                                                                                       \
     } while (0)
 #define TU_BIC2(TI, TO)          \
@@ -589,17 +642,40 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     return TU_OK;
 }
 
-extern "C" int tu_resize_bilinear_aa(const void *in, int dtype, void *out, int B, int H, int W, int outH, int outW,
-                                     int clamp, void *stream) {
+extern "C" int tu_resize_bilinear_aa_to(const void *in, int in_dtype, void *out, int out_dtype, int B, int H, int W, int outH, int outW,
+                                        int clamp, void *stream) {
     TU_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "resize_bilinear_aa: bad argument");
+    const int layout = dtype_layout(out_dtype);
+    out_dtype = dtype_base(out_dtype);
+    TU_CHECK_ARG(layout == 0 || (out_dtype == TU_U8 && layout <= 2), "resize_bilinear_aa: interleaved layouts are for uint8 frames");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(ceil_div(outW, 64), ceil_div(outH, 4), B * 3);
-    if (dtype == TU_F32)
-        resize_aa_kernel<float><<<grid, 256, 0, st>>>((const float *)in, (float *)out, H, W, outH, outW, clamp);
-    else if (dtype == TU_BF16)
-        resize_aa_kernel<bf16><<<grid, 256, 0, st>>>((const bf16 *)in, (bf16 *)out, H, W, outH, outW, clamp);
-    else
-        TU_CHECK_ARG(false, "resize_bilinear_aa: bad dtype");
+#define TU_RS(TI, TO) resize_aa_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI *)in, (TO *)out, H, W, outH, outW, clamp, layout)
+    if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_RS(float, float);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_RS(bf16, bf16);
+    else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_RS(float, bf16);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_RS(bf16, float);
+    else if (in_dtype == TU_F32 && out_dtype == TU_U8) TU_RS(float, uint8_t);
+    else if (in_dtype == TU_BF16 && out_dtype == TU_U8) TU_RS(bf16, uint8_t);
+    else TU_CHECK_ARG(false, "resize_bilinear_aa: bad dtype");
+#undef TU_RS
     TU_CHECK_LAUNCH("resize_bilinear_aa");
+    return TU_OK;
+}
+
+extern "C" int tu_resize_bilinear_aa(const void *in, int dtype, void *out, int B, int H, int W, int outH, int outW,
+                                     int clamp, void *stream) {
+    TU_CHECK_ARG(dtype == TU_F32 || dtype == TU_BF16, "resize_bilinear_aa: bad dtype");
+    return tu_resize_bilinear_aa_to(in, dtype, out, dtype, B, H, W, outH, outW, clamp, stream);
+}
+
+extern "C" int tu_frames_to_planar(const void *in, int layout, void *out, int B, int H, int W, void *stream) {
+    TU_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0, "frames_to_planar: bad argument");
+    TU_CHECK_ARG(layout == TU_LAYOUT_HWC || layout == TU_LAYOUT_HWC_BGR, "frames_to_planar: layout must be TU_LAYOUT_HWC or TU_LAYOUT_HWC_BGR");
+    const long plane = (long)H * W;
+    dim3 grid((unsigned)((plane + 1023) / 1024), B);
+    launch_pdl(frames_to_planar_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const uint8_t *)in, (uint8_t *)out, plane,
+               layout == TU_LAYOUT_HWC_BGR ? 1 : 0);
+    TU_CHECK_LAUNCH("frames_to_planar");
     return TU_OK;
 }

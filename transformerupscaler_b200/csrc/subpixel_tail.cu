@@ -31,7 +31,7 @@ struct FinFilter { float w[81]; float b[3]; };      // [(ky*3+kx)*3+ci][co], bia
 template <int R, typename TO>
 __global__ void __launch_bounds__(NT, 4)
 subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps, const float *__restrict__ bps,
-                     const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, const FinFilter fin) {
+                     const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, int layout, const FinFilter fin) {
     constexpr int NCO = 3 * R * R;
     constexpr int TH = tile_rows<R>(), IR = TH + 2;     // IR = intermediate rows held
     constexpr int NLR = TH / R + 4;            // low-res rows staged: ly0 - 2 .. ly0 + TH/R + 1
@@ -179,13 +179,20 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int co = 0; co < 3; ++co) a[co] = fmaf(win[ky][kx][c], fin.w[((ky * 3 + kx) * 3 + c) * 3 + co], a[co]);
+        float rgb[3];
 #pragma unroll
         for (int co = 0; co < 3; ++co) {
             // reference: out = upscaled_input + (conv + bias)   (FastTransformer/model.py:320)
             float r = ad[co] + (a[co] + fin.b[co]);
             if (clamp) r = fminf(fmaxf(r, 0.f), 1.f);
-            out[o + co * plane] = from_f<TO>(r);
+            rgb[co] = r;
             ad[co] = adn[co];
+        }
+        if (layout == 0) {
+#pragma unroll
+            for (int co = 0; co < 3; ++co) out[o + co * plane] = from_f<TO>(rgb[co]);
+        } else {
+            store_rgb<TO>(out, b, plane, (long)(oy0 + ry) * oW + ox, layout, rgb[0], rgb[1], rgb[2]);
         }
     }
 }
@@ -197,28 +204,28 @@ constexpr size_t tail_smem() {
 }
 
 template <int R, typename TO>
-int launch_tail(const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp,
+int launch_tail(const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp, int layout,
                 const FinFilter &fin, cudaStream_t st) {
-    static bool attr = false;
+    static PerDeviceFlag attr;
     constexpr size_t smem = tail_smem<R>();
-    if (!attr && smem > 48 * 1024) {
+    if (!attr.is_set() && smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(subpixel_tail_kernel<R, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "subpixel_tail smem attribute");
-        attr = true;
+        attr.set();
     }
     dim3 grid(ceil_div(W, TLX), ceil_div(H * R, tile_rows<R>()), B);
-    launch_pdl(subpixel_tail_kernel<R, TO>, grid, dim3(NT), smem, st, in, wps, bps, addend, out, H, W, clamp, fin);
+    launch_pdl(subpixel_tail_kernel<R, TO>, grid, dim3(NT), smem, st, in, wps, bps, addend, out, H, W, clamp, layout, fin);
     TU_CHECK_LAUNCH("subpixel_tail");
     return TU_OK;
 }
 
 template <typename TO>
-int tail_by_r(int r, const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp,
+int tail_by_r(int r, const float *in, const float *wps, const float *bps, const float *addend, TO *out, int B, int H, int W, int clamp, int layout,
               const FinFilter &fin, cudaStream_t st) {
     switch (r) {
-        case 2: return launch_tail<2, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
-        case 3: return launch_tail<3, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
-        case 6: return launch_tail<6, TO>(in, wps, bps, addend, out, B, H, W, clamp, fin, st);
+        case 2: return launch_tail<2, TO>(in, wps, bps, addend, out, B, H, W, clamp, layout, fin, st);
+        case 3: return launch_tail<3, TO>(in, wps, bps, addend, out, B, H, W, clamp, layout, fin, st);
+        case 6: return launch_tail<6, TO>(in, wps, bps, addend, out, B, H, W, clamp, layout, fin, st);
     }
     set_error("tu: subpixel_conv_add: r must be 2, 3 or 6");
     return TU_ERR_ARG;
@@ -234,12 +241,15 @@ extern "C" int tu_subpixel_conv_add(const float *in, const float *w_ps, const fl
                                     const float *addend, void *out, int out_dtype, int B, int H, int W, int clamp, void *stream) {
     TU_CHECK_ARG(in && w_ps && b_ps && host_fin_wb && addend && out && B > 0 && H > 0 && W > 0, "subpixel_conv_add: bad argument");
     TU_CHECK_ARG((long)B * 3 * H * r * W * r < (1L << 31), "subpixel_conv_add: image too large for 32-bit pixel indexing");
+    const int layout = dtype_layout(out_dtype);
+    out_dtype = dtype_base(out_dtype);
+    TU_CHECK_ARG(layout == 0 || (out_dtype == TU_U8 && layout <= 2), "subpixel_conv_add: interleaved layouts are for uint8 frames");
     cudaStream_t st = (cudaStream_t)stream;
     FinFilter fin;
     for (int i = 0; i < 81; ++i) fin.w[i] = host_fin_wb[i];
     for (int i = 0; i < 3; ++i) fin.b[i] = host_fin_wb[81 + i];
-    if (out_dtype == TU_F32) return tail_by_r<float>(r, in, w_ps, b_ps, addend, (float *)out, B, H, W, clamp, fin, st);
-    if (out_dtype == TU_BF16) return tail_by_r<bf16>(r, in, w_ps, b_ps, addend, (bf16 *)out, B, H, W, clamp, fin, st);
-    if (out_dtype == TU_U8) return tail_by_r<uint8_t>(r, in, w_ps, b_ps, addend, (uint8_t *)out, B, H, W, clamp, fin, st);
+    if (out_dtype == TU_F32) return tail_by_r<float>(r, in, w_ps, b_ps, addend, (float *)out, B, H, W, clamp, layout, fin, st);
+    if (out_dtype == TU_BF16) return tail_by_r<bf16>(r, in, w_ps, b_ps, addend, (bf16 *)out, B, H, W, clamp, layout, fin, st);
+    if (out_dtype == TU_U8) return tail_by_r<uint8_t>(r, in, w_ps, b_ps, addend, (uint8_t *)out, B, H, W, clamp, layout, fin, st);
     TU_CHECK_ARG(false, "subpixel_conv_add: bad dtype");
 }

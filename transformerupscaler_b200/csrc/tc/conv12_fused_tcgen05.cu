@@ -503,9 +503,8 @@ conv12_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count_c = 0;
-bool g_attr_set_c = false;
-int g_enable_fused = 1;
+PerDeviceFlag g_attr_set_c;
+thread_local int g_enable_fused = 1;
 
 }  // namespace
 
@@ -522,17 +521,13 @@ int tc_conv12_fused(const void *x, int in_dtype, const bf16 *w64, const float *b
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count_c) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count_c, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set_c) {
+    const int g_sm_count_c = device_sm_count();
+    if (!g_attr_set_c.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(conv12_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv12_fused_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv12_fused_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv12_fused smem attribute");
-        g_attr_set_c = true;
+        g_attr_set_c.set();
     }
     CUtensorMap tm_x, tm_w1, tm_w2, tm_out;
     {

@@ -347,9 +347,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     if (warp == 2) tmem_dealloc2(tmem_base, 512);
 }
 
-int g_sm_count2 = 0;
-bool g_attr_set2 = false;
-int g_enable_2cta = 0;       // measured slower than the single-CTA kernel on B200 (see the header comment): off unless tu_debug_set("conv_2cta", 1)
+PerDeviceFlag g_attr_set2;
+thread_local int g_enable_2cta = 0;       // measured slower than the single-CTA kernel on B200 (see the header comment): off unless tu_debug_set("conv_2cta", 1)
 
 }  // namespace
 
@@ -364,16 +363,12 @@ int tc_conv3x3_c64_pair(const bf16 *in, const bf16 *w, const float *bias, bf16 *
     if (stride == 2 && (W & 1)) return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count2) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count2, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set2) {
+    const int g_sm_count2 = device_sm_count();
+    if (!g_attr_set2.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv3x3_tc2 smem attribute");
-        g_attr_set2 = true;
+        g_attr_set2.set();
     }
     const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
     CUtensorMap tm_act, tm_w, tm_out;

@@ -284,9 +284,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count_s = 0;
-bool g_attr_set_s = false;
-int g_enable_stream = 1;
+PerDeviceFlag g_attr_set_s;
+thread_local int g_enable_stream = 1;
 
 }  // namespace
 
@@ -302,15 +301,11 @@ int tc_conv3x3_c64_stream(const bf16 *in, const bf16 *w, const float *bias, bf16
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count_s) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count_s, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set_s) {
+    const int g_sm_count_s = device_sm_count();
+    if (!g_attr_set_s.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv3x3_stream smem attribute");
-        g_attr_set_s = true;
+        g_attr_set_s.set();
     }
     CUtensorMap tm_act, tm_w, tm_out;
     {

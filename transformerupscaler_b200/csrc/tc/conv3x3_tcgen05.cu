@@ -357,16 +357,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------- host side
-int g_sm_count = 0;
-int g_base_off_mode = 0;   // measured on B200: the UMMA swizzle is a function of the absolute smem address (like TMA's),
+thread_local int g_base_off_mode = 0;   // measured on B200: the UMMA swizzle is a function of the absolute smem address (like TMA's),
                            // so row-shifted operand views need base_offset 0 (tools/tc_probe.py, profiles/r01_tc_probe.log)
-bool g_attr_set = false;
+PerDeviceFlag g_attr_set;
 
 }  // namespace
 
 // debug key "snake": bit k set = kernel k walks its work items last to first, so that it starts on the part of its input the
 // previous kernel wrote last (still in L2).  bit 0 downsample, 1 the 64 -> 3 head, 2 window stack + unembed, 3 tile conv 64 -> 64
-int g_snake_mask = 0;
+thread_local int g_snake_mask = 0;
 void tc_set_snake(int mask) { g_snake_mask = mask; }
 
 TcEncodeFn tc_encode_fn() {
@@ -391,17 +390,13 @@ static int launch_conv(const bf16 *in, const bf16 *w, const float *bias, bf16 *o
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set) {
+    const int g_sm_count = device_sm_count();
+    if (!g_attr_set.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "conv3x3_tc smem attribute");
-        g_attr_set = true;
+        g_attr_set.set();
     }
     CUtensorMap tm_act, tm_w;
     {

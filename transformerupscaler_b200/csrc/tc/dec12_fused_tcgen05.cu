@@ -395,10 +395,9 @@ dec12_fused_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count_d = 0;
-int g_enable_dec12 = 1;
-int g_dec12_defer = 1;
-int g_dec12_variant = 1;      // 0: 6 input slots, 2 staged rows, lag 1;  1: 5 input slots, 3 staged rows, lag 2
+thread_local int g_enable_dec12 = 1;
+thread_local int g_dec12_defer = 1;
+thread_local int g_dec12_variant = 1;      // 0: 6 input slots, 2 staged rows, lag 1;  1: 5 input slots, 3 staged rows, lag 2
 
 }  // namespace
 
@@ -437,11 +436,7 @@ int tc_dec12_fused(const bf16 *in, const bf16 *w1, const float *bias1, const bf1
         return TU_TC_UNSUPPORTED;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count_d) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count_d, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int g_sm_count_d = device_sm_count();
     CUtensorMap tm_act, tm_w, tm_w2;
     {
         cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -482,13 +477,13 @@ int tc_dec12_fused(const bf16 *in, const bf16 *w1, const float *bias1, const bf1
     p.bias1 = bias1; p.bias2 = bias2; p.out3 = out3;
     p.defer = g_dec12_defer;
     const int grid = p.total_items < g_sm_count_d ? p.total_items : g_sm_count_d;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(dec12_fused_kernel<6, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<6, 2>());
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(dec12_fused_kernel<5, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<5, 3>());
         if (e != cudaSuccess) return cuda_fail(e, "dec12_fused smem attribute");
-        attr_set = true;
+        attr_set.set();
     }
     if (g_dec12_variant == 0)
         launch_pdl(dec12_fused_kernel<6, 2, 1>, dim3(grid), dim3(NUM_THREADS), smem_bytes<6, 2>(), st, tm_act, tm_w, tm_w2, p);

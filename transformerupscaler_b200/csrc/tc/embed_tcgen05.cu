@@ -181,7 +181,7 @@ embed_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 // stages multicast inside clusters of two CTAs; +4 also at dim 192; +8 L2 prefetch of whole patch rows one ky ahead.
 // Measured (profiles/r05e_ab.log, r05f_ab.log): dim 128: 69.1 -> 62.1 us (1), 63.5 us (2), 75.3 us (1 + 8); dim 192 (two 40 KB stages per
 // CTA): 134 -> 140 (1 + 4) / 145 (2 + 4) / 171 us (1 + 4 + 8): only the plain dim-128 variant is on
-int g_embed_pair = 1;
+thread_local int g_embed_pair = 1;
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
@@ -236,14 +236,14 @@ int tc_patch_embed_pair(const bf16 *feat, const bf16 *W, const float *bias, cons
             return TU_ERR_CUDA;
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(embed_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmbedCfg<128>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(embed_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmbedCfg<192>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(embed_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmbedCfg<128>::SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(embed_tc_kernel<192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmbedCfg<192>::SMEM);
         if (e != cudaSuccess) return cuda_fail(e, "embed_tc smem attribute");
-        attr_set = true;
+        attr_set.set();
     }
     EmbedParams p;
     p.B = B; p.Ht = Ht; p.Wt = Wt; p.nWy = (Ht + 7) / 8; p.nWx = (Wt + 7) / 8; p.window = window;

@@ -65,7 +65,7 @@ struct GemmParams {
                         // moves 104 KB through the TMA engine instead of 128 KB per tile
     int rev;            // tiles are walked last to first (debug key "snake", bit 2: unembed behind a reversed window stack)
 };
-int g_unembed_areuse = 0;  // debug key "unembed_areuse"
+thread_local int g_unembed_areuse = 0;  // debug key "unembed_areuse"
 constexpr int QD = 4;      // depth of the tile-index queue between the scheduler thread and the three roles
 
 struct Barriers {
@@ -588,8 +588,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count = 0;
-int g_smem_set = 0;
+PerDeviceMax g_smem_set;
 
 int pick_bn(int N) {
     if (N % 256 == 0) return 256;
@@ -613,16 +612,12 @@ int encode_2d(CUtensorMap *tm, const void *ptr, uint64_t rows, uint64_t cols, ui
 
 int launch(const CUtensorMap &ta, const CUtensorMap &tw, GemmParams &p, cudaStream_t st, const CUtensorMap *tskip = nullptr,
            const CUtensorMap *to5 = nullptr) {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int g_sm_count = device_sm_count();
     const int smem = NSTAGE * (A_STAGE + p.BN * 128) + 512 + (p.epi == EPI_UNEMBED ? UE_BYTES : p.epi == EPI_UNEMBED_TMA ? UT_BYTES : 0) + 1024;
-    if (smem > g_smem_set) {
+    if (smem > g_smem_set.get()) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "gemm_tc smem attribute");
-        g_smem_set = smem;
+        g_smem_set.set(smem);
     }
     p.tiles_n = p.N / p.BN;
     p.total_tiles = p.tiles_m * p.tiles_n;

@@ -302,8 +302,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (warp == 8) ptx::tmem_dealloc(tmem_base, 256);
 }
 
-int g_sm_count = 0;
-bool g_attr_set = false;
+PerDeviceFlag g_attr_set;
 
 }  // namespace
 
@@ -311,12 +310,8 @@ bool g_attr_set = false;
 int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias, bf16 *out, int B, int H, int W, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
     if (!enc || (reinterpret_cast<uintptr_t>(w64) & 127) || (reinterpret_cast<uintptr_t>(out) & 15)) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set) {
+    const int g_sm_count = device_sm_count();
+    if (!g_attr_set.is_set()) {
         cudaError_t e = cudaSuccess;
 #define TU_STEM_ATTR(TI, R) \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<TI, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)
@@ -325,7 +320,7 @@ int tc_stem_conv(const void *x, int in_dtype, const bf16 *w64, const float *bias
         TU_STEM_ATTR(uint8_t, false); TU_STEM_ATTR(uint8_t, true);
 #undef TU_STEM_ATTR
         if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem attribute");
-        g_attr_set = true;
+        g_attr_set.set();
     }
     CUtensorMap tw;
     cuuint64_t wd[2] = {64, 64}, ws[1] = {128};

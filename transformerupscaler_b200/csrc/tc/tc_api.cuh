@@ -15,12 +15,12 @@ bool tc_enabled();
 // debug: 0 = UMMA descriptor base_offset 0, 1 = base_offset (addr>>7)&7 for row-shifted operand views
 void tc_set_base_off_mode(int m);
 // debug: reversed work-item order per kernel (bit mask, see conv3x3_tcgen05.cu)
-extern int g_snake_mask;
+extern thread_local int g_snake_mask;
 void tc_set_snake(int mask);
 
 // debug: device buffer of (time, tag) event pairs written by the window stack and the unembed GEMM (tu_debug_trace); word 0 = count
-extern unsigned long long *g_trace_buf;
-extern unsigned int g_trace_cap;
+extern thread_local unsigned long long *g_trace_buf;
+extern thread_local unsigned int g_trace_cap;
 __device__ __forceinline__ void trace_event(unsigned long long *buf, unsigned int cap, unsigned int kind, unsigned int value) {
     if (!buf) return;
     unsigned long long t;

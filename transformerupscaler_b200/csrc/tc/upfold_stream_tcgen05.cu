@@ -379,23 +379,18 @@ upfold_ring_kernel(const bf16 *__restrict__ in, const float *__restrict__ ring_w
     }
 }
 
-int g_sm_count_f = 0;
 
 template <int NO, int R, int KS>
 int launch_fold(const bf16 *in, const void *wbank, const float *bias, int relu, float *out, int B, int H, int W, cudaStream_t st) {
     using Cfg = FoldCfg<NO, R, KS>;
-    static bool attr = false;
+    static PerDeviceFlag attr;
     TcEncodeFn enc = tc_encode_fn();
     if (!enc) return TU_TC_UNSUPPORTED;
-    if (!g_sm_count_f) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count_f, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!attr) {
+    const int g_sm_count_f = device_sm_count();
+    if (!attr.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(upfold_stream_kernel<NO, R, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "upfold_stream smem attribute");
-        attr = true;
+        attr.set();
     }
     CUtensorMap tm_act, tm_w, tm_out;
     {

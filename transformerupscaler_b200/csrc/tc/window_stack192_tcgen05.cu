@@ -540,8 +540,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
     if (warp == NMATH + 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count = 0;
-bool g_attr_set = false;
+PerDeviceFlag g_attr_set;
 
 }  // namespace
 
@@ -553,15 +552,11 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
         (reinterpret_cast<uintptr_t>(tok) & 15))
         return TU_TC_UNSUPPORTED;
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set) {
+    const int g_sm_count = device_sm_count();
+    if (!g_attr_set.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(window_stack192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "window_stack192 smem attribute");
-        g_attr_set = true;
+        g_attr_set.set();
     }
     CUtensorMap t96, t192;
     cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * ROWS_PER_BLOCK}, ws[1] = {128};

@@ -534,9 +534,8 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     if (warp == NMATH + 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-int g_sm_count = 0;
-bool g_attr_set = false;
-int g_stack_split = 0;       // measured (profiles/r05c_ab.log): 342 -> 290 us serialised, but inside a forward the unembed overlap already uses
+PerDeviceFlag g_attr_set;
+thread_local int g_stack_split = 0;       // measured (profiles/r05c_ab.log): 342 -> 290 us serialised, but inside a forward the unembed overlap already uses
                              // the SMs the whole-tile schedule leaves idle: 1.2605 -> 1.2637 ms (dim 128), 2.0515 -> 2.0694 ms (dim 192)
 
 }  // namespace
@@ -552,15 +551,11 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     if (!enc || !stack_w || !stack_p || !rel_bias || (M % 128) || (reinterpret_cast<uintptr_t>(stack_w) & 127) ||
         (reinterpret_cast<uintptr_t>(tok) & 15))
         return TU_TC_UNSUPPORTED;
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (!g_attr_set) {
+    const int g_sm_count = device_sm_count();
+    if (!g_attr_set.is_set()) {
         cudaError_t e = cudaFuncSetAttribute(window_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return cuda_fail(e, "window_stack smem attribute");
-        g_attr_set = true;
+        g_attr_set.set();
     }
     CUtensorMap tw;
     cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * SLABS_PER_BLOCK * 128}, ws[1] = {128};

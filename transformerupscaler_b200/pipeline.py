@@ -3,12 +3,39 @@ with the H2D copy, the forward and the D2H copy of consecutive batches overlappe
 
 This is the end-to-end entry a video caller uses (the reference's speed_test.py / app_overlay.py do a
 synchronous batch-1 `.to(device)` -> model -> `.cpu()` loop, speed_test.py:60-67, app_overlay.py:365-391).
+
+Buffer lifetime contract: `submit(host_in, host_out)` returns as soon as the work is ENQUEUED.  The caller may overwrite
+`host_in` only after `ticket.input_consumed()` (or `ticket.wait_input()`), and may read `host_out` only after `ticket.wait()`;
+`drain()` waits for everything submitted so far.
 """
 from __future__ import annotations
 
 from typing import List, Optional
 
 import torch
+
+
+class Ticket:
+    """Handle of one submitted batch: tells when its pinned input has been read and when its pinned output is complete."""
+
+    __slots__ = ("_ev_in", "_ev_out", "index")
+
+    def __init__(self, index: int, ev_in: torch.cuda.Event, ev_out: torch.cuda.Event):
+        self.index, self._ev_in, self._ev_out = index, ev_in, ev_out
+
+    def input_consumed(self) -> bool:
+        """True once the H2D copy has read host_in (the buffer may be reused)."""
+        return self._ev_in.query()
+
+    def wait_input(self) -> None:
+        self._ev_in.synchronize()
+
+    def done(self) -> bool:
+        """True once host_out holds the upscaled frames."""
+        return self._ev_out.query()
+
+    def wait(self) -> None:
+        self._ev_out.synchronize()
 
 
 class FramePipeline:
@@ -21,35 +48,40 @@ class FramePipeline:
         self.s_comps = [torch.cuda.Stream(self.device) for _ in range(max(1, min(compute_streams, depth)))]
         self.dev_in: List[Optional[torch.Tensor]] = [None] * depth
         self.dev_out: List[Optional[torch.Tensor]] = [None] * depth
-        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
         self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.tickets: List[Optional[Ticket]] = [None] * depth
         self.n = 0
 
     @torch.no_grad()
-    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
-        """Enqueue one batch: host_in (pinned, NCHW) is upscaled into host_out (pinned). Returns immediately."""
+    def submit(self, host_in: torch.Tensor, host_out: torch.Tensor) -> Ticket:
+        """Enqueue one batch: host_in (pinned) is upscaled into host_out (pinned).  Returns immediately with the batch's Ticket
+        (see the buffer lifetime contract in the module docstring)."""
         slot = self.n % self.depth
-        if self.n >= self.depth:
-            self.ev_out[slot].synchronize()          # slot's previous result has left the device
+        if self.tickets[slot] is not None:
+            self.tickets[slot].wait()                # slot's previous result has left the device
+        # fresh events per batch: a Ticket stays valid after its slot has been reused
+        ev_in, ev_out = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(self.s_in):
             if self.dev_in[slot] is None or self.dev_in[slot].shape != host_in.shape or self.dev_in[slot].dtype != host_in.dtype:
                 # allocated on the stream that fills it (the caching allocator orders reuse per stream)
                 self.dev_in[slot] = torch.empty(host_in.shape, dtype=host_in.dtype, device=self.device)
             self.dev_in[slot].copy_(host_in, non_blocking=True)
-            self.ev_in[slot].record(self.s_in)
+            ev_in.record(self.s_in)
         s_comp = self.s_comps[self.n % len(self.s_comps)]
         with torch.cuda.stream(s_comp):
-            s_comp.wait_event(self.ev_in[slot])
+            s_comp.wait_event(ev_in)
             out = self.model(self.dev_in[slot], **self.kw)
             self.ev_comp[slot].record(s_comp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[slot])
             host_out.copy_(out, non_blocking=True)
-            self.ev_out[slot].record(self.s_out)
+            ev_out.record(self.s_out)
         out.record_stream(self.s_out)
         self.dev_out[slot] = out
+        t = Ticket(self.n, ev_in, ev_out)
+        self.tickets[slot] = t
         self.n += 1
+        return t
 
     def drain(self) -> None:
         for s in (self.s_in, *self.s_comps, self.s_out):
