@@ -2,7 +2,7 @@
 # round-2 validation: full GPU parity suite, smoke, bench (+ reference arm)
 TAG=${1:-r2a}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu_$TAG.log 2>&1
+timeout 1500 python -m pytest tests -q -m gpu --timeout 600 -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
 grep -E "^FAILED|^ERROR|passed|failed|rc=|Error|assert" gpurun_out/pytest_gpu_$TAG.log | head -30
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -33,5 +33,6 @@ class TransformerModel(EngineModel):
         self.decoder_conv1 = nn.Conv2d(base_channels, base_channels, kernel_size=3, stride=1, padding=1)
         self.decoder_conv2 = nn.Conv2d(base_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
-    def forward(self, x, res_out: Tuple[int, int] = (1080, 1920), upscale_factor: int = None, require_ratio: bool = True):
-        return super().forward(x, res_out, upscale_factor, require_ratio)
+    def forward(self, x, res_out: Tuple[int, int] = (1080, 1920), upscale_factor: int = None, require_ratio: bool = True,
+                in_layout: str = "chw", out_layout: str = "chw"):
+        return super().forward(x, res_out, upscale_factor, require_ratio, in_layout, out_layout)
