@@ -70,7 +70,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0,1} (bicubic kernel with two output columns per thread, default on), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral) */
+ * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0,1} (bicubic kernel with two output columns per thread, default on), "global_attn_tc" {0,1} (ResidualTransformer: tcgen05 flash attention, default on; 0 = the mma.sync kernel), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral) */
 int tu_debug_set(const char *key, int value);
 /* debug only: while device_buffer != NULL the window stack and the unembed GEMM append (globaltimer ns, kind << 48 | smid << 32 | value)
  * pairs behind a 64-bit event counter in word 0 (caller zeroes it); capacity in events; buffer of (1 + 2 * capacity) * 8 bytes */
@@ -222,6 +222,9 @@ int tu_patch_unembed(const float *tokens, const void *w, const float *b, const v
 /* one pre-LN transformer block in place on the fp32 token stream x (M, dim).
  * window != 0: M = nWin*64, 8x8 window attention with rel_bias; else global attention over S tokens per frame. */
 size_t tu_block_workspace_bytes(int M, int dim, int dtype);
+/* the same including the scratch of the tcgen05 global attention (window == 0, S tokens per frame, TU_BF16): with only
+ * tu_block_workspace_bytes() the block falls back to the mma.sync attention kernel */
+size_t tu_block_workspace_bytes_for(int M, int dim, int dtype, int window, int S);
 int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                          int dtype, void *workspace, size_t workspace_bytes, void *stream);
 /* all window-transformer blocks of a bf16 WindowTransformer / FastTransformer in one fused kernel, in place on the fp32

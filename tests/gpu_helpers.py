@@ -149,10 +149,12 @@ def patch_unembed(tok, w, b, skip, B, Ht, Wt, Hc, Wc, dim, window):
     return out
 
 
-def transformer_block(x, bw, dim, heads, window, S, dtype):
+def transformer_block(x, bw, dim, heads, window, S, dtype, full_workspace=False):
+    """full_workspace: size the workspace with tu_block_workspace_bytes_for (enables the tcgen05 global attention)"""
     lib = _lib.load()
     M = x.shape[0]
-    n = lib.tu_block_workspace_bytes(M, dim, DT[dtype])
+    n = (lib.tu_block_workspace_bytes_for(M, dim, DT[dtype], int(window), S) if full_workspace
+         else lib.tu_block_workspace_bytes(M, dim, DT[dtype]))
     ws = torch.empty(n, dtype=torch.uint8, device=x.device)
     chk(lib.tu_transformer_block(p(x), C.byref(bw), M, dim, heads, int(window), S, DT[dtype], p(ws), n, stream()))
     return x

@@ -432,3 +432,34 @@ def test_frames_to_planar(shape, bgr):
                                        torch.cuda.current_stream().cuda_stream))
     want = (x[..., [2, 1, 0]] if bgr else x).permute(0, 3, 1, 2)
     assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("B,S", [(2, 3600), (3, 328), (1, 128), (1, 1032), (5, 256)])
+def test_global_attention_tcgen05_block(dev, B, S):
+    """ResidualTransformer's TransformerBlock (R:22-50) with the tcgen05 flash attention (S tile in TMEM, P through shared memory, K / V^T
+    by TMA, key range split evenly over the SMs with merged partials) vs the oracle's nn.MultiheadAttention restatement and vs the
+    mma.sync kernel it replaces; token counts with partial query / key tiles and inactive second query tiles included."""
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200 import _lib
+    from transformerupscaler_b200.packing import PackedWeights
+    lib = _lib.load()
+    rs = np.random.RandomState(20 + S)
+    sd = synth_state_dict("ResidualTransformer", 6)
+    pw = PackedWeights("ResidualTransformer", sd, BF16, dev)
+    dim, heads = pw.dim, pw.heads
+    x = torch.from_numpy((1.5 * rs.standard_normal((B, S, dim))).astype(np.float32))
+    sdq = {k: (v.to(BF16).float() if v.dim() == 2 else v) for k, v in sd.items()}
+    ref = orc.mha_block(x, sdq, "transformer_blocks.2.", heads, F32)
+    n0 = lib.tu_launch_count()
+    new = G.transformer_block(x.reshape(B * S, dim).to(dev).clone(), pw.blocks[2], dim, heads, False, S, BF16, full_workspace=True)
+    torch.cuda.synchronize()
+    n_new = lib.tu_launch_count() - n0
+    old = G.transformer_block(x.reshape(B * S, dim).to(dev).clone(), pw.blocks[2], dim, heads, False, S, BF16)
+    torch.cuda.synchronize()
+    n_old = lib.tu_launch_count() - n0 - n_new
+    assert n_new == n_old + 2, (n_new, n_old)            # V^T + attention + merge instead of one kernel: the new path really ran
+    assert _maxerr(new.reshape(B, S, dim), ref) < 6e-2
+    assert _maxerr(new, old) < 3e-2
+    # run-to-run: the partials are merged in a fixed order, no atomics
+    again = G.transformer_block(x.reshape(B * S, dim).to(dev).clone(), pw.blocks[2], dim, heads, False, S, BF16, full_workspace=True)
+    assert torch.equal(again, new)

@@ -85,6 +85,7 @@ SIGNATURES = {
     "tu_patch_embed": (i32, [vp, i32, vp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_patch_unembed": (i32, [fp, vp, fp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_block_workspace_bytes": (sz, [i32, i32, i32]),
+    "tu_block_workspace_bytes_for": (sz, [i32, i32, i32, i32, i32]),
     "tu_transformer_block": (i32, [fp, C.POINTER(TuBlockWeights), i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "tu_window_stack": (i32, [fp, C.POINTER(TuModelWeights), i32, vp]),
     "tu_window_attention": (i32, [vp, fp, vp, i32, i32, i32, i32, vp]),

@@ -27,6 +27,7 @@ SOURCES = [
     "tc/gemm_tcgen05.cu",
     "tc/embed_tcgen05.cu",
     "tc/stem_tcgen05.cu",
+    "tc/global_attn_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",
     "tc/window_stack192_tcgen05.cu",
 ]

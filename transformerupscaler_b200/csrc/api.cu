@@ -164,7 +164,7 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
     T *fd = fast ? f2 : (T *)a.get((size_t)B * Hd * Wd * 64 * sizeof(T));
     float *tok = (float *)a.get((size_t)Mtok * dim * sizeof(float));
     bf16 *tok16 = (bf16 *)a.get((size_t)Mtok * dim * sizeof(bf16));   // bf16 copy of the final stream (tensor-core unembed)
-    const size_t bws = tu_block_workspace_bytes(Mtok, dim, dt);
+    const size_t bws = block_workspace_bytes_ex(Mtok, dim, dt, window ? 1 : 0, Ht * Wt);
     void *blk = a.get(bws);
     T *comb = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
     T *dec = (T *)a.get((size_t)B * Hc * Wc * 64 * sizeof(T));
@@ -411,6 +411,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "snake")) {
         tc_set_snake(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "global_attn_tc")) {
+        tc_set_global_attn(value);
         return TU_OK;
     }
     if (key && !strcmp(key, "fused_stack")) {

@@ -111,6 +111,15 @@ bool tc_stack_split_enabled();
 int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                        const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st);
 
+// ResidualTransformer's global attention on tcgen05 (global_attn_tcgen05.cu): qkv (B*S, 3*dim) bf16 with q pre-scaled -> out (B*S, dim)
+// bf16.  vt: B*dim*S bf16 scratch (V transposed), scratch: tc_global_attention_scratch_bytes() of fp32 partials
+size_t tc_global_attention_scratch_bytes(int B, int S, int heads);
+int tc_global_attention(const bf16 *qkv, bf16 *out, bf16 *vt, float *scratch, size_t scratch_bytes, int B, int S, int heads,
+                        cudaStream_t st);
+void tc_set_global_attn(int on);
+// workspace of one transformer block including the scratch of the tcgen05 global attention (window == 0)
+size_t block_workspace_bytes_ex(int M, int dim, int dtype, int window, int S);
+
 // one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
 int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
                          void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st);

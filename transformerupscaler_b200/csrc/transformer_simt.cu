@@ -443,6 +443,13 @@ static size_t block_ws(int M, int dim, int dtype) {
     return align_up((size_t)M * dim * e, 256) + align_up((size_t)M * 4 * dim * e, 256) + align_up((size_t)M * dim * e, 256);
 }
 
+// the tcgen05 global attention keeps fp32 partials behind the three buffers above (bf16 path, window == 0)
+size_t block_workspace_bytes_ex(int M, int dim, int dtype, int window, int S) {
+    size_t n = block_ws(M, dim, dtype);
+    if (!window && dtype == TU_BF16 && S > 0 && M % S == 0 && tc_available()) n += align_up(tc_global_attention_scratch_bytes(M / S, S, dim / 16), 256);
+    return n;
+}
+
 // Dense layer of the block: tensor-core GEMM for bf16 when enabled, else the exact-fp32 SIMT GEMM.
 //   mode 0: out = A W^T + b   mode 2: out = gelu(A W^T + b)   mode 1: x += A W^T + b (fp32 stream)
 template <typename T>
@@ -469,7 +476,7 @@ static int block_linear(const T *A, long lda, const void *W, const float *bias, 
 
 // x_bf16_out (optional, tensor-core path only): receives a bf16 copy of the block's output stream
 template <typename T>
-int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, void *ws,
+int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, void *ws, size_t ws_bytes,
                            bool tc, bf16 *x_bf16_out, cudaStream_t st) {
     char *p = (char *)ws;
     T *ln = (T *)p;
@@ -489,9 +496,19 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
         window_attn_kernel<T><<<grid, 64, 0, st>>>(big, w->rel_bias, att, dim, heads);
         TU_CHECK_LAUNCH("window_attn");
     } else if (tc && sizeof(T) == 2) {
-        dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
-        global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
-        TU_CHECK_LAUNCH("global_attn_mma");
+        // tcgen05 flash attention when the caller's workspace holds its partials (block_workspace_bytes_ex); V^T lives in the unused
+        // last quarter of the qkv / hidden buffer.  Otherwise the mma.sync kernel.
+        rc = TU_TC_UNSUPPORTED;
+        const size_t base = block_ws(M, dim, TU_BF16);
+        if (ws_bytes > base)
+            rc = tc_global_attention((const bf16 *)big, (bf16 *)att, (bf16 *)big + (size_t)M * 3 * dim, (float *)((char *)ws + base), ws_bytes - base,
+                                     M / S, S, heads, st);
+        if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+        if (rc == TU_TC_UNSUPPORTED) {
+            dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
+            global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
+            TU_CHECK_LAUNCH("global_attn_mma");
+        }
     } else {
         dim3 grid(ceil_div(S, 128), heads, M / S);
         global_attn_kernel<T><<<grid, 128, 0, st>>>(big, att, S, dim);
@@ -504,8 +521,8 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
     return TU_OK;
 }
 
-template int transformer_block_impl<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, bool, bf16 *, cudaStream_t);
-template int transformer_block_impl<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, bool, bf16 *, cudaStream_t);
+template int transformer_block_impl<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, size_t, bool, bf16 *, cudaStream_t);
+template int transformer_block_impl<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, size_t, bool, bf16 *, cudaStream_t);
 
 static int block_check(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype, void *workspace,
                        size_t workspace_bytes) {
@@ -524,8 +541,8 @@ int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int 
                          void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st) {
     int rc = block_check(x, w, M, dim, heads, window, S, dtype, workspace, workspace_bytes);
     if (rc) return rc;
-    if (dtype == TU_F32) return transformer_block_impl<float>(x, w, M, dim, heads, window, S, workspace, false, nullptr, st);
-    return transformer_block_impl<bf16>(x, w, M, dim, heads, window, S, workspace, tc_enabled(), x_bf16_out, st);
+    if (dtype == TU_F32) return transformer_block_impl<float>(x, w, M, dim, heads, window, S, workspace, workspace_bytes, false, nullptr, st);
+    return transformer_block_impl<bf16>(x, w, M, dim, heads, window, S, workspace, workspace_bytes, tc_enabled(), x_bf16_out, st);
 }
 
 }  // namespace tu
@@ -533,6 +550,7 @@ int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int 
 using namespace tu;
 
 extern "C" size_t tu_block_workspace_bytes(int M, int dim, int dtype) { return block_ws(M, dim, dtype); }
+extern "C" size_t tu_block_workspace_bytes_for(int M, int dim, int dtype, int window, int S) { return block_workspace_bytes_ex(M, dim, dtype, window, S); }
 
 // Stand-alone window attention (softmax(q k^T + bias) v per 8x8 window and head, head_dim 16) on qkv rows (nWin*64, 3*dim):
 // the op inside WindowAttention.forward between `qkv` and `proj` (WindowTransformer/model.py:104-127).  Exported so that the
