@@ -70,7 +70,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0,1} (bicubic kernel with two output columns per thread, default on), "global_attn_tc" {0,1} (ResidualTransformer: tcgen05 flash attention, default on; 0 = the mma.sync kernel), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral) */
+ * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0,1} (bicubic kernel with two output columns per thread, default on), "global_attn_tc" {0,1} (ResidualTransformer: tcgen05 flash attention instead of the mma.sync kernel; default off: measured 6 % / 26 % slower at 2 / 16 frames), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral) */
 int tu_debug_set(const char *key, int value);
 /* debug only: while device_buffer != NULL the window stack and the unembed GEMM append (globaltimer ns, kind << 48 | smid << 32 | value)
  * pairs behind a 64-bit event counter in word 0 (caller zeroes it); capacity in events; buffer of (1 + 2 * capacity) * 8 bytes */
@@ -233,6 +233,12 @@ int tu_window_stack(float *tokens, const TuModelWeights *w, int M, void *stream)
 /* window attention alone: softmax(q k^T + rel_bias) v per 8x8 window and head (head_dim 16) on qkv rows (nWin*64, 3*dim) with q
  * pre-scaled; rel_bias dense (heads,64,64) fp32; out (nWin*64, dim).  WindowTransformer/model.py:104-127 between qkv and proj. */
 int tu_window_attention(const void *qkv, const float *rel_bias, void *out, int nWin, int dim, int heads, int dtype, void *stream);
+/* global attention alone (ResidualTransformer/model.py:31,44 between in_proj and out_proj): softmax(q k^T) v over the S tokens of a
+ * frame per head (head_dim 16) on qkv rows (B*S, 3*heads*16) bf16 with q pre-scaled; out (B*S, heads*16) bf16.  With a workspace of
+ * tu_global_attention_workspace_bytes() AND tu_debug_set("global_attn_tc", 1) the tcgen05 kernel runs (S % 8 == 0, S >= 128), otherwise
+ * the mma.sync kernel (the default: measured faster at head_dim 16). */
+size_t tu_global_attention_workspace_bytes(int B, int S, int heads);
+int tu_global_attention(const void *qkv, void *out, int B, int S, int heads, void *workspace, size_t workspace_bytes, void *stream);
 /* out = clamp?(bicubic(x -> outH,outW) + bicubic(res -> outH,outW)); res may be NULL */
 int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW,
                          void *out, int out_dtype, int B, int outH, int outW, int clamp, void *stream);

@@ -471,3 +471,28 @@ def test_non_default_transformer_dim_and_copies():
         del C1, C2
         a2 = M2(x, res_out=(108, 156))
     assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, a2)
+
+
+def test_residual_forward_with_tcgen05_attention():
+    """ResidualTransformer's forward with the opt-in tcgen05 global attention (tu_debug_set("global_attn_tc", 1)): same golden, same
+    tolerance as the default mma.sync attention."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    c = CASES["residual_720p_1080p"]
+    B, _, H, W = c["shape"]
+    M, sd = build(c["model"], c["wseed"])
+    x = synth_frames(B, H, W, seed=c["xseed"]).cuda()
+    g = np.load(os.path.join(GOLD, "residual_720p_1080p.npz"))
+    st = c["stride"]
+    try:
+        lib.tu_debug_set(b"global_attn_tc", 1)
+        n0 = lib.tu_launch_count()
+        pre = engine_pre_clamp(M, x, c["kw"], bf16=True).cpu().numpy()[..., ::st, ::st]
+        n_tc = lib.tu_launch_count() - n0
+    finally:
+        lib.tu_debug_set(b"global_attn_tc", 0)
+    n0 = lib.tu_launch_count()
+    pre_default = engine_pre_clamp(M, x, c["kw"], bf16=True).cpu().numpy()[..., ::st, ::st]
+    assert n_tc == (lib.tu_launch_count() - n0) + 16          # 8 layers x (V^T, attention, merge) instead of one kernel each
+    assert bf16_pre_clamp_err(pre, g["pre"]) < TOL_BF16
+    assert bf16_pre_clamp_err(pre_default, g["pre"]) < TOL_BF16

@@ -9,13 +9,19 @@
 // (row max m, row sum l, un-normalised o[16]) per query row in a scratch buffer; `global_attn_merge_kernel` combines the (at most a
 // few) partials of a row and writes the normalised bf16 output.  A partial of the whole key range merges to itself.
 //
-// CTA = 12 warps:
-//   warp 0      TMA producer: the two Q tiles of a segment, then per key tile the K slab and the V^T slabs (3-stage ring)
-//   warp 1      MMA issuer: S_w = Q_w K^T (one 128x128x16 UMMA per tile and query tile), O_w = P_w V (eight 128x16x16 UMMAs)
-//   warps 4-7   softmax warpgroup 0 (query tile 0), warps 8-11 softmax warpgroup 1 (query tile 1): a thread owns one query row
-//               (its TMEM lane): row max over the tile, alpha = 2^((m_old - m_new) c), P = 2^(S c - m_new c) rounded to bf16 into
-//               a 128-byte-swizzled K-major shared-memory operand, o = (o + O_prev) alpha in registers.
-// The two warpgroups run half a tile apart: while one waits for its next S tile or its PV product the other keeps the MUFU busy
+// CTA = 18 warps:
+//   warps 0-7   softmax group 0 (query tile 0), warps 8-15 softmax group 1 (query tile 1).  TWO threads share a query row (its TMEM
+//               lane): warp w of a group owns lane quadrant w mod 4 and key half w / 4 of every tile (64 scores, = one 64-key slab of
+//               the P operand).  The 64 scores are read from TMEM ONCE (the S buffer goes straight back to the MMA warp, which issues
+//               the next tile's Q K^T while this one is being exponentiated); the two halves exchange their row maxima through
+//               shared memory (one 256-thread named barrier per tile), alpha = 2^((m_old - m_new) c),
+//               P = 2^(S c - m_new c) rounded to bf16 into 128-byte-swizzled K-major shared memory; each half keeps 8 of the 16
+//               running outputs, acc = (acc + O_prev) alpha, in spare TMEM columns (updated half way through the exponentials,
+//               when half of the score registers are free).
+//   warp 16     TMA producer: the two Q tiles of a segment (double buffered), then per key tile the K slab and the V^T slabs
+//               (3-stage ring)
+//   warp 17     MMA issuer: S_w = Q_w K^T (one 128x128x16 UMMA per tile and query tile), O_w = P_w V (eight 128x16x16 UMMAs)
+// The two groups run half a tile apart: while one waits for its S tile or its PV product the other keeps the MUFU busy
 // (the kernel is bound by the exponentials: 16 per clock and SM).
 //
 // Operand layouts: only the K-major 128-byte-swizzle descriptors every other kernel of this library uses.  q / k of FOUR heads are
@@ -32,7 +38,7 @@ namespace tu {
 
 namespace {
 
-constexpr int GA_THREADS = 384;
+constexpr int GA_THREADS = 576;
 constexpr int GA_KV_STAGES = 3;
 constexpr int GA_Q_BYTES = 128 * 128;            // one query tile: 128 rows x 64 bf16 (four heads)
 constexpr int GA_K_BYTES = 128 * 128;            // one key tile, same shape
@@ -41,11 +47,12 @@ constexpr int GA_KV_STAGE = GA_K_BYTES + 2 * GA_VT_SLAB;
 constexpr int GA_P_SLAB = 128 * 128;             // 128 rows x 64 keys bf16
 constexpr int GA_P_BYTES = 2 * GA_P_SLAB;        // per warpgroup
 constexpr int GA_OFF_Q = 0;
-constexpr int GA_OFF_KV = GA_OFF_Q + 2 * GA_Q_BYTES;
+constexpr int GA_OFF_KV = GA_OFF_Q + 4 * GA_Q_BYTES;       // two segments' worth of Q tiles
 constexpr int GA_OFF_P = GA_OFF_KV + GA_KV_STAGES * GA_KV_STAGE;
-constexpr int GA_OFF_BAR = GA_OFF_P + 2 * GA_P_BYTES;
+constexpr int GA_OFF_X = GA_OFF_P + 2 * GA_P_BYTES;        // row-max / row-sum exchange: [parity 2][group 2][half 2][128] floats
+constexpr int GA_OFF_BAR = GA_OFF_X + 2 * 2 * 2 * 128 * 4;
 constexpr int GA_SMEM = GA_OFF_BAR + 256 + 1024;
-constexpr int GA_TMEM_COLS = 512;                // S0 [0,128) S1 [128,256) O0 [256,272) O1 [272,288)
+constexpr int GA_TMEM_COLS = 512;                // S0 [0,128) S1 [128,256); P V products [256,288): 16 per group; running o [288,320)
 constexpr int GA_PART_FLOATS = 18;               // m, l, o[16]
 static_assert(GA_OFF_KV % 1024 == 0 && GA_OFF_P % 1024 == 0 && GA_KV_STAGE % 1024 == 0 && GA_SMEM <= 232448, "shared memory layout");
 
@@ -56,12 +63,13 @@ struct GaParams {
     long long units;         // B * heads * qpairs * ktiles
     int max_parts;
     float *scratch;          // [item][part][18][256]
+    unsigned long long *trace;   // debug (tu_debug_trace): clock64 at the phase boundaries of CTA 0's softmax warps 0 and 8, 8 words per tile
 };
 
 struct GaBars {
-    uint64_t q_full, q_free;
+    uint64_t q_full[2], q_free[2];
     uint64_t kv_full[GA_KV_STAGES], kv_empty[GA_KV_STAGES];
-    uint64_t s_full[2], p_full[2], o_full[2];
+    uint64_t s_full[2], s_free[2], p_full[2], o_full[2];
     uint32_t tmem_base;
 };
 
@@ -70,6 +78,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *m, 
                  "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_barrier_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// The two softmax groups take turns on the MUFU pipe: group 0 exponentiates tile t, then group 1 its tile t, then group 0 tile t + 1 ...
+// (left alone they fall into lock step -- both in the exponentials at half rate, then both out of them: MUFU 52 % busy, profiles/r2_ga1).
+// Barrier GA_BAR_GO0 is "group 0 may go" (group 1 arrives on it when its exponentials are done), GA_BAR_GO1 the reverse.
+constexpr int GA_BAR_GO0 = 3, GA_BAR_GO1 = 4;
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     uint32_t r;
@@ -97,6 +122,8 @@ __device__ __forceinline__ bool next_segment(const GaParams &p, long long &u, lo
     return true;
 }
 
+// 18 warps are allocated as 20 (granularity 4): 96 registers per thread.  A softmax thread holds 64 scores of its row; its share of the
+// running output therefore lives in spare TMEM columns between tiles.
 __global__ void __launch_bounds__(GA_THREADS, 1)
 global_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_vt, const GaParams p) {
     pdl_trigger();
@@ -106,25 +133,28 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
     GaBars *bars = reinterpret_cast<GaBars *>(sm + GA_OFF_BAR);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        ptx::mbar_init(ptx::smem_u32(&bars->q_full), 1);
-        ptx::mbar_init(ptx::smem_u32(&bars->q_free), 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(ptx::smem_u32(&bars->q_full[i]), 1);
+            ptx::mbar_init(ptx::smem_u32(&bars->q_free[i]), 1);
+        }
         for (int i = 0; i < GA_KV_STAGES; ++i) {
             ptx::mbar_init(ptx::smem_u32(&bars->kv_full[i]), 1);
             ptx::mbar_init(ptx::smem_u32(&bars->kv_empty[i]), 1);
         }
         for (int w = 0; w < 2; ++w) {
             ptx::mbar_init(ptx::smem_u32(&bars->s_full[w]), 1);
-            ptx::mbar_init(ptx::smem_u32(&bars->p_full[w]), 128);
+            ptx::mbar_init(ptx::smem_u32(&bars->s_free[w]), 8);      // one arrival per warp of the group
+            ptx::mbar_init(ptx::smem_u32(&bars->p_full[w]), 8);
             ptx::mbar_init(ptx::smem_u32(&bars->o_full[w]), 1);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tmap(&tmap_qkv);
         ptx::prefetch_tmap(&tmap_vt);
     }
-    // P starts as zeros: key chunks past S are never written and must multiply the zero-filled V^T as finite numbers
+    // P starts as zeros (never read uninitialised by the tensor core)
     for (int i = threadIdx.x; i < 2 * GA_P_BYTES / 16; i += GA_THREADS) reinterpret_cast<uint4 *>(sm + GA_OFF_P)[i] = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async();
-    if (warp == 1) {
+    if (warp == 17) {
         ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), GA_TMEM_COLS);
         ptx::tmem_relinquish();
     }
@@ -136,29 +166,30 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
 
     const long long u_begin = ga_range_start((int)blockIdx.x, p.units, (int)gridDim.x);
     const long long u_end = ga_range_start((int)blockIdx.x + 1, p.units, (int)gridDim.x);
-    const int qcol_per_slab = 64;
 
-    if (warp == 0) {
+    if (warp == 16) {
         if (lane == 0) {
             // ================================ TMA producer ================================
-            int stage = 0;
-            uint32_t phase = 0, qphase = 0;
+            int stage = 0, seg = 0;
+            uint32_t phase = 0;
             long long u = u_begin;
             Segment s;
             while (next_segment(p, u, u_end, s)) {
-                ptx::mbar_wait(ptx::smem_u32(&bars->q_free), qphase ^ 1);
-                const uint32_t qf = ptx::smem_u32(&bars->q_full);
+                const int qb = seg & 1;
+                ptx::mbar_wait(ptx::smem_u32(&bars->q_free[qb]), ((seg >> 1) & 1) ^ 1);
+                const uint32_t qf = ptx::smem_u32(&bars->q_full[qb]);
                 ptx::mbar_expect_tx(qf, (s.act1 ? 2 : 1) * GA_Q_BYTES);
                 const int slab = s.h >> 2;
-                tma_load_3d(smem0 + GA_OFF_Q, &tmap_qkv, qf, slab * qcol_per_slab, s.qp * 256, s.b);
-                if (s.act1) tma_load_3d(smem0 + GA_OFF_Q + GA_Q_BYTES, &tmap_qkv, qf, slab * qcol_per_slab, s.qp * 256 + 128, s.b);
-                qphase ^= 1;
+                const uint32_t qdst = smem0 + GA_OFF_Q + qb * 2 * GA_Q_BYTES;
+                tma_load_3d(qdst, &tmap_qkv, qf, slab * 64, s.qp * 256, s.b);
+                if (s.act1) tma_load_3d(qdst + GA_Q_BYTES, &tmap_qkv, qf, slab * 64, s.qp * 256 + 128, s.b);
+                ++seg;
                 for (int kt = s.kt0; kt < s.kt1; ++kt) {
                     ptx::mbar_wait(ptx::smem_u32(&bars->kv_empty[stage]), phase ^ 1);
                     const uint32_t fb = ptx::smem_u32(&bars->kv_full[stage]);
                     const uint32_t dst = smem0 + GA_OFF_KV + stage * GA_KV_STAGE;
                     ptx::mbar_expect_tx(fb, GA_KV_STAGE);
-                    tma_load_3d(dst, &tmap_qkv, fb, p.dim + slab * qcol_per_slab, kt * 128, s.b);
+                    tma_load_3d(dst, &tmap_qkv, fb, p.dim + slab * 64, kt * 128, s.b);
                     const int vrow = (s.b * p.heads + s.h) * 16;
                     ptx::tma_load_2d(dst + GA_K_BYTES, &tmap_vt, fb, kt * 128, vrow);
                     ptx::tma_load_2d(dst + GA_K_BYTES + GA_VT_SLAB, &tmap_vt, fb, kt * 128 + 64, vrow);
@@ -166,34 +197,46 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 17) {
         // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
         const uint32_t leader = ptx::elect_one();
         const uint32_t idesc_qk = ptx::make_idesc_bf16(128, 128), idesc_pv = ptx::make_idesc_bf16(128, 16);
-        int stage = 0;
-        uint32_t phase = 0, qphase = 0, pph[2] = {0u, 0u};
+        int stage = 0, seg = 0;
+        uint32_t phase = 0, pph[2] = {0u, 0u}, fph[2] = {0u, 0u};
         long long u = u_begin;
         Segment s;
         while (next_segment(p, u, u_end, s)) {
-            const int T = s.kt1 - s.kt0, nw = s.act1 ? 2 : 1;
+            const int T = s.kt1 - s.kt0, nw = s.act1 ? 2 : 1, qb = seg & 1;
             const uint32_t hoff = (uint32_t)(s.h & 3) * 2u;                    // 32 bytes per head inside the four-head slab
-            ptx::mbar_wait(ptx::smem_u32(&bars->q_full), qphase);
-            qphase ^= 1;
+            const uint32_t q_lo = ptx::sdesc_lo(smem0 + GA_OFF_Q + qb * 2 * GA_Q_BYTES) + hoff;
+            ptx::mbar_wait(ptx::smem_u32(&bars->q_full[qb]), (seg >> 1) & 1);
             ptx::mbar_wait(ptx::smem_u32(&bars->kv_full[stage]), phase);
             ptx::tc_fence_after();
             for (int w = 0; w < nw; ++w) {
-                ptx::umma_bf16_lo<0>(tmem_base + w * 128, ptx::sdesc_lo(smem0 + GA_OFF_Q + w * GA_Q_BYTES) + hoff,
-                                     ptx::sdesc_lo(smem0 + GA_OFF_KV + stage * GA_KV_STAGE) + hoff, idesc_qk, leader);
+                ptx::umma_bf16_lo<0>(tmem_base + w * 128, q_lo + w * (GA_Q_BYTES >> 4), ptx::sdesc_lo(smem0 + GA_OFF_KV + stage * GA_KV_STAGE) + hoff,
+                                     idesc_qk, leader);
                 ptx::umma_commit_pred(ptx::smem_u32(&bars->s_full[w]), leader);
             }
             for (int t = 0; t < T; ++t) {
                 int nstage = stage + 1;
                 uint32_t nphase = phase;
                 if (nstage == GA_KV_STAGES) { nstage = 0; nphase ^= 1; }
+                // next tile's scores as soon as the warpgroup has S(t) in registers
                 if (t + 1 < T) ptx::mbar_wait(ptx::smem_u32(&bars->kv_full[nstage]), nphase);
+                for (int w = 0; w < nw; ++w) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->s_free[w]), fph[w]);
+                    fph[w] ^= 1;
+                    if (t + 1 < T) {
+                        ptx::tc_fence_after();
+                        ptx::umma_bf16_lo<0>(tmem_base + w * 128, q_lo + w * (GA_Q_BYTES >> 4),
+                                             ptx::sdesc_lo(smem0 + GA_OFF_KV + nstage * GA_KV_STAGE) + hoff, idesc_qk, leader);
+                        ptx::umma_commit_pred(ptx::smem_u32(&bars->s_full[w]), leader);
+                    }
+                }
+                if (t + 1 == T) ptx::umma_commit_pred(ptx::smem_u32(&bars->q_free[qb]), leader);     // the segment's last Q K^T has been issued
                 const uint32_t vt_lo = ptx::sdesc_lo(smem0 + GA_OFF_KV + stage * GA_KV_STAGE + GA_K_BYTES);
                 for (int w = 0; w < nw; ++w) {
-                    ptx::mbar_wait(ptx::smem_u32(&bars->p_full[w]), pph[w]);   // P_w(t) written, S_w(t) and O_w(t-1) read
+                    ptx::mbar_wait(ptx::smem_u32(&bars->p_full[w]), pph[w]);   // P_w(t) written, O_w(t-1) read
                     pph[w] ^= 1;
                     ptx::tc_fence_after();
                     const uint32_t p_lo = ptx::sdesc_lo(smem0 + GA_OFF_P + w * GA_P_BYTES);
@@ -204,137 +247,168 @@ global_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid
                         ptx::umma_bf16_lo<1>(od, p_lo + (ks >> 2) * (GA_P_SLAB >> 4) + (ks & 3) * 2, vt_lo + (ks >> 2) * (GA_VT_SLAB >> 4) + (ks & 3) * 2,
                                              idesc_pv, leader);
                     ptx::umma_commit_pred(ptx::smem_u32(&bars->o_full[w]), leader);
-                    if (t + 1 < T) {
-                        ptx::umma_bf16_lo<0>(tmem_base + w * 128, ptx::sdesc_lo(smem0 + GA_OFF_Q + w * GA_Q_BYTES) + hoff,
-                                             ptx::sdesc_lo(smem0 + GA_OFF_KV + nstage * GA_KV_STAGE) + hoff, idesc_qk, leader);
-                        ptx::umma_commit_pred(ptx::smem_u32(&bars->s_full[w]), leader);
-                    }
                 }
                 ptx::umma_commit_pred(ptx::smem_u32(&bars->kv_empty[stage]), leader);
                 stage = nstage;
                 phase = nphase;
             }
-            ptx::umma_commit_pred(ptx::smem_u32(&bars->q_free), leader);
+            ++seg;
         }
-    } else if (warp >= 4) {
-        // ================================ softmax warpgroups ================================
-        const int w = (warp - 4) >> 2, q = warp & 3, row = q * 32 + lane;
+    } else {
+        // ================================ softmax groups ================================
+        const int w = warp >> 3, half = (warp >> 2) & 1, q = warp & 3, row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t s_addr = tmem_base + lane_off + w * 128, o_addr = tmem_base + lane_off + 256 + w * 16;
-        uint8_t *prow = sm + GA_OFF_P + w * GA_P_BYTES + row * 128;
+        const uint32_t s_addr = tmem_base + lane_off + w * 128 + half * 64;
+        const uint32_t o_addr = tmem_base + lane_off + 256 + w * 16 + half * 8;          // this thread's 8 of the 16 outputs of P V
+        const uint32_t acc_addr = tmem_base + lane_off + 288 + w * 16 + half * 8;        // ... and of the running un-normalised output
+        uint8_t *prow = sm + GA_OFF_P + w * GA_P_BYTES + half * GA_P_SLAB + row * 128;
+        float *xch = reinterpret_cast<float *>(sm + GA_OFF_X);                            // [parity][group][half][row]
         const uint32_t sw = (uint32_t)(row & 7);
         const float L2E = 1.4426950408889634f;
         uint32_t sph = 0, oph = 0;
+        int xpar = 0;
+        // phase timeline for tools/probes/attn_trace.py: compiled in only with -DTU_GA_TRACE (the marks cost registers in a loop that has none to spare)
+#ifdef TU_GA_TRACE
+        int trc = 0;
+        const bool tracing = p.trace && blockIdx.x == 0 && lane == 0 && q == 0 && half == 0;
+#define GA_MARK(k) do { if (tracing && trc < 96) p.trace[(w * 96 + trc) * 8 + (k)] = (unsigned long long)clock64(); } while (0)
+#define GA_NEXT_TILE() ++trc
+#else
+#define GA_MARK(k) do { } while (0)
+#define GA_NEXT_TILE() do { } while (0)
+#endif
         long long u = u_begin;
         Segment s;
+        if (w == 1) named_barrier_arrive(GA_BAR_GO0, 512);      // group 0 starts; the arrival group 1 leaves behind after its last tile of a
+                                                                // segment is the "go" for group 0's first tile of the next one
         while (next_segment(p, u, u_end, s)) {
             if (w == 1 && !s.act1) continue;
+            const bool pingpong = s.act1 != 0;                  // with the second query tile empty, group 0 runs alone
             const int T = s.kt1 - s.kt0;
-            float m = -INFINITY, l = 0.f, o[16];
-#pragma unroll
-            for (int d = 0; d < 16; ++d) o[d] = 0.f;
+            float m = -INFINITY, l = 0.f;
             for (int t = 0; t < T; ++t) {
-                const int nvalid = min(128, p.S - (s.kt0 + t) * 128);
+                const int nvalid = min(128, p.S - (s.kt0 + t) * 128) - half * 64;      // valid columns of this half (may be <= 0)
+                GA_MARK(0);
                 ptx::mbar_wait(ptx::smem_u32(&bars->s_full[w]), sph);
                 sph ^= 1;
                 ptx::tc_fence_after();
-                // ---- pass A: row max of the tile
-                float mx = -INFINITY;
-                if (nvalid == 128) {
+                GA_MARK(1);
+                // ---- this thread's 64 scores into registers, then the S buffer goes back to the MMA warp
+                uint32_t v[64];
+                ptx::tmem_ld_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                ptx::tmem_ld_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->s_free[w]));
+                GA_MARK(2);
+                if (nvalid < 64) {                                           // keys past S: score -inf -> probability 0
 #pragma unroll
-                    for (int c = 0; c < 4; c += 2) {
-                        uint32_t v0[32], v1[32];
-                        ptx::tmem_ld_x32(s_addr + c * 32, v0);
-                        ptx::tmem_ld_x32(s_addr + c * 32 + 32, v1);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])));
-                            mx = fmaxf(mx, fmaxf(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])));
-                        }
-                    }
-                } else {
-                    for (int c = 0; c * 32 < nvalid; ++c) {
-                        uint32_t v0[32];
-                        ptx::tmem_ld_x32(s_addr + c * 32, v0);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (c * 32 + j < nvalid) mx = fmaxf(mx, __uint_as_float(v0[j]));
-                    }
+                    for (int j = 0; j < 64; ++j)
+                        if (j >= nvalid) v[j] = 0xff800000u;
                 }
-                const float m_new = fmaxf(m, mx);
+                // ---- row max: four independent chains over the own half, then the other half's through shared memory
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 64; j += 8) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+                }
+                const float mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                float *xp = xch + ((xpar * 2 + w) * 2) * 128 + row;
+                xp[half * 128] = mloc;
+                named_barrier(1 + w, 256);
+                const float m_new = fmaxf(m, fmaxf(mloc, xp[(half ^ 1) * 128]));
+                xpar ^= 1;
+                GA_MARK(3);
                 const float alpha = ex2f((m - m_new) * L2E);                   // 2^(-inf) = 0 on a segment's first tile
                 if (t > 0) {
-                    ptx::mbar_wait(ptx::smem_u32(&bars->o_full[w]), oph);       // O_w(t-1) = P_w(t-1) V(t-1): also frees the P buffer
+                    ptx::mbar_wait(ptx::smem_u32(&bars->o_full[w]), oph);       // P_w(t-1) V(t-1) is complete: the P buffer is free
                     oph ^= 1;
                     ptx::tc_fence_after();
-                    uint32_t ov[16];
-                    ptx::tmem_ld_x16(o_addr, ov);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int d = 0; d < 16; ++d) o[d] = (o[d] + __uint_as_float(ov[d])) * alpha;
                 }
-                l *= alpha;
+                GA_MARK(4);
                 m = m_new;
-                // ---- pass B: P = 2^(S c - m c) -> bf16, 128-byte swizzled K-major rows of two 64-key slabs
+                // ---- my group's turn on the MUFU: P = 2^(S c - m c) -> bf16, one 64-key slab of 128-byte swizzled K-major rows
                 const ptx::f32x2 c2 = ptx::pk2(L2E, L2E), nb2 = ptx::pk2(-m_new * L2E, -m_new * L2E);
-                ptx::f32x2 rs = ptx::pk2(0.f, 0.f);
-                for (int c = 0; c * 32 < nvalid; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_x32(s_addr + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    uint32_t pk[16];
-                    const int lim = nvalid - c * 32;                         // >= 32 for a full chunk
+                ptx::f32x2 rs0 = ptx::pk2(0.f, 0.f), rs1 = rs0;
+                if (pingpong) named_barrier(w == 0 ? GA_BAR_GO0 : GA_BAR_GO1, 512);
+                GA_MARK(5);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float e0, e1;
-                        ptx::up2(ptx::fma2(ptx::pk2u(v[j], v[j + 1]), c2, nb2), e0, e1);
-                        float p0 = ex2f(e0), p1 = ex2f(e1);
-                        if (lim < 32) {
-                            if (j >= lim) p0 = 0.f;
-                            if (j + 1 >= lim) p1 = 0.f;
-                        }
-                        rs = ptx::add2(rs, ptx::pk2(p0, p1));
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                    uint8_t *slab = prow + (c >> 1) * GA_P_SLAB;
+                for (int g = 0; g < 8; ++g) {                                // 8 keys = one 16-byte unit of the operand row
+                    if (g == 4 && t > 0) {
+                        // half of the scores have been consumed: registers are free for the running output
+                        // acc = (acc + O(t-1)) alpha, kept in spare TMEM columns between tiles
+                        uint32_t ov[8], oa[8];
+                        tmem_ld_x8(o_addr, ov);
+                        if (t > 1) tmem_ld_x8(acc_addr, oa);
+                        ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t unit = (uint32_t)((c & 1) * 4 + g) ^ sw;
-                        *reinterpret_cast<uint4 *>(slab + unit * 16) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                        for (int d = 0; d < 8; ++d)
+                            oa[d] = __float_as_uint(((t > 1 ? __uint_as_float(oa[d]) : 0.f) + __uint_as_float(ov[d])) * alpha);
+                        tmem_st_x8(acc_addr, oa);
+                        ptx::tmem_st_wait();
                     }
+                    float e[8];
+                    ptx::up2(ptx::fma2(ptx::pk2u(v[8 * g + 0], v[8 * g + 1]), c2, nb2), e[0], e[1]);
+                    ptx::up2(ptx::fma2(ptx::pk2u(v[8 * g + 2], v[8 * g + 3]), c2, nb2), e[2], e[3]);
+                    ptx::up2(ptx::fma2(ptx::pk2u(v[8 * g + 4], v[8 * g + 5]), c2, nb2), e[4], e[5]);
+                    ptx::up2(ptx::fma2(ptx::pk2u(v[8 * g + 6], v[8 * g + 7]), c2, nb2), e[6], e[7]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) e[i] = ex2f(e[i]);
+                    rs0 = ptx::add2(rs0, ptx::add2(ptx::pk2(e[0], e[1]), ptx::pk2(e[2], e[3])));
+                    rs1 = ptx::add2(rs1, ptx::add2(ptx::pk2(e[4], e[5]), ptx::pk2(e[6], e[7])));
+                    const uint32_t unit = (uint32_t)g ^ sw;
+                    *reinterpret_cast<uint4 *>(prow + unit * 16) =
+                        make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
                 }
+                GA_MARK(6);
+                if (pingpong) named_barrier_arrive(w == 0 ? GA_BAR_GO1 : GA_BAR_GO0, 512);
                 {
-                    float a, b2;
-                    ptx::up2(rs, a, b2);
-                    l += a + b2;
+                    float a0, a1;
+                    ptx::up2(ptx::add2(rs0, rs1), a0, a1);
+                    l = fmaf(l, alpha, a0 + a1);
                 }
-                ptx::tc_fence_before();            // our reads of S_w / O_w are ordered before the MMAs that p_full releases
+                ptx::tc_fence_before();            // our read of O_w is ordered before the PV MMAs that p_full releases
                 ptx::fence_proxy_async();          // P is read by the tensor core (async proxy)
-                ptx::mbar_arrive(ptx::smem_u32(&bars->p_full[w]));
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->p_full[w]));
+                GA_MARK(7);
+                GA_NEXT_TILE();
             }
             ptx::mbar_wait(ptx::smem_u32(&bars->o_full[w]), oph);
             oph ^= 1;
             ptx::tc_fence_after();
+            float o[8];
             {
-                uint32_t ov[16];
-                ptx::tmem_ld_x16(o_addr, ov);
+                uint32_t ov[8], oa[8];
+                tmem_ld_x8(o_addr, ov);
+                if (T > 1) tmem_ld_x8(acc_addr, oa);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int d = 0; d < 16; ++d) o[d] += __uint_as_float(ov[d]);
+                for (int d = 0; d < 8; ++d) o[d] = (T > 1 ? __uint_as_float(oa[d]) : 0.f) + __uint_as_float(ov[d]);
             }
             ptx::tc_fence_before();
+            // the row sum of the two halves (same exchange buffer and parity discipline as the row maxima)
+            float *xp = xch + ((xpar * 2 + w) * 2) * 128 + row;
+            xp[half * 128] = l;
+            named_barrier(1 + w, 256);
+            const float lsum = l + xp[(half ^ 1) * 128];
+            xpar ^= 1;
             float *dst = p.scratch + ((long long)s.item * p.max_parts + s.part) * (GA_PART_FLOATS * 256) + w * 128 + row;
-            dst[0] = m;
-            dst[256] = l;
+            if (half == 0) {
+                dst[0] = m;
+                dst[256] = lsum;
+            }
 #pragma unroll
-            for (int d = 0; d < 16; ++d) dst[(2 + d) * 256] = o[d];
+            for (int d = 0; d < 8; ++d) dst[(2 + half * 8 + d) * 256] = o[d];
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, GA_TMEM_COLS);
+    if (warp == 17) ptx::tmem_dealloc(tmem_base, GA_TMEM_COLS);
 }
 
 // combine the partials of every query row and write softmax(q k^T) v as bf16 at (frame, token, head * 16 + d)
@@ -399,7 +473,11 @@ __global__ void __launch_bounds__(256) global_attn_vt_kernel(const bf16 *__restr
 }
 
 PerDeviceFlag g_ga_attr;
-thread_local int g_ga_enable = 1;
+// Measured on B200 (tools/probes/attn_probe.py, profiles/r2_attn_*.log): 109 us per layer for 2 frames and 756 us for 16 against 103 / 599 us of the
+// mma.sync kernel it was meant to replace -- at head_dim 16 the tensor pipe is 5 % busy either way and the kernel is bound by the
+// exponentials and by moving S (TMEM -> registers) and P (registers -> shared memory) around them, which mma.sync keeps in registers.
+// The forward therefore uses this kernel only when asked to: tu_debug_set("global_attn_tc", 1).
+thread_local int g_ga_enable = 0;
 
 }  // namespace
 
@@ -450,6 +528,7 @@ int tc_global_attention(const bf16 *qkv, bf16 *out, bf16 *vt, float *scratch, si
     GaParams p;
     ga_geometry(B, S, heads, grid, p);
     p.scratch = scratch;
+    p.trace = g_trace_buf;
     CUtensorMap tq, tv;
     {
         cuuint64_t d3[3] = {(cuuint64_t)3 * dim, (cuuint64_t)S, (cuuint64_t)B};

@@ -573,6 +573,30 @@ extern "C" int tu_window_attention(const void *qkv, const float *rel_bias, void 
     return TU_OK;
 }
 
+// Stand-alone global attention (ResidualTransformer: softmax(q k^T) v over the S tokens of a frame per head, head_dim 16) on qkv rows
+// (B*S, 3*dim) bf16 with q pre-scaled; out (B*S, dim) bf16.  workspace: tu_global_attention_workspace_bytes(B, S, heads) enables the
+// tcgen05 kernel; with workspace == NULL (or too small / unsupported S) the mma.sync kernel runs.  Exported so that the "attention
+// TFLOP/s" of the headline metric can be measured on its own for this model too.
+extern "C" size_t tu_global_attention_workspace_bytes(int B, int S, int heads) {
+    if (B <= 0 || S <= 0 || heads <= 0 || !tc_available()) return 0;
+    return align_up((size_t)B * S * heads * 16 * sizeof(bf16), 256) + tc_global_attention_scratch_bytes(B, S, heads);
+}
+extern "C" int tu_global_attention(const void *qkv, void *out, int B, int S, int heads, void *workspace, size_t workspace_bytes, void *stream) {
+    TU_CHECK_ARG(qkv && out && B > 0 && S > 0 && (heads == 8 || heads == 12), "global_attention: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int dim = heads * 16;
+    int rc = TU_TC_UNSUPPORTED;
+    const size_t vt_bytes = align_up((size_t)B * S * dim * sizeof(bf16), 256);
+    if (workspace && workspace_bytes > vt_bytes && tc_enabled())
+        rc = tc_global_attention((const bf16 *)qkv, (bf16 *)out, (bf16 *)workspace, (float *)((char *)workspace + vt_bytes), workspace_bytes - vt_bytes,
+                                 B, S, heads, st);
+    if (rc != TU_TC_UNSUPPORTED) return rc;
+    dim3 grid(ceil_div(S, GA_QPB), heads, B);
+    global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)qkv, (bf16 *)out, S, dim);
+    TU_CHECK_LAUNCH("global_attn_mma");
+    return TU_OK;
+}
+
 extern "C" int tu_transformer_block(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S,
                                     int dtype, void *workspace, size_t workspace_bytes, void *stream) {
     return transformer_block_ex(x, w, M, dim, heads, window, S, dtype, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
