@@ -2,7 +2,10 @@
 """Secondary measurements (not the headline bench): the other BASELINE.json configs through the public model classes,
 device-resident, CUDA events, with the per-kernel breakdown of tu_profile_*.  Writes gpurun_out/configs_<tag>.json.
 
-  python tools/bench_configs.py [tag] [--only substring]
+  python tools/bench_configs.py [tag] [--only substring[,substring...]]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 tools/bench_configs.py r2 --only cfg4_fast_720p_x2,cfg5a
+      (frame-sharded: every rank runs the case's batch on its own GPU -- B frames per GPU, no data-path collective; the timing is the
+       max over ranks after a barrier, fps = world * B / that)
 """
 import ctypes as C
 import json
@@ -37,16 +40,31 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "x"
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""
     import importlib
+    import torch.distributed as dist
     lib = _lib.load()
-    dev = torch.device("cuda:0")
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                 # NCCL's banner goes to stderr
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     out = []
     for name, model, (B, H, W), kw, prec, gflop in CASES:
-        if only and only not in name:
+        if only and not any(o in name for o in only.split(",")):
             continue
         M = importlib.import_module(f"transformerupscaler_b200.models.{model}.model").TransformerModel().eval()
         M.load_state_dict(synth_state_dict(model, 0), strict=True)
         M = M.to(dev)
-        x = synth_frames(B, H, W, seed=5).to(dev)
+        x = synth_frames(B, H, W, seed=5 + rank).to(dev)
         if prec == "bf16":
             M, x = M.bfloat16(), x.bfloat16()
         rec = {"case": name, "model": model, "shape": [B, 3, H, W], "kw": {k: list(v) if isinstance(v, tuple) else v for k, v in kw.items()},
@@ -56,6 +74,8 @@ def main():
                 for _ in range(3):
                     y = M(x, **kw)
                 torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
                 iters = 10
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -64,6 +84,10 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / iters
+                if world > 1:
+                    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                    ms = tms.item()
                 lib.tu_profile_reset()
                 lib.tu_profile_enable(2)
                 for _ in range(3):
@@ -78,17 +102,24 @@ def main():
                     k, tot, cnt = ln.split()
                     br[k] = round(float(tot) / 3, 4)            # ms per forward (all launches of that op)
                 lib.tu_profile_reset()
-            rec.update(ms_per_batch=round(ms, 4), fps=round(B / ms * 1e3, 1), model_tflops=round(gflop * B / ms, 1),
+            rec.update(n_gpus=world, frames_per_gpu=B, ms_per_batch=round(ms, 4), fps=round(world * B / ms * 1e3, 1),
+                       model_tflops_per_gpu=round(gflop * B / ms, 1),
+                       flops_note="reference-graph FLOPs (SURVEY.md 8d) over the measured time: FastTransformer's folded up1 branch executes 8.04x fewer",
                        out_shape=list(y.shape), ms_by_op=br, peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 2))
         except Exception as ex:  # noqa: BLE001
             rec["error"] = repr(ex)[:300]
-        print(json.dumps(rec), flush=True)
+        if rank == 0:
+            print(json.dumps(rec), flush=True)
         out.append(rec)
         del M, x
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"configs_{tag}.json"), "w"), indent=1)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"configs_{tag}{'_n%d' % world if world > 1 else ''}.json"), "w"), indent=1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
