@@ -151,6 +151,28 @@ typedef struct TuModelWeights {
                                 /* parameters of the fused tail kernel, tu_subpixel_conv_add), or NULL                  */
 } TuModelWeights;
 
+/* ---- packing a state dict on the host side, without Python (csrc/pack_weights.cu) -----------------------------------------
+ * tensors: the model's state_dict as HOST arrays under the reference's parameter names (fp32, contiguous, the reference's shapes;
+ * `attn.relative_position_index` buffers are int64 and optional).  tu_pack_weights repacks them into the layouts above, uploads them
+ * with one cudaMemcpyAsync on `stream` into `device_buf` (caller-owned, tu_packed_weights_bytes() bytes) and fills `out`, a
+ * caller-allocated host struct: out->w is the TuModelWeights to hand to tu_forward.  out->w.blocks and out->w.host_finconv_wb point
+ * INSIDE *out: keep the struct where it is.  Same results as transformerupscaler_b200/packing.py (which the PyTorch classes use). */
+#define TU_MAX_BLOCKS 16
+typedef struct TuNamedTensor {
+    const char *name;       /* e.g. "window_blocks.3.attn.qkv.weight"                                          */
+    const void *data;       /* host pointer: float32 (int64 for relative_position_index), contiguous           */
+    long long numel;        /* number of elements                                                              */
+} TuNamedTensor;
+typedef struct TuPackedModel {
+    TuModelWeights w;
+    TuBlockWeights blocks[TU_MAX_BLOCKS];
+    float host_finconv_wb[84];
+    size_t device_bytes_used;
+} TuPackedModel;
+size_t tu_packed_weights_bytes(int model, int dim, int n_blocks, int compute_dtype);
+int tu_pack_weights(int model, const TuNamedTensor *tensors, int n_tensors, int compute_dtype, void *device_buf, size_t device_bytes,
+                    TuPackedModel *out, void *stream);
+
 /* ---- whole-model forward (what TransformerModel.forward calls) --------------------------------
  * x:   (B,3,H,W) NCHW, dtype in_dtype.     out: (B,3,outH,outW) NCHW, dtype out_dtype, clamped to [0,1]
  *      (or un-clamped when clamp == 0; tests compare pre-clamp tensors).

@@ -496,3 +496,31 @@ def test_residual_forward_with_tcgen05_attention():
     assert n_tc == (lib.tu_launch_count() - n0) + 16          # 8 layers x (V^T, attention, merge) instead of one kernel each
     assert bf16_pre_clamp_err(pre, g["pre"]) < TOL_BF16
     assert bf16_pre_clamp_err(pre_default, g["pre"]) < TOL_BF16
+
+
+@pytest.mark.parametrize("model,shape,kws", [("WindowTransformer", (2, 72, 104), [dict(res_out=(108, 156))]),
+                                             ("ResidualTransformer", (1, 720, 1280), [dict(res_out=(1080, 1920))]),
+                                             ("FastTransformer", (1, 40, 56), [dict(upscale_factor=s) for s in (2, 3, 4, 6)])])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_c_packer_matches_python_packer(model, shape, kws, bf16):
+    """tu_pack_weights (C ABI, csrc/pack_weights.cu: what a non-Python host calls) produces the weights packing.py produces: the same
+    forward through both gives the same image -- bitwise for the tensors that are pure permutations / casts, to fp32 rounding of the
+    fp64-folded up1 filter for FastTransformer."""
+    from transformerupscaler_b200 import engine
+    from transformerupscaler_b200.packing import CPackedWeights, PackedWeights
+    B, H, W = shape
+    sd = synth_state_dict(model, 12)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    dev = torch.device("cuda:0")
+    pw_py, pw_c = PackedWeights(model, sd, dt, dev), CPackedWeights(model, sd, dt, dev)
+    assert (pw_c.dim, pw_c.heads, pw_c.n_blocks) == (pw_py.dim, pw_py.heads, pw_py.n_blocks)
+    torch.cuda.synchronize()
+    h_py, h_c = engine.register_weights(pw_py), engine.register_weights(pw_c)
+    x = synth_frames(B, H, W, seed=66).cuda()
+    for kw in kws:
+        a = engine.run_forward(h_py, model, x, kw.get("res_out", (1080, 1920)), kw.get("upscale_factor"), True, bf16, torch.float32, clamp=False)
+        b = engine.run_forward(h_c, model, x, kw.get("res_out", (1080, 1920)), kw.get("upscale_factor"), True, bf16, torch.float32, clamp=False)
+        if model == "FastTransformer":
+            assert (a - b).abs().max().item() < 1e-5, kw
+        else:
+            assert torch.equal(a, b), kw

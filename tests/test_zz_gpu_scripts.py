@@ -76,6 +76,11 @@ def test_reference_inference_script_runs_on_the_drop_in_models(tmp_path, model, 
     x = T.ToTensor()(Image.open(str(tmp_path / "in.png")).convert("RGB")).unsqueeze(0).cuda()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         y = M(x, upscale_factor=scale)
-    want = np.asarray(T.ToPILImage()(y.squeeze(0).float().cpu())).astype(np.float64)
+    # through the same JPEG encoder the script used (random-init weights give noisy images: the codec's loss is large, so the
+    # comparison is between two encodings of what must be the same pixels)
+    import io
+    bio = io.BytesIO()
+    T.ToPILImage()(y.squeeze(0).float().cpu()).save(bio, "JPEG")
+    want = np.asarray(Image.open(io.BytesIO(bio.getvalue())).convert("RGB")).astype(np.float64)
     got = np.asarray(out.convert("RGB")).astype(np.float64)
-    assert np.abs(got - want).mean() < 4.0          # JPEG quantisation of the saved file
+    assert np.abs(got - want).mean() < 0.5

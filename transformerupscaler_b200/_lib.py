@@ -56,6 +56,18 @@ class TuModelWeights(C.Structure):
     ]
 
 
+TU_MAX_BLOCKS = 16
+
+
+class TuNamedTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_longlong)]
+
+
+class TuPackedModel(C.Structure):
+    _fields_ = [("w", TuModelWeights), ("blocks", TuBlockWeights * TU_MAX_BLOCKS), ("host_finconv_wb", C.c_float * 84),
+                ("device_bytes_used", C.c_size_t)]
+
+
 # name -> (restype, argtypes); must list every symbol include/tu_b200.h declares
 SIGNATURES = {
     "tu_version": (i32, []),
@@ -69,6 +81,8 @@ SIGNATURES = {
     "tu_profile_collect": (i32, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "tu_profile_report": (i32, [C.c_char_p, sz]),
     "tu_profile_reset": (None, []),
+    "tu_packed_weights_bytes": (sz, [i32, i32, i32, i32]),
+    "tu_pack_weights": (i32, [i32, C.POINTER(TuNamedTensor), i32, i32, vp, sz, C.POINTER(TuPackedModel), vp]),
     "tu_forward_workspace_bytes": (sz, [i32] * 8),
     "tu_forward_workspace_bytes_for": (sz, [C.POINTER(TuModelWeights)] + [i32] * 7),
     "tu_forward": (i32, [C.POINTER(TuModelWeights), vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),

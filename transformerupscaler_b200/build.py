@@ -14,6 +14,7 @@ OBJ = os.path.join(HERE, "build")
 
 SOURCES = [
     "api.cu",
+    "pack_weights.cu",
     "small_convs.cu",
     "subpixel_tail.cu",
     "transformer_simt.cu",

@@ -313,3 +313,31 @@ class PackedWeights:
         mw.stack_w = ptr(dev(torch.stack(slabs).reshape(-1, 64), torch.bfloat16))
         mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
         mw.stack_rel = ptr(dev(torch.stack(rels), f32))
+
+
+class CPackedWeights:
+    """The same packed weights produced by the C ABI's tu_pack_weights (csrc/pack_weights.cu) instead of the torch code above:
+    what a non-Python host does.  Same interface as PackedWeights (`.struct`, `.model`, `.dim`, `.heads`, `.n_blocks`)."""
+
+    def __init__(self, model: str, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device: torch.device):
+        lib = _lib.load()
+        self.model, self.dtype, self.device = model, dtype, device
+        host = {k: (v.detach().to("cpu", torch.int64 if v.dtype == torch.int64 else torch.float32).contiguous()) for k, v in sd.items()}
+        arr = (_lib.TuNamedTensor * len(host))()
+        self._names = [k.encode() for k in host]
+        for i, (k, v) in enumerate(host.items()):
+            arr[i].name, arr[i].data, arr[i].numel = self._names[i], v.data_ptr(), v.numel()
+        dim = sd["patch_embed.weight"].shape[0]
+        pre = "transformer_blocks." if model == "ResidualTransformer" else "window_blocks."
+        nb = 1 + max(int(k[len(pre):].split(".")[0]) for k in sd if k.startswith(pre))
+        cdt = _lib.TU_BF16 if dtype == torch.bfloat16 else _lib.TU_F32
+        nbytes = lib.tu_packed_weights_bytes(_lib.MODEL_IDS[model], dim, nb, cdt)
+        if nbytes == 0:
+            raise ValueError("tu_packed_weights_bytes: unsupported configuration")
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.packed = _lib.TuPackedModel()
+        with torch.cuda.device(device):
+            _lib.check(lib.tu_pack_weights(_lib.MODEL_IDS[model], arr, len(host), cdt, self.buf.data_ptr(), nbytes, C.byref(self.packed),
+                                           torch.cuda.current_stream(device).cuda_stream))
+        self.struct = self.packed.w
+        self.dim, self.heads, self.n_blocks = self.struct.dim, self.struct.heads, self.struct.n_blocks
