@@ -18,6 +18,7 @@ static thread_local int g_unembed_overlap = 1;   // unembed starts on the SMs th
 static thread_local int g_head_stream = 0; // 64 -> 3 heads on the streaming kernel (debug switch "head_stream"): measured slower than the tile kernel
 static thread_local int g_fold_up1 = 1;    // FastTransformer: folded last up1 stage + up1_conv (debug switch "fold_up1")
 static thread_local int g_use_stack = 1;   // fused window-transformer stack kernel (debug switch "fused_stack")
+static thread_local int g_frame_chunk = 0;  // debug switch "frame_chunk": conv1+conv2 and the downsample run in chunks of this many frames (0 = whole batch)
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -188,21 +189,29 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
         if (e != cudaSuccess) return cuda_fail(e, "memset tile flags");
     }
     if (!dry) {
-        // conv1 fused into conv2 (its 64-channel output never reaches HBM) when the tensor-core path and the image pitch allow it
-        rc = TU_TC_UNSUPPORTED;
-        if (tc_on(dt) && w->conv1_w64) {
-            g_prof_name = "conv1_conv2";
-            prof_begin(st);
-            rc = tc_conv12_fused(x, in_dtype, (const bf16 *)w->conv1_w64, w->conv1_b, (const bf16 *)w->conv2_w, w->conv2_b, (bf16 *)f2, B, H, W, st);
-            if (rc == TU_OK) prof_end(st, "conv1_conv2");
-            else if (g_prof_open) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; }
-            if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+        // conv1 fused into conv2 (its 64-channel output never reaches HBM) when the tensor-core path and the image pitch allow it.
+        // "frame_chunk" = c > 0 runs {conv1+conv2, downsample} c frames at a time: the downsample then reads what conv2 just wrote while
+        // (part of) it is still in the 126 MB L2 (one 720p map is 118 MB)
+        const int chunk = (!fast && g_frame_chunk > 0 && g_frame_chunk < B) ? g_frame_chunk : B;
+        for (int b0 = 0; b0 < B; b0 += chunk) {
+            const int nb = min(chunk, B - b0);
+            const void *xb = (const char *)x + (size_t)b0 * 3 * H * W * dtype_size(in_dtype);
+            T *f1b = f1 + (size_t)b0 * H * W * 64, *f2b = f2 + (size_t)b0 * H * W * 64, *fdb = fd + (size_t)b0 * Hd * Wd * 64;
+            rc = TU_TC_UNSUPPORTED;
+            if (tc_on(dt) && w->conv1_w64) {
+                g_prof_name = "conv1_conv2";
+                prof_begin(st);
+                rc = tc_conv12_fused(xb, in_dtype, (const bf16 *)w->conv1_w64, w->conv1_b, (const bf16 *)w->conv2_w, w->conv2_b, (bf16 *)f2b, nb, H, W, st);
+                if (rc == TU_OK) prof_end(st, "conv1_conv2");
+                else if (g_prof_open) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; }
+                if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+            }
+            if (rc == TU_TC_UNSUPPORTED) {
+                TU_STEP("conv1", tu_stem_conv(xb, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1b, dt, nb, H, W, stv));
+                TU_STEP("conv2", tu_conv3x3_c64(f1b, w->conv2_w, w->conv2_b, f2b, dt, nb, H, W, 1, 1, 1, 0, stv));
+            }
+            if (!fast) TU_STEP("downsample", tu_conv3x3_c64(f2b, w->down_w, w->down_b, fdb, dt, nb, H, W, 2, 0, 1, 0, stv));
         }
-        if (rc == TU_TC_UNSUPPORTED) {
-            TU_STEP("conv1", tu_stem_conv(x, in_dtype, w->conv1_w, w->conv1_w64, w->conv1_b, f1, dt, B, H, W, stv));
-            TU_STEP("conv2", tu_conv3x3_c64(f1, w->conv2_w, w->conv2_b, f2, dt, B, H, W, 1, 1, 1, 0, stv));
-        }
-        if (!fast) TU_STEP("downsample", tu_conv3x3_c64(f2, w->down_w, w->down_b, fd, dt, B, H, W, 2, 0, 1, 0, stv));
     }
 
     // ---- FastTransformer branch A: sub-pixel upsample of feat, then 64->3 (+ReLU)
@@ -415,6 +424,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "global_attn_tc")) {
         tc_set_global_attn(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "frame_chunk")) {
+        g_frame_chunk = value;
         return TU_OK;
     }
     if (key && !strcmp(key, "fused_stack")) {
