@@ -524,3 +524,64 @@ def test_c_packer_matches_python_packer(model, shape, kws, bf16):
             assert (a - b).abs().max().item() < 1e-5, kw
         else:
             assert torch.equal(a, b), kw
+
+
+def test_second_device_and_host_threads():
+    """(a) the kernels' dynamic-shared-memory attributes and SM count are kept per device: a process that has run on cuda:0
+    runs on cuda:1 as well (skipped on a one-GPU box); (b) the bring-up switches are thread-local: a thread flipping a switch does not
+    change what another thread computes, and two host threads can run forwards concurrently."""
+    import threading
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    M, sd = build("WindowTransformer", 3)
+    x = synth_frames(2, 72, 104, seed=5)
+    with torch.no_grad():
+        want = M.bfloat16()(x.cuda().bfloat16(), res_out=(108, 156)).cpu()
+        if torch.cuda.device_count() >= 2:
+            M1 = importlib.import_module("transformerupscaler_b200.models.WindowTransformer.model").TransformerModel().eval()
+            M1.load_state_dict(sd, strict=True)
+            M1 = M1.to("cuda:1").bfloat16()
+            got = M1(x.to("cuda:1").bfloat16(), res_out=(108, 156)).cpu()
+            assert torch.equal(got, want)
+            Mf, _ = build("FastTransformer", 4)
+            Mf1 = importlib.import_module("transformerupscaler_b200.models.FastTransformer.model").TransformerModel().eval()
+            Mf1.load_state_dict(synth_state_dict("FastTransformer", 4), strict=True)
+            xf = synth_frames(1, 40, 56, seed=6)
+            a = Mf.bfloat16()(xf.cuda().bfloat16(), upscale_factor=3).cpu()
+            b = Mf1.to("cuda:1").bfloat16()(xf.to("cuda:1").bfloat16(), upscale_factor=3).cpu()
+            assert torch.equal(a, b)
+    results, errors = {}, []
+
+    def worker(name, flip):
+        try:
+            torch.cuda.set_device(0)
+            s = torch.cuda.Stream()
+            if flip:                         # this thread runs the unfused op graph; the other must keep the defaults
+                for key in (b"fuse_conv12", b"fuse_dec12", b"fused_stack", b"unembed_overlap"):
+                    lib.tu_debug_set(key, 0)
+            outs = []
+            with torch.no_grad(), torch.cuda.stream(s):
+                xin = x.cuda().bfloat16()
+                for _ in range(6):
+                    outs.append(M(xin, res_out=(108, 156)))
+                s.synchronize()
+            results[name] = [o.cpu() for o in outs]
+        except Exception as e:  # noqa: BLE001
+            errors.append((name, repr(e)))
+
+    n0 = lib.tu_launch_count()
+    ts = [threading.Thread(target=worker, args=("default", False)), threading.Thread(target=worker, args=("unfused", True))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for o in results["default"]:
+        assert torch.equal(o, want)          # the default thread computed exactly what a lone thread computes
+    for o in results["unfused"]:
+        assert (o.float() - want.float()).abs().max().item() < 1e-2      # a different op graph: close, not bitwise
+    # the unfused thread launched more kernels per forward than the default one (its switches really were in effect)
+    assert lib.tu_launch_count() - n0 > 2 * 6 * 8
+    # and the main thread's switches are untouched
+    with torch.no_grad():
+        assert torch.equal(M(x.cuda().bfloat16(), res_out=(108, 156)).cpu(), want)
