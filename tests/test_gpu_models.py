@@ -585,3 +585,33 @@ def test_second_device_and_host_threads():
     # and the main thread's switches are untouched
     with torch.no_grad():
         assert torch.equal(M(x.cuda().bfloat16(), res_out=(108, 156)).cpu(), want)
+
+
+@pytest.mark.parametrize("B", [1, 2, 3])
+def test_residual_fused_block_kernels(B):
+    """ResidualTransformer (R:22-50): LN1 + in_proj and out_proj + LN2 + MLP as two fused tcgen05 kernels per layer (3600 tokens per frame
+    is not a multiple of the 128-token tile: the last tile of a launch is partial) against the reference golden, and against the
+    six-kernel path they replace."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    c = CASES["residual_720p_1080p"]
+    M, sd = build(c["model"], c["wseed"])
+    x1 = synth_frames(1, 720, 1280, seed=c["xseed"])
+    x = torch.cat([x1] + [synth_frames(1, 720, 1280, seed=900 + i) for i in range(B - 1)], 0).cuda()
+    g = np.load(os.path.join(GOLD, "residual_720p_1080p.npz"))
+    st = c["stride"]
+    n0 = lib.tu_launch_count()
+    fused = engine_pre_clamp(M, x, c["kw"], bf16=True)
+    n_fused = lib.tu_launch_count() - n0
+    try:
+        lib.tu_debug_set(b"resid_fused", 0)
+        n0 = lib.tu_launch_count()
+        plain = engine_pre_clamp(M, x, c["kw"], bf16=True)
+        n_plain = lib.tu_launch_count() - n0
+    finally:
+        lib.tu_debug_set(b"resid_fused", 1)
+    assert n_plain == n_fused + 8 * 4, (n_plain, n_fused)         # per layer: 6 kernels -> 2
+    assert bf16_pre_clamp_err(fused[:1].cpu().numpy()[..., ::st, ::st], g["pre"]) < TOL_BF16
+    assert (fused - plain).abs().max().item() < 1e-2
+    again = engine_pre_clamp(M, x, c["kw"], bf16=True)
+    assert torch.equal(again, fused)

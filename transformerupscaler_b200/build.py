@@ -29,6 +29,7 @@ SOURCES = [
     "tc/embed_tcgen05.cu",
     "tc/stem_tcgen05.cu",
     "tc/global_attn_tcgen05.cu",
+    "tc/residual_block_tcgen05.cu",
     "tc/window_stack_tcgen05.cu",
     "tc/window_stack192_tcgen05.cu",
 ]

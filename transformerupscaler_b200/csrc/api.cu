@@ -273,10 +273,14 @@ static int forward_impl(const TuModelWeights *w, const void *x, int in_dtype, vo
                                     overlap ? sync_words + 16 : nullptr, stack_flags ? sync_words + 16 + n_tok_tiles : nullptr, st);
         if (rc != TU_TC_UNSUPPORTED && rc != TU_OK) return rc;
         const bool stack_done = rc == TU_OK;
-        for (int i = 0; i < w->n_blocks && !stack_done; ++i)
-            if ((rc = transformer_block_ex(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws,
-                                           (tc && i == w->n_blocks - 1) ? tok16 : nullptr, st)))
-                return rc;
+        for (int i = 0; i < w->n_blocks && !stack_done; ++i) {
+            bf16 *x16 = (tc && i == w->n_blocks - 1) ? tok16 : nullptr;
+            rc = TU_TC_UNSUPPORTED;
+            if (tc && !window && w->stack_w) rc = resid_layer_fused(tok, w, i, Mtok, Ht * Wt, blk, bws, x16, st);      // two fused kernels + attention
+            if (rc == TU_TC_UNSUPPORTED)
+                rc = transformer_block_ex(tok, &w->blocks[i], Mtok, dim, heads, window ? 1 : 0, Ht * Wt, dt, blk, bws, x16, st);
+            if (rc) return rc;
+        }
         prof_end(st, "transformer_blocks");
         g_prof_name = "patch_unembed";
         prof_begin(st);
@@ -424,6 +428,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
     }
     if (key && !strcmp(key, "global_attn_tc")) {
         tc_set_global_attn(value);
+        return TU_OK;
+    }
+    if (key && !strcmp(key, "resid_fused")) {
+        tc_set_resid_fused(value);
         return TU_OK;
     }
     if (key && !strcmp(key, "frame_chunk")) {

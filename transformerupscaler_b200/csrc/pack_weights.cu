@@ -377,6 +377,41 @@ extern "C" int tu_pack_weights(int model, const TuNamedTensor *tensors, int n_te
         mw.stack_rel = P.st.put_f32(rels);
     }
 
+    // ---- ResidualTransformer (bf16, dim 128): the 24 slabs per layer of tc/residual_block_tcgen05.cu and 1792 parameters per layer
+    if (bf && resid && dim == 128 && P.err.empty()) {
+        std::vector<float> slabs, pars;
+        auto slab = [&](const float *w, int ld, int r0, int nrows, int k0) {
+            for (int r = 0; r < nrows; ++r)
+                for (int k = 0; k < 64; ++k) slabs.push_back(w[(size_t)(r0 + r) * ld + k0 + k]);
+        };
+        for (int i = 0; i < nb; ++i) {
+            const std::string p = bpre + std::to_string(i) + ".";
+            const float *qw = qw_s[i].data(), *qb = qb_s[i].data();
+            const float *pw = P.need(p + "attn.out_proj.weight", (size_t)dim * dim), *pb = P.need(p + "attn.out_proj.bias", dim);
+            const float *w1 = P.need(p + "mlp.0.weight", (size_t)4 * dim * dim), *b1 = P.need(p + "mlp.0.bias", (size_t)4 * dim);
+            const float *w2 = P.need(p + "mlp.2.weight", (size_t)4 * dim * dim), *b2 = P.need(p + "mlp.2.bias", dim);
+            const float *n1w = P.need(p + "norm1.weight", dim), *n1b = P.need(p + "norm1.bias", dim);
+            const float *n2w = P.need(p + "norm2.weight", dim), *n2b = P.need(p + "norm2.bias", dim);
+            for (int nc = 0; nc < 3; ++nc)
+                for (int ks = 0; ks < 2; ++ks) slab(qw, dim, nc * 128, 128, ks * 64);
+            for (int ks = 0; ks < 2; ++ks) slab(pw, dim, 0, 128, ks * 64);
+            for (int h = 0; h < 2; ++h) {
+                for (int nc = 0; nc < 2; ++nc)
+                    for (int ks = 0; ks < 2; ++ks) slab(w1, dim, h * 256 + nc * 128, 128, ks * 64);
+                for (int ks = 0; ks < 4; ++ks) slab(w2, 4 * dim, 0, 128, h * 256 + ks * 64);
+            }
+            pars.insert(pars.end(), dim, 0.f);
+            pars.insert(pars.end(), n1w, n1w + dim); pars.insert(pars.end(), n1b, n1b + dim);
+            pars.insert(pars.end(), qb, qb + 3 * dim);
+            pars.insert(pars.end(), pb, pb + dim);
+            pars.insert(pars.end(), n2w, n2w + dim); pars.insert(pars.end(), n2b, n2b + dim);
+            pars.insert(pars.end(), b1, b1 + 4 * dim);
+            for (int k = 0; k < dim; ++k) pars.push_back((float)((double)pb[k] + (double)b2[k]));
+        }
+        mw.stack_w = P.st.put_bf16(slabs.data(), slabs.size());
+        mw.stack_p = P.st.put_f32(pars);
+    }
+
     // ---- FastTransformer: sub-pixel branches, folded up1 stage, 3 -> 3 tail
     if (fast && P.err.empty()) {
         const float *w2c = P.need("up1_conv.conv.weight", 3 * 64 * 9);

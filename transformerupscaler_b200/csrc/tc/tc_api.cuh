@@ -120,6 +120,17 @@ void tc_set_global_attn(int on);
 // workspace of one transformer block including the scratch of the tcgen05 global attention (window == 0)
 size_t block_workspace_bytes_ex(int M, int dim, int dtype, int window, int S);
 
+// ResidualTransformer's block around the attention in two fused kernels (residual_block_tcgen05.cu): LN1 + in_proj -> qkv, and
+// out_proj + residual + LN2 + MLP + residual in place on the fp32 stream.  stack_w / stack_p as packed for TU_MODEL_RESIDUAL.
+int tc_resid_pre(const float *tok, bf16 *qkv, int M, int layer, int n_layers, const bf16 *stack_w, const float *stack_p, cudaStream_t st);
+int tc_resid_post(float *tok, bf16 *tok16, const bf16 *att, int M, int layer, int n_layers, const bf16 *stack_w, const float *stack_p,
+                  cudaStream_t st);
+void tc_set_resid_fused(int on);
+// one ResidualTransformer layer through the two fused kernels and the global attention (transformer_simt.cu); workspace as for
+// transformer_block_ex.  TU_TC_UNSUPPORTED when the fused kernels cannot run.
+int resid_layer_fused(float *x, const TuModelWeights *w, int layer, int M, int S, void *workspace, size_t workspace_bytes, bf16 *x_bf16_out,
+                      cudaStream_t st);
+
 // one pre-LN transformer block (transformer_simt.cu); x_bf16_out optionally receives a bf16 copy of the output stream
 int transformer_block_ex(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype,
                          void *workspace, size_t workspace_bytes, bf16 *x_bf16_out, cudaStream_t st);

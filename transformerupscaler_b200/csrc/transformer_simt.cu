@@ -524,6 +524,38 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
 template int transformer_block_impl<float>(float *, const TuBlockWeights *, int, int, int, int, int, void *, size_t, bool, bf16 *, cudaStream_t);
 template int transformer_block_impl<bf16>(float *, const TuBlockWeights *, int, int, int, int, int, void *, size_t, bool, bf16 *, cudaStream_t);
 
+// One ResidualTransformer layer: resid_pre (LN1 + in_proj) -> global attention -> resid_post (out_proj, LN2, MLP), bf16 tensor-core path.
+// Workspace layout as in transformer_block_impl: ln (unused here) | qkv in the 4 dim buffer (+ V^T in its last quarter) | att [| partials]
+int resid_layer_fused(float *x, const TuModelWeights *w, int layer, int M, int S, void *ws, size_t ws_bytes, bf16 *x_bf16_out,
+                      cudaStream_t st) {
+    const int dim = w->dim, heads = w->heads;
+    if (dim != 128 || !w->stack_w || !w->stack_p || !tc_enabled() || S <= 0 || M % S) return TU_TC_UNSUPPORTED;
+    const size_t base = block_ws(M, dim, TU_BF16);
+    if (ws_bytes < base) return TU_TC_UNSUPPORTED;
+    char *p = (char *)ws;
+    p += align_up((size_t)M * dim * sizeof(bf16), 256);
+    bf16 *big = (bf16 *)p;
+    p += align_up((size_t)M * 4 * dim * sizeof(bf16), 256);
+    bf16 *att = (bf16 *)p;
+    int rc = tc_resid_pre(x, big, M, layer, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, st);
+    if (rc) return rc;             // TU_TC_UNSUPPORTED before anything was launched, or an error
+    rc = TU_TC_UNSUPPORTED;
+    if (ws_bytes > base)
+        rc = tc_global_attention(big, att, big + (size_t)M * 3 * dim, (float *)((char *)ws + base), ws_bytes - base, M / S, S, heads, st);
+    if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
+    if (rc == TU_TC_UNSUPPORTED) {
+        dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
+        global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>(big, att, S, dim);
+        TU_CHECK_LAUNCH("global_attn_mma");
+    }
+    rc = tc_resid_post(x, x_bf16_out, att, M, layer, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, st);
+    if (rc == TU_TC_UNSUPPORTED) {
+        set_error("tu: resid_post unavailable after resid_pre ran");
+        return TU_ERR_ARG;
+    }
+    return rc;
+}
+
 static int block_check(float *x, const TuBlockWeights *w, int M, int dim, int heads, int window, int S, int dtype, void *workspace,
                        size_t workspace_bytes) {
     TU_CHECK_ARG(x && w && workspace && M > 0, "transformer_block: bad argument");

@@ -183,6 +183,8 @@ class PackedWeights:
             self._pack_fused_stack(sd, mw, nb, dim, bprefix, dev, ptr)
         if dtype == torch.bfloat16 and not resid and dim == 192:
             self._pack_fused_stack192(sd, mw, nb, bprefix, dev, ptr)
+        if dtype == torch.bfloat16 and resid and dim == 128:
+            self._pack_resid_stack(sd, mw, nb, dim, bprefix, dev, ptr)
 
         if fast:
             for slot, s in enumerate(SCALES):
@@ -273,6 +275,30 @@ class PackedWeights:
         mw.stack_w = ptr(dev(flat, torch.bfloat16))
         mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
         mw.stack_rel = ptr(dev(torch.stack(rels), f32))
+
+    def _pack_resid_stack(self, sd, mw, nb, dim, bprefix, dev, ptr):
+        """ResidualTransformer, tc/residual_block_tcgen05.cu: per layer the same 24 slabs as the window stack (in_proj 3 n-chunks x 2
+        k-slabs with the q rows pre-scaled, out_proj 2, then per hidden half fc1 rows (2 x 2) and fc2 columns (4)) and 1792 parameters:
+        c0 = 0 | ln1 w,b | in_proj bias | c1 = out_proj bias | ln2 w,b | fc1 bias | c_final = out_proj bias + fc2 bias.  Every layer
+        stores the true residual stream, so the offsets do not run across layers."""
+        slabs, pars = [], []
+        for i in range(nb):
+            p = f"{bprefix}{i}."
+            qw, qb = sd[p + "attn.in_proj_weight"].float().cpu().clone(), sd[p + "attn.in_proj_bias"].float().cpu().clone()
+            qw[:dim] *= 0.25
+            qb[:dim] *= 0.25
+            pw, pb = sd[p + "attn.out_proj.weight"].float().cpu(), sd[p + "attn.out_proj.bias"].float().cpu()
+            w1, b1 = sd[p + "mlp.0.weight"].float().cpu(), sd[p + "mlp.0.bias"].float().cpu()
+            w2, b2 = sd[p + "mlp.2.weight"].float().cpu(), sd[p + "mlp.2.bias"].float().cpu()
+            slabs += self._slabs(qw, 3, 2) + self._slabs(pw, 1, 2)
+            for h in range(2):
+                slabs += self._slabs(w1[h * 256:(h + 1) * 256], 2, 2) + self._slabs(w2[:, h * 256:(h + 1) * 256], 1, 4)
+            pars += [torch.zeros(dim), sd[p + "norm1.weight"].float().cpu(), sd[p + "norm1.bias"].float().cpu(), qb,
+                     pb, sd[p + "norm2.weight"].float().cpu(), sd[p + "norm2.bias"].float().cpu(), b1,
+                     (pb.double() + b2.double()).float()]
+        assert len(slabs) == 24 * nb
+        mw.stack_w = ptr(dev(torch.stack(slabs).reshape(-1, 64), torch.bfloat16))
+        mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), torch.float32))
 
     @staticmethod
     def _slabs(w: torch.Tensor, n_chunks: int, k_slabs: int):
