@@ -129,7 +129,8 @@ typedef struct TuModelWeights {
     /* (c0 = 0 | ln1 w,b | in_proj bias | c1 = out_proj bias | ln2 w,b | fc1 bias | c_final = out_proj bias + fc2 bias), stack_rel NULL   */
     const void *stack_w;        /* bf16 (n_blocks*24*128, 64): weight slabs [128 n][64 k] in consumption order   */
     const float *stack_p;       /* fp32 n_blocks*1664 + 128: per block c0|ln1w|ln1b|qkvb|c1|ln2w|ln2b|fc1b, then c_final */
-    const float *stack_rel;     /* fp32 (n_blocks, heads, 64, 64) dense relative-position bias            */
+    const float *stack_rel;     /* fp32 (n_blocks, heads, 4096) relative-position bias in mma C-fragment order: */
+                                /* [rg 4][n 8][lane 32][half 2][e 2] = bias[rg*16+half*8+lane/4][n*8+(lane%4)*2+e] */
     const void *unembed_w;      /* T (4096, dim): row n = (ky*8+kx)*64 + co                       */
     const float *unembed_b;     /* (64)                                                           */
     const void *dec1_w;         /* T (9,64,64)                                                    */

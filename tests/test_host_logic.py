@@ -43,11 +43,11 @@ def test_fast_forward_shape_logic(monkeypatch):
     from transformerupscaler_b200 import engine
     calls = []
 
-    def fake_forward(x, handle, oh, ow, scale, cbf, obf, clamp):
+    def fake_forward(x, handle, oh, ow, scale, cbf, obf, clamp, in_layout=0):
         calls.append(("fwd", oh, ow, scale, clamp))
         return torch.zeros(x.shape[0], 3, oh, ow)
 
-    def fake_resize(x, oh, ow, clamp):
+    def fake_resize(x, oh, ow, clamp, out_code=-1):
         calls.append(("resize", oh, ow, clamp))
         return torch.zeros(x.shape[0], 3, oh, ow)
 
@@ -198,3 +198,15 @@ def test_stack_split_enumeration(tmp_path):
     subprocess.run([gxx, "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "host", "stack_split_check.cpp")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def test_frag_rel_bias_is_the_mma_fragment_order():
+    """packing.frag_rel_bias: [h][rg][n][lane][half][e] = dense[h][rg*16 + half*8 + lane//4][n*8 + (lane%4)*2 + e]
+    (what window_stack{,192}_tcgen05.cu fetch with one 16-byte load per lane; pack_weights.cu::frag_rel is the same loop)."""
+    from transformerupscaler_b200.packing import frag_rel_bias
+    g = torch.Generator().manual_seed(5)
+    dense = torch.randn(3, 64, 64, generator=g)
+    f = frag_rel_bias(dense).reshape(3, 4, 8, 32, 2, 2)
+    for h, rg, n, lane, half, e in [(0, 0, 0, 0, 0, 0), (2, 3, 7, 31, 1, 1), (1, 2, 5, 13, 0, 1), (1, 1, 3, 22, 1, 0)]:
+        assert f[h, rg, n, lane, half, e] == dense[h, rg * 16 + half * 8 + lane // 4, n * 8 + (lane % 4) * 2 + e]
+    assert torch.equal(torch.sort(f.reshape(3, -1), dim=1).values, torch.sort(dense.reshape(3, -1), dim=1).values)

@@ -138,6 +138,21 @@ struct Packer {
             }
         return o;
     }
+    // the same values in the mma.sync C-fragment order the fused stack kernels fetch (packing.py::frag_rel_bias):
+    // [head][rg][n][lane = g*4 + tq][half][e] <- dense[head][rg*16 + half*8 + g][n*8 + tq*2 + e]
+    static std::vector<float> frag_rel(const std::vector<float> &dense, int heads) {
+        std::vector<float> o(dense.size());
+        size_t k = 0;
+        for (int h = 0; h < heads; ++h)
+            for (int rg = 0; rg < 4; ++rg)
+                for (int n = 0; n < 8; ++n)
+                    for (int g = 0; g < 8; ++g)
+                        for (int tq = 0; tq < 4; ++tq)
+                            for (int half = 0; half < 2; ++half)
+                                for (int e = 0; e < 2; ++e)
+                                    o[k++] = dense[((size_t)h * 64 + rg * 16 + half * 8 + g) * 64 + n * 8 + tq * 2 + e];
+        return o;
+    }
 };
 
 // folded last up1 stage + up1_conv (packing.py::fold_up1), fp64.  Wf[vy][vx][(c r + i) r + j][ci][dy][dx], bf[vy][vx][o]
@@ -369,7 +384,7 @@ extern "C" int tu_pack_weights(int model, const TuNamedTensor *tensors, int n_te
             for (int k = 0; k < dim; ++k) pars.push_back((float)c1[k]);
             pars.insert(pars.end(), n2w, n2w + dim); pars.insert(pars.end(), n2b, n2b + dim);
             pars.insert(pars.end(), b1, b1 + 4 * dim);
-            rels.insert(rels.end(), rel_s[i].begin(), rel_s[i].end());
+            { const std::vector<float> fr = Packer::frag_rel(rel_s[i], heads); rels.insert(rels.end(), fr.begin(), fr.end()); }
         }
         for (int k = 0; k < dim; ++k) pars.push_back((float)c[k]);
         mw.stack_w = P.st.put_bf16(slabs.data(), slabs.size());

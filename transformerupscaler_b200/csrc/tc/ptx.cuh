@@ -213,6 +213,12 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 ld2(const float *p) { return *reinterpret_cast<const f32x2 *>(p); }     // 8-byte aligned pair
+// two pairs with one 16-byte load (a broadcast parameter read costs a shared-memory wavefront whatever its width)
+__device__ __forceinline__ void ld4(const float *p, f32x2 &a, f32x2 &b) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    a = v.x;
+    b = v.y;
+}
 
 // ---- UMMA descriptors ----------------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major operand stored as rows of 128 bytes (64 bf16) with the

@@ -55,11 +55,13 @@ struct Stack192Params {
     float *tok;            // (M, 192) fp32 token stream, window-ordered; updated in place
     bf16 *tok16;           // optional bf16 copy of the result
     const float *par;      // nblocks * PAR_FLOATS + 192 (final offset vector)
-    const float *rel_bias; // nblocks x (12, 64, 64) fp32 dense relative-position bias
+    const float *rel_bias; // nblocks x (12, 4096) fp32 relative-position bias in mma C-fragment order (packing.py::frag_rel_bias)
     int n_tiles, n_blocks;
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
     int *seg_flags;        // optional: block-level work split (stack_split.cuh); seg_flags[t] = 1 once the first part of tile t is stored
     int units_per_cta;
+    unsigned long long *trace;      // debug (tu_debug_trace)
+    unsigned int trace_cap;
 };
 
 struct Barriers {
@@ -152,7 +154,7 @@ __device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[24], const float *ga
     ptx::up2(s2, s_lo, s_hi);
     ptx::up2(q2, q_lo, q_hi);
     stat[i * 4 + part] = make_float2(s_lo + s_hi, q_lo + q_hi);
-    math_barrier();
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + (i >> 5)) : "memory");      // only the four warps holding this row's quarters
     const float4 p01 = *reinterpret_cast<const float4 *>(stat + i * 4), p23 = *reinterpret_cast<const float4 *>(stat + i * 4 + 2);
     const float mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.0f / DIM);
     const float ex2 = ((p01.y + p01.w) + (p23.y + p23.w)) * (1.0f / DIM);
@@ -161,9 +163,12 @@ __device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[24], const float *ga
 #pragma unroll
     for (int ch = 0; ch < 6; ++ch) {
         uint32_t w[4];
+        f32x2 gm[4], bt[4];
+        ptx::ld4(gam + ch * 8, gm[0], gm[1]); ptx::ld4(gam + ch * 8 + 4, gm[2], gm[3]);
+        ptx::ld4(bet + ch * 8, bt[0], bt[1]); ptx::ld4(bet + ch * 8 + 4, bt[2], bt[3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e)      // ((x - mean) * rstd) * gamma + beta, two columns per instruction
-            w[e] = pk_pair(ptx::fma2(ptx::mul2(ptx::add2(x[ch * 4 + e], nmean), rs), ptx::ld2(gam + ch * 8 + 2 * e), ptx::ld2(bet + ch * 8 + 2 * e)));
+            w[e] = pk_pair(ptx::fma2(ptx::mul2(ptx::add2(x[ch * 4 + e], nmean), rs), gm[e], bt[e]));
         uint4 u;
         u.x = w[0]; u.y = w[1]; u.z = w[2]; u.w = w[3];
         *reinterpret_cast<uint4 *>(a32 + slab_chunk_off(part * 48 + ch * 8, i)) = u;
@@ -299,7 +304,12 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             uint32_t v[48];
             tmem_ld48(TX + lane_base + part * 48, v);
 #pragma unroll
-            for (int j = 0; j < 24; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 48 + 2 * j));
+            for (int j = 0; j < 24; j += 2) {
+                f32x2 c0v, c1v;
+                ptx::ld4(cvec + part * 48 + 2 * j, c0v, c1v);
+                x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), c0v);
+                x[j + 1] = ptx::add2(ptx::pk2u(v[2 * j + 2], v[2 * j + 3]), c1v);
+            }
         };
 
         Seg sg;
@@ -328,16 +338,23 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
             }
+            // per-block parameters -> smem: the first block's here, the next block's while the last fc2 of a block runs
+            auto load_params = [&](int bk) {
+                math_barrier();       // everyone is done with the previous parameters
+                const float4 *g4 = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
+                float4 *d = reinterpret_cast<float4 *>(par);
+                for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g4[e];
+            };
+            int tr_b = 0;
+            auto phase_ev = [&](int ph) {      // debug (tu_debug_trace): phase boundaries of warp 0
+                if (p.trace && mt == 0) trace_event(p.trace, p.trace_cap, 10, (unsigned)(t * 256 + tr_b * 16 + ph));
+            };
+            load_params(sg.lo);
             for (int bk = sg.lo; bk < sg.hi; ++bk) {
-                // ---- per-block parameters -> smem
-                math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
+                math_barrier();       // parameters (and the X stores of a new tile) are visible
                 ptx::tc_fence_after();
-                {
-                    const float4 *g4 = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
-                    float4 *d = reinterpret_cast<float4 *>(par);
-                    for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g4[e];
-                }
-                math_barrier();
+                tr_b = bk;
+                phase_ev(0);
                 // ---- LN1(x + c0) -> A32
                 {
                     f32x2 x[24];
@@ -345,24 +362,28 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     layernorm_to_a32(x, par + P_LN1W + part * 48, par + P_LN1B + part * 48, stat, a32, i, part);
                 }
                 signal_a();
+                phase_ev(1);
                 // ---- six groups of two heads: qkv epilogue of group g, then its attention while the MMAs of g+1 run
-                const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
+                const ulonglong2 *relb = reinterpret_cast<const ulonglong2 *>(p.rel_bias) + (long)bk * HEADS * 1024;
                 // relative-position bias of this thread's 2 rows x 16 columns of head (2g + hl): fetched one group ahead of its
-                // use (the 17 KB of L1 left beside the shared memory cannot hold it, so every fetch is an L2 round trip)
+                // use (the 17 KB of L1 left beside the shared memory cannot hold it, so every fetch is an L2 round trip); stored in
+                // mma C-fragment order (packing.py::frag_rel_bias): one coalesced 16-byte load per lane and key octet
                 f32x2 ba[8], bb2[8];
                 auto load_bias = [&](int g) {
-                    const int gq = lane >> 2, tq = lane & 3, hl = (warp >> 2) & 1, rg = warp & 3;
-                    const float *bp0 = relb + ((long)(g * 2 + hl) * 64 + rg * 16 + gq) * 64 + tq * 2, *bp1 = bp0 + 8 * 64;
+                    const int hl = (warp >> 2) & 1, rg = warp & 3;
+                    const ulonglong2 *bp = relb + ((g * 2 + hl) * 4 + rg) * 256 + lane;
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
-                        ba[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp0 + n * 8));
-                        bb2[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp1 + n * 8));
+                        const ulonglong2 v = __ldg(bp + n * 32);
+                        ba[n] = v.x;
+                        bb2[n] = v.y;
                     }
                 };
                 load_bias(0);
 #pragma unroll 1
                 for (int g = 0; g < NGROUP; ++g) {
                     wait_acc(ACC_QKV0 + g);
+                    if (g == 0) phase_ev(2);
                     if (g > 0) math_barrier();            // every warp is done reading the previous group's q, k, v
                     if (part < 3) {                       // 96 columns: q | k | v of the group, 32 columns per part
                         uint32_t v[32];
@@ -373,10 +394,12 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 u;
-                            u.x = pk_pair(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(bb + j + 0)));
-                            u.y = pk_pair(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(bb + j + 2)));
-                            u.z = pk_pair(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(bb + j + 4)));
-                            u.w = pk_pair(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(bb + j + 6)));
+                            f32x2 b0v, b1v, b2v, b3v;
+                            ptx::ld4(bb + j, b0v, b1v); ptx::ld4(bb + j + 4, b2v, b3v);
+                            u.x = pk_pair(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v));
+                            u.y = pk_pair(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v));
+                            u.z = pk_pair(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v));
+                            u.w = pk_pair(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v));
                             *reinterpret_cast<uint4 *>(rowp + j * 2) = u;
                         }
                     }
@@ -462,33 +485,42 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     }
                 }
                 signal_a();                               // attention output of all 12 heads is in AO
+                phase_ev(3);
                 // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
                 wait_acc(ACC_PROJ);
+                phase_ev(4);
                 {
                     f32x2 x[24];
                     load_x(x, par + P_C1);
                     layernorm_to_a32(x, par + P_LN2W + part * 48, par + P_LN2B + part * 48, stat + 128 * 4, a32, i, part);
                 }
                 signal_a();
+                phase_ev(5);
                 // ---- MLP: four quarters of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs (AO region)
 #pragma unroll 1
                 for (int q4 = 0; q4 < NPASS; ++q4) {
                     wait_acc(ACC_FC1_0 + q4);
+                    if (q4 == 0) phase_ev(6);
                     uint32_t v[48];
                     tmem_ld48(TACC + lane_base + part * 48, v);
                     const float *bb = par + P_FC1B + q4 * 192 + part * 48;
 #pragma unroll
                     for (int j = 0; j < 48; j += 8) {
                         uint4 u;
-                        u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(bb + j + 0))));
-                        u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(bb + j + 2))));
-                        u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(bb + j + 4))));
-                        u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(bb + j + 6))));
+                        f32x2 b0v, b1v, b2v, b3v;
+                        ptx::ld4(bb + j, b0v, b1v); ptx::ld4(bb + j + 4, b2v, b3v);
+                        u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v)));
+                        u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
+                        u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
+                        u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
                         *reinterpret_cast<uint4 *>(aout + slab_chunk_off(part * 48 + j, i)) = u;
                     }
                     signal_a();
+                    phase_ev(7 + q4);
                 }
+                if (bk + 1 < sg.hi) load_params(bk + 1);
                 wait_acc(ACC_FC2L);      // fc2 of the last quarter accumulated: X holds the block output (minus folded biases)
+                phase_ev(11);
                 cph ^= 1;
             }
             if (sg.hi < p.n_blocks) {
@@ -545,7 +577,7 @@ PerDeviceFlag g_attr_set;
 }  // namespace
 
 // stack_w: bf16 (n_blocks * 6912, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*2496 + 192;
-// rel_bias: fp32 n_blocks x (12,64,64).  tok: (M,192) fp32 with M % 128 == 0.
+// rel_bias: fp32 n_blocks x (12,4096) in fragment order.  tok: (M,192) fp32 with M % 128 == 0.
 int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                        const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
@@ -572,6 +604,7 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     }
     Stack192Params p;
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
+    p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     p.seg_flags = (seg_flags && tc_stack_split_enabled() && p.n_tiles % grid != 0) ? seg_flags : nullptr;

@@ -50,9 +50,10 @@ struct StackParams {
     float *tok;            // (M, 128) fp32 token stream, window-ordered; updated in place
     bf16 *tok16;           // optional bf16 copy of the result
     const float *par;      // nblocks * PAR_FLOATS + 128 (final offset vector)
-    const float *rel_bias; // nblocks x (8, 64, 64) fp32 dense relative-position bias
+    const float *rel_bias; // nblocks x (8, 4096) fp32 relative-position bias in mma C-fragment order (packing.py::frag_rel_bias)
     int n_tiles, n_blocks;
     int rev;               // token tiles are walked last to first (debug key "snake", bit 2)
+    int var;               // debug variants (tu_debug_set("stack_var", mask))
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
     // Block-level work split (seg_flags != nullptr, zeroed by the caller): the n_tiles * n_blocks (tile, block) units are dealt out in
     // equal contiguous shares, so a CTA may take a tile through its first blocks only and hand the residual stream (raw TMEM X, fp32,
@@ -65,13 +66,18 @@ struct StackParams {
 };
 
 
-// commit points of one block, in issue order: qkv column thirds, proj, fc1 (first half) column halves, fc1 (second half)
-// column halves, fc2 (second half).  A part's epilogue starts while the MMAs of the next part are still running.
-enum { ACC_QKV0 = 0, ACC_QKV1, ACC_QKV2, ACC_PROJ, ACC_FC1A0, ACC_FC1A1, ACC_FC1B0, ACC_FC1B1, ACC_FC2B, NACC };
+// commit points of one block, in issue order: qkv column thirds, proj, then the MLP in four 128-column chunks of the hidden layer
+// through a ring of three ACC slots and two HID buffers: fc1 chunks 0-2, {fc2 chunk 0 + fc1 chunk 3}, fc2 chunk 1, fc2 chunks 2-3.
+// A part's epilogue starts while the MMAs of the next part are still running.
+enum { ACC_QKV0 = 0, ACC_QKV1, ACC_QKV2, ACC_PROJ, ACC_FC1_0, ACC_FC1_1, ACC_FC1_2, ACC_FC1_3, ACC_FC2_1, ACC_FC2_3, NACC };
 
 struct Barriers {
     uint64_t full[NRING], empty[NRING];
     uint64_t a_ready;
+    uint64_t a_half;             // math -> MMA: attention output of heads 0-3 stored (its own barrier: no MMA result is awaited between
+                                 // this arrival and the next one on a_ready, so a fast warp could otherwise arrive twice in one phase)
+    uint64_t g_ready[2];         // math -> MMA: GELU(chunk c) stored in HID buffer c & 1 (alternating: consecutive chunks have no MMA
+                                 // result between their arrivals)
     uint64_t acc[NACC];          // MMA -> math, one barrier per commit point of a block (each completes once per block)
     uint32_t tmem_base;
 };
@@ -146,7 +152,7 @@ __device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[16], const float *ga
     ptx::up2(s2, s_lo, s_hi);
     ptx::up2(q2, q_lo, q_hi);
     stat[i * 4 + part] = make_float2(s_lo + s_hi, q_lo + q_hi);
-    math_barrier();
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + (i >> 5)) : "memory");      // only the four warps holding this row's quarters
     const float4 p01 = *reinterpret_cast<const float4 *>(stat + i * 4), p23 = *reinterpret_cast<const float4 *>(stat + i * 4 + 2);
     const float mean = ((p01.x + p01.z) + (p23.x + p23.z)) * (1.0f / DIM);
     const float ex2 = ((p01.y + p01.w) + (p23.y + p23.w)) * (1.0f / DIM);
@@ -156,9 +162,12 @@ __device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[16], const float *ga
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         uint32_t w[4];
+        f32x2 gm[4], bt[4];
+        ptx::ld4(gam + ch * 8, gm[0], gm[1]); ptx::ld4(gam + ch * 8 + 4, gm[2], gm[3]);
+        ptx::ld4(bet + ch * 8, bt[0], bt[1]); ptx::ld4(bet + ch * 8 + 4, bt[2], bt[3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e)      // ((x - mean) * rstd) * gamma + beta, two columns per instruction
-            w[e] = pk_pair(ptx::fma2(ptx::mul2(ptx::add2(x[ch * 4 + e], nmean), rs), ptx::ld2(gam + ch * 8 + 2 * e), ptx::ld2(bet + ch * 8 + 2 * e)));
+            w[e] = pk_pair(ptx::fma2(ptx::mul2(ptx::add2(x[ch * 4 + e], nmean), rs), gm[e], bt[e]));
         uint4 u;
         u.x = w[0]; u.y = w[1]; u.z = w[2]; u.w = w[3];
         *reinterpret_cast<uint4 *>(rowp + ((((part & 1) * 4 + ch) ^ (i & 7)) << 4)) = u;
@@ -182,6 +191,9 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
         }
         ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH);
+        ptx::mbar_init(ptx::smem_u32(&bars->a_half), NMATH);
+        ptx::mbar_init(ptx::smem_u32(&bars->g_ready[0]), NMATH);
+        ptx::mbar_init(ptx::smem_u32(&bars->g_ready[1]), NMATH);
         for (int i = 0; i < NACC; ++i) ptx::mbar_init(ptx::smem_u32(&bars->acc[i]), 1);
         ptx::fence_barrier_init();
     }
@@ -205,10 +217,15 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             Seg sg;
             for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
                 for (int s = sg.lo * SLABS_PER_BLOCK; s < sg.hi * SLABS_PER_BLOCK; ++s) {
+                    // packed order of the MLP slab pairs (packing.py): fc1 c0, fc1 c1, fc2 c0, fc2 c1, fc1 c2, fc1 c3, fc2 c2, fc2 c3;
+                    // consumed as fc1 c0, fc1 c1, fc1 c2, fc2 c0, fc1 c3, fc2 c1, fc2 c2, fc2 c3
+                    const int sb = s % SLABS_PER_BLOCK;
+                    int src = s;
+                    if (sb >= 8) src = s - sb + 8 + ((0x76352410u >> (((sb - 8) >> 1) * 4)) & 7) * 2 + (sb & 1);
                     ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                     const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
                     ptx::mbar_expect_tx(fb, SLAB);
-                    ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB, &tmap_w, fb, 0, s * 128);
+                    ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB, &tmap_w, fb, 0, src * 128);
                     if (++stage == NRING) { stage = 0; phase ^= 1; }
                 }
         }
@@ -218,7 +235,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
         const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
         const uint32_t ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
         int stage = 0;
-        uint32_t phase = 0, aph = 0;
+        uint32_t phase = 0, aph = 0, hph = 0, gph = 0;
         // one weight slab: D[128 x 128] (+)= A_slab[128 x 64] * W_slab[128 x 64]^T
         auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, bool first_clears) {
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
@@ -245,23 +262,30 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);
                     ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_QKV0 + nc]), leader);
                 }
-                wait_a();                                       // attention output in A32
-                for (int ks = 0; ks < 2; ++ks) slab_mma(TX, a32 + ks * SL, false);            // x += att Wp^T
+                ptx::mbar_wait(ptx::smem_u32(&bars->a_half), hph);      // attention output of heads 0-3 in A32 K-slab 0
+                hph ^= 1;
+                ptx::tc_fence_after();
+                slab_mma(TX, a32, false);                       // x += att Wp^T, first K half
+                wait_a();                                       // heads 4-7 in K-slab 1
+                slab_mma(TX, a32 + SL, false);
                 ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_PROJ]), leader);
                 wait_a();                                       // LN2 output in A32
-                for (int nc = 0; nc < 2; ++nc) {
-                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 0
-                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1A0 + nc]), leader);
+                for (int c = 0; c < 3; ++c) {                   // fc1 chunks 0-2 into the three ACC slots
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + c * 128, a32 + ks * SL, ks == 0);
+                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1_0 + c]), leader);
                 }
-                wait_a();                                       // GELU(half 0) in HID, ACC drained
-                for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);            // x += h0 W2[:, h0]^T
-                for (int nc = 0; nc < 2; ++nc) {
-                    for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + nc * 128, a32 + ks * SL, ks == 0);   // fc1, half 1
-                    ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1B0 + nc]), leader);
+                for (int c = 0; c < 4; ++c) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->g_ready[c & 1]), (gph >> (c & 1)) & 1);       // GELU(chunk c) in HID buffer c & 1
+                    gph ^= 1u << (c & 1);
+                    ptx::tc_fence_after();
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, hid + ((c & 1) * 2 + ks) * SL, false);     // x += h_c W2[:, chunk c]^T
+                    if (c == 0) {                               // ACC slot 0 is drained: fc1 chunk 3
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC, a32 + ks * SL, ks == 0);
+                        ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1_3]), leader);      // also: HID buffer 0 is free again
+                    }
+                    if (c == 1) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2_1]), leader);      // HID buffer 1 is free again
+                    if (c == 3) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2_3]), leader);
                 }
-                wait_a();                                       // GELU(half 1) in HID
-                for (int ks = 0; ks < 4; ++ks) slab_mma(TX, hid + ks * SL, false);
-                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2B]), leader);
             }
     } else {
         // ================================ math warps ================================
@@ -287,12 +311,22 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             ptx::tmem_ld_x32(TX + lane_base + part * 32, v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), ptx::ld2(cvec + part * 32 + 2 * j));
+            for (int j = 0; j < 16; j += 2) {
+                f32x2 c0v, c1v;
+                ptx::ld4(cvec + part * 32 + 2 * j, c0v, c1v);
+                x[j] = ptx::add2(ptx::pk2u(v[2 * j], v[2 * j + 1]), c0v);
+                x[j + 1] = ptx::add2(ptx::pk2u(v[2 * j + 2], v[2 * j + 3]), c1v);
+            }
         };
 
         Seg sg;
+        int tr_t = 0, tr_b = 0;
+        auto phase_ev = [&](int ph) {      // debug (tu_debug_trace): phase boundaries of warps 0 and 15
+            if (p.trace && (mt == 0 || mt == 480)) trace_event(p.trace, p.trace_cap, mt == 0 ? 10 : 11, (unsigned)(tr_t * 256 + tr_b * 16 + ph));
+        };
         for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k) {
             const int t = p.rev ? p.n_tiles - 1 - sg.tile : sg.tile;
+            tr_t = t;
             if (sg.lo > 0) {          // the CTA that ran blocks [0, lo) of this tile has stored and fenced the raw residual stream
                 if (mt == 0) wait_flag_acquire(p.seg_flags + t);
                 math_barrier();
@@ -311,16 +345,37 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
             }
+            // per-block parameters -> smem: the first block's here, the next block's while the last fc2 of a block runs
+            auto load_params = [&](int bk) {
+                math_barrier();       // everyone is done with the previous parameters
+                const float4 *g = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
+                float4 *d = reinterpret_cast<float4 *>(par);
+                for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g[e];
+            };
+            load_params(sg.lo);
             for (int bk = sg.lo; bk < sg.hi; ++bk) {
-                // ---- per-block parameters -> smem
-                math_barrier();       // everyone is done with the previous block's parameters (and X stores are visible)
+                math_barrier();       // parameters (and the X stores of a new tile) are visible
                 ptx::tc_fence_after();
-                {
-                    const float4 *g = reinterpret_cast<const float4 *>(p.par + (long)bk * PAR_FLOATS);
-                    float4 *d = reinterpret_cast<float4 *>(par);
-                    for (int e = mt; e < PAR_FLOATS / 4; e += NMATH * 32) d[e] = g[e];
-                }
-                math_barrier();
+                tr_b = bk;
+                phase_ev(0);
+                // relative-position bias of this thread's 2 rows x 16 columns: a warp's four attention tasks are (head hw, window 0),
+                // (hw, window 1), (hw + 4, window 0), (hw + 4, window 1) with the same 16-row group, so two fetches serve four tasks;
+                // the first is issued here, before LayerNorm (64 KB per SM: half a microsecond of the SM's L2 read path, which
+                // delays everything else that returns through it -- issued next to the qkv MMAs it held up their completion wait), the second right after the first's last use
+                // (fragment order, packing.py::frag_rel_bias: one coalesced 16-byte load per lane and key octet -- the dense layout cost
+                // sixteen 8-byte loads per lane, each warp instruction touching eight cache lines: ~1.3 us per block of L1 tag lookups)
+                const ulonglong2 *relb = reinterpret_cast<const ulonglong2 *>(p.rel_bias) + (long)bk * HEADS * 1024;
+                f32x2 ba[8], bb[8];
+                auto load_bias = [&](int h) {
+                    const ulonglong2 *bp = relb + (h * 4 + (warp & 3)) * 256 + lane;
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        const ulonglong2 v = __ldg(bp + n * 32);
+                        ba[n] = v.x;
+                        bb[n] = v.y;
+                    }
+                };
+                if (!(p.var & 1)) load_bias(warp >> 2);
                 // ---- LN1(x + c0) -> A32
                 {
                     f32x2 x[16];
@@ -328,26 +383,14 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     layernorm_to_a32(x, par + P_LN1W + part * 32, par + P_LN1B + part * 32, stat, a32, i, part);
                 }
                 signal_a();
-                // relative-position bias of this thread's 2 rows x 16 columns: a warp's four attention tasks are (head hw, window 0),
-                // (hw, window 1), (hw + 4, window 0), (hw + 4, window 1) with the same 16-row group, so two fetches serve four tasks;
-                // the first is issued here and flies during the qkv epilogue, the second right after the first's last use
-                const float *relb = p.rel_bias + (long)bk * HEADS * 4096;
-                f32x2 ba[8], bb[8];
-                auto load_bias = [&](int h) {
-                    const float *bp0 = relb + ((long)h * 64 + (warp & 3) * 16 + (lane >> 2)) * 64 + (lane & 3) * 2, *bp1 = bp0 + 8 * 64;
-#pragma unroll
-                    for (int n = 0; n < 8; ++n) {
-                        ba[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp0 + n * 8));
-                        bb[n] = __ldg(reinterpret_cast<const unsigned long long *>(bp1 + n * 8));
-                    }
-                };
-                load_bias(warp >> 2);
+                phase_ev(1);
                 // ---- qkv epilogue: ACC -> (+bias) -> bf16 staging rows, one column third at a time as its MMAs retire
                 {
                     uint8_t *rowp = stg + i * STG_PITCH;
 #pragma unroll
                     for (int nc = 0; nc < 3; ++nc) {
                         wait_acc(ACC_QKV0 + nc);
+                        if (nc == 0) { phase_ev(2); if (p.var & 1) load_bias(warp >> 2); }
                         uint32_t v[32];
                         const int col = nc * 128 + part * 32;
                         ptx::tmem_ld_x32(TACC + lane_base + col, v);
@@ -356,15 +399,18 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             uint4 u;
-                            u.x = pk_pair(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(qb + j + 0)));
-                            u.y = pk_pair(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(qb + j + 2)));
-                            u.z = pk_pair(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(qb + j + 4)));
-                            u.w = pk_pair(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(qb + j + 6)));
+                            f32x2 b0v, b1v, b2v, b3v;
+                            ptx::ld4(qb + j, b0v, b1v); ptx::ld4(qb + j + 4, b2v, b3v);
+                            u.x = pk_pair(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v));
+                            u.y = pk_pair(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v));
+                            u.z = pk_pair(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v));
+                            u.w = pk_pair(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v));
                             *reinterpret_cast<uint4 *>(rowp + (col + j) * 2) = u;
                         }
                     }
                 }
                 math_barrier();
+                phase_ev(3);
                 // ---- window attention: 2 windows x 8 heads x 4 row groups = 64 warp tasks, 4 per warp
                 {
                     const int g = lane >> 2, tq = lane & 3;
@@ -398,6 +444,12 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
                         if (tk == 1) load_bias((warp >> 2) + 4);       // the second head's bias flies during this task's softmax and PV
+                        if (tk == 2) {                                 // heads 0-3 of both windows are in A32 K-slab 0: proj starts on it
+                            ptx::fence_proxy_async();
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_half));
+                        }
                         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
                         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
                         float l0 = 0.f, l1 = 0.f;
@@ -446,40 +498,50 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     }
                 }
                 signal_a();
+                phase_ev(4);
                 // ---- LN2(x + c1) -> A32 (after proj has been accumulated onto X)
                 wait_acc(ACC_PROJ);
+                phase_ev(5);
                 {
                     f32x2 x[16];
                     load_x(x, par + P_C1);
                     layernorm_to_a32(x, par + P_LN2W + part * 32, par + P_LN2B + part * 32, stat + 128 * 4, a32, i, part);
                 }
                 signal_a();
-                // ---- MLP: two halves of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs
+                phase_ev(6);
+                // ---- MLP: four 128-column chunks of the hidden layer: ACC slot c % 3 -> +bias -> GELU -> bf16 HID buffer c & 1
 #pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+                for (int c = 0; c < 4; ++c) {
+                    wait_acc(ACC_FC1_0 + c);
+                    if (c == 0) phase_ev(7);
+                    if (c == 2) wait_acc(ACC_FC1_3);      // fc2 of chunk 0 has read HID buffer 0
+                    if (c == 3) wait_acc(ACC_FC2_1);      // fc2 of chunk 1 has read HID buffer 1
+                    uint8_t *rowp = stg + ((c & 1) * 2 + (part >> 1)) * SLAB + i * 128;      // K-slab of the buffer = chunk column / 64
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(TACC + lane_base + (c == 3 ? 0 : c) * 128 + part * 32, v);
+                    ptx::tmem_ld_wait();
+                    const float *bb = par + P_FC1B + c * 128 + part * 32;
 #pragma unroll
-                    for (int nc = 0; nc < 2; ++nc) {
-                        wait_acc((half ? ACC_FC1B0 : ACC_FC1A0) + nc);
-                        const int col = nc * 128 + part * 32;                       // column of this 256-wide half
-                        uint8_t *rowp = stg + (col >> 6) * SLAB + i * 128;          // HID K-slab = hidden column / 64
-                        uint32_t v[32];
-                        ptx::tmem_ld_x32(TACC + lane_base + col, v);
-                        ptx::tmem_ld_wait();
-                        const float *bb = par + P_FC1B + half * 256 + col;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 u;
-                            u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), ptx::ld2(bb + j + 0))));
-                            u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), ptx::ld2(bb + j + 2))));
-                            u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), ptx::ld2(bb + j + 4))));
-                            u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), ptx::ld2(bb + j + 6))));
-                            const int ch = ((col & 63) + j) >> 3;
-                            *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
-                        }
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        f32x2 b0v, b1v, b2v, b3v;
+                        ptx::ld4(bb + j, b0v, b1v); ptx::ld4(bb + j + 4, b2v, b3v);
+                        u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v)));
+                        u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
+                        u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
+                        u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
+                        const int ch = ((part & 1) * 32 + j) >> 3;
+                        *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
                     }
-                    signal_a();
+                    ptx::fence_proxy_async();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->g_ready[c & 1]));
+                    phase_ev(8 + c);
                 }
-                wait_acc(ACC_FC2B);      // fc2 of the second half accumulated: X holds the block output (minus folded biases)
+                if (bk + 1 < sg.hi) load_params(bk + 1);
+                wait_acc(ACC_FC2_3);      // the last fc2 is accumulated: X holds the block output (minus folded biases)
+                phase_ev(12);
                 cph ^= 1;
             }
             if (sg.hi < p.n_blocks) {
@@ -535,16 +597,18 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
 }
 
 PerDeviceFlag g_attr_set;
+thread_local int g_stack_var = 0;
 thread_local int g_stack_split = 0;       // measured (profiles/r05c_ab.log): 342 -> 290 us serialised, but inside a forward the unembed overlap already uses
                              // the SMs the whole-tile schedule leaves idle: 1.2605 -> 1.2637 ms (dim 128), 2.0515 -> 2.0694 ms (dim 192)
 
 }  // namespace
 
 void tc_set_stack_split(int on) { g_stack_split = on; }
+void tc_set_stack_var(int mask) { g_stack_var = mask; }
 bool tc_stack_split_enabled() { return g_stack_split != 0; }
 
 // stack_w: bf16 (n_blocks * 24 * 128, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*1664 + 128;
-// rel_bias: fp32 n_blocks x (8,64,64).  tok: (M,128) fp32 with M % 128 == 0.
+// rel_bias: fp32 n_blocks x (8,4096) in fragment order.  tok: (M,128) fp32 with M % 128 == 0.
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                     const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st) {
     TcEncodeFn enc = tc_encode_fn();
@@ -570,6 +634,7 @@ int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *st
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     p.rev = (g_snake_mask >> 2) & 1;
+    p.var = g_stack_var;
     p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     // split tiles between CTAs at block boundaries only when whole tiles do not divide evenly (and the caller provided flags)

@@ -23,6 +23,16 @@ def dense_rel_bias_t(table: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
     return b.permute(2, 0, 1).contiguous()                               # (h, i, j)
 
 
+def frag_rel_bias(dense: torch.Tensor) -> torch.Tensor:
+    """Dense (heads, 64, 64) bias in the order the fused stack kernels read it (window_stack{,192}_tcgen05.cu): per (head, 16-row
+    group rg, key octet n) the 32 lanes of a warp each own four floats -- (row rg*16 + g, columns n*8 + tq*2, +1) and the same
+    columns of row rg*16 + g + 8, lane = g*4 + tq: the C fragment of mma.sync m16n8k16 -- so a fetch is one coalesced 16-byte
+    load per lane instead of sixteen 8-byte loads scattered over eight cache lines each."""
+    h = dense.shape[0]
+    v = dense.reshape(h, 4, 2, 8, 8, 4, 2)                 # (h, rg, half, g, n, tq, e)
+    return v.permute(0, 1, 4, 3, 5, 2, 6).contiguous().reshape(h, 64, 64)   # (h, rg, n, g, tq, half, e)
+
+
 FOLD_CFG = {2: (16, 6, 1), 3: (32, 9, 1), 6: (48, 6, 3)}      # r -> (NO, (c,i) rows per chunk, chunks); tc/upfold_stream_tcgen05.cu
 
 
@@ -274,7 +284,7 @@ class PackedWeights:
         assert flat.shape[0] == 6912 * nb
         mw.stack_w = ptr(dev(flat, torch.bfloat16))
         mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
-        mw.stack_rel = ptr(dev(torch.stack(rels), f32))
+        mw.stack_rel = ptr(dev(torch.stack([frag_rel_bias(r) for r in rels]), f32))
 
     def _pack_resid_stack(self, sd, mw, nb, dim, bprefix, dev, ptr):
         """ResidualTransformer, tc/residual_block_tcgen05.cu: per layer the same 24 slabs as the window stack (in_proj 3 n-chunks x 2
@@ -338,7 +348,7 @@ class PackedWeights:
         assert len(slabs) == 24 * nb
         mw.stack_w = ptr(dev(torch.stack(slabs).reshape(-1, 64), torch.bfloat16))
         mw.stack_p = ptr(dev(torch.cat([t.reshape(-1) for t in pars]), f32))
-        mw.stack_rel = ptr(dev(torch.stack(rels), f32))
+        mw.stack_rel = ptr(dev(torch.stack([frag_rel_bias(r) for r in rels]), f32))
 
 
 class CPackedWeights:
