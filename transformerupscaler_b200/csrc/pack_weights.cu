@@ -358,8 +358,7 @@ extern "C" int tu_pack_weights(int model, const TuNamedTensor *tensors, int n_te
                 }
                 qb_order.assign(qb, qb + 3 * dim);
             } else {
-                // dim 192: per group g of two heads and K-slab: rows q | k | v (32 each); then proj (3), fc1 quarter 0 (3), per quarter p:
-                // fc2 columns of quarter p (3) and fc1 rows of quarter p + 1 (3)
+                // dim 192: per group g of two heads and K-slab: rows q | k | v (32 each); then proj (3 slabs of 192 rows)
                 for (int g = 0; g < 6; ++g) {
                     for (int ks = 0; ks < 3; ++ks)
                         for (int s = 0; s < 3; ++s) slab(qw, dim, s * dim + g * 32, 32, ks * 64);
@@ -367,11 +366,14 @@ extern "C" int tu_pack_weights(int model, const TuNamedTensor *tensors, int n_te
                         for (int r = 0; r < 32; ++r) qb_order.push_back(qb[s * dim + g * 32 + r]);
                 }
                 for (int ks = 0; ks < 3; ++ks) slab(pw, dim, 0, 192, ks * 64);
-                for (int ks = 0; ks < 3; ++ks) slab(w1, dim, 0, 192, ks * 64);
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    for (int ks = 0; ks < 3; ++ks) slab(w2, 4 * dim, 0, 192, q4 * 192 + ks * 64);
-                    if (q4 < 3)
-                        for (int ks = 0; ks < 3; ++ks) slab(w1, dim, (q4 + 1) * 192, 192, ks * 64);
+                // MLP in six chunks of 128 hidden units: fc1 chunk = 3 slabs [128 n x 64 k], fc2 chunk = 2 slabs [192 n x 64 k];
+                // order fc1 c0, fc1 c1, then per chunk c: fc2 c, fc1 c+2 (packing.py::_pack_fused_stack192)
+                auto fc1_chunk = [&](int cc) { for (int ks = 0; ks < 3; ++ks) slab(w1, dim, cc * 128, 128, ks * 64); };
+                auto fc2_chunk = [&](int cc) { for (int ks = 0; ks < 2; ++ks) slab(w2, 4 * dim, 0, 192, cc * 128 + ks * 64); };
+                fc1_chunk(0); fc1_chunk(1);
+                for (int cc = 0; cc < 6; ++cc) {
+                    fc2_chunk(cc);
+                    if (cc + 2 < 6) fc1_chunk(cc + 2);
                 }
             }
             std::vector<double> c0 = c, c1(dim);

@@ -28,7 +28,7 @@ namespace tu {
 namespace {
 
 constexpr int DIM = 192, HEADS = 12, HID = 768;
-constexpr int NGROUP = 6, NPASS = 4;
+constexpr int NGROUP = 6, NCHUNK = 6;               // qkv head groups; MLP chunks of 128 hidden units
 constexpr int NMATH = 16;
 constexpr int NUM_THREADS = (NMATH + 2) * 32;     // 576
 constexpr int SLAB_A = 128 * 128;                 // activation K-slab: 128 rows x 64 bf16
@@ -46,10 +46,20 @@ constexpr int P_C0 = 0, P_LN1W = 192, P_LN1B = 384, P_QKVB = 576, P_C1 = 1152, P
 constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
 constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4 * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int SLABS96 = NGROUP * 3, SLABS192 = 3 + NPASS * 6;       // 18 + 27 per block
-constexpr int ROWS_PER_BLOCK = SLABS96 * 96 + SLABS192 * 192;       // 6912 rows of 64 bf16
+constexpr int SLABS96 = NGROUP * 3;                                  // qkv: 18 slabs of 96 rows
+constexpr int SLABS_PER_BLOCK = SLABS96 + 3 + NCHUNK * 5;            // + proj 3 x 192 rows + per MLP chunk fc1 3 x 128 rows and fc2 2 x 192 rows = 51
+constexpr int ROWS_PER_BLOCK = SLABS96 * 96 + 3 * 192 + NCHUNK * (3 * 128 + 2 * 192);       // 6912 rows of 64 bf16
+// rows of the s-th slab of a block in consumption order (packing.py::_pack_fused_stack192): qkv, proj, fc1 c0, fc1 c1, then per
+// chunk c: fc2 c (2 slabs), fc1 c + 2 (3 slabs, c < 4)
+__device__ __forceinline__ int slab_rows(int s) {
+    if (s < SLABS96) return 96;
+    if (s < SLABS96 + 3) return 192;
+    if (s < SLABS96 + 9) return 128;
+    const int t = s - (SLABS96 + 9);
+    return (t >= 20 || t % 5 < 2) ? 192 : 128;
+}
 
-enum { ACC_QKV0 = 0, ACC_PROJ = NGROUP, ACC_FC1_0, ACC_FC2L = ACC_FC1_0 + NPASS, NACC };
+enum { ACC_QKV0 = 0, ACC_PROJ = NGROUP, ACC_FC1_0, ACC_FC2L = ACC_FC1_0 + NCHUNK, NACC };
 
 struct Stack192Params {
     float *tok;            // (M, 192) fp32 token stream, window-ordered; updated in place
@@ -67,6 +77,7 @@ struct Stack192Params {
 struct Barriers {
     uint64_t full[NRING], empty[NRING];
     uint64_t a_ready;
+    uint64_t g_ready[2];         // math -> MMA: GELU(chunk c) stored in HID buffer c & 1
     uint64_t acc[NACC];
     uint32_t tmem_base;
 };
@@ -176,8 +187,8 @@ __device__ __forceinline__ void layernorm_to_a32(f32x2 (&x)[24], const float *ga
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __grid_constant__ CUtensorMap tmap_w192,
-                       const Stack192Params p) {
+window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __grid_constant__ CUtensorMap tmap_w128,
+                       const __grid_constant__ CUtensorMap tmap_w192, const Stack192Params p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -193,6 +204,8 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
         }
         ptx::mbar_init(ptx::smem_u32(&bars->a_ready), NMATH);
+        ptx::mbar_init(ptx::smem_u32(&bars->g_ready[0]), NMATH);
+        ptx::mbar_init(ptx::smem_u32(&bars->g_ready[1]), NMATH);
         for (int i = 0; i < NACC; ++i) ptx::mbar_init(ptx::smem_u32(&bars->acc[i]), 1);
         ptx::fence_barrier_init();
     }
@@ -202,6 +215,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
     }
     if (warp == NMATH && lane == 0) {
         ptx::prefetch_tmap(&tmap_w96);
+        ptx::prefetch_tmap(&tmap_w128);
         ptx::prefetch_tmap(&tmap_w192);
     }
     ptx::tc_fence_before();
@@ -220,13 +234,13 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
             for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
                 for (int bk = sg.lo; bk < sg.hi; ++bk) {
                     int row = bk * ROWS_PER_BLOCK;
-                    for (int s = 0; s < SLABS96 + SLABS192; ++s) {
-                        const bool small = s < SLABS96;
+                    for (int s = 0; s < SLABS_PER_BLOCK; ++s) {
+                        const int nr = slab_rows(s);
                         ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                         const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
-                        ptx::mbar_expect_tx(fb, (small ? 96 : 192) * 128);
-                        ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB_W, small ? &tmap_w96 : &tmap_w192, fb, 0, row);
-                        row += small ? 96 : 192;
+                        ptx::mbar_expect_tx(fb, nr * 128);
+                        ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB_W, nr == 96 ? &tmap_w96 : nr == 128 ? &tmap_w128 : &tmap_w192, fb, 0, row);
+                        row += nr;
                         if (++stage == NRING) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -234,10 +248,10 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
     } else if (warp == NMATH + 1) {
         // ================================ MMA issuer (whole warp converged, elected lane issues) ================================
         const uint32_t leader = ptx::elect_one();
-        const uint32_t id96 = ptx::make_idesc_bf16(128, 96), id192 = ptx::make_idesc_bf16(128, 192);
+        const uint32_t id96 = ptx::make_idesc_bf16(128, 96), id128 = ptx::make_idesc_bf16(128, 128), id192 = ptx::make_idesc_bf16(128, 192);
         const uint32_t ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
         int stage = 0;
-        uint32_t phase = 0, aph = 0;
+        uint32_t phase = 0, aph = 0, gph = 0;
         // one weight slab: D[128 x N] (+)= A_slab[128 x 64] * W_slab[N x 64]^T
         auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, bool first_clears) {
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
@@ -269,18 +283,21 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, false);          // x += att Wp^T
                 commit(ACC_PROJ);
                 wait_a();                                       // LN2 output in A32
-                for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id192, ks == 0);     // fc1, quarter 0
-                commit(ACC_FC1_0);
-                for (int q4 = 0; q4 < NPASS; ++q4) {
-                    wait_a();                                   // GELU(quarter q4) in HID (= AO region), ACC drained
-                    for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, false);      // x += h W2[:, quarter]^T
-                    if (q4 + 1 < NPASS) {
-                        for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id192, ks == 0);
-                        commit(ACC_FC1_0 + q4 + 1);
-                    } else {
-                        commit(ACC_FC2L);
+                for (int c = 0; c < 2; ++c) {                   // fc1 chunks 0, 1 into the two accumulator slots
+                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + c * 128, a32 + ks * SL, id128, ks == 0);
+                    commit(ACC_FC1_0 + c);
+                }
+                for (int c = 0; c < NCHUNK; ++c) {
+                    ptx::mbar_wait(ptx::smem_u32(&bars->g_ready[c & 1]), (gph >> (c & 1)) & 1);       // GELU(chunk c) in HID buffer c & 1
+                    gph ^= 1u << (c & 1);
+                    ptx::tc_fence_after();
+                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, ao + ((c & 1) * 2 + ks) * SL, id192, false);      // x += h_c W2[:, chunk c]^T
+                    if (c + 2 < NCHUNK) {                       // accumulator slot c & 1 is drained: fc1 chunk c + 2
+                        for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + (c & 1) * 128, a32 + ks * SL, id128, ks == 0);
+                        commit(ACC_FC1_0 + c + 2);              // (its arrival also says: fc2 of chunk c has read HID buffer c & 1)
                     }
                 }
+                commit(ACC_FC2L);
             }
     } else {
         // ================================ math warps ================================
@@ -496,16 +513,20 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 }
                 signal_a();
                 phase_ev(5);
-                // ---- MLP: four quarters of the hidden layer: ACC -> +bias -> GELU -> bf16 HID slabs (AO region)
+                // ---- MLP: six chunks of 128 hidden units: accumulator slot c & 1 -> +bias -> GELU -> bf16 HID buffer c & 1 (two
+                // 32 KB buffers over the AO and staging regions, both idle now).  fc1 of chunk c + 2 is committed behind fc2 of chunk c,
+                // so its arrival also frees the HID buffer this chunk writes.
 #pragma unroll 1
-                for (int q4 = 0; q4 < NPASS; ++q4) {
-                    wait_acc(ACC_FC1_0 + q4);
-                    if (q4 == 0) phase_ev(6);
-                    uint32_t v[48];
-                    tmem_ld48(TACC + lane_base + part * 48, v);
-                    const float *bb = par + P_FC1B + q4 * 192 + part * 48;
+                for (int c = 0; c < NCHUNK; ++c) {
+                    wait_acc(ACC_FC1_0 + c);
+                    if (c == 0) phase_ev(6);
+                    uint32_t v[32];
+                    ptx::tmem_ld_x32(TACC + lane_base + (c & 1) * 128 + part * 32, v);
+                    ptx::tmem_ld_wait();
+                    const float *bb = par + P_FC1B + c * 128 + part * 32;
+                    uint8_t *hb = aout + (c & 1) * 2 * SLAB_A;
 #pragma unroll
-                    for (int j = 0; j < 48; j += 8) {
+                    for (int j = 0; j < 32; j += 8) {
                         uint4 u;
                         f32x2 b0v, b1v, b2v, b3v;
                         ptx::ld4(bb + j, b0v, b1v); ptx::ld4(bb + j + 4, b2v, b3v);
@@ -513,10 +534,13 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
                         u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
                         u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
-                        *reinterpret_cast<uint4 *>(aout + slab_chunk_off(part * 48 + j, i)) = u;
+                        *reinterpret_cast<uint4 *>(hb + slab_chunk_off(part * 32 + j, i)) = u;
                     }
-                    signal_a();
-                    phase_ev(7 + q4);
+                    ptx::fence_proxy_async();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->g_ready[c & 1]));
+                    if (c < 4) phase_ev(7 + c);
                 }
                 if (bk + 1 < sg.hi) load_params(bk + 1);
                 wait_acc(ACC_FC2L);      // fc2 of the last quarter accumulated: X holds the block output (minus folded biases)
@@ -590,11 +614,14 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
         if (e != cudaSuccess) return cuda_fail(e, "window_stack192 smem attribute");
         g_attr_set.set();
     }
-    CUtensorMap t96, t192;
+    CUtensorMap t96, t128, t192;
     cuuint64_t wd[2] = {64, (cuuint64_t)n_blocks * ROWS_PER_BLOCK}, ws[1] = {128};
-    cuuint32_t b96[2] = {64, 96}, b192[2] = {64, 192}, we[2] = {1, 1};
+    cuuint32_t b96[2] = {64, 96}, b128[2] = {64, 128}, b192[2] = {64, 192}, we[2] = {1, 1};
     CUresult r = enc(&t96, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, b96, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+        r = enc(&t128, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, b128, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS)
         r = enc(&t192, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)stack_w, wd, ws, b192, we, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -609,7 +636,7 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     p.seg_flags = (seg_flags && tc_stack_split_enabled() && p.n_tiles % grid != 0) ? seg_flags : nullptr;
     p.units_per_cta = ceil_div(p.n_tiles * n_blocks, grid);
-    launch_pdl(window_stack192_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, t96, t192, p);
+    launch_pdl(window_stack192_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, t96, t128, t192, p);
     TU_CHECK_LAUNCH("window_stack192");
     return TU_OK;
 }

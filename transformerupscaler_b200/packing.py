@@ -240,8 +240,9 @@ class PackedWeights:
         """Weights / parameters of all blocks in the order window_stack192_tcgen05.cu consumes them (dim 192, 12 heads).
 
         Per block 18 slabs [96 n x 64 k]: for each group g of two heads and each K-slab, the rows q | k | v (32 each) of the
-        group (q pre-scaled); then 27 slabs [192 n x 64 k]: proj (3), fc1 rows of hidden quarter 0 (3), then per quarter p:
-        fc2 columns of quarter p (3) and fc1 rows of quarter p+1 (3, p < 3).  Parameters per block: c0 | ln1 w,b | qkv bias in
+        group (q pre-scaled); then proj: 3 slabs [192 n x 64 k]; then the MLP in six chunks of 128 hidden units: fc1 chunk c = 3 slabs
+        [128 n x 64 k], fc2 chunk c = 2 slabs [192 n x 64 k], in the order fc1 c0, fc1 c1, then per chunk c: fc2 c, fc1 c+2 (c < 4).
+        6912 rows of 64 per block.  Parameters per block: c0 | ln1 w,b | qkv bias in
         the same group-major order | c1 | ln2 w,b | fc1 bias; proj / fc2 biases folded into the offsets c0, c1, c_final.
         """
         f32 = torch.float32
@@ -264,14 +265,16 @@ class PackedWeights:
                 qb_g.append(qb[rows])
             for ks in range(3):
                 slabs.append(pw[:, ks * 64:(ks + 1) * 64])
-            for ks in range(3):
-                slabs.append(w1[0:192, ks * 64:(ks + 1) * 64])
-            for q4 in range(4):
-                for ks in range(3):
-                    slabs.append(w2[:, q4 * 192 + ks * 64: q4 * 192 + (ks + 1) * 64])
-                if q4 < 3:
-                    for ks in range(3):
-                        slabs.append(w1[(q4 + 1) * 192:(q4 + 2) * 192, ks * 64:(ks + 1) * 64])
+            # MLP in six chunks of 128 hidden units through two accumulator slots: fc1 c0, fc1 c1, then per chunk c: fc2 c, fc1 c+2
+            def fc1_chunk(cc):
+                return [w1[cc * 128:(cc + 1) * 128, ks * 64:(ks + 1) * 64] for ks in range(3)]      # [128 n x 64 k]
+            def fc2_chunk(cc):
+                return [w2[:, cc * 128 + ks * 64: cc * 128 + (ks + 1) * 64] for ks in range(2)]      # [192 n x 64 k]
+            slabs += fc1_chunk(0) + fc1_chunk(1)
+            for cc in range(6):
+                slabs += fc2_chunk(cc)
+                if cc + 2 < 6:
+                    slabs += fc1_chunk(cc + 2)
             c0 = c.clone()
             c1 = c0 + pb.double()
             c = c1 + b2.double()
