@@ -439,24 +439,22 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         for (int n = 0; n < 8; ++n) {
                             const uint8_t *kp = wbase + (n * 8 + gq) * STG_PITCH + (32 + hl * 16 + tq * 2) * 2;
                             const uint32_t b0 = *reinterpret_cast<const uint32_t *>(kp), b1 = *reinterpret_cast<const uint32_t *>(kp + 16);
-                            s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+                            ptx::up2(ba[n], s[n][0], s[n][1]);          // accumulators start at the relative-position bias
+                            ptx::up2(bb2[n], s[n][2], s[n][3]);
                             mma16816(s[n], qa, b0, b1);
                         }
                         float m0 = -INFINITY, m1 = -INFINITY;
                         f32x2 sa[8], sb[8];                       // (row r0: columns c, c+1), (row r0 + 8: columns c, c+1)
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
-                            sa[n] = ptx::add2(ptx::pk2(s[n][0], s[n][1]), ba[n]);
-                            sb[n] = ptx::add2(ptx::pk2(s[n][2], s[n][3]), bb2[n]);
-                            ptx::up2(sa[n], s[n][0], s[n][1]);
-                            ptx::up2(sb[n], s[n][2], s[n][3]);
+                            sa[n] = ptx::pk2(s[n][0], s[n][1]);
+                            sb[n] = ptx::pk2(s[n][2], s[n][3]);
                             m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
                             m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
                         }
                         if (g + 1 < NGROUP) load_bias(g + 1);         // in flight during softmax, PV and the next group's epilogue
                         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
                         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-                        float l0 = 0.f, l1 = 0.f;
                         const float L2E = 1.4426950408889634f;
                         const float mm0 = m0 * L2E, mm1 = m1 * L2E;
                         const f32x2 l2e2 = ptx::pk2(L2E, L2E), nm0 = ptx::pk2(-mm0, -mm0), nm1 = ptx::pk2(-mm1, -mm1);
@@ -467,11 +465,10 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                             ptx::up2(ptx::fma2(sb[n], l2e2, nm1), e2, e3);
                             s[n][0] = ex2_fast(e0); s[n][1] = ex2_fast(e1);
                             s[n][2] = ex2_fast(e2); s[n][3] = ex2_fast(e3);
-                            l0 += s[n][0] + s[n][1];
-                            l1 += s[n][2] + s[n][3];
                         }
-                        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-                        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+                        // row sums come from the tensor core as well: P times a column of ones (exactly the bf16 probabilities PV uses,
+                        // summed in fp32; every column of the result holds the row sum, so no shuffles)
+                        float ls[4] = {0.f, 0.f, 0.f, 0.f};
                         float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
                         for (int kt = 0; kt < 4; ++kt) {
@@ -488,8 +485,9 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                                          : "r"(addr));
                             mma16816(o[0], pa, v0, v1);
                             mma16816(o[1], pa, v2, v3);
+                            mma16816(ls, pa, 0x3f803f80u, 0x3f803f80u);
                         }
-                        const float i0 = rcp_fast(l0), i1 = rcp_fast(l1);      // l >= 1: the row maximum contributes exp2(0)
+                        const float i0 = rcp_fast(ls[0]), i1 = rcp_fast(ls[2]);      // l >= 1: the row maximum contributes exp2(0)
                         // attention output -> AO (row = token of the tile, column = h*16 + d), swizzled K-slabs
                         const int row0 = win * 64 + r0, row1 = row0 + 8;
 #pragma unroll
