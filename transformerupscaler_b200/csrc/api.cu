@@ -410,6 +410,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
         tc_set_stack_split(value);
         return TU_OK;
     }
+    if (key && !strcmp(key, "ga_shape")) {
+        g_ga_shape = value;
+        return TU_OK;
+    }
     if (key && !strcmp(key, "stack_var")) {
         tc_set_stack_var(value);
         return TU_OK;

@@ -99,6 +99,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D = A B: the C operand is the constant zero, so the destination needs no initialisation (saves four moves per MMA)
+__device__ __forceinline__ void mma_bf16_16816_z(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t *>(&h);
@@ -204,8 +210,9 @@ __device__ __forceinline__ float ga_ex2(float x) { float y; asm("ex2.approx.ftz.
 // GA_MT m16 query tiles per warp, GA_WARPS warps per CTA (128 queries per CTA either way).  Measured on cfg5a (2 frames, 8 layers,
 // transformer blocks in total): GA_MT = 1 1.33 ms, 2 1.21 ms, 4 1.33 ms -- one tile per warp doubles the K/V fragment loads per
 // query, four tiles leave too few warps per SM.
-constexpr int GA_MT = 2, GA_WARPS = 4, GA_QPB = GA_WARPS * 16 * GA_MT;      // queries per CTA
+template <int GA_MT, int GA_WARPS>
 __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
+    constexpr int GA_QPB = GA_WARPS * 16 * GA_MT;      // queries per CTA
     __shared__ __align__(16) bf16 ks[2][GA_KT][GA_PITCH];
     __shared__ __align__(16) bf16 vs[2][GA_KT][GA_PITCH];
     const int b = blockIdx.z, h = blockIdx.y;
@@ -238,13 +245,14 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
         qa[mt][2] = *reinterpret_cast<const uint32_t *>(base + (long)r0 * ld + tq * 2 + 8);
         qa[mt][3] = *reinterpret_cast<const uint32_t *>(base + (long)r1 * ld + tq * 2 + 8);
     }
-    float o[GA_MT][2][4], m[GA_MT][2], l[GA_MT][2];
+    // o[mt][2] is the running row sum: P times a column of ones on the tensor core (the bf16 probabilities the PV product uses,
+    // summed in fp32; every column of that accumulator tile holds the same sum, so no shuffles and no packed adds)
+    float o[GA_MT][3][4], m[GA_MT][2];
 #pragma unroll
     for (int mt = 0; mt < GA_MT; ++mt) {
         m[mt][0] = m[mt][1] = -INFINITY;
-        l[mt][0] = l[mt][1] = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+        for (int nt = 0; nt < 3; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
     }
     const int ntiles = (S + GA_KT - 1) / GA_KT;
     stage(0, 0);
@@ -277,10 +285,7 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
         for (int mt = 0; mt < GA_MT; ++mt) {
             float s[8][4];
 #pragma unroll
-            for (int n = 0; n < 8; ++n) {
-                s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-                mma_bf16_16816(s[n], qa[mt], kb[n][0], kb[n][1]);
-            }
+            for (int n = 0; n < 8; ++n) mma_bf16_16816_z(s[n], qa[mt], kb[n][0], kb[n][1]);
             if (nk < GA_KT) {
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
@@ -300,12 +305,11 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
             const float n0 = fmaxf(m[mt][0], t0), n1 = fmaxf(m[mt][1], t1);
             const float c0 = ga_ex2((m[mt][0] - n0) * L2E), c1 = ga_ex2((m[mt][1] - n1) * L2E);   // exp2(-inf) = 0 on the first tile
             m[mt][0] = n0; m[mt][1] = n1;
-            l[mt][0] *= c0; l[mt][1] *= c1;
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) { o[mt][nt][0] *= c0; o[mt][nt][1] *= c0; o[mt][nt][2] *= c1; o[mt][nt][3] *= c1; }
+            o[mt][2][0] *= c0; o[mt][2][2] *= c1;
             // exponent arguments on packed fp32 pairs (FFMA2), one MUFU per exponential, row sums on packed pairs
             const uint64_t l2e2 = ga_pk2(L2E, L2E), nb0 = ga_pk2(-n0 * L2E, -n0 * L2E), nb1 = ga_pk2(-n1 * L2E, -n1 * L2E);
-            uint64_t ls0 = ga_pk2(0.f, 0.f), ls1 = ga_pk2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 float e0, e1, e2, e3;
@@ -313,13 +317,6 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
                 ga_up2(ga_fma2(ga_pk2(s[n][2], s[n][3]), l2e2, nb1), e2, e3);
                 s[n][0] = ga_ex2(e0); s[n][1] = ga_ex2(e1);
                 s[n][2] = ga_ex2(e2); s[n][3] = ga_ex2(e3);
-                ls0 = ga_add2(ls0, ga_pk2(s[n][0], s[n][1]));
-                ls1 = ga_add2(ls1, ga_pk2(s[n][2], s[n][3]));
-            }
-            {
-                float x0, x1;
-                ga_up2(ls0, x0, x1); l[mt][0] += x0 + x1;
-                ga_up2(ls1, x0, x1); l[mt][1] += x0 + x1;
             }
 #pragma unroll
             for (int kt = 0; kt < 4; ++kt) {
@@ -330,16 +327,14 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
                 pa[3] = pack_bf16x2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
                 mma_bf16_16816(o[mt][0], pa, vb[kt][0], vb[kt][1]);
                 mma_bf16_16816(o[mt][1], pa, vb[kt][2], vb[kt][3]);
+                mma_bf16_16816(o[mt][2], pa, 0x3f803f80u, 0x3f803f80u);
             }
         }
         __syncthreads();       // everyone is done with this buffer before the next prefetch overwrites it
     }
 #pragma unroll
     for (int mt = 0; mt < GA_MT; ++mt) {
-        float l0 = l[mt][0], l1 = l[mt][1];
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float i0 = 1.f / l0, i1 = 1.f / l1;
+        const float i0 = 1.f / o[mt][2][0], i1 = 1.f / o[mt][2][2];
         const int r0 = q0 + mt * 16 + g, r1 = r0 + 8;
         bf16 *op0 = out + ((long)b * S + r0) * dim + h * 16 + tq * 2, *op1 = out + ((long)b * S + r1) * dim + h * 16 + tq * 2;
         if (r0 < S) {
@@ -350,6 +345,24 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
             *reinterpret_cast<uint32_t *>(op1) = pack_bf16x2(o[mt][0][2] * i1, o[mt][0][3] * i1);
             *reinterpret_cast<uint32_t *>(op1 + 8) = pack_bf16x2(o[mt][1][2] * i1, o[mt][1][3] * i1);
         }
+    }
+}
+
+// CTA shape of the mma.sync kernel (debug key "ga_shape", -1 = automatic): 0 = 4 warps x 32 queries (128 queries per CTA), 1 = 2 warps x 32 queries
+// (64 per CTA: twice as many, smaller CTAs spread more evenly over the SMs), 2 = 4 warps x 16, 3 = 8 warps x 16
+}  // namespace tu
+thread_local int tu::g_ga_shape = -1;       // -1: by CTA count
+namespace tu {
+static void launch_global_attn_mma(const bf16 *qkv, bf16 *out, int B, int S, int heads, int dim, cudaStream_t st) {
+    // measured (profiles/r2b_attn_shape.log, S = 3600): 64-query CTAs are 5 % faster while 128-query CTAs do not fill eight rounds
+    // of the SMs (2 and 4 frames), 128-query CTAs 2 % faster beyond (16 frames)
+    int shape = g_ga_shape;
+    if (shape < 0) shape = (long)ceil_div(S, 128) * heads * B <= 8L * device_sm_count() ? 2 : 0;
+    switch (shape) {
+        case 1: global_attn_mma_kernel<2, 2><<<dim3(ceil_div(S, 64), heads, B), 64, 0, st>>>(qkv, out, S, dim); break;
+        case 2: global_attn_mma_kernel<1, 4><<<dim3(ceil_div(S, 64), heads, B), 128, 0, st>>>(qkv, out, S, dim); break;
+        case 3: global_attn_mma_kernel<1, 8><<<dim3(ceil_div(S, 128), heads, B), 256, 0, st>>>(qkv, out, S, dim); break;
+        default: global_attn_mma_kernel<2, 4><<<dim3(ceil_div(S, 128), heads, B), 128, 0, st>>>(qkv, out, S, dim); break;
     }
 }
 
@@ -505,8 +518,7 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
                                      M / S, S, heads, st);
         if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
         if (rc == TU_TC_UNSUPPORTED) {
-            dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
-            global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)big, (bf16 *)att, S, dim);
+            launch_global_attn_mma((const bf16 *)big, (bf16 *)att, M / S, S, heads, dim, st);
             TU_CHECK_LAUNCH("global_attn_mma");
         }
     } else {
@@ -544,8 +556,7 @@ int resid_layer_fused(float *x, const TuModelWeights *w, int layer, int M, int S
         rc = tc_global_attention(big, att, big + (size_t)M * 3 * dim, (float *)((char *)ws + base), ws_bytes - base, M / S, S, heads, st);
     if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
     if (rc == TU_TC_UNSUPPORTED) {
-        dim3 grid(ceil_div(S, GA_QPB), heads, M / S);
-        global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>(big, att, S, dim);
+        launch_global_attn_mma(big, att, M / S, S, heads, dim, st);
         TU_CHECK_LAUNCH("global_attn_mma");
     }
     rc = tc_resid_post(x, x_bf16_out, att, M, layer, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, st);
@@ -623,8 +634,7 @@ extern "C" int tu_global_attention(const void *qkv, void *out, int B, int S, int
         rc = tc_global_attention((const bf16 *)qkv, (bf16 *)out, (bf16 *)workspace, (float *)((char *)workspace + vt_bytes), workspace_bytes - vt_bytes,
                                  B, S, heads, st);
     if (rc != TU_TC_UNSUPPORTED) return rc;
-    dim3 grid(ceil_div(S, GA_QPB), heads, B);
-    global_attn_mma_kernel<<<grid, GA_WARPS * 32, 0, st>>>((const bf16 *)qkv, (bf16 *)out, S, dim);
+    launch_global_attn_mma((const bf16 *)qkv, (bf16 *)out, B, S, heads, dim, st);
     TU_CHECK_LAUNCH("global_attn_mma");
     return TU_OK;
 }
