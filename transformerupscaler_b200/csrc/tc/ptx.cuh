@@ -150,6 +150,18 @@ __device__ __forceinline__ void umma_bf16_lo_rt(uint32_t d_tmem, uint32_t a_lo, 
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(leader), "r"(SDESC_HI_SW128), "r"(accumulate)
         : "memory");
 }
+// A operand in tensor memory (lane = row, one 32-bit column = two consecutive K elements): D[tmem] (+)= A[tmem] * B[smem]^T
+template <int ACC>
+__device__ __forceinline__ void umma_bf16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred pl, pa;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 pl, %4, 0;\n\t"
+        "setp.ne.b32 pa, %6, 0;\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "@pl tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, pa;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(leader), "r"(SDESC_HI_SW128), "n"(ACC)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_pred(uint32_t bar, uint32_t leader) {
     asm volatile(
         "{\n\t.reg .pred pl;\n\tsetp.ne.b32 pl, %1, 0;\n\t"
@@ -181,6 +193,9 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
         "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
         "r"(r[31])
         : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(

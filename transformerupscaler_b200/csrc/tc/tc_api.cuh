@@ -105,7 +105,8 @@ int tc_conv3x3_c64_to3_stream(const bf16 *in, const bf16 *wst, const float *bias
 int tc_window_stack(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 *stack_w, const float *stack_p,
                     const float *rel_bias, int *tile_flags, int *seg_flags, cudaStream_t st);
 void tc_set_stack_split(int on);
-void tc_set_stack_var(int mask);      // debug variants of the dim-128 stack kernel
+void tc_set_stack_var(int mask);      // debug variants of the stack kernels
+int tc_stack_var();
 bool tc_stack_split_enabled();
 
 // the same for FastTransformer (dim 192, 12 heads; window_stack192_tcgen05.cu)

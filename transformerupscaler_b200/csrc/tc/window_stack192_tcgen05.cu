@@ -70,6 +70,7 @@ struct Stack192Params {
     int *tile_flags;       // optional: tile_flags[t] = 1 once tile t's tokens are written and fenced (consumed by the unembed kernel)
     int *seg_flags;        // optional: block-level work split (stack_split.cuh); seg_flags[t] = 1 once the first part of tile t is stored
     int units_per_cta;
+    int var;               // debug variants (tu_debug_set("stack_var", mask)); none at the moment
     unsigned long long *trace;      // debug (tu_debug_trace)
     unsigned int trace_cap;
 };
@@ -222,7 +223,7 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const uint32_t TX = tmem_base, TACC = tmem_base + DIM;
+    const uint32_t TX = tmem_base, TACC = tmem_base + DIM, THID = tmem_base + DIM + 256;      // X 192 | two accumulator slots 256 | HID 64
     pdl_wait();
 
     if (warp == NMATH) {
@@ -291,7 +292,23 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     ptx::mbar_wait(ptx::smem_u32(&bars->g_ready[c & 1]), (gph >> (c & 1)) & 1);       // GELU(chunk c) in HID buffer c & 1
                     gph ^= 1u << (c & 1);
                     ptx::tc_fence_after();
-                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, ao + ((c & 1) * 2 + ks) * SL, id192, false);      // x += h_c W2[:, chunk c]^T
+                    // x += h_c W2[:, chunk c]^T.  Even chunks: A = GELU(chunk c) in TENSOR MEMORY (columns [448, 512): lane = token row, one
+                    // column = two consecutive hidden units as a bf16 pair): the MMA reads only the weight slab from shared memory -- half
+                    // the port load of the SS form -- and the math warps store the activation with tcgen05.st.  Tensor memory has room for
+                    // one such buffer beside X and the two accumulator slots, so odd chunks keep the shared-memory buffer (SS form).
+                    if (c & 1) {
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TX, ao + ks * SL, id192, false);
+                    } else {
+                        for (int ks = 0; ks < 2; ++ks) {
+                            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+                            ptx::tc_fence_after();
+                            const uint32_t w_lo = ring_lo + ((stage * SLAB_W) >> 4);
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_ts_lo<1>(TX, THID + ks * 32 + k4 * 8, w_lo + k4 * 2, id192, leader);
+                            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
+                            if (++stage == NRING) { stage = 0; phase ^= 1; }
+                        }
+                    }
                     if (c + 2 < NCHUNK) {                       // accumulator slot c & 1 is drained: fc1 chunk c + 2
                         for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + (c & 1) * 128, a32 + ks * SL, id128, ks == 0);
                         commit(ACC_FC1_0 + c + 2);              // (its arrival also says: fc2 of chunk c has read HID buffer c & 1)
@@ -522,7 +539,6 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     ptx::tmem_ld_x32(TACC + lane_base + (c & 1) * 128 + part * 32, v);
                     ptx::tmem_ld_wait();
                     const float *bb = par + P_FC1B + c * 128 + part * 32;
-                    uint8_t *hb = aout + (c & 1) * 2 * SLAB_A;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 u;
@@ -532,9 +548,11 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                         u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
                         u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
                         u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
-                        *reinterpret_cast<uint4 *>(hb + slab_chunk_off(part * 32 + j, i)) = u;
+                        if (c & 1) *reinterpret_cast<uint4 *>(aout + slab_chunk_off(part * 32 + j, i)) = u;      // odd chunks: shared-memory buffer
+                        else ptx::tmem_st_x4(THID + lane_base + part * 16 + j / 2, u.x, u.y, u.z, u.w);          // even chunks: tensor memory
                     }
-                    ptx::fence_proxy_async();
+                    if (c & 1) ptx::fence_proxy_async();
+                    else ptx::tmem_st_wait();
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->g_ready[c & 1]));
@@ -630,6 +648,7 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     Stack192Params p;
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
+    p.var = tc_stack_var();
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     p.seg_flags = (seg_flags && tc_stack_split_enabled() && p.n_tiles % grid != 0) ? seg_flags : nullptr;

@@ -67,9 +67,9 @@ struct StackParams {
 
 
 // commit points of one block, in issue order: qkv column thirds, proj, then the MLP in four 128-column chunks of the hidden layer
-// through a ring of three ACC slots and two HID buffers: fc1 chunks 0-2, {fc2 chunk 0 + fc1 chunk 3}, fc2 chunk 1, fc2 chunks 2-3.
+// through two ACC slots and two HID buffers IN TENSOR MEMORY: fc1 chunks 0-1, then per chunk c {fc2 chunk c, fc1 chunk c + 2}.
 // A part's epilogue starts while the MMAs of the next part are still running.
-enum { ACC_QKV0 = 0, ACC_QKV1, ACC_QKV2, ACC_PROJ, ACC_FC1_0, ACC_FC1_1, ACC_FC1_2, ACC_FC1_3, ACC_FC2_1, ACC_FC2_3, NACC };
+enum { ACC_QKV0 = 0, ACC_QKV1, ACC_QKV2, ACC_PROJ, ACC_FC1_0, ACC_FC1_1, ACC_FC1_2, ACC_FC1_3, ACC_FC2_3, NACC };
 
 struct Barriers {
     uint64_t full[NRING], empty[NRING];
@@ -206,7 +206,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const uint32_t TX = tmem_base, TACC = tmem_base + 128;
+    const uint32_t TX = tmem_base, TACC = tmem_base + 128, THID = tmem_base + 384;      // X 128 | ACC slots 2 x 128 | HID 2 x 64 (= third qkv slot)
     pdl_wait();
 
     if (warp == NMATH) {
@@ -218,10 +218,10 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
                 for (int s = sg.lo * SLABS_PER_BLOCK; s < sg.hi * SLABS_PER_BLOCK; ++s) {
                     // packed order of the MLP slab pairs (packing.py): fc1 c0, fc1 c1, fc2 c0, fc2 c1, fc1 c2, fc1 c3, fc2 c2, fc2 c3;
-                    // consumed as fc1 c0, fc1 c1, fc1 c2, fc2 c0, fc1 c3, fc2 c1, fc2 c2, fc2 c3
+                    // consumed as fc1 c0, fc1 c1, fc2 c0, fc1 c2, fc2 c1, fc1 c3, fc2 c2, fc2 c3
                     const int sb = s % SLABS_PER_BLOCK;
                     int src = s;
-                    if (sb >= 8) src = s - sb + 8 + ((0x76352410u >> (((sb - 8) >> 1) * 4)) & 7) * 2 + (sb & 1);
+                    if (sb >= 8) src = s - sb + 8 + ((0x76534210u >> (((sb - 8) >> 1) * 4)) & 7) * 2 + (sb & 1);
                     ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
                     const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
                     ptx::mbar_expect_tx(fb, SLAB);
@@ -252,7 +252,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
             aph ^= 1;
             ptx::tc_fence_after();
         };
-        const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32), hid = ptx::sdesc_lo(smem0 + OFF_STG);
+        const uint32_t a32 = ptx::sdesc_lo(smem0 + OFF_A32);
         constexpr uint32_t SL = SLAB >> 4;
         Seg sg;
         for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
@@ -270,7 +270,7 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 slab_mma(TX, a32 + SL, false);
                 ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_PROJ]), leader);
                 wait_a();                                       // LN2 output in A32
-                for (int c = 0; c < 3; ++c) {                   // fc1 chunks 0-2 into the three ACC slots
+                for (int c = 0; c < 2; ++c) {                   // fc1 chunks 0, 1 into the two ACC slots
                     for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + c * 128, a32 + ks * SL, ks == 0);
                     ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1_0 + c]), leader);
                 }
@@ -278,14 +278,24 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                     ptx::mbar_wait(ptx::smem_u32(&bars->g_ready[c & 1]), (gph >> (c & 1)) & 1);       // GELU(chunk c) in HID buffer c & 1
                     gph ^= 1u << (c & 1);
                     ptx::tc_fence_after();
-                    for (int ks = 0; ks < 2; ++ks) slab_mma(TX, hid + ((c & 1) * 2 + ks) * SL, false);     // x += h_c W2[:, chunk c]^T
-                    if (c == 0) {                               // ACC slot 0 is drained: fc1 chunk 3
-                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC, a32 + ks * SL, ks == 0);
-                        ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1_3]), leader);      // also: HID buffer 0 is free again
+                    // x += h_c W2[:, chunk c]^T with the A operand in TENSOR MEMORY (lane = token row, one column = two consecutive hidden
+                    // units as a bf16 pair): the MMA reads only the weight slab from shared memory, half the port load of the SS form
+                    for (int ks = 0; ks < 2; ++ks) {
+                        ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+                        ptx::tc_fence_after();
+                        const uint32_t w_lo = ring_lo + ((stage * SLAB) >> 4);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            ptx::umma_bf16_ts_lo<1>(TX, THID + (c & 1) * 64 + ks * 32 + k4 * 8, w_lo + k4 * 2, idesc, leader);
+                        ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
+                        if (++stage == NRING) { stage = 0; phase ^= 1; }
                     }
-                    if (c == 1) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2_1]), leader);      // HID buffer 1 is free again
-                    if (c == 3) ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2_3]), leader);
+                    if (c + 2 < 4) {                            // ACC slot c & 1 is drained: fc1 chunk c + 2
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TACC + (c & 1) * 128, a32 + ks * SL, ks == 0);
+                        ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC1_0 + c + 2]), leader);      // (also: fc2 of chunk c has read HID buffer c & 1)
+                    }
                 }
+                ptx::umma_commit_pred(ptx::smem_u32(&bars->acc[ACC_FC2_3]), leader);
             }
     } else {
         // ================================ math warps ================================
@@ -507,31 +517,28 @@ window_stack_kernel(const __grid_constant__ CUtensorMap tmap_w, const StackParam
                 }
                 signal_a();
                 phase_ev(6);
-                // ---- MLP: four 128-column chunks of the hidden layer: ACC slot c % 3 -> +bias -> GELU -> bf16 HID buffer c & 1
+                // ---- MLP: four 128-column chunks of the hidden layer: ACC slot c & 1 -> +bias -> GELU -> bf16 pairs into HID buffer c & 1
+                // in tensor memory (tcgen05.st: no swizzle arithmetic, no proxy fence, no shared-memory traffic).  fc1 of chunk c + 2 is
+                // committed behind fc2 of chunk c, so its arrival also frees the HID buffer this chunk writes.
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     wait_acc(ACC_FC1_0 + c);
                     if (c == 0) phase_ev(7);
-                    if (c == 2) wait_acc(ACC_FC1_3);      // fc2 of chunk 0 has read HID buffer 0
-                    if (c == 3) wait_acc(ACC_FC2_1);      // fc2 of chunk 1 has read HID buffer 1
-                    uint8_t *rowp = stg + ((c & 1) * 2 + (part >> 1)) * SLAB + i * 128;      // K-slab of the buffer = chunk column / 64
                     uint32_t v[32];
-                    ptx::tmem_ld_x32(TACC + lane_base + (c == 3 ? 0 : c) * 128 + part * 32, v);
+                    ptx::tmem_ld_x32(TACC + lane_base + (c & 1) * 128 + part * 32, v);
                     ptx::tmem_ld_wait();
                     const float *bb = par + P_FC1B + c * 128 + part * 32;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        uint4 u;
                         f32x2 b0v, b1v, b2v, b3v;
                         ptx::ld4(bb + j, b0v, b1v); ptx::ld4(bb + j + 4, b2v, b3v);
-                        u.x = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v)));
-                        u.y = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
-                        u.z = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
-                        u.w = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
-                        const int ch = ((part & 1) * 32 + j) >> 3;
-                        *reinterpret_cast<uint4 *>(rowp + ((ch ^ (i & 7)) << 4)) = u;
+                        const uint32_t h0 = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 0], v[j + 1]), b0v)));
+                        const uint32_t h1 = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 2], v[j + 3]), b1v)));
+                        const uint32_t h2 = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 4], v[j + 5]), b2v)));
+                        const uint32_t h3 = pk_pair(gelu_fast2(ptx::add2(ptx::pk2u(v[j + 6], v[j + 7]), b3v)));
+                        ptx::tmem_st_x4(THID + lane_base + (c & 1) * 64 + part * 16 + j / 2, h0, h1, h2, h3);
                     }
-                    ptx::fence_proxy_async();
+                    ptx::tmem_st_wait();
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->g_ready[c & 1]));
@@ -603,6 +610,7 @@ thread_local int g_stack_split = 0;       // measured (profiles/r05c_ab.log): 34
 
 void tc_set_stack_split(int on) { g_stack_split = on; }
 void tc_set_stack_var(int mask) { g_stack_var = mask; }
+int tc_stack_var() { return g_stack_var; }
 bool tc_stack_split_enabled() { return g_stack_split != 0; }
 
 // stack_w: bf16 (n_blocks * 24 * 128, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*1664 + 128;

@@ -210,18 +210,48 @@ __device__ __forceinline__ float ga_ex2(float x) { float y; asm("ex2.approx.ftz.
 // GA_MT m16 query tiles per warp, GA_WARPS warps per CTA (128 queries per CTA either way).  Measured on cfg5a (2 frames, 8 layers,
 // transformer blocks in total): GA_MT = 1 1.33 ms, 2 1.21 ms, 4 1.33 ms -- one tile per warp doubles the K/V fragment loads per
 // query, four tiles leave too few warps per SM.
-template <int GA_MT, int GA_WARPS>
-__global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim) {
+//
+// BAL (balanced launch, few frames): the CTAs of the plain launch are all resident at once and each streams the whole key range, so
+// the last wave -- the CTAs that do not fit -- starts when everything else ends (2 frames: 912 CTAs on 888 slots: + 20 %).  With
+// BAL the (query tile, key tile) units of the launch are laid out in one sequence and cut into gridDim.x equal contiguous ranges, one
+// per resident CTA (the decomposition of tc/global_attn_tcgen05.cu); a CTA that sees only part of a query tile's keys leaves an
+// online-softmax partial (m, l, o[16]) per row in `scratch`, and global_attn_mma_merge_kernel combines the partials of those rows.
+struct GaBal {
+    float *scratch;          // [item][part][18][GA_QPB] fp32
+    long long units;         // items * ktiles
+    int ktiles, qtiles, heads, max_parts;
+};
+__host__ __device__ __forceinline__ int ga_bal_owner(long long u, long long U, int G) { return (int)(((u + 1) * G - 1) / U); }
+
+template <int GA_MT, int GA_WARPS, bool BAL>
+__global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int S, int dim,
+                                                                        const GaBal bal) {
     constexpr int GA_QPB = GA_WARPS * 16 * GA_MT;      // queries per CTA
     __shared__ __align__(16) bf16 ks[2][GA_KT][GA_PITCH];
     __shared__ __align__(16) bf16 vs[2][GA_KT][GA_PITCH];
-    const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tq = lane & 3;
     const long ld = 3L * dim;
-    const bf16 *base = qkv + (long)b * S * ld + h * 16;
-    const int q0 = blockIdx.x * GA_QPB + warp * 16 * GA_MT;
     const float L2E = 1.4426950408889634f;
+    const int ntiles_all = (S + GA_KT - 1) / GA_KT;
+    long long u = 0, u1 = 1;
+    if (BAL) { u = bal.units * blockIdx.x / gridDim.x; u1 = bal.units * (blockIdx.x + 1) / gridDim.x; }
+    for (; u < u1;) {
+    int b, h, qt, kt0, kt1, item = 0;
+    if (BAL) {
+        item = (int)(u / bal.ktiles);
+        kt0 = (int)(u - (long long)item * bal.ktiles);
+        kt1 = (int)min((long long)bal.ktiles, kt0 + (u1 - u));
+        qt = item % bal.qtiles;
+        const int bh = item / bal.qtiles;
+        h = bh % bal.heads; b = bh / bal.heads;
+        u += kt1 - kt0;
+    } else {
+        b = blockIdx.z; h = blockIdx.y; qt = blockIdx.x; kt0 = 0; kt1 = ntiles_all;
+        u = u1;
+    }
+    const bf16 *base = qkv + (long)b * S * ld + h * 16;
+    const int q0 = qt * GA_QPB + warp * 16 * GA_MT;
 
     auto stage = [&](int buf, int k0) {
         for (int e = threadIdx.x; e < 2 * GA_KT; e += GA_WARPS * 32) {
@@ -254,9 +284,9 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
 #pragma unroll
         for (int nt = 0; nt < 3; ++nt) o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
     }
-    const int ntiles = (S + GA_KT - 1) / GA_KT;
-    stage(0, 0);
-    for (int t = 0; t < ntiles; ++t) {
+    const int ntiles = kt1;
+    stage(kt0 & 1, kt0 * GA_KT);
+    for (int t = kt0; t < ntiles; ++t) {
         const int buf = t & 1;
         if (t + 1 < ntiles) {
             stage(buf ^ 1, (t + 1) * GA_KT);
@@ -332,6 +362,26 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
         }
         __syncthreads();       // everyone is done with this buffer before the next prefetch overwrites it
     }
+    if (BAL && (kt0 > 0 || kt1 < ntiles_all)) {
+        // partial of this query tile: part index = distance from the first CTA that owns one of the tile's units
+        const int part = (int)blockIdx.x - ga_bal_owner((long long)item * bal.ktiles, bal.units, (int)gridDim.x);
+        float *dst = bal.scratch + ((long long)item * bal.max_parts + part) * (18 * GA_QPB);
+#pragma unroll
+        for (int mt = 0; mt < GA_MT; ++mt) {
+            const int r0 = warp * 16 * GA_MT + mt * 16 + g, r1 = r0 + 8;
+            if (tq == 0) {
+                dst[r0] = m[mt][0]; dst[r1] = m[mt][1];
+                dst[GA_QPB + r0] = o[mt][2][0]; dst[GA_QPB + r1] = o[mt][2][2];
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int d = nt * 8 + tq * 2;
+                dst[(2 + d) * GA_QPB + r0] = o[mt][nt][0]; dst[(3 + d) * GA_QPB + r0] = o[mt][nt][1];
+                dst[(2 + d) * GA_QPB + r1] = o[mt][nt][2]; dst[(3 + d) * GA_QPB + r1] = o[mt][nt][3];
+            }
+        }
+        continue;
+    }
 #pragma unroll
     for (int mt = 0; mt < GA_MT; ++mt) {
         const float i0 = 1.f / o[mt][2][0], i1 = 1.f / o[mt][2][2];
@@ -346,23 +396,108 @@ __global__ void __launch_bounds__(GA_WARPS * 32) global_attn_mma_kernel(const bf
             *reinterpret_cast<uint32_t *>(op1 + 8) = pack_bf16x2(o[mt][1][2] * i1, o[mt][1][3] * i1);
         }
     }
+    }      // segments
 }
 
 // CTA shape of the mma.sync kernel (debug key "ga_shape", -1 = automatic): 0 = 4 warps x 32 queries (128 queries per CTA), 1 = 2 warps x 32 queries
 // (64 per CTA: twice as many, smaller CTAs spread more evenly over the SMs), 2 = 4 warps x 16, 3 = 8 warps x 16
+
+// rows of the query tiles that were split between CTAs: combine their partials and write softmax(q k^T) v
+template <int QPB>
+__global__ void __launch_bounds__(QPB) global_attn_mma_merge_kernel(const GaBal bal, int grid_attn, bf16 *__restrict__ out, int S, int dim) {
+    const int item = blockIdx.x, r = threadIdx.x;
+    const int qt = item % bal.qtiles, bh = item / bal.qtiles, h = bh % bal.heads, b = bh / bal.heads;
+    const int tok = qt * QPB + r;
+    const int first = ga_bal_owner((long long)item * bal.ktiles, bal.units, grid_attn);
+    const int last = ga_bal_owner((long long)item * bal.ktiles + bal.ktiles - 1, bal.units, grid_attn);
+    if (first == last || tok >= S) return;          // written by its only CTA
+    const int n = last - first + 1;
+    const float *base = bal.scratch + (long long)item * bal.max_parts * (18 * QPB) + r;
+    const float L2E = 1.4426950408889634f;
+    float M = -INFINITY;
+    for (int i = 0; i < n; ++i) M = fmaxf(M, base[(long long)i * 18 * QPB]);
+    float L = 0.f, o[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[d] = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const float *pp = base + (long long)i * 18 * QPB;
+        const float f = ga_ex2((pp[0] - M) * L2E);
+        L = fmaf(pp[QPB], f, L);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o[d] = fmaf(pp[(2 + d) * QPB], f, o[d]);
+    }
+    const float inv = 1.f / L;
+    uint32_t w[8];
+#pragma unroll
+    for (int d = 0; d < 16; d += 2) w[d >> 1] = pack_bf16x2(o[d] * inv, o[d + 1] * inv);
+    uint4 *op = reinterpret_cast<uint4 *>(out + ((long)b * S + tok) * dim + h * 16);
+    op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 }  // namespace tu
-thread_local int tu::g_ga_shape = -1;       // -1: by CTA count
+// CTA shape of the mma.sync kernel (debug key "ga_shape", -1 = automatic): 0 = 4 warps x 32 queries (128 queries per CTA), 1 = 2 warps
+// x 32 queries, 2 = 4 warps x 16 (64 per CTA), 3 = 8 warps x 16, 4 = shape 2 with the balanced launch (needs scratch)
+thread_local int tu::g_ga_shape = -1;
 namespace tu {
-static void launch_global_attn_mma(const bf16 *qkv, bf16 *out, int B, int S, int heads, int dim, cudaStream_t st) {
-    // measured (profiles/r2b_attn_shape.log, S = 3600): 64-query CTAs are 5 % faster while 128-query CTAs do not fill eight rounds
-    // of the SMs (2 and 4 frames), 128-query CTAs 2 % faster beyond (16 frames)
+// resident CTAs of the balanced kernel with MT m16 tiles per warp (a property of the code, not of the device ordinal)
+template <int MT> static int ga_bal_grid() {
+    static const int occ = [] {
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, global_attn_mma_kernel<MT, 4, true>, 128, 0) != cudaSuccess || o < 1) o = 4;
+        return o;
+    }();
+    return device_sm_count() * occ;
+}
+static void ga_bal_geometry(int B, int S, int heads, int grid, int qpb, GaBal &g) {
+    g.ktiles = ceil_div(S, GA_KT);
+    g.qtiles = ceil_div(S, qpb);
+    g.heads = heads;
+    g.units = (long long)B * heads * g.qtiles * g.ktiles;
+    const long long per = g.units / grid > 0 ? g.units / grid : 1;
+    g.max_parts = (int)((g.ktiles + per - 1) / per) + 1;
+}
+size_t global_attn_mma_scratch_bytes(int B, int S, int heads) {
+    GaBal g1, g2;
+    ga_bal_geometry(B, S, heads, ga_bal_grid<1>(), 64, g1);
+    ga_bal_geometry(B, S, heads, ga_bal_grid<2>(), 128, g2);
+    const size_t a = (size_t)B * heads * g1.qtiles * g1.max_parts * 18 * 64 * sizeof(float);
+    const size_t b = (size_t)B * heads * g2.qtiles * g2.max_parts * 18 * 128 * sizeof(float);
+    return a > b ? a : b;
+}
+template <int MT>
+static bool launch_global_attn_bal(const bf16 *qkv, bf16 *out, int B, int S, int heads, int dim, float *scratch, size_t scratch_bytes,
+                                   cudaStream_t st) {
+    constexpr int QPB = 64 * MT;
+    const int grid = ga_bal_grid<MT>();
+    GaBal g;
+    ga_bal_geometry(B, S, heads, grid, QPB, g);
+    g.scratch = scratch;
+    if (!scratch || scratch_bytes < global_attn_mma_scratch_bytes(B, S, heads) || g.units < grid) return false;
+    global_attn_mma_kernel<MT, 4, true><<<grid, 128, 0, st>>>(qkv, out, S, dim, g);
+    global_attn_mma_merge_kernel<QPB><<<B * heads * g.qtiles, QPB, 0, st>>>(g, grid, out, S, dim);
+    return true;
+}
+// scratch (optional): global_attn_mma_scratch_bytes() of fp32 partials for the balanced launches
+static void launch_global_attn_mma(const bf16 *qkv, bf16 *out, int B, int S, int heads, int dim, float *scratch, size_t scratch_bytes,
+                                   cudaStream_t st) {
+    // measured (profiles/r2b_attn_shape.log, S = 3600): see DESIGN.md section 3.5c
     int shape = g_ga_shape;
-    if (shape < 0) shape = (long)ceil_div(S, 128) * heads * B <= 8L * device_sm_count() ? 2 : 0;
+    const GaBal none{nullptr, 0, 0, 0, 0, 0};
+    if (shape < 0) {
+        const long n128 = (long)ceil_div(S, 128) * heads * B;
+        shape = n128 <= 8L * device_sm_count() ? 2 : 0;
+        if (scratch && n128 <= 4L * device_sm_count()) shape = 5;
+    }
+    if (shape == 4 && launch_global_attn_bal<1>(qkv, out, B, S, heads, dim, scratch, scratch_bytes, st)) return;
+    if (shape == 5 && launch_global_attn_bal<2>(qkv, out, B, S, heads, dim, scratch, scratch_bytes, st)) return;
+    if (shape == 4) shape = 2;
+    if (shape == 5) shape = 0;
     switch (shape) {
-        case 1: global_attn_mma_kernel<2, 2><<<dim3(ceil_div(S, 64), heads, B), 64, 0, st>>>(qkv, out, S, dim); break;
-        case 2: global_attn_mma_kernel<1, 4><<<dim3(ceil_div(S, 64), heads, B), 128, 0, st>>>(qkv, out, S, dim); break;
-        case 3: global_attn_mma_kernel<1, 8><<<dim3(ceil_div(S, 128), heads, B), 256, 0, st>>>(qkv, out, S, dim); break;
-        default: global_attn_mma_kernel<2, 4><<<dim3(ceil_div(S, 128), heads, B), 128, 0, st>>>(qkv, out, S, dim); break;
+        case 1: global_attn_mma_kernel<2, 2, false><<<dim3(ceil_div(S, 64), heads, B), 64, 0, st>>>(qkv, out, S, dim, none); break;
+        case 2: global_attn_mma_kernel<1, 4, false><<<dim3(ceil_div(S, 64), heads, B), 128, 0, st>>>(qkv, out, S, dim, none); break;
+        case 3: global_attn_mma_kernel<1, 8, false><<<dim3(ceil_div(S, 128), heads, B), 256, 0, st>>>(qkv, out, S, dim, none); break;
+        default: global_attn_mma_kernel<2, 4, false><<<dim3(ceil_div(S, 128), heads, B), 128, 0, st>>>(qkv, out, S, dim, none); break;
     }
 }
 
@@ -456,10 +591,13 @@ static size_t block_ws(int M, int dim, int dtype) {
     return align_up((size_t)M * dim * e, 256) + align_up((size_t)M * 4 * dim * e, 256) + align_up((size_t)M * dim * e, 256);
 }
 
-// the tcgen05 global attention keeps fp32 partials behind the three buffers above (bf16 path, window == 0)
+// the global attention kernels (tcgen05, or mma.sync with the balanced launch) keep fp32 partials behind the three buffers above (bf16 path, window == 0)
 size_t block_workspace_bytes_ex(int M, int dim, int dtype, int window, int S) {
     size_t n = block_ws(M, dim, dtype);
-    if (!window && dtype == TU_BF16 && S > 0 && M % S == 0 && tc_available()) n += align_up(tc_global_attention_scratch_bytes(M / S, S, dim / 16), 256);
+    if (!window && dtype == TU_BF16 && S > 0 && M % S == 0 && tc_available()) {
+        const size_t a = tc_global_attention_scratch_bytes(M / S, S, dim / 16), b = global_attn_mma_scratch_bytes(M / S, S, dim / 16);
+        n += align_up(a > b ? a : b, 256);
+    }
     return n;
 }
 
@@ -518,7 +656,8 @@ int transformer_block_impl(float *x, const TuBlockWeights *w, int M, int dim, in
                                      M / S, S, heads, st);
         if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
         if (rc == TU_TC_UNSUPPORTED) {
-            launch_global_attn_mma((const bf16 *)big, (bf16 *)att, M / S, S, heads, dim, st);
+            launch_global_attn_mma((const bf16 *)big, (bf16 *)att, M / S, S, heads, dim, ws_bytes > base ? (float *)((char *)ws + base) : nullptr,
+                                   ws_bytes > base ? ws_bytes - base : 0, st);
             TU_CHECK_LAUNCH("global_attn_mma");
         }
     } else {
@@ -556,7 +695,7 @@ int resid_layer_fused(float *x, const TuModelWeights *w, int layer, int M, int S
         rc = tc_global_attention(big, att, big + (size_t)M * 3 * dim, (float *)((char *)ws + base), ws_bytes - base, M / S, S, heads, st);
     if (rc != TU_OK && rc != TU_TC_UNSUPPORTED) return rc;
     if (rc == TU_TC_UNSUPPORTED) {
-        launch_global_attn_mma(big, att, M / S, S, heads, dim, st);
+        launch_global_attn_mma(big, att, M / S, S, heads, dim, ws_bytes > base ? (float *)((char *)ws + base) : nullptr, ws_bytes > base ? ws_bytes - base : 0, st);
         TU_CHECK_LAUNCH("global_attn_mma");
     }
     rc = tc_resid_post(x, x_bf16_out, att, M, layer, w->n_blocks, (const bf16 *)w->stack_w, w->stack_p, st);
@@ -622,7 +761,8 @@ extern "C" int tu_window_attention(const void *qkv, const float *rel_bias, void 
 // TFLOP/s" of the headline metric can be measured on its own for this model too.
 extern "C" size_t tu_global_attention_workspace_bytes(int B, int S, int heads) {
     if (B <= 0 || S <= 0 || heads <= 0 || !tc_available()) return 0;
-    return align_up((size_t)B * S * heads * 16 * sizeof(bf16), 256) + tc_global_attention_scratch_bytes(B, S, heads);
+    const size_t a = tc_global_attention_scratch_bytes(B, S, heads), b = global_attn_mma_scratch_bytes(B, S, heads);
+    return align_up((size_t)B * S * heads * 16 * sizeof(bf16), 256) + (a > b ? a : b);
 }
 extern "C" int tu_global_attention(const void *qkv, void *out, int B, int S, int heads, void *workspace, size_t workspace_bytes, void *stream) {
     TU_CHECK_ARG(qkv && out && B > 0 && S > 0 && (heads == 8 || heads == 12), "global_attention: bad argument");
@@ -634,7 +774,8 @@ extern "C" int tu_global_attention(const void *qkv, void *out, int B, int S, int
         rc = tc_global_attention((const bf16 *)qkv, (bf16 *)out, (bf16 *)workspace, (float *)((char *)workspace + vt_bytes), workspace_bytes - vt_bytes,
                                  B, S, heads, st);
     if (rc != TU_TC_UNSUPPORTED) return rc;
-    launch_global_attn_mma((const bf16 *)qkv, (bf16 *)out, B, S, heads, dim, st);
+    launch_global_attn_mma((const bf16 *)qkv, (bf16 *)out, B, S, heads, dim, workspace && workspace_bytes > vt_bytes ? (float *)((char *)workspace + vt_bytes) : nullptr,
+                           workspace && workspace_bytes > vt_bytes ? workspace_bytes - vt_bytes : 0, st);
     TU_CHECK_LAUNCH("global_attn_mma");
     return TU_OK;
 }
