@@ -33,19 +33,21 @@ constexpr int NMATH = 16;
 constexpr int NUM_THREADS = (NMATH + 2) * 32;     // 576
 constexpr int SLAB_A = 128 * 128;                 // activation K-slab: 128 rows x 64 bf16
 constexpr int SLAB_W = 192 * 128;                 // weight slab slot: up to 192 rows x 64 bf16
-constexpr int NRING = 3;
+constexpr int NRING = 8;                          // weight slabs in flight at most (barrier pairs)
+constexpr int RING_BYTES = 84 * 1024;             // byte-granular weight ring: slabs of 12 / 16 / 24 KB are packed back to back
 constexpr int STG_PITCH = 96 * 2 + 16;            // 208 B per token row (conflict-free fragment loads)
 constexpr int OFF_A32 = 0;
 constexpr int OFF_AO = 3 * SLAB_A;                // 49152
 constexpr int OFF_STG = OFF_AO + 3 * SLAB_A;      // 98304
 constexpr int STG_BYTES = 27 * 1024;              // >= 128 * 208 = 26624
 constexpr int OFF_RING = OFF_STG + STG_BYTES;     // 125952 = 123 * 1024
-constexpr int OFF_PAR = OFF_RING + NRING * SLAB_W;
+constexpr int OFF_PAR = OFF_RING + RING_BYTES;
 constexpr int PAR_FLOATS = 2496;                  // c0 | ln1w | ln1b | qkvb(576, group-major) | c1 | ln2w | ln2b | fc1b(768)
 constexpr int P_C0 = 0, P_LN1W = 192, P_LN1B = 384, P_QKVB = 576, P_C1 = 1152, P_LN2W = 1344, P_LN2B = 1536, P_FC1B = 1728;
 constexpr int OFF_STAT = OFF_PAR + PAR_FLOATS * 4;
 constexpr int OFF_BAR = OFF_STAT + 2 * 128 * 4 * 8;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 384 + 1024;
+static_assert(SMEM_BYTES <= 232448 && OFF_RING % 1024 == 0, "shared memory layout");
 constexpr int SLABS96 = NGROUP * 3;                                  // qkv: 18 slabs of 96 rows
 constexpr int SLABS_PER_BLOCK = SLABS96 + 3 + NCHUNK * 5;            // + proj 3 x 192 rows + per MLP chunk fc1 3 x 128 rows and fc2 2 x 192 rows = 51
 constexpr int ROWS_PER_BLOCK = SLABS96 * 96 + 3 * 192 + NCHUNK * (3 * 128 + 2 * 192);       // 6912 rows of 64 bf16
@@ -59,6 +61,19 @@ __device__ __forceinline__ int slab_rows(int s) {
     return (t >= 20 || t % 5 < 2) ? 192 : 128;
 }
 
+// Byte-granular weight ring.  Slab n of `bytes` goes to the current head, or to offset 0 when it would not fit before the end of the
+// ring (the tail stays unused for that lap); every block starts at offset 0 again, so the layout is the same for all blocks and the
+// host can tell the producer which older slabs each load overwrites (plan_ring).
+struct RingPos {
+    int head = 0;
+    __device__ __forceinline__ int place(int bytes) {
+        if (head + bytes > RING_BYTES) head = 0;
+        const int off = head;
+        head += bytes;
+        return off;
+    }
+};
+
 enum { ACC_QKV0 = 0, ACC_PROJ = NGROUP, ACC_FC1_0, ACC_FC2L = ACC_FC1_0 + NCHUNK, NACC };
 
 struct Stack192Params {
@@ -71,6 +86,11 @@ struct Stack192Params {
     int *seg_flags;        // optional: block-level work split (stack_split.cuh); seg_flags[t] = 1 once the first part of tile t is stored
     int units_per_cta;
     int var;               // debug variants (tu_debug_set("stack_var", mask)); none at the moment
+    // byte-granular weight ring, the same for every block (the ring restarts at offset 0 with a block's first slab): offset of slab s
+    // in KB, and the newest slab -- index relative to the block, negative = a slab of the previous block -- that must have been released
+    // before slab s may be loaded (computed on the host: plan_ring)
+    unsigned char w_off[64];
+    signed char w_need[64];
     unsigned long long *trace;      // debug (tu_debug_trace)
     unsigned int trace_cap;
 };
@@ -82,7 +102,7 @@ struct Barriers {
     uint64_t acc[NACC];
     uint32_t tmem_base;
 };
-static_assert(sizeof(Barriers) <= 256, "barrier block too large");
+static_assert(sizeof(Barriers) <= 384, "barrier block too large");
 
 __device__ __forceinline__ void math_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -229,20 +249,22 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
     if (warp == NMATH) {
         if (lane == 0) {
             // ================================ TMA producer: weight slabs in consumption order ================================
-            int stage = 0;
-            uint32_t phase = 0;
+            // In flight: slabs [tail_n, n), laid out circularly in allocation order.  Before slab n is loaded, every older slab whose bytes it
+            // would overwrite must have been released by the MMAs (releases arrive in order), and at most NRING slabs are in flight
+            // (barrier pair n % NRING, parity (n / NRING) & 1).
+            int nb0 = 0, tail_n = 0;          // slab number of the current block's first slab; slabs [tail_n, ..) may still be unreleased
             Seg sg;
             for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
-                for (int bk = sg.lo; bk < sg.hi; ++bk) {
+                for (int bk = sg.lo; bk < sg.hi; ++bk, nb0 += SLABS_PER_BLOCK) {
                     int row = bk * ROWS_PER_BLOCK;
                     for (int s = 0; s < SLABS_PER_BLOCK; ++s) {
-                        const int nr = slab_rows(s);
-                        ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1);
-                        const uint32_t fb = ptx::smem_u32(&bars->full[stage]);
+                        const int nr = slab_rows(s), n = nb0 + s;
+                        for (const int need = nb0 + p.w_need[s]; tail_n <= need; ++tail_n)      // releases arrive in order
+                            ptx::mbar_wait(ptx::smem_u32(&bars->empty[tail_n % NRING]), (uint32_t)(tail_n / NRING) & 1);
+                        const uint32_t fb = ptx::smem_u32(&bars->full[n % NRING]);
                         ptx::mbar_expect_tx(fb, nr * 128);
-                        ptx::tma_load_2d(smem0 + OFF_RING + stage * SLAB_W, nr == 96 ? &tmap_w96 : nr == 128 ? &tmap_w128 : &tmap_w192, fb, 0, row);
+                        ptx::tma_load_2d(smem0 + OFF_RING + p.w_off[s] * 1024, nr == 96 ? &tmap_w96 : nr == 128 ? &tmap_w128 : &tmap_w192, fb, 0, row);
                         row += nr;
-                        if (++stage == NRING) { stage = 0; phase ^= 1; }
                     }
                 }
         }
@@ -251,18 +273,27 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
         const uint32_t leader = ptx::elect_one();
         const uint32_t id96 = ptx::make_idesc_bf16(128, 96), id128 = ptx::make_idesc_bf16(128, 128), id192 = ptx::make_idesc_bf16(128, 192);
         const uint32_t ring_lo = ptx::sdesc_lo(smem0 + OFF_RING);
-        int stage = 0;
-        uint32_t phase = 0, aph = 0, gph = 0;
-        // one weight slab: D[128 x N] (+)= A_slab[128 x 64] * W_slab[N x 64]^T
-        auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, bool first_clears) {
-            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+        RingPos ring;
+        int n = 0;                    // running slab number: barrier pair n % NRING, parity (n / NRING) & 1
+        uint32_t aph = 0, gph = 0;
+        // next weight slab (nrows x 64 k) of the ring: waits for it and returns the low descriptor word of its first byte
+        auto next_slab = [&](int nrows) -> uint32_t {
+            const int off = ring.place(nrows * 128);
+            ptx::mbar_wait(ptx::smem_u32(&bars->full[n % NRING]), (uint32_t)(n / NRING) & 1);
             ptx::tc_fence_after();
-            const uint32_t w_lo = ring_lo + ((stage * SLAB_W) >> 4);
+            return ring_lo + (off >> 4);
+        };
+        auto release_slab = [&]() {
+            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[n % NRING]), leader);
+            ++n;
+        };
+        // one weight slab: D[128 x N] (+)= A_slab[128 x 64] * W_slab[N x 64]^T
+        auto slab_mma = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, int nrows, bool first_clears) {
+            const uint32_t w_lo = next_slab(nrows);
             ptx::umma_bf16_lo_rt(d_tmem, a_lo, w_lo, idesc, first_clears ? 0u : 1u, leader);
 #pragma unroll
             for (int k4 = 1; k4 < 4; ++k4) ptx::umma_bf16_lo<1>(d_tmem, a_lo + k4 * 2, w_lo + k4 * 2, idesc, leader);
-            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
-            if (++stage == NRING) { stage = 0; phase ^= 1; }
+            release_slab();
         };
         auto wait_a = [&]() {
             ptx::mbar_wait(ptx::smem_u32(&bars->a_ready), aph);
@@ -275,17 +306,18 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
         Seg sg;
         for (int k = 0; get_seg(p.n_tiles, p.n_blocks, p.seg_flags != nullptr, p.units_per_cta, k, sg); ++k)
             for (int bk = sg.lo; bk < sg.hi; ++bk) {
+                ring.head = 0;                                  // every block lays its slabs out from offset 0
                 for (int g = 0; g < NGROUP; ++g) {
                     wait_a();                                   // g = 0: LN1 output in A32; g > 0: ACC drained by the previous group
-                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id96, ks == 0);
+                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC, a32 + ks * SL, id96, 96, ks == 0);
                     commit(ACC_QKV0 + g);
                 }
                 wait_a();                                       // attention output of all heads in AO
-                for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, false);          // x += att Wp^T
+                for (int ks = 0; ks < 3; ++ks) slab_mma(TX, ao + ks * SL, id192, 192, false);          // x += att Wp^T
                 commit(ACC_PROJ);
                 wait_a();                                       // LN2 output in A32
                 for (int c = 0; c < 2; ++c) {                   // fc1 chunks 0, 1 into the two accumulator slots
-                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + c * 128, a32 + ks * SL, id128, ks == 0);
+                    for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + c * 128, a32 + ks * SL, id128, 128, ks == 0);
                     commit(ACC_FC1_0 + c);
                 }
                 for (int c = 0; c < NCHUNK; ++c) {
@@ -297,20 +329,17 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                     // the port load of the SS form -- and the math warps store the activation with tcgen05.st.  Tensor memory has room for
                     // one such buffer beside X and the two accumulator slots, so odd chunks keep the shared-memory buffer (SS form).
                     if (c & 1) {
-                        for (int ks = 0; ks < 2; ++ks) slab_mma(TX, ao + ks * SL, id192, false);
+                        for (int ks = 0; ks < 2; ++ks) slab_mma(TX, ao + ks * SL, id192, 192, false);
                     } else {
                         for (int ks = 0; ks < 2; ++ks) {
-                            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-                            ptx::tc_fence_after();
-                            const uint32_t w_lo = ring_lo + ((stage * SLAB_W) >> 4);
+                            const uint32_t w_lo = next_slab(192);
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) ptx::umma_bf16_ts_lo<1>(TX, THID + ks * 32 + k4 * 8, w_lo + k4 * 2, id192, leader);
-                            ptx::umma_commit_pred(ptx::smem_u32(&bars->empty[stage]), leader);
-                            if (++stage == NRING) { stage = 0; phase ^= 1; }
+                            release_slab();
                         }
                     }
                     if (c + 2 < NCHUNK) {                       // accumulator slot c & 1 is drained: fc1 chunk c + 2
-                        for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + (c & 1) * 128, a32 + ks * SL, id128, ks == 0);
+                        for (int ks = 0; ks < 3; ++ks) slab_mma(TACC + (c & 1) * 128, a32 + ks * SL, id128, 128, ks == 0);
                         commit(ACC_FC1_0 + c + 2);              // (its arrival also says: fc2 of chunk c has read HID buffer c & 1)
                     }
                 }
@@ -614,6 +643,36 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
 
 PerDeviceFlag g_attr_set;
 
+int host_slab_rows(int s) {
+    if (s < SLABS96) return 96;
+    if (s < SLABS96 + 3) return 192;
+    if (s < SLABS96 + 9) return 128;
+    const int t = s - (SLABS96 + 9);
+    return (t >= 20 || t % 5 < 2) ? 192 : 128;
+}
+// layout of a block's slabs in the ring and, per slab, the newest older slab its bytes (or its barrier pair) still belong to
+void plan_ring(Stack192Params &p) {
+    int off[2 * SLABS_PER_BLOCK], len[2 * SLABS_PER_BLOCK];
+    for (int blk = 0; blk < 2; ++blk) {
+        int head = 0;
+        for (int s = 0; s < SLABS_PER_BLOCK; ++s) {
+            const int b = host_slab_rows(s) * 128;
+            if (head + b > RING_BYTES) head = 0;
+            off[blk * SLABS_PER_BLOCK + s] = head;
+            len[blk * SLABS_PER_BLOCK + s] = b;
+            head += b;
+        }
+    }
+    for (int s = 0; s < SLABS_PER_BLOCK; ++s) {          // steady state = the second block
+        const int n = SLABS_PER_BLOCK + s;
+        int need = n - NRING;                             // its barrier pair was last used by slab n - NRING
+        for (int m = n - 1; m > need && m >= 0; --m)
+            if (off[m] < off[n] + len[n] && off[n] < off[m] + len[m]) { need = m; break; }
+        p.w_off[s] = (unsigned char)(off[n] / 1024);
+        p.w_need[s] = (signed char)(need - SLABS_PER_BLOCK);
+    }
+}
+
 }  // namespace
 
 // stack_w: bf16 (n_blocks * 6912, 64) weight slabs in consumption order; stack_p: fp32 n_blocks*2496 + 192;
@@ -649,6 +708,7 @@ int tc_window_stack192(float *tok, bf16 *tok16, int M, int n_blocks, const bf16 
     p.tok = tok; p.tok16 = tok16; p.par = stack_p; p.rel_bias = rel_bias;
     p.trace = g_trace_buf; p.trace_cap = g_trace_cap;
     p.var = tc_stack_var();
+    plan_ring(p);
     p.n_tiles = M / 128; p.n_blocks = n_blocks; p.tile_flags = tile_flags;
     const int grid = p.n_tiles < g_sm_count ? p.n_tiles : g_sm_count;
     p.seg_flags = (seg_flags && tc_stack_split_enabled() && p.n_tiles % grid != 0) ? seg_flags : nullptr;
