@@ -7,16 +7,20 @@
 //
 //   TMEM columns [0,192)    X: fp32 residual stream (one lane per token); proj and fc2 accumulate straight onto it, their
 //                           biases folded into offset vectors added on read (c0 before LN1, c1 before LN2, c_final at the end)
-//   TMEM columns [192,384)  ACC: one qkv head-group (96 columns) or one MLP hidden quarter (192 columns) at a time
+//   TMEM columns [192,448)  two accumulator slots of 128 columns: one qkv head-group (96 columns) at a time, then the fc1 chunks
+//   TMEM columns [448,512)  HID of the even MLP chunks: GELU(fc1 chunk) as bf16 pairs, the A operand of fc2 in tensor memory
 //   smem A32  (48 KB)       LayerNorm output: three 128 x 64 swizzled K-slabs (A operand of qkv and fc1)
-//   smem AO   (48 KB)       attention output (A operand of proj); later aliased by HID = GELU(fc1 quarter) (A operand of fc2)
+//   smem AO   (48 KB)       attention output (A operand of proj); later its first 32 KB hold HID of the odd MLP chunks
 //   smem STG  (27 KB)       q | k | v (32 + 32 + 32 columns, bf16) of the CURRENT group of two heads, 128 token rows
-//   smem ring (3 x 24 KB)   weight slabs streamed by TMA in consumption order (packing.py): per block 18 slabs [96 n x 64 k]
-//                           (qkv: 6 head-groups x 3 K-slabs, rows q|k|v of the group) then 27 slabs [192 n x 64 k]
-//                           (proj 3; fc1 quarter 0: 3; then per quarter p: fc2 p: 3, fc1 p+1: 3)
+//   smem ring (84 KB)       weight slabs streamed by TMA in consumption order (packing.py), packed back to back (byte-granular ring,
+//                           layout planned on the host: plan_ring): per block 18 slabs [96 n x 64 k] (qkv: 6 head-groups x 3 K-slabs,
+//                           rows q|k|v of the group), 3 slabs [192 n x 64 k] (proj), then the MLP in six chunks of 128 hidden units:
+//                           fc1 chunk = 3 slabs [128 n x 64 k], fc2 chunk = 2 slabs [192 n x 64 k]; order fc1 c0, fc1 c1, then per
+//                           chunk c: fc2 c, fc1 c+2
 // Head-group pipeline: the qkv MMAs of group g+1 run while the math warps do the attention of group g (one (window, head,
-// 16-row) task per warp: mma.sync QK^T, + dense bias, softmax, PV).
+// 16-row) task per warp: mma.sync QK^T seeded with the bias, softmax, PV and the row sums on the tensor core).
 // Roles: warps 0-15 math (thread = token row x column quarter), warp 16 TMA producer, warp 17 MMA issuer + TMEM allocation.
+// DESIGN.md section 3.4 has the measured timeline of a block.
 #include <cuda.h>
 
 #include "ptx.cuh"
@@ -557,9 +561,9 @@ window_stack192_kernel(const __grid_constant__ CUtensorMap tmap_w96, const __gri
                 }
                 signal_a();
                 phase_ev(5);
-                // ---- MLP: six chunks of 128 hidden units: accumulator slot c & 1 -> +bias -> GELU -> bf16 HID buffer c & 1 (two
-                // 32 KB buffers over the AO and staging regions, both idle now).  fc1 of chunk c + 2 is committed behind fc2 of chunk c,
-                // so its arrival also frees the HID buffer this chunk writes.
+                // ---- MLP: six chunks of 128 hidden units: accumulator slot c & 1 -> +bias -> GELU -> bf16 HID (even chunks: tensor memory,
+                // odd chunks: 32 KB of the idle AO region).  fc1 of chunk c + 2 is committed behind fc2 of chunk c, so its arrival also
+                // frees the HID buffer this chunk writes.
 #pragma unroll 1
                 for (int c = 0; c < NCHUNK; ++c) {
                     wait_acc(ACC_FC1_0 + c);

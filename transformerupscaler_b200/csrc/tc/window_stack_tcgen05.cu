@@ -9,15 +9,17 @@
 //   TMEM columns [0,128)   X: the fp32 residual stream, one TMEM lane per token.  proj and fc2 are issued with
 //                          accumulate=1 straight onto X, so the two residual adds of a block cost nothing; their
 //                          constant biases are folded into a running offset vector c that LayerNorm adds on read.
-//   TMEM columns [128,512) ACC: qkv (384 columns), then the two 256-wide halves of the MLP hidden layer.
+//   TMEM columns [128,384) two accumulator slots of 128 columns: q and k, then the fc1 chunks of the MLP.
+//   TMEM columns [384,512) v's accumulators, then two HID buffers of 64 columns: GELU(fc1 chunk) as bf16 pairs, lane = token row --
+//                          the A operand of fc2 straight from tensor memory (tcgen05.mma TS form).
 //   smem A32  (32 KB)      LayerNorm output / attention output as a 128-byte-swizzled K-major UMMA A operand.
-//   smem STG  (99 KB)      q,k,v of the 128 tokens in bf16 for the attention (mma.sync); later aliased by
-//                          HID: GELU(fc1) half-tiles (64 KB) as the A operand of fc2.
+//   smem STG  (99 KB)      q,k,v of the 128 tokens in bf16 for the attention (mma.sync).
 //   smem ring (5 x 16 KB)  weight slabs [128 n x 64 k] streamed by TMA in exactly the order the MMAs consume them
 //                          (24 slabs = 384 KB per block, pre-packed on the host).
 // Roles: warps 0-15 "math" (LN, epilogues, attention; thread = token row x column quarter: warp w may only touch TMEM
 // lanes 32*(w%4).., so the four warps of a lane quadrant split the columns), warp 16 TMA producer, warp 17 MMA issuer
-// + TMEM allocation.  Hand-offs are mbarriers: a_ready (math -> MMA), acc[] (MMA -> math, one per commit point).
+// + TMEM allocation.  Hand-offs are mbarriers: a_ready / a_half / g_ready (math -> MMA), acc[] (MMA -> math, one per commit point).
+// DESIGN.md section 3.4 has the measured timeline of a block and the experiments that shaped this layout.
 #include <cuda.h>
 
 #include "ptx.cuh"
