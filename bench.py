@@ -362,7 +362,10 @@ def main():
     # around the model); the ToTensor scaling and the (out*255).clamp().to(uint8) are fused into the first / last kernel.
     # The same pipeline with bf16 host tensors (the float signature of the reference) is reported beside it.
     def run_e2e(hin, hout):
-        pipe = FramePipeline(model, depth=3, device=dev, compute_streams=int(os.environ.get("TU_COMPUTE_STREAMS", "2")), res_out=(OH, OW))
+        # depth 4 with three alternating compute streams: measured best of depth 3-6 x 2-4 streams (tools/probes/e2e_probe.py,
+        # profiles/r2b_e2e_probe.log: 6,630 frames/s against 6,450 for depth 3 / two streams)
+        pipe = FramePipeline(model, depth=int(os.environ.get("TU_PIPE_DEPTH", "4")), device=dev,
+                             compute_streams=int(os.environ.get("TU_COMPUTE_STREAMS", "3")), res_out=(OH, OW))
         # untimed: enough batches for every pipeline slot and both compute streams to have run (their workspaces and output buffers
         # come from torch's stream-aware caching allocator; the first use of a stream / slot would otherwise cudaMalloc in the timed loop)
         for i in range(max(warmup, 3 * pipe.depth)):
@@ -458,7 +461,7 @@ def main():
             "config": cfg,
             "roofline": roof,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "how": "pinned host uint8 frames -> H2D -> model(x_u8) -> uint8 frames -> D2H, copy-in / copy-out streams + alternating compute streams (TU_COMPUTE_STREAMS, default 2), depth-3 pipeline, "
+                    "how": "pinned host uint8 frames -> H2D -> model(x_u8) -> uint8 frames -> D2H, copy-in / copy-out streams + alternating compute streams (TU_COMPUTE_STREAMS, default 3), depth-4 pipeline (TU_PIPE_DEPTH), "
                            "wall clock; x/255 and (out*255).clamp().to(uint8) fused into the first/last kernel; bytes are the whole step's (all ranks)",
                     "output_mean_u8": checksum8,
                     "bf16_host_tensors": {"value": e2e_bf16_fps, "h2d_bytes_per_step": hin[0].numel() * 2 * world,
