@@ -469,3 +469,41 @@ def test_global_attention_tcgen05_block(dev, B, S):
     assert _maxerr(new.reshape(B, S, dim), ref) < 6e-2
     assert _maxerr(new, old) < 3e-2
     assert torch.equal(again, new)
+
+
+@pytest.mark.parametrize("B,S", [(2, 3600), (1, 3600), (3, 328), (1, 130), (5, 256), (2, 1032)])
+def test_global_attention_balanced_launch(dev, B, S):
+    """ResidualTransformer's attention (R:31,44: nn.MultiheadAttention, head_dim 16) with the BALANCED launches of the mma.sync kernel
+    (units of (query tile, key tile) cut into equal contiguous ranges per resident CTA, partial (m, l, o) of split query tiles merged by a
+    second kernel: debug key ga_shape 4 = 64-query tiles, 5 = 128-query tiles) against the plain launch (one CTA per query tile) and a
+    float64 softmax(q k^T) v of the same bf16 inputs; ragged token counts split tiles in every possible place."""
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    heads, dim = 8, 128
+    g = torch.Generator().manual_seed(100 + S)
+    qkv = torch.randn(B * S, 3 * dim, generator=g).bfloat16()
+    qkv[:, :dim] *= 0.25
+    q, k, v = (qkv[:, i * dim:(i + 1) * dim].double().reshape(B, S, heads, 16).permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, dim)
+    d_qkv = qkv.to(dev)
+    nws = lib.tu_global_attention_workspace_bytes(B, S, heads)
+    assert nws > 0
+    ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    try:
+        for shape in (0, 4, 5, -1):
+            lib.tu_debug_set(b"ga_shape", shape)
+            out = torch.full((B * S, dim), float("nan"), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.tu_global_attention(d_qkv.data_ptr(), out.data_ptr(), B, S, heads, ws.data_ptr(), nws, st))
+            again = torch.empty_like(out)
+            _lib.check(lib.tu_global_attention(d_qkv.data_ptr(), again.data_ptr(), B, S, heads, ws.data_ptr(), nws, st))
+            torch.cuda.synchronize()
+            assert torch.equal(out, again), shape                      # partials are merged in a fixed order
+            outs[shape] = out.float().cpu()
+    finally:
+        lib.tu_debug_set(b"ga_shape", -1)
+    for shape, out in outs.items():
+        assert torch.isfinite(out).all(), shape
+        assert (out.double() - ref).abs().max().item() < 2e-2, shape   # bf16 probabilities and outputs
+        assert (out - outs[0]).abs().max().item() < 8e-3, shape        # same arithmetic per key tile, different merge points
