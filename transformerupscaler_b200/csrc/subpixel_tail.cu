@@ -13,7 +13,11 @@
 //   3. a thread slides a 3x3x3 register window down a column of the intermediate tile (9 shared loads per pixel) and
 //      applies the 3 -> 3 filter, whose 84 coefficients ride in the kernel parameters (constant-bank operands of the FMAs),
 //      adds the other branch and writes the clamped image in its final dtype.
-// Arithmetic is fp32 FFMA throughout (this kernel also serves the 1e-4 fp32 path).
+// Arithmetic is fp32 throughout (this kernel also serves the 1e-4 fp32 path), on packed pairs (fma.rn.f32x2 = FFMA2: two IEEE FMAs per issue
+// slot) in the sub-pixel convolution: even and odd taps accumulate in the two halves of a pair, added at the end.  The 3 -> 3 convolution
+// stays scalar: its 81 coefficients are constant-bank operands of FFMA, while FFMA2 takes its pair from (uniform) registers -- 45 pairs
+// exceed the uniform register file and spill (measured: 800 bytes of spills at 64 registers).
+#include "tc/ptx.cuh"
 #include "tu_common.cuh"
 
 namespace tu {
@@ -26,12 +30,16 @@ template <int R> constexpr int tile_rows() { return R == 6 ? 18 : 36; }
 constexpr int TLX = 30;         // low-res columns per tile -> 30 r output columns; + 2 halo columns = 32 lanes
 constexpr int NT = 256;
 
-struct FinFilter { float w[81]; float b[3]; };      // [(ky*3+kx)*3+ci][co], bias
+// [(ky*3+kx)*3+ci][co], bias.  THREE identical copies of the filter: the row loop of step 3 is unrolled three times (rotating window rows) and a
+// coefficient that is read by all three copies would be hoisted into a register by the compiler (81 registers: spills); a copy per unrolled
+// body keeps every coefficient a constant-bank operand of exactly one FFMA.
+struct FinFilter { float w[3][81]; float b[3]; };
 
 template <int R, typename TO>
 __global__ void __launch_bounds__(NT, 4)
 subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps, const float *__restrict__ bps,
-                     const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, int layout, const FinFilter fin) {
+                     const float *__restrict__ addend, TO *__restrict__ out, int H, int W, int clamp, int layout,
+                     const FinFilter fin) {
     constexpr int NCO = 3 * R * R;
     constexpr int TH = tile_rows<R>(), IR = TH + 2;     // IR = intermediate rows held
     constexpr int NLR = TH / R + 4;            // low-res rows staged: ly0 - 2 .. ly0 + TH/R + 1
@@ -104,29 +112,33 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
         }
         const int ly = hy / R, i = hy - ly * R;
         const float *src = lr_s + (ly - ly0 + 1) * LRW + lane;       // tap (ky, kx) -> row ly - 1 + ky, column lx - 1 + kx
-        float v[27];
+        float v[28];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = src[c * NLR * LRW + ky * LRW + kx];
+        v[27] = 0.f;
+        ptx::f32x2 vp[14];                                   // (tap 2k, tap 2k + 1)
+#pragma unroll
+        for (int k = 0; k < 14; ++k) vp[k] = ptx::pk2(v[2 * k], v[2 * k + 1]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const int o = c * R * R + i * R + j;
-                const float4 *wr = reinterpret_cast<const float4 *>(w_s + o * 28);
-                float acc = b_s[o];
+                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w_s + o * 28);      // warp-uniform: broadcast 128-bit loads
+                ptx::f32x2 acc = ptx::pk2(b_s[o], 0.f);       // even taps (+ bias) | odd taps
 #pragma unroll
                 for (int q = 0; q < 7; ++q) {
-                    const float4 ww = wr[q];
-                    acc = fmaf(v[q * 4 + 0], ww.x, acc);
-                    acc = fmaf(v[q * 4 + 1], ww.y, acc);
-                    acc = fmaf(v[q * 4 + 2], ww.z, acc);
-                    if (q < 6) acc = fmaf(v[q * 4 + 3], ww.w, acc);
+                    const ulonglong2 ww = wr[q];
+                    acc = ptx::fma2(vp[2 * q], ww.x, acc);
+                    acc = ptx::fma2(vp[2 * q + 1], ww.y, acc);
                 }
-                dst[c * IR * IW + j] = acc;
+                float lo, hi;
+                ptx::up2(acc, lo, hi);
+                dst[c * IR * IW + j] = lo + hi;
             }
         }
     }
@@ -144,58 +156,66 @@ subpixel_tail_kernel(const float *__restrict__ in, const float *__restrict__ wps
     if (r0 >= r1) return;
     // output row oy0 + ry reads intermediate rows ry .. ry + 2, columns cx + R - 1 .. cx + R + 1
     const float *col = im_s + cx + R - 1;
-    float win[3][3][3];                                 // [row][kx][ci]
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) win[rr + 1][kx][c] = col[c * IR * IW + (r0 + rr) * IW + kx];
+    // a row of the 3 x 3 x 3 window = nine values e = kx * 3 + ci; the three rows live in three register sets whose roles rotate
+    // (the row loop is unrolled three times, so no window moves: they were 18 of the ~130 instructions per pixel of this step)
+#define TU_TAIL_LOAD_ROW(row, ir)                                                                           \
+    do {                                                                                                    \
+        _Pragma("unroll") for (int kx = 0; kx < 3; ++kx)                                                    \
+            _Pragma("unroll") for (int c = 0; c < 3; ++c) row[kx * 3 + c] = col[c * IR * IW + (ir) * IW + kx]; \
+    } while (0)
     const long plane = (long)oH * oW;
     long o = (long)b * 3 * plane + (long)(oy0 + r0) * oW + ox;
     float ad[3];                                        // the other branch, fetched one row ahead of its use
 #pragma unroll
     for (int co = 0; co < 3; ++co) ad[co] = addend[o + co * plane];
+    // one output pixel of the 3 -> 3 convolution from the three window rows (the filter's coefficients are constant-bank operands of the
+    // FMAs), + the other branch (+ clamp), stored in its final dtype.  Macros, not lambdas: with lambdas the three unrolled copies kept
+    // the window rows in local memory (ptxas: 400 bytes of stack, 700 bytes of spills).
+#define TU_TAIL_ROW(top, mid, bot, ry, cp)                                                                     \
+    do {                                                                                                    \
+        float a[3] = {0.f, 0.f, 0.f}, adn[3];                                                               \
+        const long on = (ry) + 1 < r1 ? o + oW : o;                                                         \
+        _Pragma("unroll") for (int co = 0; co < 3; ++co) adn[co] = addend[on + co * plane];                 \
+        _Pragma("unroll") for (int e = 0; e < 9; ++e)                                                       \
+            _Pragma("unroll") for (int co = 0; co < 3; ++co) a[co] = fmaf(top[e], fin.w[cp][e * 3 + co], a[co]);      \
+        _Pragma("unroll") for (int e = 0; e < 9; ++e)                                                       \
+            _Pragma("unroll") for (int co = 0; co < 3; ++co) a[co] = fmaf(mid[e], fin.w[cp][(9 + e) * 3 + co], a[co]); \
+        _Pragma("unroll") for (int e = 0; e < 9; ++e)                                                       \
+            _Pragma("unroll") for (int co = 0; co < 3; ++co) a[co] = fmaf(bot[e], fin.w[cp][(18 + e) * 3 + co], a[co]); \
+        float rgb[3];                                                                                       \
+        _Pragma("unroll") for (int co = 0; co < 3; ++co) {                                                  \
+            /* reference: out = upscaled_input + (conv + bias)   (FastTransformer/model.py:320) */          \
+            float r = ad[co] + (a[co] + fin.b[co]);                                                         \
+            if (clamp) r = fminf(fmaxf(r, 0.f), 1.f);                                                       \
+            rgb[co] = r;                                                                                    \
+            ad[co] = adn[co];                                                                               \
+        }                                                                                                   \
+        if (layout == 0) {                                                                                  \
+            _Pragma("unroll") for (int co = 0; co < 3; ++co) out[o + co * plane] = from_f<TO>(rgb[co]);     \
+        } else {                                                                                            \
+            store_rgb<TO>(out, b, plane, (long)(oy0 + (ry)) * oW + ox, layout, rgb[0], rgb[1], rgb[2]);     \
+        }                                                                                                   \
+        o += oW;                                                                                            \
+    } while (0)
+    float ra[9], rb[9], rc[9];
+    TU_TAIL_LOAD_ROW(ra, r0);
+    TU_TAIL_LOAD_ROW(rb, r0 + 1);
 #pragma unroll 1
-    for (int ry = r0; ry < r1; ++ry, o += oW) {
-        float adn[3];
-        const long on = ry + 1 < r1 ? o + oW : o;
-#pragma unroll
-        for (int co = 0; co < 3; ++co) adn[co] = addend[on + co * plane];
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                win[0][kx][c] = win[1][kx][c];
-                win[1][kx][c] = win[2][kx][c];
-                win[2][kx][c] = col[c * IR * IW + (ry + 2) * IW + kx];
-            }
-        float a[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int co = 0; co < 3; ++co) a[co] = fmaf(win[ky][kx][c], fin.w[((ky * 3 + kx) * 3 + c) * 3 + co], a[co]);
-        float rgb[3];
-#pragma unroll
-        for (int co = 0; co < 3; ++co) {
-            // reference: out = upscaled_input + (conv + bias)   (FastTransformer/model.py:320)
-            float r = ad[co] + (a[co] + fin.b[co]);
-            if (clamp) r = fminf(fmaxf(r, 0.f), 1.f);
-            rgb[co] = r;
-            ad[co] = adn[co];
+    for (int ry = r0; ry < r1; ry += 3) {
+        TU_TAIL_LOAD_ROW(rc, ry + 2);
+        TU_TAIL_ROW(ra, rb, rc, ry, 0);
+        if (ry + 1 < r1) {
+            TU_TAIL_LOAD_ROW(ra, ry + 3);
+            TU_TAIL_ROW(rb, rc, ra, ry + 1, 1);
         }
-        if (layout == 0) {
-#pragma unroll
-            for (int co = 0; co < 3; ++co) out[o + co * plane] = from_f<TO>(rgb[co]);
-        } else {
-            store_rgb<TO>(out, b, plane, (long)(oy0 + ry) * oW + ox, layout, rgb[0], rgb[1], rgb[2]);
+        if (ry + 2 < r1) {
+            TU_TAIL_LOAD_ROW(rb, ry + 4);
+            TU_TAIL_ROW(rc, ra, rb, ry + 2, 2);
         }
     }
 }
+#undef TU_TAIL_LOAD_ROW
+#undef TU_TAIL_ROW
 
 template <int R>
 constexpr size_t tail_smem() {
@@ -246,7 +266,8 @@ extern "C" int tu_subpixel_conv_add(const float *in, const float *w_ps, const fl
     TU_CHECK_ARG(layout == 0 || (out_dtype == TU_U8 && layout <= 2), "subpixel_conv_add: interleaved layouts are for uint8 frames");
     cudaStream_t st = (cudaStream_t)stream;
     FinFilter fin;
-    for (int i = 0; i < 81; ++i) fin.w[i] = host_fin_wb[i];
+    for (int cp = 0; cp < 3; ++cp)
+        for (int i = 0; i < 81; ++i) fin.w[cp][i] = host_fin_wb[i];
     for (int i = 0; i < 3; ++i) fin.b[i] = host_fin_wb[81 + i];
     if (out_dtype == TU_F32) return tail_by_r<float>(r, in, w_ps, b_ps, addend, (float *)out, B, H, W, clamp, layout, fin, st);
     if (out_dtype == TU_BF16) return tail_by_r<bf16>(r, in, w_ps, b_ps, addend, (bf16 *)out, B, H, W, clamp, layout, fin, st);
