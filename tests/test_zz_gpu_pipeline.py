@@ -12,17 +12,17 @@ from oracle.weights import synth_state_dict, synth_frames
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("compute_streams", [1, 2])
-def test_frame_pipeline_matches_direct_calls(compute_streams):
+@pytest.mark.parametrize("compute_streams,depth", [(1, 3), (2, 3), (3, 4)])      # (3, 4): what bench.py's e2e region runs
+def test_frame_pipeline_matches_direct_calls(compute_streams, depth):
     from transformerupscaler_b200.pipeline import FramePipeline
     M = importlib.import_module("transformerupscaler_b200.models.WindowTransformer.model").TransformerModel().eval()
     M.load_state_dict(synth_state_dict("WindowTransformer", 47), strict=True)
     M = M.to("cuda:0").bfloat16()
     H, W, OH, OW = 72, 104, 108, 156
-    frames = [(synth_frames(2, H, W, seed=300 + i) * 255).round().clamp(0, 255).to(torch.uint8) for i in range(7)]
+    frames = [(synth_frames(2, H, W, seed=300 + i) * 255).round().clamp(0, 255).to(torch.uint8) for i in range(9)]
     hin = [f.pin_memory() for f in frames]
     hout = [torch.zeros((2, 3, OH, OW), dtype=torch.uint8).pin_memory() for _ in frames]
-    pipe = FramePipeline(M, depth=3, device=torch.device("cuda:0"), compute_streams=compute_streams, res_out=(OH, OW))
+    pipe = FramePipeline(M, depth=depth, device=torch.device("cuda:0"), compute_streams=compute_streams, res_out=(OH, OW))
     for a, b in zip(hin, hout):
         pipe.submit(a, b)
     pipe.drain()
