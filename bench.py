@@ -234,7 +234,7 @@ def main():
     # The steps of the headline loop alternate between NSTREAMS CUDA streams (default 3): consecutive batches are independent, so the
     # HBM-bound kernels of one forward overlap the tensor-bound kernels of another (+3-4 % over one stream, tools/probes/
     # multistream_probe.py).  Kernel timings for the roofline come from a single-stream pass (overlap would inflate them).
-    nstreams = max(1, int(os.environ.get("TU_BENCH_STREAMS", "3")))
+    nstreams = max(1, int(os.environ.get("TU_BENCH_STREAMS", "4")))      # measured 2 / 3 / 4 / 5 / 6 streams: 6,812 / 6,840 / 6,940 / 6,929 / 6,900 frames/s
     side = [torch.cuda.Stream(dev) for _ in range(nstreams)]
 
     def timed_forwards(n, profile_dominant=True, multi=False):
