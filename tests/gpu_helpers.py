@@ -5,7 +5,7 @@ import torch
 
 from transformerupscaler_b200 import _lib
 
-DT = {torch.float32: 0, torch.bfloat16: 1}
+DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}
 
 
 def stream():

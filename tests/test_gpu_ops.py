@@ -409,6 +409,40 @@ def test_bicubic_add_clamp(dev, in_dt, out_dt, geom):
     assert _maxerr(out1, orc.bicubic_nchw(x.float(), (oH, oW))) < tol
 
 
+@pytest.mark.parametrize("in_dt,out_dt", [(BF16, BF16), (torch.uint8, torch.uint8), (BF16, F32), (torch.uint8, BF16), (BF16, torch.uint8)])
+@pytest.mark.parametrize("geom", [((720, 1280), (360, 640), (1080, 1920)), ((72, 104), (36, 52), (108, 156)), ((48, 64), (24, 40), (72, 250)),
+                                  ((24, 304), (12, 152), (36, 456))])
+def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
+    """The unrolled 3:2 / 3:1 kernel (outH = 3/2 H = 3 rH: 720p -> 1080p) against the pair kernel it replaces (bitwise: same sums in
+    the same order, zero-weight taps are exact no-ops) and against the oracle.  W:224-305 (241, 301, 304-305)."""
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    (H, W), (rH, rW), (oH, oW) = geom
+    B = 2
+    x = synth_frames(B, H, W, seed=3)
+    if in_dt == torch.uint8:
+        x = (x * 255).round().clamp(0, 255).to(torch.uint8)
+    else:
+        x = x.to(in_dt)
+    rs = np.random.RandomState(11)
+    res = torch.from_numpy(rs.uniform(-0.3, 0.3, (B, 3, rH, rW)).astype(np.float32))
+    outs = {}
+    try:
+        for variant in (2, 1):
+            lib.tu_debug_set(b"bicubic_pair", variant)
+            outs[variant] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, True).cpu()
+    finally:
+        lib.tu_debug_set(b"bicubic_pair", 2)
+    assert torch.equal(outs[2], outs[1])
+    if H <= 128:
+        xf = x.float() / 255 if in_dt == torch.uint8 else x.float()
+        ref = (orc.bicubic_nchw(xf, (oH, oW)) + orc.bicubic_nchw(res, (oH, oW))).clamp(0, 1)
+        got = outs[2].float() / 255 if out_dt == torch.uint8 else outs[2].float()
+        tol = 2e-6 if out_dt == F32 else (1.01 / 255 if out_dt == torch.uint8 else 8e-3)     # uint8: truncation of v * 255
+        assert _maxerr(got, ref) < tol
+
+
 @pytest.mark.parametrize("geom", [((80, 112), (60, 84)), ((144, 192), (100, 150)), ((50, 70), (50, 35))])
 def test_resize_aa(dev, geom):
     from tests import gpu_helpers as G

@@ -453,6 +453,206 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const 
     }
 }
 
+// ---- fixed row pattern: x at 3:2, residual at 3:1 (720p -> 1080p and every other x1.5 output) ------------------------------------
+// The pair kernel spends more than half of its issue slots on bookkeeping: window moves (28 MOVs per source row), per-row
+// compare / branch chains, 16-bit tap loads with one shift each, and a local-memory round trip of the pixel values.  When
+// outH = 3/2 H = 3 rH the source-row schedule is periodic (x: rows step 0,1,1 per three output rows, residual: 0,1,0 — checked
+// on the host with the same fp32 coordinate arithmetic, row_pattern_32 below), so the strip loop unrolls over twelve output rows
+// with the four window rows in FIXED registers (a circular window: no moves, no compares).  Taps are fetched as aligned words:
+// the two columns of a pair need at most six consecutive source elements starting at an even index (three 32-bit loads for
+// bf16, three 16-bit loads for uint8) against 6-entry weight vectors padded with zeros — fma(e, 0, t) == t, so every sum is
+// bitwise the pair kernel's.  Vertical weights enter the packed FMAs as broadcast scalars.  Planar output, clamp on, outH a
+// multiple of 12 (a CTA's rows are whole unrolled blocks).
+constexpr int R32_H = 36;       // output rows per CTA: a multiple of 12 (window period) — 1080 = 30 * 36
+
+template <typename TS> __device__ __forceinline__ void ld6(uint32_t a, float (&e)[6]);
+template <> __device__ __forceinline__ void ld6<bf16>(uint32_t a, float (&e)[6]) {
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
+    e[0] = __uint_as_float(w0 << 16); e[1] = __uint_as_float(w0 & 0xffff0000u);
+    e[2] = __uint_as_float(w1 << 16); e[3] = __uint_as_float(w1 & 0xffff0000u);
+    e[4] = __uint_as_float(w2 << 16); e[5] = __uint_as_float(w2 & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void ld6<uint8_t>(uint32_t a, float (&e)[6]) {
+    unsigned short h0, h1, h2;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h0) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1+2];" : "=h"(h1) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1+4];" : "=h"(h2) : "r"(a));
+    // byte -> 0x4B0000bb (2^23 + b) with one byte permute, minus 2^23: u8_to_float
+    e[0] = __uint_as_float(__byte_perm(h0, 0x4B000000u, 0x7440)) - 8388608.f; e[1] = __uint_as_float(__byte_perm(h0, 0x4B000000u, 0x7441)) - 8388608.f;
+    e[2] = __uint_as_float(__byte_perm(h1, 0x4B000000u, 0x7440)) - 8388608.f; e[3] = __uint_as_float(__byte_perm(h1, 0x4B000000u, 0x7441)) - 8388608.f;
+    e[4] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7440)) - 8388608.f; e[5] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7441)) - 8388608.f;
+}
+// horizontal sums of a column pair over one staged source row: six elements from an aligned address, zero-padded weights
+template <typename TS>
+__device__ __forceinline__ ptx::f32x2 hsum6(uint32_t a, const ptx::f32x2 (&w)[6]) {
+    float e[6];
+    ld6<TS>(a, e);
+    ptx::f32x2 t = ptx::mul2(w[0], ptx::pk2(e[0], e[0]));
+#pragma unroll
+    for (int j = 1; j < 6; ++j) t = ptx::fma2(w[j], ptx::pk2(e[j], e[j]), t);
+    if (sizeof(TS) == 1) t = ptx::mul2(t, ptx::pk2(0.00392156862745098f, 0.00392156862745098f));
+    return t;
+}
+// the same over a fp32 row (residual): five elements from the first tap of the left column
+__device__ __forceinline__ ptx::f32x2 hsum5(uint32_t a, const ptx::f32x2 (&w)[5]) {
+    float e[5];
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e[0]) : "r"(a));
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(e[1]) : "r"(a));
+    asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(e[2]) : "r"(a));
+    asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(e[3]) : "r"(a));
+    asm volatile("ld.shared.f32 %0, [%1+16];" : "=f"(e[4]) : "r"(a));
+    ptx::f32x2 t = ptx::mul2(w[0], ptx::pk2(e[0], e[0]));
+#pragma unroll
+    for (int j = 1; j < 5; ++j) t = ptx::fma2(w[j], ptx::pk2(e[j], e[j]), t);
+    return t;
+}
+// w[j] of a 4-tap filter shifted right by `off` inside a longer zero-padded vector
+__device__ __forceinline__ float tap_or_zero(const float (&w)[4], int j) {
+    return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : j == 3 ? w[3] : 0.f;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                         const __grid_constant__ CUtensorMap tmap_r,
+                                                                         const BicubicTileGeom g, int H, int W, int rH, int rW,
+                                                                         TO *__restrict__ out, int oH, int oW) {
+    pdl_trigger();
+    pdl_wait();          // the residual image is written by the previous kernel of the stream
+    __shared__ __align__(16) float yw[2][R32_H][4];
+    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ uint8_t tile_dyn[];
+    uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
+    const int t = threadIdx.x;
+    const int ox0 = blockIdx.x * BS_W, ox = ox0 + 2 * t, oy0 = blockIdx.y * R32_H, b = blockIdx.z;
+    const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
+    const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
+    constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
+    const int xr0 = src_floor(oy0, H, oH) - 1, xc0 = (src_floor(ox0, W, oW) - 1) & ~(XA - 1);
+    const int rr0 = src_floor(oy0, rH, oH) - 1, rc0 = (src_floor(ox0, rW, oW) - 1) & ~3;
+    if (t == 0) {
+        const uint32_t bar_a = ptx::smem_u32(&bar);
+        ptx::mbar_init(bar_a, 1);
+        ptx::fence_barrier_init();
+        ptx::mbar_expect_tx(bar_a, x_bytes + 3u * g.rr * g.rc * 4u);
+        ptx::tma_load_4d(ptx::smem_u32(tile_raw), &tmap_x, bar_a, xc0, xr0, 0, b);
+        ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
+    }
+    for (int i = t; i < 2 * R32_H; i += BS_W / 2) {
+        const int s = i / R32_H, r = i % R32_H;
+        const int in_size = s ? rH : H;
+        const float scale = (float)in_size / (float)oH;
+        const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        const float A = -0.75f;
+        yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
+    }
+    __syncthreads();
+    ptx::mbar_wait(ptx::smem_u32(&bar), 0);
+    replicate_pad(reinterpret_cast<TI *>(tile_raw), xr0, xc0, g.xr, g.xc, H, W);
+    replicate_pad(reinterpret_cast<float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc, rH, rW);
+    if (ox >= oW) return;           // oW is even: a pair is inside or outside as a whole
+
+    // ---- horizontal filters of the pair: six (x) / five (residual) consecutive elements, zero-padded weights
+    ptx::f32x2 wx6[6], wr5[5];
+    uint32_t px, pr;                // shared addresses of the pair's first element in tile row 0, channel 0
+    {
+        const Cubic cA = cubic_taps(ox, W, oW), cB = cubic_taps(ox + 1, W, oW);
+        const int iA = src_floor(ox, W, oW), iB = src_floor(ox + 1, W, oW);
+        const int p0 = (iA - 1) & ~1;                           // even source column (the tile starts on an even column too)
+        const int offA = iA - 1 - p0, offB = iB - 1 - p0;         // 0..1, 0..2
+#pragma unroll
+        for (int j = 0; j < 6; ++j) wx6[j] = ptx::pk2(tap_or_zero(cA.w, j - offA), tap_or_zero(cB.w, j - offB));
+        px = ptx::smem_u32(tile_raw) + (uint32_t)(p0 - xc0) * (uint32_t)sizeof(TI);
+        const Cubic rA = cubic_taps(ox, rW, oW), rB = cubic_taps(ox + 1, rW, oW);
+        const int jA = src_floor(ox, rW, oW), d = src_floor(ox + 1, rW, oW) - jA;       // d = 0 or 1
+#pragma unroll
+        for (int j = 0; j < 5; ++j) wr5[j] = ptx::pk2(tap_or_zero(rA.w, j), tap_or_zero(rB.w, j - d));
+        pr = ptx::smem_u32(tile_raw) + x_bytes_al + (uint32_t)(jA - 1 - rc0) * 4u;
+    }
+    const uint32_t xpitch = g.xc * sizeof(TI), rpitch = g.rc * 4u;
+    const uint32_t xcs = g.xr * xpitch, rcs = g.rr * rpitch;      // channel strides of the two tiles
+    const long oplane = (long)oH * oW;
+    TO *o0 = out + (long)b * 3 * oplane + (long)oy0 * oW + ox, *o1 = o0 + oplane, *o2 = o1 + oplane;
+    const int nrows = min(R32_H, oH - oy0);
+
+    // window rows live in fixed registers: tile row n of a source sits in slot n & 3
+    ptx::f32x2 wx[3][4], wr[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            wx[c][i] = hsum6<TI>(px + c * xcs + i * xpitch, wx6);
+            wr[c][i] = hsum5(pr + c * rcs + i * rpitch, wr5);
+        }
+    px += 4u * xpitch;
+    pr += 4u * rpitch;
+    const float *ywx = &yw[0][0][0], *ywr = &yw[1][0][0];
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += 12) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int k = q / 3, j = q % 3;
+            const int relx = 2 * k + j;             // first tile row of the x window (mod 8 per iteration: slots unchanged)
+            const int relr = k + (j >= 1 ? 1 : 0);  // first tile row of the residual window
+            if (j != 0) {                           // x steps one source row on two output rows of three
+#pragma unroll
+                for (int c = 0; c < 3; ++c) wx[c][(relx + 3) & 3] = hsum6<TI>(px + c * xcs, wx6);
+                px += xpitch;
+            }
+            if (j == 1) {                           // the residual steps on one of three
+#pragma unroll
+                for (int c = 0; c < 3; ++c) wr[c][(relr + 3) & 3] = hsum5(pr + c * rcs, wr5);
+                pr += rpitch;
+            }
+            const float4 a = *reinterpret_cast<const float4 *>(ywx + (r0 + q) * 4);
+            const float4 gg = *reinterpret_cast<const float4 *>(ywr + (r0 + q) * 4);
+            float lo[3], hi[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                ptx::f32x2 v = ptx::mul2(wx[c][relx & 3], ptx::pk2(a.x, a.x));
+                v = ptx::fma2(wx[c][(relx + 1) & 3], ptx::pk2(a.y, a.y), v);
+                v = ptx::fma2(wx[c][(relx + 2) & 3], ptx::pk2(a.z, a.z), v);
+                v = ptx::fma2(wx[c][(relx + 3) & 3], ptx::pk2(a.w, a.w), v);
+                ptx::f32x2 u = ptx::mul2(wr[c][relr & 3], ptx::pk2(gg.x, gg.x));
+                u = ptx::fma2(wr[c][(relr + 1) & 3], ptx::pk2(gg.y, gg.y), u);
+                u = ptx::fma2(wr[c][(relr + 2) & 3], ptx::pk2(gg.z, gg.z), u);
+                u = ptx::fma2(wr[c][(relr + 3) & 3], ptx::pk2(gg.w, gg.w), u);
+                v = ptx::add2(v, u);
+                ptx::up2(v, lo[c], hi[c]);
+                lo[c] = fminf(fmaxf(lo[c], 0.f), 1.f); hi[c] = fminf(fmaxf(hi[c], 0.f), 1.f);
+            }
+            store_pair(o0, lo[0], hi[0]); store_pair(o1, lo[1], hi[1]); store_pair(o2, lo[2], hi[2]);       // outH % 12 == 0 (host): whole blocks of 12 rows
+            o0 += oW; o1 += oW; o2 += oW;
+        }
+    }
+}
+
+// The r32 kernel's row schedule, checked with the device's own fp32 coordinate arithmetic (ATen's): source row of output row oy
+// must be floor((4 oy - 1) / 6) for x (3:2) and floor((oy - 1) / 3) for the residual (3:1) on every row.  The 3:1 coordinate
+// (oy - 1) / 3 is an integer on every third row, where the rounding of scale = (float)rH / oH decides which side the floor falls.
+static bool row_pattern_32(int H, int rH, int oH) {
+    if ((long)H * 3 != (long)oH * 2 || (long)rH * 3 != (long)oH) return false;
+    static thread_local int key[3] = {0, 0, 0};
+    static thread_local bool val = false;
+    if (key[0] == H && key[1] == rH && key[2] == oH) return val;
+    const float sx = (float)H / (float)oH, sr = (float)rH / (float)oH;
+    bool ok = true;
+    for (int oy = 0; oy < oH && ok; ++oy) {
+        int ix = (int)floorf(fmaf(sx, (float)oy + 0.5f, -0.5f));
+        int ir = (int)floorf(fmaf(sr, (float)oy + 0.5f, -0.5f));
+        if (ix > H - 1) ix = H - 1;
+        if (ir > rH - 1) ir = rH - 1;
+        const int ex = (4 * oy - 1 + 6) / 6 - 1, er = (oy - 1 + 3) / 3 - 1;       // floors of (4 oy - 1) / 6 and (oy - 1) / 3
+        ok = ix == ex && ir == er;
+    }
+    key[0] = H; key[1] = rH; key[2] = oH; val = ok;
+    return ok;
+}
+
 // triangle-filter taps for one output index: [lo, lo+n) and the normalisation 1/sum
 __device__ __forceinline__ void aa_range(int dst, int in_size, int out_size, int &lo, int &n, float &center, float &inv,
                                          float &norm) {
@@ -533,7 +733,7 @@ __global__ void __launch_bounds__(256) frames_to_planar_kernel(const uint8_t *__
 
 using namespace tu;
 
-thread_local int tu::g_bicubic_pair = 1;      // debug key "bicubic_pair": two output columns per thread (default) / the one-column strip kernel
+thread_local int tu::g_bicubic_pair = 2;      // debug key "bicubic_pair": 2 = two output columns per thread + the unrolled fixed-row-pattern kernel where it applies (default), 1 = the pair kernel only, 0 = the one-column strip kernel
 
 // (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
 static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, int B, int H, int W, int box_rows, int box_cols) {
@@ -563,9 +763,9 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     // source footprint of a bh x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
     auto plan = [&](int bh) -> bool {
         g.xr = (int)((long)(bh - 1) * H / outH) + 6;
-        g.xc = ((int)((long)(BS_W - 1) * W / outW) + 6 + (16 / eb - 1) + 15) & ~15;        // + alignment slack of the first column
+        g.xc = ((int)((long)(BS_W - 1) * W / outW) + 8 + (16 / eb - 1) + 15) & ~15;        // + alignment slack of the first column
         g.rr = res ? (int)((long)(bh - 1) * rH / outH) + 6 : 0;
-        g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 6 + 3 + 3) & ~3 : 0;
+        g.rc = res ? ((int)((long)(BS_W - 1) * rW / outW) + 8 + 3 + 3) & ~3 : 0;
         const size_t x_bytes = ((size_t)3 * g.xr * g.xc * eb + 127) & ~(size_t)127;
         tile_bytes = x_bytes + (size_t)3 * g.rr * g.rc * 4;
         memset(&tx, 0, sizeof(tx));
@@ -576,6 +776,9 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     };
     // two output columns per thread: TMA tiles, even output width, pair stores aligned
     const bool pair = g_bicubic_pair && (outW % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % (2 * ob)) == 0 && plan(PAIR_H);
+    // fixed 3:2 / 3:1 row schedule (x1.5 outputs such as 720p -> 1080p): the unrolled circular-window kernel
+    const bool r32 = pair && g_bicubic_pair >= 2 && res && clamp && layout == 0 && (in_dtype == TU_BF16 || in_dtype == TU_U8) &&
+                     W <= outW && rW <= outW && outH % 12 == 0 && row_pattern_32(H, rH, outH);
     const bool tma = pair || plan(BS_H);
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
 #define TU_BIC_PAIR(TI, TO)                                                                                                     \
@@ -626,6 +829,26 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
         if (pair) TU_BIC_PAIR(TI, TO); \
         else TU_BIC(TI, TO);     \
     } while (0)
+#define TU_BIC_R32(TI, TO)                                                                                                      \
+    do {                                                                                                                        \
+        static PerDeviceFlag attr_done;                                                                                          \
+        if (!attr_done.is_set()) {                                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 96 * 1024);                                                                    \
+            if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
+            attr_done.set();                                                                                                    \
+        }                                                                                                                       \
+        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW,     \
+                   (TO *)out, outH, outW);                                                                                      \
+    } while (0)
+    if (r32) {
+        if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC_R32(bf16, bf16);
+        else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC_R32(bf16, float);
+        else if (in_dtype == TU_BF16) TU_BIC_R32(bf16, uint8_t);
+        else if (out_dtype == TU_U8) TU_BIC_R32(uint8_t, uint8_t);
+        else if (out_dtype == TU_BF16) TU_BIC_R32(uint8_t, bf16);
+        else TU_BIC_R32(uint8_t, float);
+    } else
     if (in_dtype == TU_F32 && out_dtype == TU_F32) TU_BIC2(float, float);
     else if (in_dtype == TU_F32 && out_dtype == TU_BF16) TU_BIC2(float, bf16);
     else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC2(bf16, float);
@@ -636,6 +859,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     else if (in_dtype == TU_F32 && out_dtype == TU_U8) TU_BIC2(float, uint8_t);
     else TU_BIC2(bf16, uint8_t);
 #undef TU_BIC2
+#undef TU_BIC_R32
 #undef TU_BIC_PAIR
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
