@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const 
 // with the four window rows in FIXED registers (a circular window: no moves, no compares).  Taps are fetched as aligned words:
 // the two columns of a pair need at most six consecutive source elements starting at an even index (three 32-bit loads for
 // bf16, three 16-bit loads for uint8) against 6-entry weight vectors padded with zeros — fma(e, 0, t) == t, so every sum is
-// bitwise the pair kernel's.  Vertical weights enter the packed FMAs as broadcast scalars.  Planar output, clamp on, outH a
+// bitwise the pair kernel's.  Vertical weights enter the packed FMAs as broadcast scalars; a thread works on one channel.  Planar output, clamp on, outH a
 // multiple of 12 (a CTA's rows are whole unrolled blocks).
 constexpr int R32_H = 36;       // output rows per CTA: a multiple of 12 (window period) — 1080 = 30 * 36
 
@@ -509,24 +509,31 @@ __device__ __forceinline__ ptx::f32x2 hsum5(uint32_t a, const ptx::f32x2 (&w)[5]
     for (int j = 1; j < 5; ++j) t = ptx::fma2(w[j], ptx::pk2(e[j], e[j]), t);
     return t;
 }
-// w[j] of a 4-tap filter shifted right by `off` inside a longer zero-padded vector
-__device__ __forceinline__ float tap_or_zero(const float (&w)[4], int j) {
-    return j == 0 ? w[0] : j == 1 ? w[1] : j == 2 ? w[2] : j == 3 ? w[3] : 0.f;
-}
+// w[k] of a 4-tap filter, zero outside 0..3 (k is a compile-time constant after unrolling: no branches, selects only)
+__device__ __forceinline__ float tap_or_zero(const float (&w)[4], int k) { return (k >= 0 && k < 4) ? w[k] : 0.f; }
+
+// A thread is (channel, column pair): 192 threads share the staged tile of a 36 x 128 output block — three times the warps of a
+// three-channels-per-thread layout for the same shared memory, which is what hides the FMA-chain and shared-memory latencies
+// (measured: 2 warps per CTA, 12 per SM -> issue slots 50 % busy).  The per-column filters (four cubic_taps per pair: two
+// columns x two sources) are computed once per CTA by 256 tasks spread over the threads and handed over in shared memory, so
+// the three channels do not repeat them.
+constexpr int R32_T = 3 * (BS_W / 2);
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
+__global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                          const __grid_constant__ CUtensorMap tmap_r,
                                                                          const BicubicTileGeom g, int H, int W, int rH, int rW,
                                                                          TO *__restrict__ out, int oH, int oW) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
     __shared__ __align__(16) float yw[2][R32_H][4];
+    __shared__ float tapw[4][4][BS_W / 2];       // [x left, x right, residual left, residual right][tap][pair]
+    __shared__ int tapi[4][BS_W / 2];            // source column of the second tap (floor of the source coordinate)
     __shared__ __align__(8) uint64_t bar;
     extern __shared__ uint8_t tile_dyn[];
     uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
     const int t = threadIdx.x;
-    const int ox0 = blockIdx.x * BS_W, ox = ox0 + 2 * t, oy0 = blockIdx.y * R32_H, b = blockIdx.z;
+    const int ox0 = blockIdx.x * BS_W, oy0 = blockIdx.y * R32_H, b = blockIdx.z;
     const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
     const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
     constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
@@ -540,54 +547,70 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_r32_kernel(const _
         ptx::tma_load_4d(ptx::smem_u32(tile_raw), &tmap_x, bar_a, xc0, xr0, 0, b);
         ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
     }
-    for (int i = t; i < 2 * R32_H; i += BS_W / 2) {
-        const int s = i / R32_H, r = i % R32_H;
+    const float A = -0.75f;
+    if (t < 2 * R32_H) {                            // vertical filters of the block's rows, both sources
+        const int s = t / R32_H, r = t % R32_H;
         const int in_size = s ? rH : H;
         const float scale = (float)in_size / (float)oH;
         const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
         const int i0 = min((int)floorf(src), in_size - 1);
         const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
-        const float A = -0.75f;
         yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
+    }
+    for (int i = t; i < 4 * (BS_W / 2); i += R32_T) {       // horizontal filters: (source, left / right column) x pair
+        const int which = i / (BS_W / 2), pair = i % (BS_W / 2);
+        const int in_size = (which & 2) ? rW : W;
+        const float scale = (float)in_size / (float)oW;
+        const float src = fmaf(scale, (float)(ox0 + 2 * pair + (which & 1)) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        tapi[which][pair] = i0;
+        tapw[which][0][pair] = cubic2(tt + 1.f, A); tapw[which][1][pair] = cubic1(tt, A);
+        tapw[which][2][pair] = cubic1(u, A); tapw[which][3][pair] = cubic2(u + 1.f, A);
     }
     __syncthreads();
     ptx::mbar_wait(ptx::smem_u32(&bar), 0);
     replicate_pad(reinterpret_cast<TI *>(tile_raw), xr0, xc0, g.xr, g.xc, H, W);
     replicate_pad(reinterpret_cast<float *>(tile_raw + x_bytes_al), rr0, rc0, g.rr, g.rc, rH, rW);
+    const int ch = t / (BS_W / 2), pair = t % (BS_W / 2), ox = ox0 + 2 * pair;
     if (ox >= oW) return;           // oW is even: a pair is inside or outside as a whole
 
     // ---- horizontal filters of the pair: six (x) / five (residual) consecutive elements, zero-padded weights
+    const uint32_t xpitch = g.xc * sizeof(TI), rpitch = g.rc * 4u;
     ptx::f32x2 wx6[6], wr5[5];
-    uint32_t px, pr;                // shared addresses of the pair's first element in tile row 0, channel 0
+    uint32_t px, pr;                // shared addresses of the pair's first element in tile row 0 of the thread's channel
     {
-        const Cubic cA = cubic_taps(ox, W, oW), cB = cubic_taps(ox + 1, W, oW);
-        const int iA = src_floor(ox, W, oW), iB = src_floor(ox + 1, W, oW);
+        float wA[4], wB[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { wA[k] = tapw[0][k][pair]; wB[k] = tapw[1][k][pair]; }
+        const int iA = tapi[0][pair], iB = tapi[1][pair];
         const int p0 = (iA - 1) & ~1;                           // even source column (the tile starts on an even column too)
         const int offA = iA - 1 - p0, offB = iB - 1 - p0;         // 0..1, 0..2
 #pragma unroll
-        for (int j = 0; j < 6; ++j) wx6[j] = ptx::pk2(tap_or_zero(cA.w, j - offA), tap_or_zero(cB.w, j - offB));
-        px = ptx::smem_u32(tile_raw) + (uint32_t)(p0 - xc0) * (uint32_t)sizeof(TI);
-        const Cubic rA = cubic_taps(ox, rW, oW), rB = cubic_taps(ox + 1, rW, oW);
-        const int jA = src_floor(ox, rW, oW), d = src_floor(ox + 1, rW, oW) - jA;       // d = 0 or 1
+        for (int j = 0; j < 6; ++j) {
+            const float a = offA ? tap_or_zero(wA, j - 1) : tap_or_zero(wA, j);
+            const float bb = offB == 0 ? tap_or_zero(wB, j) : offB == 1 ? tap_or_zero(wB, j - 1) : tap_or_zero(wB, j - 2);
+            wx6[j] = ptx::pk2(a, bb);
+        }
+        px = ptx::smem_u32(tile_raw) + (uint32_t)(p0 - xc0) * (uint32_t)sizeof(TI) + (uint32_t)ch * g.xr * xpitch;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) wr5[j] = ptx::pk2(tap_or_zero(rA.w, j), tap_or_zero(rB.w, j - d));
-        pr = ptx::smem_u32(tile_raw) + x_bytes_al + (uint32_t)(jA - 1 - rc0) * 4u;
+        for (int k = 0; k < 4; ++k) { wA[k] = tapw[2][k][pair]; wB[k] = tapw[3][k][pair]; }
+        const int jA = tapi[2][pair], d = tapi[3][pair] - jA;       // d = 0 or 1
+#pragma unroll
+        for (int j = 0; j < 5; ++j) wr5[j] = ptx::pk2(tap_or_zero(wA, j), d ? tap_or_zero(wB, j - 1) : tap_or_zero(wB, j));
+        pr = ptx::smem_u32(tile_raw) + x_bytes_al + (uint32_t)(jA - 1 - rc0) * 4u + (uint32_t)ch * g.rr * rpitch;
     }
-    const uint32_t xpitch = g.xc * sizeof(TI), rpitch = g.rc * 4u;
-    const uint32_t xcs = g.xr * xpitch, rcs = g.rr * rpitch;      // channel strides of the two tiles
     const long oplane = (long)oH * oW;
-    TO *o0 = out + (long)b * 3 * oplane + (long)oy0 * oW + ox, *o1 = o0 + oplane, *o2 = o1 + oplane;
+    TO *o = out + ((long)b * 3 + ch) * oplane + (long)oy0 * oW + ox;
     const int nrows = min(R32_H, oH - oy0);
 
     // window rows live in fixed registers: tile row n of a source sits in slot n & 3
-    ptx::f32x2 wx[3][4], wr[3][4];
+    ptx::f32x2 wx[4], wr[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            wx[c][i] = hsum6<TI>(px + c * xcs + i * xpitch, wx6);
-            wr[c][i] = hsum5(pr + c * rcs + i * rpitch, wr5);
-        }
+    for (int i = 0; i < 4; ++i) {
+        wx[i] = hsum6<TI>(px + i * xpitch, wx6);
+        wr[i] = hsum5(pr + i * rpitch, wr5);
+    }
     px += 4u * xpitch;
     pr += 4u * rpitch;
     const float *ywx = &yw[0][0][0], *ywr = &yw[1][0][0];
@@ -599,34 +622,29 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_r32_kernel(const _
             const int relx = 2 * k + j;             // first tile row of the x window (mod 8 per iteration: slots unchanged)
             const int relr = k + (j >= 1 ? 1 : 0);  // first tile row of the residual window
             if (j != 0) {                           // x steps one source row on two output rows of three
-#pragma unroll
-                for (int c = 0; c < 3; ++c) wx[c][(relx + 3) & 3] = hsum6<TI>(px + c * xcs, wx6);
+                wx[(relx + 3) & 3] = hsum6<TI>(px, wx6);
                 px += xpitch;
             }
             if (j == 1) {                           // the residual steps on one of three
-#pragma unroll
-                for (int c = 0; c < 3; ++c) wr[c][(relr + 3) & 3] = hsum5(pr + c * rcs, wr5);
+                wr[(relr + 3) & 3] = hsum5(pr, wr5);
                 pr += rpitch;
             }
             const float4 a = *reinterpret_cast<const float4 *>(ywx + (r0 + q) * 4);
             const float4 gg = *reinterpret_cast<const float4 *>(ywr + (r0 + q) * 4);
-            float lo[3], hi[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                ptx::f32x2 v = ptx::mul2(wx[c][relx & 3], ptx::pk2(a.x, a.x));
-                v = ptx::fma2(wx[c][(relx + 1) & 3], ptx::pk2(a.y, a.y), v);
-                v = ptx::fma2(wx[c][(relx + 2) & 3], ptx::pk2(a.z, a.z), v);
-                v = ptx::fma2(wx[c][(relx + 3) & 3], ptx::pk2(a.w, a.w), v);
-                ptx::f32x2 u = ptx::mul2(wr[c][relr & 3], ptx::pk2(gg.x, gg.x));
-                u = ptx::fma2(wr[c][(relr + 1) & 3], ptx::pk2(gg.y, gg.y), u);
-                u = ptx::fma2(wr[c][(relr + 2) & 3], ptx::pk2(gg.z, gg.z), u);
-                u = ptx::fma2(wr[c][(relr + 3) & 3], ptx::pk2(gg.w, gg.w), u);
-                v = ptx::add2(v, u);
-                ptx::up2(v, lo[c], hi[c]);
-                lo[c] = fminf(fmaxf(lo[c], 0.f), 1.f); hi[c] = fminf(fmaxf(hi[c], 0.f), 1.f);
-            }
-            store_pair(o0, lo[0], hi[0]); store_pair(o1, lo[1], hi[1]); store_pair(o2, lo[2], hi[2]);       // outH % 12 == 0 (host): whole blocks of 12 rows
-            o0 += oW; o1 += oW; o2 += oW;
+            ptx::f32x2 v = ptx::mul2(wx[relx & 3], ptx::pk2(a.x, a.x));
+            v = ptx::fma2(wx[(relx + 1) & 3], ptx::pk2(a.y, a.y), v);
+            v = ptx::fma2(wx[(relx + 2) & 3], ptx::pk2(a.z, a.z), v);
+            v = ptx::fma2(wx[(relx + 3) & 3], ptx::pk2(a.w, a.w), v);
+            ptx::f32x2 u = ptx::mul2(wr[relr & 3], ptx::pk2(gg.x, gg.x));
+            u = ptx::fma2(wr[(relr + 1) & 3], ptx::pk2(gg.y, gg.y), u);
+            u = ptx::fma2(wr[(relr + 2) & 3], ptx::pk2(gg.z, gg.z), u);
+            u = ptx::fma2(wr[(relr + 3) & 3], ptx::pk2(gg.w, gg.w), u);
+            v = ptx::add2(v, u);
+            float lo, hi;
+            ptx::up2(v, lo, hi);
+            lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
+            store_pair(o, lo, hi);                  // outH % 12 == 0 (host): whole blocks of 12 rows
+            o += oW;
         }
     }
 }
@@ -838,7 +856,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
             attr_done.set();                                                                                                    \
         }                                                                                                                       \
-        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO>, grid, dim3(BS_W / 2), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW,     \
+        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO>, grid, dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW,     \
                    (TO *)out, outH, outW);                                                                                      \
     } while (0)
     if (r32) {
