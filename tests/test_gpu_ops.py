@@ -413,7 +413,7 @@ def test_bicubic_add_clamp(dev, in_dt, out_dt, geom):
 @pytest.mark.parametrize("geom", [((720, 1280), (360, 640), (1080, 1920)), ((72, 104), (36, 52), (108, 156)), ((48, 64), (24, 40), (72, 250)),
                                   ((24, 304), (12, 152), (36, 456))])
 def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
-    """The unrolled 3:2 / 3:1 kernel (outH = 3/2 H = 3 rH: 720p -> 1080p) against the pair kernel it replaces (bitwise: same sums in
+    """The unrolled 3:2 / 3:1 kernels (outH = 3/2 H = 3 rH: 720p -> 1080p; streaming and tile forms) against the pair kernel they replace (bitwise: same sums in
     the same order, zero-weight taps are exact no-ops) and against the oracle.  W:224-305 (241, 301, 304-305)."""
     from tests import gpu_helpers as G
     from transformerupscaler_b200 import _lib
@@ -429,12 +429,13 @@ def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
     res = torch.from_numpy(rs.uniform(-0.3, 0.3, (B, 3, rH, rW)).astype(np.float32))
     outs = {}
     try:
-        for variant in (2, 1):
+        for variant in (3, 2, 1):     # streaming form, tile form, pair kernel
             lib.tu_debug_set(b"bicubic_pair", variant)
             outs[variant] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, True).cpu()
     finally:
         lib.tu_debug_set(b"bicubic_pair", 2)
-    assert torch.equal(outs[2], outs[1])
+    for variant in (3, 2):
+        assert torch.equal(outs[variant], outs[1]), variant
     if H <= 128:
         xf = x.float() / 255 if in_dt == torch.uint8 else x.float()
         ref = (orc.bicubic_nchw(xf, (oH, oW)) + orc.bicubic_nchw(res, (oH, oW))).clamp(0, 1)

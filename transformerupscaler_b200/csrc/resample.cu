@@ -9,6 +9,8 @@
 //    FastTransformer when the integer factor overshoots res_out (FastTransformer/model.py:323-325).
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "tc/ptx.cuh"
 #include "tc/tc_api.cuh"
 #include "tu_common.cuh"
@@ -127,7 +129,13 @@ __device__ __forceinline__ int src_floor(int dst, int in_size, int out_size) {
     return min((int)floorf(fmaf(scale, (float)dst + 0.5f, -0.5f)), in_size - 1);
 }
 
-struct BicubicTileGeom { int xr, xc, rr, rc; };     // TMA box sizes: rows / cols of the x tile and of the residual tile
+struct BicubicTileGeom {
+    int xr, xc, rr, rc;             // TMA box sizes: rows / cols of the x tile and of the residual tile
+    float sxh, sxw, srh, srw;       // (float)in / (float)out per axis and source, divided once on the host (same IEEE quotient)
+};
+__device__ __forceinline__ int src_floor_s(int dst, float scale, int in_size) {
+    return min((int)floorf(fmaf(scale, (float)dst + 0.5f, -0.5f)), in_size - 1);
+}
 
 // shared-memory element -> float with an immediate byte offset (the four taps of a row are contiguous)
 template <int OFF> __device__ __forceinline__ float lds_raw(uint32_t a, float) {
@@ -453,6 +461,14 @@ __global__ void __launch_bounds__(BS_W / 2) bicubic_add_clamp_pair_kernel(const 
     }
 }
 
+// pair store of values already clamped to [0, 1]: from_f<uint8_t> without its (then no-op) clamp to [0, 255] — the same product
+// and the same round-down add, the two result bytes packed by one permute; other output types store as usual
+template <typename T> __device__ __forceinline__ void store_pair_unit(T *o, float a, float b) { store_pair(o, a, b); }
+template <> __device__ __forceinline__ void store_pair_unit<uint8_t>(uint8_t *o, float a, float b) {
+    const uint32_t ua = __float_as_uint(__fadd_rd(__fmul_rn(a, 255.f), 8388608.f)), ub = __float_as_uint(__fadd_rd(__fmul_rn(b, 255.f), 8388608.f));
+    *reinterpret_cast<unsigned short *>(o) = (unsigned short)__byte_perm(ua, ub, 0x0040);
+}
+
 // ---- fixed row pattern: x at 3:2, residual at 3:1 (720p -> 1080p and every other x1.5 output) ------------------------------------
 // The pair kernel spends more than half of its issue slots on bookkeeping: window moves (28 MOVs per source row), per-row
 // compare / branch chains, 16-bit tap loads with one shift each, and a local-memory round trip of the pixel values.  When
@@ -537,8 +553,8 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
     const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
     const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
     constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
-    const int xr0 = src_floor(oy0, H, oH) - 1, xc0 = (src_floor(ox0, W, oW) - 1) & ~(XA - 1);
-    const int rr0 = src_floor(oy0, rH, oH) - 1, rc0 = (src_floor(ox0, rW, oW) - 1) & ~3;
+    const int xr0 = src_floor_s(oy0, g.sxh, H) - 1, xc0 = (src_floor_s(ox0, g.sxw, W) - 1) & ~(XA - 1);
+    const int rr0 = src_floor_s(oy0, g.srh, rH) - 1, rc0 = (src_floor_s(ox0, g.srw, rW) - 1) & ~3;
     if (t == 0) {
         const uint32_t bar_a = ptx::smem_u32(&bar);
         ptx::mbar_init(bar_a, 1);
@@ -551,7 +567,7 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
     if (t < 2 * R32_H) {                            // vertical filters of the block's rows, both sources
         const int s = t / R32_H, r = t % R32_H;
         const int in_size = s ? rH : H;
-        const float scale = (float)in_size / (float)oH;
+        const float scale = s ? g.srh : g.sxh;
         const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
         const int i0 = min((int)floorf(src), in_size - 1);
         const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
@@ -560,7 +576,7 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
     for (int i = t; i < 4 * (BS_W / 2); i += R32_T) {       // horizontal filters: (source, left / right column) x pair
         const int which = i / (BS_W / 2), pair = i % (BS_W / 2);
         const int in_size = (which & 2) ? rW : W;
-        const float scale = (float)in_size / (float)oW;
+        const float scale = (which & 2) ? g.srw : g.sxw;
         const float src = fmaf(scale, (float)(ox0 + 2 * pair + (which & 1)) + 0.5f, -0.5f);
         const int i0 = min((int)floorf(src), in_size - 1);
         const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
@@ -643,9 +659,176 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
             float lo, hi;
             ptx::up2(v, lo, hi);
             lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
-            store_pair(o, lo, hi);                  // outH % 12 == 0 (host): whole blocks of 12 rows
+            store_pair_unit(o, lo, hi);             // outH % 12 == 0 (host): whole blocks of 12 rows
             o += oW;
         }
+    }
+}
+
+// ---- the same, streaming ---------------------------------------------------------------------------------------------------
+// The tile kernel pays its set-up (column filters, vertical table, four window rows per source, the wait for the tile) once per
+// 36 output rows: 30 % of its instructions.  Here a CTA walks DOWN a 128-column strip for up to 16 blocks of 12 output rows; the
+// window registers simply carry over, and the source rows arrive through a ring of three small stages (8 x rows + 4 residual rows
+// = the new rows of one block), loaded by TMA two blocks ahead.  full[] barriers carry the TMA bytes, empty[] barriers count one
+// arrival per warp; warp 0 refills the stage released one block earlier.  Load 0 is the window's initial four rows (an 8-row x
+// box whose upper half is not used, so that every box has the same shape).  The grid is sized to be co-resident: strips x
+// segments <= 5 CTAs per SM.
+constexpr int R32S_NST = 3, R32S_MAXBLK = 16;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32s_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                          const __grid_constant__ CUtensorMap tmap_r, int xc, int rc,
+                                                                          int H, int W, int rH, int rW, TO *__restrict__ out, int oH,
+                                                                          int oW, int blocks_per_seg) {
+    pdl_trigger();
+    pdl_wait();          // the residual image is written by the previous kernel of the stream
+    __shared__ __align__(16) float yw[2][R32S_MAXBLK * 12][4];
+    __shared__ float tapw[4][4][BS_W / 2];       // [x left, x right, residual left, residual right][tap][pair]
+    __shared__ int tapi[4][BS_W / 2];            // source column of the second tap (floor of the source coordinate)
+    __shared__ __align__(8) uint64_t full[R32S_NST], empty[R32S_NST];
+    extern __shared__ uint8_t tile_dyn[];
+    uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int ox0 = blockIdx.x * BS_W, b = blockIdx.z;
+    const int kb0 = blockIdx.y * blocks_per_seg, nblk = min(blocks_per_seg, oH / 12 - kb0), oy0 = kb0 * 12;
+    const int X0 = 8 * kb0 - 6, R0 = 4 * kb0 - 2;   // first source rows of load 0: the window of output row oy0 is x rows 8 kb0 - 2 .. + 1
+    constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
+    const int xc0 = (src_floor(ox0, W, oW) - 1) & ~(XA - 1), rc0 = (src_floor(ox0, rW, oW) - 1) & ~3;
+    const uint32_t xpitch = xc * sizeof(TI), rpitch = rc * 4u;
+    const uint32_t x_bytes = 3u * 8u * xpitch, r_bytes = 3u * 4u * rpitch;
+    const uint32_t xst = (x_bytes + 127u) & ~127u, stage_bytes = xst + ((r_bytes + 127u) & ~127u);
+    const uint32_t ring = ptx::smem_u32(tile_raw), full_a = ptx::smem_u32(&full[0]), empty_a = ptx::smem_u32(&empty[0]);
+    const int total = nblk + 1;
+    auto issue = [&](int L) {
+        const uint32_t st = (uint32_t)(L % R32S_NST), bar_a = full_a + 8u * st;
+        ptx::mbar_expect_tx(bar_a, x_bytes + r_bytes);
+        ptx::tma_load_4d(ring + st * stage_bytes, &tmap_x, bar_a, xc0, X0 + 8 * L, 0, b);
+        ptx::tma_load_4d(ring + st * stage_bytes + xst, &tmap_r, bar_a, rc0, R0 + 4 * L, 0, b);
+    };
+    if (t == 0) {
+        for (int i = 0; i < R32S_NST; ++i) { ptx::mbar_init(full_a + 8u * i, 1); ptx::mbar_init(empty_a + 8u * i, R32_T / 32); }
+        ptx::fence_barrier_init();
+        for (int L = 0; L < R32S_NST && L < total; ++L) issue(L);
+    }
+    const float A = -0.75f;
+    for (int i = t; i < 2 * 12 * nblk; i += R32_T) {      // vertical filters of the segment's rows, both sources
+        const int s = i / (12 * nblk), r = i % (12 * nblk);
+        const int in_size = s ? rH : H;
+        const float scale = (float)in_size / (float)oH;
+        const float src = fmaf(scale, (float)(oy0 + r) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        yw[s][r][0] = cubic2(tt + 1.f, A); yw[s][r][1] = cubic1(tt, A); yw[s][r][2] = cubic1(u, A); yw[s][r][3] = cubic2(u + 1.f, A);
+    }
+    for (int i = t; i < 4 * (BS_W / 2); i += R32_T) {       // horizontal filters: (source, left / right column) x pair
+        const int which = i / (BS_W / 2), pair = i % (BS_W / 2);
+        const int in_size = (which & 2) ? rW : W;
+        const float scale = (float)in_size / (float)oW;
+        const float src = fmaf(scale, (float)(ox0 + 2 * pair + (which & 1)) + 0.5f, -0.5f);
+        const int i0 = min((int)floorf(src), in_size - 1);
+        const float tt = fminf(fmaxf(src - (float)i0, 0.f), 1.f), u = 1.f - tt;
+        tapi[which][pair] = i0;
+        tapw[which][0][pair] = cubic2(tt + 1.f, A); tapw[which][1][pair] = cubic1(tt, A);
+        tapw[which][2][pair] = cubic1(u, A); tapw[which][3][pair] = cubic2(u + 1.f, A);
+    }
+    __syncthreads();
+    const int ch = t / (BS_W / 2), pair = t % (BS_W / 2), ox = ox0 + 2 * pair;
+    const bool active = ox < oW;    // oW is even: a pair is inside or outside as a whole; idle threads keep the barrier counts
+
+    // ---- horizontal filters of the pair: six (x) / five (residual) consecutive elements, zero-padded weights
+    ptx::f32x2 wx6[6], wr5[5];
+    uint32_t pxo, pro;              // byte offsets of the pair's first element inside a stage, in tile row 0 of the thread's channel
+    {
+        float wA[4], wB[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { wA[k] = tapw[0][k][pair]; wB[k] = tapw[1][k][pair]; }
+        const int iA = tapi[0][pair], iB = tapi[1][pair];
+        const int p0 = (iA - 1) & ~1;                           // even source column (the tile starts on an even column too)
+        const int offA = iA - 1 - p0, offB = iB - 1 - p0;         // 0..1, 0..2
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const float a = offA ? tap_or_zero(wA, j - 1) : tap_or_zero(wA, j);
+            const float bb = offB == 0 ? tap_or_zero(wB, j) : offB == 1 ? tap_or_zero(wB, j - 1) : tap_or_zero(wB, j - 2);
+            wx6[j] = ptx::pk2(a, bb);
+        }
+        pxo = (active ? (uint32_t)(p0 - xc0) * (uint32_t)sizeof(TI) : 0u) + (uint32_t)ch * 8u * xpitch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { wA[k] = tapw[2][k][pair]; wB[k] = tapw[3][k][pair]; }
+        const int jA = tapi[2][pair], d = tapi[3][pair] - jA;       // d = 0 or 1
+#pragma unroll
+        for (int j = 0; j < 5; ++j) wr5[j] = ptx::pk2(tap_or_zero(wA, j), d ? tap_or_zero(wB, j - 1) : tap_or_zero(wB, j));
+        pro = xst + (active ? (uint32_t)(jA - 1 - rc0) * 4u : 0u) + (uint32_t)ch * 4u * rpitch;
+    }
+    const long oplane = (long)oH * oW;
+    TO *o = out + ((long)b * 3 + ch) * oplane + (long)oy0 * oW + (active ? ox : 0);
+    // loads whose boxes reach outside the image (uniform over the CTA): every one of a strip at the left / right edge, else the
+    // first ones of the top segment and the last ones of the bottom segment
+    int kpad_lo = 0, kpad_hi = total;
+    if (xc0 < 0 || xc0 + xc > W || rc0 < 0 || rc0 + rc > rW) kpad_lo = total;
+    else {
+        while (kpad_lo < total && (X0 + 8 * kpad_lo < 0 || R0 + 4 * kpad_lo < 0)) ++kpad_lo;
+        while (kpad_hi > kpad_lo && (X0 + 8 * (kpad_hi - 1) + 8 > H || R0 + 4 * (kpad_hi - 1) + 4 > rH)) --kpad_hi;
+    }
+
+    // window rows live in fixed registers: row n of a source (counted from the window's first row at oy0) sits in slot n & 3
+    ptx::f32x2 wx[4], wr[4];
+    const float *ywx = &yw[0][0][0], *ywr = &yw[1][0][0];
+#pragma unroll 1
+    for (int k = 0; k < total; ++k) {
+        const uint32_t st = (uint32_t)(k % R32S_NST);
+        if (warp == 0 && k >= 1 && k - 1 + R32S_NST < total) {      // refill the stage every warp released one block ago
+            ptx::mbar_wait(empty_a + 8u * (uint32_t)((k - 1) % R32S_NST), (uint32_t)((k - 1) / R32S_NST) & 1u);
+            if (lane == 0) issue(k - 1 + R32S_NST);
+        }
+        ptx::mbar_wait(full_a + 8u * st, (uint32_t)(k / R32S_NST) & 1u);
+        const bool pad = k < kpad_lo || k >= kpad_hi;
+        if (pad) {          // the TMA zero-fills outside the image; bicubic taps clamp to the border
+            replicate_pad(reinterpret_cast<TI *>(tile_raw + st * stage_bytes), X0 + 8 * k, xc0, 8, xc, H, W);
+            replicate_pad(reinterpret_cast<float *>(tile_raw + st * stage_bytes + xst), R0 + 4 * k, rc0, 4, rc, rH, rW);
+        }
+        uint32_t px = ring + st * stage_bytes + pxo, pr = ring + st * stage_bytes + pro;
+        if (k == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                wx[i] = hsum6<TI>(px + (4 + i) * xpitch, wx6);
+                wr[i] = hsum5(pr + i * rpitch, wr5);
+            }
+        } else {
+            const int r0 = (k - 1) * 12;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const int kk = q / 3, j = q % 3;
+                const int relx = 2 * kk + j;            // first row of the x window (8 rows per block: slots unchanged)
+                const int relr = kk + (j >= 1 ? 1 : 0); // first row of the residual window
+                if (j != 0) {                           // x steps one source row on two output rows of three
+                    wx[(relx + 3) & 3] = hsum6<TI>(px, wx6);
+                    px += xpitch;
+                }
+                if (j == 1) {                           // the residual steps on one of three
+                    wr[(relr + 3) & 3] = hsum5(pr, wr5);
+                    pr += rpitch;
+                }
+                const float4 a = *reinterpret_cast<const float4 *>(ywx + (r0 + q) * 4);
+                const float4 gg = *reinterpret_cast<const float4 *>(ywr + (r0 + q) * 4);
+                ptx::f32x2 v = ptx::mul2(wx[relx & 3], ptx::pk2(a.x, a.x));
+                v = ptx::fma2(wx[(relx + 1) & 3], ptx::pk2(a.y, a.y), v);
+                v = ptx::fma2(wx[(relx + 2) & 3], ptx::pk2(a.z, a.z), v);
+                v = ptx::fma2(wx[(relx + 3) & 3], ptx::pk2(a.w, a.w), v);
+                ptx::f32x2 u = ptx::mul2(wr[relr & 3], ptx::pk2(gg.x, gg.x));
+                u = ptx::fma2(wr[(relr + 1) & 3], ptx::pk2(gg.y, gg.y), u);
+                u = ptx::fma2(wr[(relr + 2) & 3], ptx::pk2(gg.z, gg.z), u);
+                u = ptx::fma2(wr[(relr + 3) & 3], ptx::pk2(gg.w, gg.w), u);
+                v = ptx::add2(v, u);
+                float lo, hi;
+                ptx::up2(v, lo, hi);
+                lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
+                if (active) store_pair_unit(o, lo, hi);
+                o += oW;
+            }
+        }
+        __syncwarp();
+        if (pad) ptx::fence_proxy_async();      // the stage was rewritten through the generic proxy; the next writer is the TMA
+        if (lane == 0) ptx::mbar_arrive(empty_a + 8u * st);
     }
 }
 
@@ -751,7 +934,7 @@ __global__ void __launch_bounds__(256) frames_to_planar_kernel(const uint8_t *__
 
 using namespace tu;
 
-thread_local int tu::g_bicubic_pair = 2;      // debug key "bicubic_pair": 2 = two output columns per thread + the unrolled fixed-row-pattern kernel where it applies (default), 1 = the pair kernel only, 0 = the one-column strip kernel
+thread_local int tu::g_bicubic_pair = 2;      // debug key "bicubic_pair": 2 = two output columns per thread + the unrolled fixed-row-pattern kernel where it applies (default), 3 = the same with the streaming form of that kernel (measured slower), 1 = the pair kernel only, 0 = the one-column strip kernel
 
 // (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
 static bool encode_image_map(CUtensorMap *tm, const void *ptr, int elem_bytes, int B, int H, int W, int box_rows, int box_cols) {
@@ -776,6 +959,8 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     cudaStream_t st = (cudaStream_t)stream;
     const int eb = (int)dtype_size(in_dtype), ob = (int)dtype_size(out_dtype);
     BicubicTileGeom g;
+    g.sxh = (float)H / (float)outH; g.sxw = (float)W / (float)outW;
+    g.srh = res ? (float)rH / (float)outH : 0.f; g.srw = res ? (float)rW / (float)outW : 0.f;
     size_t tile_bytes = 0;
     CUtensorMap tx, tr;
     // source footprint of a bh x 128 output tile (+4 taps, +2 for fp32 rounding of the coordinates), cols padded to 16 bytes
@@ -859,6 +1044,44 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
         launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO>, grid, dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW,     \
                    (TO *)out, outH, outW);                                                                                      \
     } while (0)
+    if (r32 && g_bicubic_pair >= 3) {
+        // streaming variant: strips x segments co-resident (5 CTAs per SM), <= 16 blocks of 12 rows per segment
+        const int nblk = outH / 12, strips = (int)grid.x * B;
+        const size_t stage = (((size_t)3 * 8 * g.xc * eb + 127) & ~(size_t)127) + (((size_t)3 * 4 * g.rc * 4 + 127) & ~(size_t)127);
+        const size_t ring_bytes = R32S_NST * stage + 128;
+        // CTAs per SM: 5 by registers (64 x 192 threads), fewer if the ring + 12 KB of static tables + 1 KB reserved do not fit 227 KB
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(5, (size_t)227 * 1024 / (ring_bytes + 13 * 1024)));
+        int nseg = std::max(1, std::min(nblk, device_sm_count() * per_sm / std::max(strips, 1)));
+        int bps = std::min(std::max(ceil_div(nblk, nseg), std::min(3, nblk)), R32S_MAXBLK);      // at least 36 rows per CTA
+        nseg = ceil_div(nblk, bps);
+        CUtensorMap sx, sr;
+        memset(&sx, 0, sizeof(sx));
+        memset(&sr, 0, sizeof(sr));
+        if (ring_bytes <= 96 * 1024 && encode_image_map(&sx, x, eb, B, H, W, 8, g.xc) && encode_image_map(&sr, res, 4, B, rH, rW, 4, g.rc)) {
+            dim3 sgrid(grid.x, nseg, B);
+#define TU_BIC_R32S(TI, TO)                                                                                                     \
+    do {                                                                                                                        \
+        static PerDeviceFlag attr_done;                                                                                          \
+        if (!attr_done.is_set()) {                                                                                               \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32s_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 96 * 1024);                                                                    \
+            if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
+            attr_done.set();                                                                                                    \
+        }                                                                                                                       \
+        launch_pdl(bicubic_add_clamp_r32s_kernel<TI, TO>, sgrid, dim3(R32_T), ring_bytes, st, sx, sr, g.xc, g.rc, H, W, rH, rW,   \
+                   (TO *)out, outH, outW, bps);                                                                                 \
+    } while (0)
+            if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC_R32S(bf16, bf16);
+            else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC_R32S(bf16, float);
+            else if (in_dtype == TU_BF16) TU_BIC_R32S(bf16, uint8_t);
+            else if (out_dtype == TU_U8) TU_BIC_R32S(uint8_t, uint8_t);
+            else if (out_dtype == TU_BF16) TU_BIC_R32S(uint8_t, bf16);
+            else TU_BIC_R32S(uint8_t, float);
+#undef TU_BIC_R32S
+            TU_CHECK_LAUNCH("bicubic_add_clamp");
+            return TU_OK;
+        }
+    }
     if (r32) {
         if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC_R32(bf16, bf16);
         else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC_R32(bf16, float);
