@@ -487,9 +487,10 @@ template <> __device__ __forceinline__ void ld6<bf16>(uint32_t a, float (&e)[6])
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
     asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
-    e[0] = __uint_as_float(w0 << 16); e[1] = __uint_as_float(w0 & 0xffff0000u);
-    e[2] = __uint_as_float(w1 << 16); e[3] = __uint_as_float(w1 & 0xffff0000u);
-    e[4] = __uint_as_float(w2 << 16); e[5] = __uint_as_float(w2 & 0xffff0000u);
+    // low half by a byte permute (ALU pipe; a shift may be issued as an integer multiply on the FMA pipe, which is the busy one here)
+    e[0] = __uint_as_float(__byte_perm(w0, 0u, 0x1044)); e[1] = __uint_as_float(w0 & 0xffff0000u);
+    e[2] = __uint_as_float(__byte_perm(w1, 0u, 0x1044)); e[3] = __uint_as_float(w1 & 0xffff0000u);
+    e[4] = __uint_as_float(__byte_perm(w2, 0u, 0x1044)); e[5] = __uint_as_float(w2 & 0xffff0000u);
 }
 template <> __device__ __forceinline__ void ld6<uint8_t>(uint32_t a, float (&e)[6]) {
     unsigned short h0, h1, h2;
