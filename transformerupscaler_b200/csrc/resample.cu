@@ -469,17 +469,17 @@ template <> __device__ __forceinline__ void store_pair_unit<uint8_t>(uint8_t *o,
     *reinterpret_cast<unsigned short *>(o) = (unsigned short)__byte_perm(ua, ub, 0x0040);
 }
 
-// ---- fixed row pattern: x at 3:2, residual at 3:1 (720p -> 1080p and every other x1.5 output) ------------------------------------
+// ---- periodic row schedules: x at 3:2 with the residual at 3:1 (720p -> 1080p, every x1.5 output), x at 3:1 with the residual at 6:1
+// (720p -> 4K) --------------------------------------------------------------------------------------------------------------------
 // The pair kernel spends more than half of its issue slots on bookkeeping: window moves (28 MOVs per source row), per-row
 // compare / branch chains, 16-bit tap loads with one shift each, and a local-memory round trip of the pixel values.  When
-// outH = 3/2 H = 3 rH the source-row schedule is periodic (x: rows step 0,1,1 per three output rows, residual: 0,1,0 — checked
-// on the host with the same fp32 coordinate arithmetic, row_pattern_32 below), so the strip loop unrolls over twelve output rows
+// outH = 3/2 H = 3 rH (or 3 H = 6 rH) the source-row schedule is periodic (RowSched below; checked on the host with the same fp32
+// coordinate arithmetic, row_pattern), so the strip loop unrolls over one period of output rows (12 / 24)
 // with the four window rows in FIXED registers (a circular window: no moves, no compares).  Taps are fetched as aligned words:
 // the two columns of a pair need at most six consecutive source elements starting at an even index (three 32-bit loads for
 // bf16, three 16-bit loads for uint8) against 6-entry weight vectors padded with zeros — fma(e, 0, t) == t, so every sum is
-// bitwise the pair kernel's.  Vertical weights enter the packed FMAs as broadcast scalars; a thread works on one channel.  Planar output, clamp on, outH a
-// multiple of 12 (a CTA's rows are whole unrolled blocks).
-constexpr int R32_H = 36;       // output rows per CTA: a multiple of 12 (window period) — 1080 = 30 * 36
+// bitwise the pair kernel's.  Vertical weights enter the packed FMAs as broadcast scalars; a thread works on one channel.
+// Planar output, clamp on, outH a multiple of the period (a CTA's rows are whole unrolled periods).
 
 template <typename TS> __device__ __forceinline__ void ld6(uint32_t a, float (&e)[6]);
 template <> __device__ __forceinline__ void ld6<bf16>(uint32_t a, float (&e)[6]) {
@@ -536,21 +536,41 @@ __device__ __forceinline__ float tap_or_zero(const float (&w)[4], int k) { retur
 // the three channels do not repeat them.
 constexpr int R32_T = 3 * (BS_W / 2);
 
-template <typename TI, typename TO>
+// Row schedules of the tile kernel: over a period of P output rows (a multiple of the 4-row window rotation for both sources), does
+// x / the residual step to a new source row before output row q?  0: outH = 3/2 H = 3 rH (720p -> 1080p; x 3:2, residual 3:1);
+// 1: outH = 3 H = 6 rH (720p -> 4K; x 3:1, residual 6:1).  A CTA covers TILE = whole periods of rows.
+template <int PAT> struct RowSched;
+template <> struct RowSched<0> {
+    static constexpr int P = 12, TILE = 36;
+    static constexpr bool xstep(int q) { return q % 3 != 0; }
+    static constexpr bool rstep(int q) { return q % 3 == 1; }
+};
+template <> struct RowSched<1> {
+    static constexpr int P = 24, TILE = 48;
+    static constexpr bool xstep(int q) { return q % 3 == 1; }
+    static constexpr bool rstep(int q) { return q % 6 == 3; }
+};
+template <int PAT> constexpr int sched_relx(int q) { int n = 0; for (int i = 0; i <= q; ++i) n += RowSched<PAT>::xstep(i) ? 1 : 0; return n; }
+template <int PAT> constexpr int sched_relr(int q) { int n = 0; for (int i = 0; i <= q; ++i) n += RowSched<PAT>::rstep(i) ? 1 : 0; return n; }
+static_assert(sched_relx<0>(11) == 8 && sched_relr<0>(11) == 4 && sched_relx<1>(23) == 8 && sched_relr<1>(23) == 4,
+              "a period must rotate both 4-row windows a whole number of times");
+
+template <typename TI, typename TO, int PAT>
 __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                          const __grid_constant__ CUtensorMap tmap_r,
                                                                          const BicubicTileGeom g, int H, int W, int rH, int rW,
                                                                          TO *__restrict__ out, int oH, int oW) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
-    __shared__ __align__(16) float yw[2][R32_H][4];
+    constexpr int TILE = RowSched<PAT>::TILE, P = RowSched<PAT>::P;
+    __shared__ __align__(16) float yw[2][TILE][4];
     __shared__ float tapw[4][4][BS_W / 2];       // [x left, x right, residual left, residual right][tap][pair]
     __shared__ int tapi[4][BS_W / 2];            // source column of the second tap (floor of the source coordinate)
     __shared__ __align__(8) uint64_t bar;
     extern __shared__ uint8_t tile_dyn[];
     uint8_t *tile_raw = tile_dyn + ((128u - (ptx::smem_u32(tile_dyn) & 127u)) & 127u);     // TMA destinations are 128-byte aligned
     const int t = threadIdx.x;
-    const int ox0 = blockIdx.x * BS_W, oy0 = blockIdx.y * R32_H, b = blockIdx.z;
+    const int ox0 = blockIdx.x * BS_W, oy0 = blockIdx.y * TILE, b = blockIdx.z;
     const uint32_t x_bytes = 3u * g.xr * g.xc * sizeof(TI);
     const uint32_t x_bytes_al = (x_bytes + 127u) & ~127u;
     constexpr int XA = 16 / (int)sizeof(TI);       // the innermost box coordinate must start on a 16-byte boundary
@@ -565,8 +585,8 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
         ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
     }
     const float A = -0.75f;
-    if (t < 2 * R32_H) {                            // vertical filters of the block's rows, both sources
-        const int s = t / R32_H, r = t % R32_H;
+    if (t < 2 * TILE) {                             // vertical filters of the block's rows, both sources
+        const int s = t / TILE, r = t % TILE;
         const int in_size = s ? rH : H;
         const float scale = s ? g.srh : g.sxh;
         const float src = fmaf(scale, (float)min(oy0 + r, oH - 1) + 0.5f, -0.5f);
@@ -619,7 +639,7 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
     }
     const long oplane = (long)oH * oW;
     TO *o = out + ((long)b * 3 + ch) * oplane + (long)oy0 * oW + ox;
-    const int nrows = min(R32_H, oH - oy0);
+    const int nrows = min(TILE, oH - oy0);
 
     // window rows live in fixed registers: tile row n of a source sits in slot n & 3
     ptx::f32x2 wx[4], wr[4];
@@ -632,17 +652,16 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
     pr += 4u * rpitch;
     const float *ywx = &yw[0][0][0], *ywr = &yw[1][0][0];
 #pragma unroll 1
-    for (int r0 = 0; r0 < nrows; r0 += 12) {
+    for (int r0 = 0; r0 < nrows; r0 += P) {
 #pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const int k = q / 3, j = q % 3;
-            const int relx = 2 * k + j;             // first tile row of the x window (mod 8 per iteration: slots unchanged)
-            const int relr = k + (j >= 1 ? 1 : 0);  // first tile row of the residual window
-            if (j != 0) {                           // x steps one source row on two output rows of three
+        for (int q = 0; q < P; ++q) {
+            const int relx = sched_relx<PAT>(q);    // first tile row of the x window (a whole number of rotations per period: slots unchanged)
+            const int relr = sched_relr<PAT>(q);    // first tile row of the residual window
+            if (RowSched<PAT>::xstep(q)) {
                 wx[(relx + 3) & 3] = hsum6<TI>(px, wx6);
                 px += xpitch;
             }
-            if (j == 1) {                           // the residual steps on one of three
+            if (RowSched<PAT>::rstep(q)) {
                 wr[(relr + 3) & 3] = hsum5(pr, wr5);
                 pr += rpitch;
             }
@@ -660,7 +679,7 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
             float lo, hi;
             ptx::up2(v, lo, hi);
             lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
-            store_pair_unit(o, lo, hi);             // outH % 12 == 0 (host): whole blocks of 12 rows
+            store_pair_unit(o, lo, hi);             // outH % P == 0 (host): whole periods of rows
             o += oW;
         }
     }
@@ -833,13 +852,18 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32s_kernel(const 
     }
 }
 
-// The r32 kernel's row schedule, checked with the device's own fp32 coordinate arithmetic (ATen's): source row of output row oy
-// must be floor((4 oy - 1) / 6) for x (3:2) and floor((oy - 1) / 3) for the residual (3:1) on every row.  The 3:1 coordinate
-// (oy - 1) / 3 is an integer on every third row, where the rounding of scale = (float)rH / oH decides which side the floor falls.
-static bool row_pattern_32(int H, int rH, int oH) {
-    if ((long)H * 3 != (long)oH * 2 || (long)rH * 3 != (long)oH) return false;
-    static thread_local int key[3] = {0, 0, 0};
-    static thread_local bool val = false;
+// The tile kernel's row schedule, checked with the device's own fp32 coordinate arithmetic (ATen's): the source row of output row oy
+// must be the exact-arithmetic floor on every row — schedule 0: floor((4 oy - 1) / 6) for x (3:2) and floor((oy - 1) / 3) for the
+// residual (3:1); schedule 1: floor((oy - 1) / 3) for x (3:1) and floor((2 oy - 5) / 12) for the residual (6:1).  The 3:1 coordinate
+// (oy - 1) / 3 is an integer on every third row, where the rounding of scale = (float)in / out decides which side the floor falls.
+// Returns the schedule, or -1 (the pair kernel handles everything else).
+static int floor_div(int a, int b) { return (a >= 0 ? a : a - b + 1) / b; }
+static int row_pattern(int H, int rH, int oH) {
+    int pat = -1;
+    if ((long)H * 3 == (long)oH * 2 && (long)rH * 3 == (long)oH && oH % RowSched<0>::P == 0) pat = 0;
+    else if ((long)H * 3 == (long)oH && (long)rH * 6 == (long)oH && oH % RowSched<1>::P == 0) pat = 1;
+    if (pat < 0) return -1;
+    static thread_local int key[3] = {0, 0, 0}, val = -1;
     if (key[0] == H && key[1] == rH && key[2] == oH) return val;
     const float sx = (float)H / (float)oH, sr = (float)rH / (float)oH;
     bool ok = true;
@@ -848,11 +872,12 @@ static bool row_pattern_32(int H, int rH, int oH) {
         int ir = (int)floorf(fmaf(sr, (float)oy + 0.5f, -0.5f));
         if (ix > H - 1) ix = H - 1;
         if (ir > rH - 1) ir = rH - 1;
-        const int ex = (4 * oy - 1 + 6) / 6 - 1, er = (oy - 1 + 3) / 3 - 1;       // floors of (4 oy - 1) / 6 and (oy - 1) / 3
+        const int ex = pat == 0 ? floor_div(4 * oy - 1, 6) : floor_div(oy - 1, 3);
+        const int er = pat == 0 ? floor_div(oy - 1, 3) : floor_div(2 * oy - 5, 12);
         ok = ix == ex && ir == er;
     }
-    key[0] = H; key[1] = rH; key[2] = oH; val = ok;
-    return ok;
+    key[0] = H; key[1] = rH; key[2] = oH; val = ok ? pat : -1;
+    return val;
 }
 
 // triangle-filter taps for one output index: [lo, lo+n) and the normalisation 1/sum
@@ -980,9 +1005,14 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     };
     // two output columns per thread: TMA tiles, even output width, pair stores aligned
     const bool pair = g_bicubic_pair && (outW % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % (2 * ob)) == 0 && plan(PAIR_H);
-    // fixed 3:2 / 3:1 row schedule (x1.5 outputs such as 720p -> 1080p): the unrolled circular-window kernel
-    const bool r32 = pair && g_bicubic_pair >= 2 && res && clamp && layout == 0 && (in_dtype == TU_BF16 || in_dtype == TU_U8) &&
-                     W <= outW && rW <= outW && outH % 12 == 0 && row_pattern_32(H, rH, outH);
+    // periodic row schedules (x1.5 outputs such as 720p -> 1080p, x3 outputs such as 720p -> 4K): the unrolled circular-window kernel
+    const int pat = pair && g_bicubic_pair >= 2 && res && clamp && layout == 0 && (in_dtype == TU_BF16 || in_dtype == TU_U8) &&
+                            W <= outW && rW <= outW
+                        ? row_pattern(H, rH, outH)
+                        : -1;
+    bool r32 = pat == 0;                                   // schedule 0's tile is the pair kernel's (36 rows)
+    if (pat == 1 && !(r32 = plan(RowSched<1>::TILE))) plan(PAIR_H);       // schedule 1: 48-row tiles (or back to the pair kernel's plan)
+    static_assert(RowSched<0>::TILE == PAIR_H, "schedule 0 reuses the pair kernel's tile plan");
     const bool tma = pair || plan(BS_H);
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
 #define TU_BIC_PAIR(TI, TO)                                                                                                     \
@@ -1037,15 +1067,22 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     do {                                                                                                                        \
         static PerDeviceFlag attr_done;                                                                                          \
         if (!attr_done.is_set()) {                                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                  96 * 1024);                                                                    \
+            if (e == cudaSuccess)                                                                                               \
+                e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         96 * 1024);                                                                            \
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
             attr_done.set();                                                                                                    \
         }                                                                                                                       \
-        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO>, grid, dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW,     \
-                   (TO *)out, outH, outW);                                                                                      \
+        if (pat == 0)                                                                                                           \
+            launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, 0>, grid, dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
+                       (TO *)out, outH, outW);                                                                                  \
+        else                                                                                                                    \
+            launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, 1>, dim3(grid.x, ceil_div(outH, RowSched<1>::TILE), B), dim3(R32_T), \
+                       tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW);                                   \
     } while (0)
-    if (r32 && g_bicubic_pair >= 3) {
+    if (r32 && pat == 0 && g_bicubic_pair >= 3) {
         // streaming variant: strips x segments co-resident (5 CTAs per SM), <= 16 blocks of 12 rows per segment
         const int nblk = outH / 12, strips = (int)grid.x * B;
         const size_t stage = (((size_t)3 * 8 * g.xc * eb + 127) & ~(size_t)127) + (((size_t)3 * 4 * g.rc * 4 + 127) & ~(size_t)127);
