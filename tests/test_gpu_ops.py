@@ -413,10 +413,14 @@ def test_bicubic_add_clamp(dev, in_dt, out_dt, geom):
 @pytest.mark.parametrize("geom", [((720, 1280), (360, 640), (1080, 1920)), ((72, 104), (36, 52), (108, 156)), ((48, 64), (24, 40), (72, 250)),
                                   ((24, 304), (12, 152), (36, 456)),
                                   # x 3:1, residual 6:1 (ResidualTransformer 720p -> 4K, R:125,160): the second row schedule
-                                  ((720, 1280), (360, 640), (2160, 3840)), ((24, 48), (12, 24), (72, 144)), ((16, 64), (8, 40), (48, 200))])
+                                  ((720, 1280), (360, 640), (2160, 3840)), ((24, 48), (12, 24), (72, 144)), ((16, 64), (8, 40), (48, 200)),
+                                  # the other integer scales of inference.py (x n:1, residual 2n:1): 2, 4, 6
+                                  ((720, 1280), (360, 640), (1440, 2560)), ((24, 48), (12, 24), (48, 96)), ((48, 64), (24, 40), (96, 250)),
+                                  ((360, 640), (180, 320), (1440, 2560)), ((8, 48), (4, 24), (32, 192)), ((16, 32), (8, 24), (64, 150)),
+                                  ((96, 128), (48, 64), (576, 768)), ((8, 48), (4, 24), (48, 288))])
 def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
-    """The unrolled periodic-row-schedule kernels (outH = 3/2 H = 3 rH: 720p -> 1080p, tile and streaming forms; outH = 3 H = 6 rH:
-    720p -> 4K) against the pair kernel they replace (bitwise: same sums in
+    """The unrolled periodic-row-schedule kernels (outH = 3/2 H = 3 rH: 720p -> 1080p, tile and streaming forms; outH = n H = 2n rH for
+    n = 2, 3, 4, 6: inference.py's scales, 720p -> 4K at n = 3) against the pair kernel they replace (bitwise: same sums in
     the same order, zero-weight taps are exact no-ops) and against the oracle.  W:224-305 (241, 301, 304-305)."""
     from tests import gpu_helpers as G
     from transformerupscaler_b200 import _lib

@@ -469,12 +469,12 @@ template <> __device__ __forceinline__ void store_pair_unit<uint8_t>(uint8_t *o,
     *reinterpret_cast<unsigned short *>(o) = (unsigned short)__byte_perm(ua, ub, 0x0040);
 }
 
-// ---- periodic row schedules: x at 3:2 with the residual at 3:1 (720p -> 1080p, every x1.5 output), x at 3:1 with the residual at 6:1
-// (720p -> 4K) --------------------------------------------------------------------------------------------------------------------
+// ---- periodic row schedules: x at 3:2 with the residual at 3:1 (720p -> 1080p, every x1.5 output), x at n:1 with the residual at 2n:1
+// for n = 2, 3, 4, 6 (720p -> 4K is n = 3) ----------------------------------------------------------------------------------------
 // The pair kernel spends more than half of its issue slots on bookkeeping: window moves (28 MOVs per source row), per-row
 // compare / branch chains, 16-bit tap loads with one shift each, and a local-memory round trip of the pixel values.  When
-// outH = 3/2 H = 3 rH (or 3 H = 6 rH) the source-row schedule is periodic (RowSched below; checked on the host with the same fp32
-// coordinate arithmetic, row_pattern), so the strip loop unrolls over one period of output rows (12 / 24)
+// outH = 3/2 H = 3 rH (or n H = 2n rH) the source-row schedule is periodic (RowSched below; checked on the host with the same fp32
+// coordinate arithmetic, row_pattern), so the strip loop unrolls over one period of output rows (12, or 8n)
 // with the four window rows in FIXED registers (a circular window: no moves, no compares).  Taps are fetched as aligned words:
 // the two columns of a pair need at most six consecutive source elements starting at an even index (three 32-bit loads for
 // bf16, three 16-bit loads for uint8) against 6-entry weight vectors padded with zeros — fma(e, 0, t) == t, so every sum is
@@ -537,23 +537,27 @@ __device__ __forceinline__ float tap_or_zero(const float (&w)[4], int k) { retur
 constexpr int R32_T = 3 * (BS_W / 2);
 
 // Row schedules of the tile kernel: over a period of P output rows (a multiple of the 4-row window rotation for both sources), does
-// x / the residual step to a new source row before output row q?  0: outH = 3/2 H = 3 rH (720p -> 1080p; x 3:2, residual 3:1);
-// 1: outH = 3 H = 6 rH (720p -> 4K; x 3:1, residual 6:1).  A CTA covers TILE = whole periods of rows.
-template <int PAT> struct RowSched;
+// x / the residual step to a new source row before output row q?  PAT 0: outH = 3/2 H = 3 rH (720p -> 1080p; x 3:2, residual 3:1).
+// PAT n = 2, 3, 4, 6: outH = n H = 2n rH (inference.py's --scale values on a 2x-downsampled residual; 3 = 720p -> 4K): the source
+// coordinate (2 oy + 1 - n) / (2n) passes an integer before oy = n m + n / 2 (n even; n odd: AT oy = n m + (n - 1) / 2, where the
+// fp32 rounding decides — the host checks every row), and likewise at ratio 2n for the residual.  A CTA covers TILE = whole periods.
+template <int PAT> struct RowSched {
+    static constexpr int P = 8 * PAT, TILE = PAT == 2 ? 48 : P;
+    static constexpr bool xstep(int q) { return q % PAT == PAT / 2; }
+    static constexpr bool rstep(int q) { return q % (2 * PAT) == PAT; }
+};
 template <> struct RowSched<0> {
     static constexpr int P = 12, TILE = 36;
     static constexpr bool xstep(int q) { return q % 3 != 0; }
     static constexpr bool rstep(int q) { return q % 3 == 1; }
 };
-template <> struct RowSched<1> {
-    static constexpr int P = 24, TILE = 48;
-    static constexpr bool xstep(int q) { return q % 3 == 1; }
-    static constexpr bool rstep(int q) { return q % 6 == 3; }
-};
 template <int PAT> constexpr int sched_relx(int q) { int n = 0; for (int i = 0; i <= q; ++i) n += RowSched<PAT>::xstep(i) ? 1 : 0; return n; }
 template <int PAT> constexpr int sched_relr(int q) { int n = 0; for (int i = 0; i <= q; ++i) n += RowSched<PAT>::rstep(i) ? 1 : 0; return n; }
-static_assert(sched_relx<0>(11) == 8 && sched_relr<0>(11) == 4 && sched_relx<1>(23) == 8 && sched_relr<1>(23) == 4,
+static_assert(sched_relx<0>(11) == 8 && sched_relr<0>(11) == 4 && sched_relx<2>(15) == 8 && sched_relr<2>(15) == 4 &&
+                  sched_relx<3>(23) == 8 && sched_relr<3>(23) == 4 && sched_relx<4>(31) == 8 && sched_relr<4>(31) == 4 &&
+                  sched_relx<6>(47) == 8 && sched_relr<6>(47) == 4,
               "a period must rotate both 4-row windows a whole number of times");
+static inline int sched_tile(int pat) { return pat == 0 ? RowSched<0>::TILE : pat == 2 ? RowSched<2>::TILE : 8 * pat; }
 
 template <typename TI, typename TO, int PAT>
 __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
@@ -854,15 +858,15 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32s_kernel(const 
 
 // The tile kernel's row schedule, checked with the device's own fp32 coordinate arithmetic (ATen's): the source row of output row oy
 // must be the exact-arithmetic floor on every row — schedule 0: floor((4 oy - 1) / 6) for x (3:2) and floor((oy - 1) / 3) for the
-// residual (3:1); schedule 1: floor((oy - 1) / 3) for x (3:1) and floor((2 oy - 5) / 12) for the residual (6:1).  The 3:1 coordinate
-// (oy - 1) / 3 is an integer on every third row, where the rounding of scale = (float)in / out decides which side the floor falls.
+// residual (3:1); schedule n: floor((2 oy + 1 - n) / 2n) for x (n:1) and floor((2 oy + 1 - 2n) / 4n) for the residual (2n:1).  Where
+// the exact coordinate is an integer (every third row at 3:1) the rounding of scale = (float)in / out decides which side the floor falls.
 // Returns the schedule, or -1 (the pair kernel handles everything else).
 static int floor_div(int a, int b) { return (a >= 0 ? a : a - b + 1) / b; }
 static int row_pattern(int H, int rH, int oH) {
     int pat = -1;
-    if ((long)H * 3 == (long)oH * 2 && (long)rH * 3 == (long)oH && oH % RowSched<0>::P == 0) pat = 0;
-    else if ((long)H * 3 == (long)oH && (long)rH * 6 == (long)oH && oH % RowSched<1>::P == 0) pat = 1;
-    if (pat < 0) return -1;
+    if ((long)H * 3 == (long)oH * 2 && (long)rH * 3 == (long)oH) pat = 0;
+    else if (H > 0 && oH % H == 0 && (long)rH * 2 * (oH / H) == (long)oH) pat = oH / H;
+    if (!(pat == 0 || pat == 2 || pat == 3 || pat == 4 || pat == 6) || oH % (pat ? 8 * pat : 12) != 0) return -1;
     static thread_local int key[3] = {0, 0, 0}, val = -1;
     if (key[0] == H && key[1] == rH && key[2] == oH) return val;
     const float sx = (float)H / (float)oH, sr = (float)rH / (float)oH;
@@ -872,8 +876,8 @@ static int row_pattern(int H, int rH, int oH) {
         int ir = (int)floorf(fmaf(sr, (float)oy + 0.5f, -0.5f));
         if (ix > H - 1) ix = H - 1;
         if (ir > rH - 1) ir = rH - 1;
-        const int ex = pat == 0 ? floor_div(4 * oy - 1, 6) : floor_div(oy - 1, 3);
-        const int er = pat == 0 ? floor_div(oy - 1, 3) : floor_div(2 * oy - 5, 12);
+        const int ex = pat == 0 ? floor_div(4 * oy - 1, 6) : floor_div(2 * oy + 1 - pat, 2 * pat);
+        const int er = pat == 0 ? floor_div(oy - 1, 3) : floor_div(2 * oy + 1 - 2 * pat, 4 * pat);
         ok = ix == ex && ir == er;
     }
     key[0] = H; key[1] = rH; key[2] = oH; val = ok ? pat : -1;
@@ -1011,7 +1015,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
                         ? row_pattern(H, rH, outH)
                         : -1;
     bool r32 = pat == 0;                                   // schedule 0's tile is the pair kernel's (36 rows)
-    if (pat == 1 && !(r32 = plan(RowSched<1>::TILE))) plan(PAIR_H);       // schedule 1: 48-row tiles (or back to the pair kernel's plan)
+    if (pat > 0 && !(r32 = plan(sched_tile(pat)))) plan(PAIR_H);          // integer schedules: 32- / 48-row tiles (or back to the pair kernel's plan)
     static_assert(RowSched<0>::TILE == PAIR_H, "schedule 0 reuses the pair kernel's tile plan");
     const bool tma = pair || plan(BS_H);
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
@@ -1063,24 +1067,25 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
         if (pair) TU_BIC_PAIR(TI, TO); \
         else TU_BIC(TI, TO);     \
     } while (0)
-#define TU_BIC_R32(TI, TO)                                                                                                      \
+#define TU_BIC_R32_P(TI, TO, PAT)                                                                                               \
     do {                                                                                                                        \
         static PerDeviceFlag attr_done;                                                                                          \
         if (!attr_done.is_set()) {                                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 96 * 1024);                                                                    \
-            if (e == cudaSuccess)                                                                                               \
-                e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                         96 * 1024);                                                                            \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, PAT>,                                     \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                       \
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
             attr_done.set();                                                                                                    \
         }                                                                                                                       \
-        if (pat == 0)                                                                                                           \
-            launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, 0>, grid, dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, \
-                       (TO *)out, outH, outW);                                                                                  \
-        else                                                                                                                    \
-            launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, 1>, dim3(grid.x, ceil_div(outH, RowSched<1>::TILE), B), dim3(R32_T), \
-                       tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW);                                   \
+        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, PAT>, dim3(grid.x, ceil_div(outH, RowSched<PAT>::TILE), B), dim3(R32_T), \
+                   tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW);                                       \
+    } while (0)
+#define TU_BIC_R32(TI, TO)                                                                                                      \
+    do {                                                                                                                        \
+        if (pat == 0) TU_BIC_R32_P(TI, TO, 0);                                                                                  \
+        else if (pat == 2) TU_BIC_R32_P(TI, TO, 2);                                                                             \
+        else if (pat == 3) TU_BIC_R32_P(TI, TO, 3);                                                                             \
+        else if (pat == 4) TU_BIC_R32_P(TI, TO, 4);                                                                             \
+        else TU_BIC_R32_P(TI, TO, 6);                                                                                           \
     } while (0)
     if (r32 && pat == 0 && g_bicubic_pair >= 3) {
         // streaming variant: strips x segments co-resident (5 CTAs per SM), <= 16 blocks of 12 rows per segment
@@ -1139,6 +1144,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     else TU_BIC2(bf16, uint8_t);
 #undef TU_BIC2
 #undef TU_BIC_R32
+#undef TU_BIC_R32_P
 #undef TU_BIC_PAIR
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
