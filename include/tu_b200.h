@@ -264,6 +264,11 @@ int tu_window_attention(const void *qkv, const float *rel_bias, void *out, int n
  * the mma.sync kernel (the default: measured faster at head_dim 16). */
 size_t tu_global_attention_workspace_bytes(int B, int S, int heads);
 int tu_global_attention(const void *qkv, void *out, int B, int S, int heads, void *workspace, size_t workspace_bytes, void *stream);
+/* Host-side query, no GPU needed: the periodic row schedule tu_bicubic_add_clamp's unrolled kernel would use for these heights
+ * (WindowTransformer/model.py:241,301: x H rows and the decoder's residual rH rows, both resampled to outH): 0 for outH = 3/2 H = 3 rH
+ * (720p -> 1080p), n = 2, 3, 4, 6 for outH = n H = 2n rH (3: 720p -> 4K), -1 when the heights have no such schedule OR when ATen's
+ * fp32 source-row arithmetic deviates from it on some output row (the general kernel runs then). */
+int tu_bicubic_row_schedule(int H, int rH, int outH);
 /* out = clamp?(bicubic(x -> outH,outW) + bicubic(res -> outH,outW)); res may be NULL */
 int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, const float *res, int rH, int rW,
                          void *out, int out_dtype, int B, int outH, int outW, int clamp, void *stream);

@@ -61,6 +61,37 @@ def test_host_side_queries_work_without_gpu(lib):
     assert "must match" in _lib.last_error()
 
 
+def test_bicubic_row_schedule_matches_aten_coordinates(lib):
+    """Host logic of the unrolled bicubic kernel: the schedule the library picks must reproduce, on EVERY output row, the source row of
+    ATen's fp32 coordinate arithmetic (UpSample.h: scale = (float)in / out, src = scale * (dst + 0.5) - 0.5 as one fma, floor) —
+    restated here in numpy float32 with the fma emulated in float64 (exact for these magnitudes)."""
+    import numpy as np
+
+    def aten_rows(n_in, n_out):
+        scale = np.float32(n_in) / np.float32(n_out)
+        dst = np.arange(n_out, dtype=np.float64) + 0.5
+        src = (np.float64(scale) * dst - 0.5).astype(np.float32)         # one rounding, like fmaf
+        return np.minimum(np.floor(src).astype(np.int64), n_in - 1)
+
+    def sched_rows(pat, n_out):
+        oy = np.arange(n_out, dtype=np.int64)
+        if pat == 0:
+            return np.floor_divide(4 * oy - 1, 6), np.floor_divide(oy - 1, 3)
+        return np.floor_divide(2 * oy + 1 - pat, 2 * pat), np.floor_divide(2 * oy + 1 - 2 * pat, 4 * pat)
+
+    cases = {(720, 360, 1080): 0, (720, 360, 1440): 2, (720, 360, 2160): 3, (720, 360, 2880): 4, (720, 360, 4320): 6,
+             (1080, 540, 1620): 0, (72, 36, 108): 0, (24, 12, 72): 3}
+    for (H, rH, oH), want in cases.items():
+        got = lib.tu_bicubic_row_schedule(H, rH, oH)
+        ex, er = sched_rows(want, oH)
+        exact = np.array_equal(aten_rows(H, oH), ex) and np.array_equal(aten_rows(rH, oH), er)
+        assert got == (want if exact else -1), (H, rH, oH, got, exact)
+        assert exact, (H, rH, oH)            # the BASELINE shapes do follow their schedule
+    # heights without a schedule, and a period that does not divide outH
+    for H, rH, oH in [(720, 360, 1000), (720, 240, 1080), (720, 360, 3600), (20, 10, 30), (0, 0, 0)]:
+        assert lib.tu_bicubic_row_schedule(H, rH, oH) == -1
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     from transformerupscaler_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)

@@ -109,6 +109,7 @@ SIGNATURES = {
     "tu_resize_bilinear_aa": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, vp]),
     "tu_resize_bilinear_aa_to": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "tu_frames_to_planar": (i32, [vp, i32, vp, i32, i32, i32, vp]),
+    "tu_bicubic_row_schedule": (i32, [i32, i32, i32]),
 }
 
 _lib = None

@@ -1151,6 +1151,8 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     return TU_OK;
 }
 
+extern "C" int tu_bicubic_row_schedule(int H, int rH, int outH) { return H > 0 && rH > 0 && outH > 0 ? row_pattern(H, rH, outH) : -1; }
+
 extern "C" int tu_resize_bilinear_aa_to(const void *in, int in_dtype, void *out, int out_dtype, int B, int H, int W, int outH, int outW,
                                         int clamp, void *stream) {
     TU_CHECK_ARG(in && out && B > 0 && H > 0 && W > 0 && outH > 0 && outW > 0, "resize_bilinear_aa: bad argument");
