@@ -451,6 +451,8 @@ def main():
                 gbs = bpf * local_frames / (breakdown[name] * 1e-3) / 1e9
                 mem[name] = {"ms": breakdown[name], "algorithmic_bytes": int(bpf * local_frames), "achieved_gbs": gbs, "peak_gbs": hbm_peak,
                              "frac": gbs / hbm_peak}
+        if "bicubic_add_clamp" in mem and ncu.get("bicubic_add_clamp_r32_kernel"):
+            mem["bicubic_add_clamp"]["ncu"] = ncu["bicubic_add_clamp_r32_kernel"]      # the kernel of x1.5 outputs (this workload)
         roof["memory_bound_kernels"] = mem
         cfg = {"workload": WORKLOAD if world == 1 else WORKLOAD_SHARDED, "frames_per_step": total_frames,
                "frames_per_gpu": local_frames, "parallelism": f"frame-sharded x{world}, no collective on the data path",
