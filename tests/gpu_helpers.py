@@ -160,12 +160,14 @@ def transformer_block(x, bw, dim, heads, window, S, dtype, full_workspace=False)
     return x
 
 
-def bicubic_add_clamp(x, res, outH, outW, out_dtype, clamp):
+def bicubic_add_clamp(x, res, outH, outW, out_dtype, clamp, layout=0):
+    """layout: 0 planar (B,3,H,W); _lib.TU_LAYOUT_HWC / TU_LAYOUT_HWC_BGR: interleaved uint8 frames (B,H,W,3)"""
     lib = _lib.load()
     B, _, H, W = x.shape
-    out = torch.empty(B, 3, outH, outW, dtype=out_dtype, device=x.device)
+    shape = (B, 3, outH, outW) if layout == 0 else (B, outH, outW, 3)
+    out = torch.empty(shape, dtype=out_dtype, device=x.device)
     rH, rW = (res.shape[2], res.shape[3]) if res is not None else (0, 0)
-    chk(lib.tu_bicubic_add_clamp(p(x), DT[x.dtype], H, W, p(res), rH, rW, p(out), DT[out_dtype], B, outH, outW,
+    chk(lib.tu_bicubic_add_clamp(p(x), DT[x.dtype], H, W, p(res), rH, rW, p(out), DT[out_dtype] | layout, B, outH, outW,
                                  int(clamp), stream()))
     return out
 

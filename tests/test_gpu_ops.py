@@ -451,6 +451,35 @@ def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
         assert _maxerr(got, ref) < tol
 
 
+@pytest.mark.parametrize("in_dt", [BF16, torch.uint8])
+@pytest.mark.parametrize("bgr", [False, True])
+@pytest.mark.parametrize("geom", [((720, 1280), (360, 640), (1080, 1920)), ((24, 304), (12, 152), (36, 456)), ((24, 48), (12, 24), (72, 144)),
+                                  ((48, 64), (24, 40), (96, 250))])
+def test_bicubic_row_schedule_kernel_interleaved_frames(dev, in_dt, bgr, geom):
+    """uint8 HWC RGB / BGR frames out of the unrolled row-schedule kernel (app_overlay.py:382-386 fused into the last kernel): bitwise the
+    pair kernel's frames, and the planar result with the channels moved / reversed."""
+    from tests import gpu_helpers as G
+    from transformerupscaler_b200 import _lib
+    lib = _lib.load()
+    (H, W), (rH, rW), (oH, oW) = geom
+    x = synth_frames(2, H, W, seed=5)
+    x = (x * 255).round().clamp(0, 255).to(torch.uint8) if in_dt == torch.uint8 else x.to(in_dt)
+    rs = np.random.RandomState(12)
+    res = torch.from_numpy(rs.uniform(-0.3, 0.3, (2, 3, rH, rW)).astype(np.float32))
+    layout = _lib.TU_LAYOUT_HWC_BGR if bgr else _lib.TU_LAYOUT_HWC
+    outs = {}
+    try:
+        for variant in (2, 1):
+            lib.tu_debug_set(b"bicubic_pair", variant)
+            outs[variant] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, torch.uint8, True, layout).cpu()
+    finally:
+        lib.tu_debug_set(b"bicubic_pair", 2)
+    assert torch.equal(outs[2], outs[1])
+    planar = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, torch.uint8, True).cpu()
+    want = planar.permute(0, 2, 3, 1)
+    assert torch.equal(outs[2], want.flip(-1) if bgr else want)
+
+
 @pytest.mark.parametrize("geom", [((80, 112), (60, 84)), ((144, 192), (100, 150)), ((50, 70), (50, 35))])
 def test_resize_aa(dev, geom):
     from tests import gpu_helpers as G

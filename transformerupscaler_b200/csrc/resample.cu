@@ -469,6 +469,13 @@ template <> __device__ __forceinline__ void store_pair_unit<uint8_t>(uint8_t *o,
     *reinterpret_cast<unsigned short *>(o) = (unsigned short)__byte_perm(ua, ub, 0x0040);
 }
 
+// one value already clamped to [0, 1] -> the output element (uint8: the same product and round-down add as from_f<uint8_t>, whose clamp
+// is a no-op here; the low byte of the sum is the result)
+template <typename T> __device__ __forceinline__ T unit_to_u8(float v) { return from_f<T>(v); }
+template <> __device__ __forceinline__ uint8_t unit_to_u8<uint8_t>(float v) {
+    return (uint8_t)__float_as_uint(__fadd_rd(__fmul_rn(v, 255.f), 8388608.f));
+}
+
 // ---- periodic row schedules: x at 3:2 with the residual at 3:1 (720p -> 1080p, every x1.5 output), x at n:1 with the residual at 2n:1
 // for n = 2, 3, 4, 6 (720p -> 4K is n = 3) ----------------------------------------------------------------------------------------
 // The pair kernel spends more than half of its issue slots on bookkeeping: window moves (28 MOVs per source row), per-row
@@ -559,11 +566,12 @@ static_assert(sched_relx<0>(11) == 8 && sched_relr<0>(11) == 4 && sched_relx<2>(
               "a period must rotate both 4-row windows a whole number of times");
 static inline int sched_tile(int pat) { return pat == 0 ? RowSched<0>::TILE : pat == 2 ? RowSched<2>::TILE : 8 * pat; }
 
-template <typename TI, typename TO, int PAT>
+// HWC (uint8 frames only): interleaved output pixels, `layout` 1 = RGB, 2 = BGR; a thread stores its channel's two bytes
+template <typename TI, typename TO, int PAT, bool HWC>
 __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                          const __grid_constant__ CUtensorMap tmap_r,
                                                                          const BicubicTileGeom g, int H, int W, int rH, int rW,
-                                                                         TO *__restrict__ out, int oH, int oW) {
+                                                                         TO *__restrict__ out, int oH, int oW, int layout) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
     constexpr int TILE = RowSched<PAT>::TILE, P = RowSched<PAT>::P;
@@ -642,7 +650,9 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
         pr = ptx::smem_u32(tile_raw) + x_bytes_al + (uint32_t)(jA - 1 - rc0) * 4u + (uint32_t)ch * g.rr * rpitch;
     }
     const long oplane = (long)oH * oW;
-    TO *o = out + ((long)b * 3 + ch) * oplane + (long)oy0 * oW + ox;
+    // planar: the channel's plane; interleaved: the channel's byte inside the pixel (reversed for BGR), three bytes per pixel
+    TO *o = HWC ? out + (((long)b * oH + oy0) * oW + ox) * 3 + (layout == 2 ? 2 - ch : ch) : out + ((long)b * 3 + ch) * oplane + (long)oy0 * oW + ox;
+    const int orow = HWC ? 3 * oW : oW;
     const int nrows = min(TILE, oH - oy0);
 
     // window rows live in fixed registers: tile row n of a source sits in slot n & 3
@@ -683,8 +693,9 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
             float lo, hi;
             ptx::up2(v, lo, hi);
             lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
-            store_pair_unit(o, lo, hi);             // outH % P == 0 (host): whole periods of rows
-            o += oW;
+            if (HWC) { o[0] = unit_to_u8<TO>(lo); o[3] = unit_to_u8<TO>(hi); }
+            else store_pair_unit(o, lo, hi);        // outH % P == 0 (host): whole periods of rows
+            o += orow;
         }
     }
 }
@@ -1010,7 +1021,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
     // two output columns per thread: TMA tiles, even output width, pair stores aligned
     const bool pair = g_bicubic_pair && (outW % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % (2 * ob)) == 0 && plan(PAIR_H);
     // periodic row schedules (x1.5 outputs such as 720p -> 1080p, x3 outputs such as 720p -> 4K): the unrolled circular-window kernel
-    const int pat = pair && g_bicubic_pair >= 2 && res && clamp && layout == 0 && (in_dtype == TU_BF16 || in_dtype == TU_U8) &&
+    const int pat = pair && g_bicubic_pair >= 2 && res && clamp && (in_dtype == TU_BF16 || in_dtype == TU_U8) &&
                             W <= outW && rW <= outW
                         ? row_pattern(H, rH, outH)
                         : -1;
@@ -1067,27 +1078,28 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
         if (pair) TU_BIC_PAIR(TI, TO); \
         else TU_BIC(TI, TO);     \
     } while (0)
-#define TU_BIC_R32_P(TI, TO, PAT)                                                                                               \
+#define TU_BIC_R32_P(TI, TO, PAT, HWC)                                                                                          \
     do {                                                                                                                        \
         static PerDeviceFlag attr_done;                                                                                          \
         if (!attr_done.is_set()) {                                                                                               \
-            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, PAT>,                                     \
+            cudaError_t e = cudaFuncSetAttribute(bicubic_add_clamp_r32_kernel<TI, TO, PAT, HWC>,                                \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                       \
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
             attr_done.set();                                                                                                    \
         }                                                                                                                       \
-        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, PAT>, dim3(grid.x, ceil_div(outH, RowSched<PAT>::TILE), B), dim3(R32_T), \
-                   tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW);                                       \
+        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, PAT, HWC>, dim3(grid.x, ceil_div(outH, RowSched<PAT>::TILE), B),        \
+                   dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW, layout);                  \
     } while (0)
-#define TU_BIC_R32(TI, TO)                                                                                                      \
+#define TU_BIC_R32_L(TI, TO, HWC)                                                                                               \
     do {                                                                                                                        \
-        if (pat == 0) TU_BIC_R32_P(TI, TO, 0);                                                                                  \
-        else if (pat == 2) TU_BIC_R32_P(TI, TO, 2);                                                                             \
-        else if (pat == 3) TU_BIC_R32_P(TI, TO, 3);                                                                             \
-        else if (pat == 4) TU_BIC_R32_P(TI, TO, 4);                                                                             \
-        else TU_BIC_R32_P(TI, TO, 6);                                                                                           \
+        if (pat == 0) TU_BIC_R32_P(TI, TO, 0, HWC);                                                                             \
+        else if (pat == 2) TU_BIC_R32_P(TI, TO, 2, HWC);                                                                        \
+        else if (pat == 3) TU_BIC_R32_P(TI, TO, 3, HWC);                                                                        \
+        else if (pat == 4) TU_BIC_R32_P(TI, TO, 4, HWC);                                                                        \
+        else TU_BIC_R32_P(TI, TO, 6, HWC);                                                                                      \
     } while (0)
-    if (r32 && pat == 0 && g_bicubic_pair >= 3) {
+#define TU_BIC_R32(TI, TO) TU_BIC_R32_L(TI, TO, false)
+    if (r32 && pat == 0 && layout == 0 && g_bicubic_pair >= 3) {
         // streaming variant: strips x segments co-resident (5 CTAs per SM), <= 16 blocks of 12 rows per segment
         const int nblk = outH / 12, strips = (int)grid.x * B;
         const size_t stage = (((size_t)3 * 8 * g.xc * eb + 127) & ~(size_t)127) + (((size_t)3 * 4 * g.rc * 4 + 127) & ~(size_t)127);
@@ -1125,7 +1137,10 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
             return TU_OK;
         }
     }
-    if (r32) {
+    if (r32 && layout != 0) {           // interleaved uint8 frames (layouts are accepted for uint8 output only)
+        if (in_dtype == TU_BF16) TU_BIC_R32_L(bf16, uint8_t, true);
+        else TU_BIC_R32_L(uint8_t, uint8_t, true);
+    } else if (r32) {
         if (in_dtype == TU_BF16 && out_dtype == TU_BF16) TU_BIC_R32(bf16, bf16);
         else if (in_dtype == TU_BF16 && out_dtype == TU_F32) TU_BIC_R32(bf16, float);
         else if (in_dtype == TU_BF16) TU_BIC_R32(bf16, uint8_t);
@@ -1145,6 +1160,7 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
 #undef TU_BIC2
 #undef TU_BIC_R32
 #undef TU_BIC_R32_P
+#undef TU_BIC_R32_L
 #undef TU_BIC_PAIR
 #undef TU_BIC
     TU_CHECK_LAUNCH("bicubic_add_clamp");
