@@ -469,6 +469,19 @@ template <> __device__ __forceinline__ void store_pair_unit<uint8_t>(uint8_t *o,
     *reinterpret_cast<unsigned short *>(o) = (unsigned short)__byte_perm(ua, ub, 0x0040);
 }
 
+// clamp a pair to [0, 1] and store it.  bf16: the conversion clamps below (cvt.rn.relu) and one packed min clamps above — rounding is
+// monotonic and 1.0 is a bf16, so min(bf16(relu(v)), 1) == bf16(clamp(v, 0, 1)) bit for bit — which takes the two saturating adds off
+// the FMA pipe, the busy one in these kernels; other types: saturate, then store
+template <typename T> __device__ __forceinline__ void clamp_store_pair(T *o, float lo, float hi) {
+    store_pair_unit(o, fminf(fmaxf(lo, 0.f), 1.f), fminf(fmaxf(hi, 0.f), 1.f));
+}
+template <> __device__ __forceinline__ void clamp_store_pair<bf16>(bf16 *o, float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    asm("min.bf16x2 %0, %0, %1;" : "+r"(d) : "r"(0x3f803f80u));
+    *reinterpret_cast<uint32_t *>(o) = d;
+}
+
 // one value already clamped to [0, 1] -> the output element (uint8: the same product and round-down add as from_f<uint8_t>, whose clamp
 // is a no-op here; the low byte of the sum is the result)
 template <typename T> __device__ __forceinline__ T unit_to_u8(float v) { return from_f<T>(v); }
@@ -692,9 +705,8 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
             v = ptx::add2(v, u);
             float lo, hi;
             ptx::up2(v, lo, hi);
-            lo = fminf(fmaxf(lo, 0.f), 1.f); hi = fminf(fmaxf(hi, 0.f), 1.f);
-            if (HWC) { o[0] = unit_to_u8<TO>(lo); o[3] = unit_to_u8<TO>(hi); }
-            else store_pair_unit(o, lo, hi);        // outH % P == 0 (host): whole periods of rows
+            if (HWC) { o[0] = unit_to_u8<TO>(fminf(fmaxf(lo, 0.f), 1.f)); o[3] = unit_to_u8<TO>(fminf(fmaxf(hi, 0.f), 1.f)); }
+            else clamp_store_pair(o, lo, hi);       // outH % P == 0 (host): whole periods of rows
             o += orow;
         }
     }
