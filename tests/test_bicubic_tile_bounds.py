@@ -17,10 +17,12 @@ def src_floor(dst, n_in, n_out):
     return np.minimum(np.floor(src).astype(np.int64), n_in - 1)
 
 
-def sched(pat):
+def sched(pat, big):
+    """period, rows per CTA (RowSched<PAT>::TILE / ::BIG), x step?, residual step?"""
     if pat == 0:
-        return 12, 36, (lambda q: q % 3 != 0), (lambda q: q % 3 == 1)
-    return 8 * pat, (48 if pat == 2 else 8 * pat), (lambda q: q % pat == pat // 2), (lambda q: q % (2 * pat) == pat)
+        return 12, (60 if big else 36), (lambda q: q % 3 != 0), (lambda q: q % 3 == 1)
+    tile = {2: 80, 3: 72, 4: 96, 6: 96}[pat] if big else (48 if pat == 2 else 8 * pat)
+    return 8 * pat, tile, (lambda q: q % pat == pat // 2), (lambda q: q % (2 * pat) == pat)
 
 
 CASES = [  # (H, W), (rH, rW), (oH, oW), schedule, element bytes of x
@@ -33,11 +35,12 @@ CASES = [  # (H, W), (rH, rW), (oH, oW), schedule, element bytes of x
 ]
 
 
+@pytest.mark.parametrize("big", [False, True])
 @pytest.mark.parametrize("case", CASES)
-def test_every_shared_memory_read_is_inside_the_tile(case):
+def test_every_shared_memory_read_is_inside_the_tile(case, big):
     (H, W), (rH, rW), (oH, oW), pat, eb = case
-    P, TILE, xstep, rstep = sched(pat)
-    assert oH % P == 0 and oW % 2 == 0
+    P, TILE, xstep, rstep = sched(pat, big)
+    assert oH % P == 0 and oW % 2 == 0 and TILE % P == 0 and 2 * TILE <= 192
     # ---- the host's plan (tu_bicubic_add_clamp: plan(bh) with bh = TILE)
     xr = (TILE - 1) * H // oH + 6
     xc = ((BS_W - 1) * W // oW + 8 + (16 // eb - 1) + 15) & ~15

@@ -439,9 +439,14 @@ def test_bicubic_fixed_row_pattern_kernel(dev, in_dt, out_dt, geom):
         for variant in (3, 2, 1):     # streaming form, tile form, pair kernel
             lib.tu_debug_set(b"bicubic_pair", variant)
             outs[variant] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, True).cpu()
+        lib.tu_debug_set(b"bicubic_pair", 2)
+        for tile in (1, 2):           # rows per CTA: the smaller / the larger tile (the default picks by grid size)
+            lib.tu_debug_set(b"bicubic_tile", tile)
+            outs[10 + tile] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, out_dt, True).cpu()
     finally:
         lib.tu_debug_set(b"bicubic_pair", 2)
-    for variant in (3, 2):
+        lib.tu_debug_set(b"bicubic_tile", 0)
+    for variant in (3, 2, 11, 12):
         assert torch.equal(outs[variant], outs[1]), variant
     if H <= 128:
         xf = x.float() / 255 if in_dt == torch.uint8 else x.float()
@@ -472,9 +477,13 @@ def test_bicubic_row_schedule_kernel_interleaved_frames(dev, in_dt, bgr, geom):
         for variant in (2, 1):
             lib.tu_debug_set(b"bicubic_pair", variant)
             outs[variant] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, torch.uint8, True, layout).cpu()
+        lib.tu_debug_set(b"bicubic_pair", 2)
+        lib.tu_debug_set(b"bicubic_tile", 2)
+        outs[12] = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, torch.uint8, True, layout).cpu()
     finally:
         lib.tu_debug_set(b"bicubic_pair", 2)
-    assert torch.equal(outs[2], outs[1])
+        lib.tu_debug_set(b"bicubic_tile", 0)
+    assert torch.equal(outs[2], outs[1]) and torch.equal(outs[12], outs[1])
     planar = G.bicubic_add_clamp(x.to(dev), res.to(dev), oH, oW, torch.uint8, True).cpu()
     want = planar.permute(0, 2, 3, 1)
     assert torch.equal(outs[2], want.flip(-1) if bgr else want)

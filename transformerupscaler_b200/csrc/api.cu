@@ -426,6 +426,10 @@ extern "C" int tu_debug_set(const char *key, int value) {
         g_bicubic_pair = value;
         return TU_OK;
     }
+    if (key && !strcmp(key, "bicubic_tile")) {
+        g_bicubic_tile = value;
+        return TU_OK;
+    }
     if (key && !strcmp(key, "fuse_dec12")) {
         tc_set_dec12_fused(value);
         return TU_OK;

@@ -560,14 +560,17 @@ constexpr int R32_T = 3 * (BS_W / 2);
 // x / the residual step to a new source row before output row q?  PAT 0: outH = 3/2 H = 3 rH (720p -> 1080p; x 3:2, residual 3:1).
 // PAT n = 2, 3, 4, 6: outH = n H = 2n rH (inference.py's --scale values on a 2x-downsampled residual; 3 = 720p -> 4K): the source
 // coordinate (2 oy + 1 - n) / (2n) passes an integer before oy = n m + n / 2 (n even; n odd: AT oy = n m + (n - 1) / 2, where the
-// fp32 rounding decides — the host checks every row), and likewise at ratio 2n for the residual.  A CTA covers TILE = whole periods.
+// fp32 rounding decides — the host checks every row), and likewise at ratio 2n for the residual.  A CTA covers whole periods of rows:
+// TILE, or BIG when the launch still fills the GPU twice over with the larger tiles (the per-tile set-up — column filters, vertical
+// table, four window rows per source — is 30 % of the instructions at TILE rows; measured at 3:2 / 3:1, profiles/r3_ab_bicubic_tile_rows.log:
+// 36 / 48 / 60 / 72 rows = 0.574 / 0.550 / 0.550 / 0.575 of the pair kernel's time, 72 rows leave three CTAs per SM).
 template <int PAT> struct RowSched {
-    static constexpr int P = 8 * PAT, TILE = PAT == 2 ? 48 : P;
+    static constexpr int P = 8 * PAT, TILE = PAT == 2 ? 48 : P, BIG = PAT == 2 ? 80 : PAT == 3 ? 72 : 96;
     static constexpr bool xstep(int q) { return q % PAT == PAT / 2; }
     static constexpr bool rstep(int q) { return q % (2 * PAT) == PAT; }
 };
 template <> struct RowSched<0> {
-    static constexpr int P = 12, TILE = 36;
+    static constexpr int P = 12, TILE = 36, BIG = 60;
     static constexpr bool xstep(int q) { return q % 3 != 0; }
     static constexpr bool rstep(int q) { return q % 3 == 1; }
 };
@@ -577,18 +580,27 @@ static_assert(sched_relx<0>(11) == 8 && sched_relr<0>(11) == 4 && sched_relx<2>(
                   sched_relx<3>(23) == 8 && sched_relr<3>(23) == 4 && sched_relx<4>(31) == 8 && sched_relr<4>(31) == 4 &&
                   sched_relx<6>(47) == 8 && sched_relr<6>(47) == 4,
               "a period must rotate both 4-row windows a whole number of times");
-static inline int sched_tile(int pat) { return pat == 0 ? RowSched<0>::TILE : pat == 2 ? RowSched<2>::TILE : 8 * pat; }
+constexpr int R32_MAXTILE = 96;
+static inline int sched_tile(int pat, bool big) {
+    switch (pat) {
+        case 0: return big ? RowSched<0>::BIG : RowSched<0>::TILE;
+        case 2: return big ? RowSched<2>::BIG : RowSched<2>::TILE;
+        case 3: return big ? RowSched<3>::BIG : RowSched<3>::TILE;
+        case 4: return big ? RowSched<4>::BIG : RowSched<4>::TILE;
+        default: return big ? RowSched<6>::BIG : RowSched<6>::TILE;
+    }
+}
 
 // HWC (uint8 frames only): interleaved output pixels, `layout` 1 = RGB, 2 = BGR; a thread stores its channel's two bytes
 template <typename TI, typename TO, int PAT, bool HWC>
 __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                          const __grid_constant__ CUtensorMap tmap_r,
                                                                          const BicubicTileGeom g, int H, int W, int rH, int rW,
-                                                                         TO *__restrict__ out, int oH, int oW, int layout) {
+                                                                         TO *__restrict__ out, int oH, int oW, int layout, int TILE) {
     pdl_trigger();
     pdl_wait();          // the residual image is written by the previous kernel of the stream
-    constexpr int TILE = RowSched<PAT>::TILE, P = RowSched<PAT>::P;
-    __shared__ __align__(16) float yw[2][TILE][4];
+    constexpr int P = RowSched<PAT>::P;             // TILE (rows per CTA, a multiple of P, <= R32_MAXTILE) is chosen per launch
+    __shared__ __align__(16) float yw[2][R32_MAXTILE][4];
     __shared__ float tapw[4][4][BS_W / 2];       // [x left, x right, residual left, residual right][tap][pair]
     __shared__ int tapi[4][BS_W / 2];            // source column of the second tap (floor of the source coordinate)
     __shared__ __align__(8) uint64_t bar;
@@ -610,7 +622,7 @@ __global__ void __launch_bounds__(R32_T, 5) bicubic_add_clamp_r32_kernel(const _
         ptx::tma_load_4d(ptx::smem_u32(tile_raw) + x_bytes_al, &tmap_r, bar_a, rc0, rr0, 0, b);
     }
     const float A = -0.75f;
-    if (t < 2 * TILE) {                             // vertical filters of the block's rows, both sources
+    if (t < 2 * TILE) {                             // vertical filters of the block's rows, both sources (2 * TILE <= 192 threads)
         const int s = t / TILE, r = t % TILE;
         const int in_size = s ? rH : H;
         const float scale = s ? g.srh : g.sxh;
@@ -987,6 +999,7 @@ __global__ void __launch_bounds__(256) frames_to_planar_kernel(const uint8_t *__
 
 using namespace tu;
 
+thread_local int tu::g_bicubic_tile = 0;      // debug key "bicubic_tile": rows per CTA of the row-schedule kernel: 0 = by grid size (default), 1 = the smaller tile, 2 = the larger
 thread_local int tu::g_bicubic_pair = 2;      // debug key "bicubic_pair": 2 = two output columns per thread + the unrolled fixed-row-pattern kernel where it applies (default), 3 = the same with the streaming form of that kernel (measured slower), 1 = the pair kernel only, 0 = the one-column strip kernel
 
 // (W, H, 3, B) view of an NCHW image for the tile loads; box = (cols, rows, 3, 1)
@@ -1037,9 +1050,17 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
                             W <= outW && rW <= outW
                         ? row_pattern(H, rH, outH)
                         : -1;
-    bool r32 = pat == 0;                                   // schedule 0's tile is the pair kernel's (36 rows)
-    if (pat > 0 && !(r32 = plan(sched_tile(pat)))) plan(PAIR_H);          // integer schedules: 32- / 48-row tiles (or back to the pair kernel's plan)
-    static_assert(RowSched<0>::TILE == PAIR_H, "schedule 0 reuses the pair kernel's tile plan");
+    // rows per CTA: the larger tile when the launch still fills the GPU twice over with it (5 CTAs per SM), else the smaller one
+    int tile_rows = 0;
+    bool r32 = false;
+    if (pat >= 0) {
+        const long ctas_big = (long)ceil_div(outW, BS_W) * ceil_div(outH, sched_tile(pat, true)) * B;
+        tile_rows = sched_tile(pat, g_bicubic_tile ? g_bicubic_tile == 2 : ctas_big >= 2L * 5 * device_sm_count());
+        if (!(r32 = plan(tile_rows))) plan(PAIR_H);            // or back to the pair kernel's plan
+    }
+    static_assert(RowSched<0>::BIG <= R32_MAXTILE && RowSched<2>::BIG <= R32_MAXTILE && RowSched<3>::BIG <= R32_MAXTILE &&
+                      RowSched<4>::BIG <= R32_MAXTILE && RowSched<6>::BIG <= R32_MAXTILE && 2 * R32_MAXTILE <= R32_T,
+                  "the vertical table is filled in one pass of the CTA's threads");
     const bool tma = pair || plan(BS_H);
     dim3 grid(ceil_div(outW, BS_W), ceil_div(outH, pair ? PAIR_H : BS_H), B);
 #define TU_BIC_PAIR(TI, TO)                                                                                                     \
@@ -1099,8 +1120,8 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
             if (e != cudaSuccess) return cuda_fail(e, "bicubic smem attribute");                                                \
             attr_done.set();                                                                                                    \
         }                                                                                                                       \
-        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, PAT, HWC>, dim3(grid.x, ceil_div(outH, RowSched<PAT>::TILE), B),        \
-                   dim3(R32_T), tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW, layout);                  \
+        launch_pdl(bicubic_add_clamp_r32_kernel<TI, TO, PAT, HWC>, dim3(grid.x, ceil_div(outH, tile_rows), B), dim3(R32_T),     \
+                   tile_bytes + 128, st, tx, tr, g, H, W, rH, rW, (TO *)out, outH, outW, layout, tile_rows);                    \
     } while (0)
 #define TU_BIC_R32_L(TI, TO, HWC)                                                                                               \
     do {                                                                                                                        \

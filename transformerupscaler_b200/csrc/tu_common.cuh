@@ -132,6 +132,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 extern thread_local int g_use_pdl;      // api.cu (debug key "pdl")
 extern thread_local int g_ga_shape;      // transformer_simt.cu (debug key "ga_shape")
 extern thread_local int g_bicubic_pair; // resample.cu (debug key "bicubic_pair")
+extern thread_local int g_bicubic_tile; // resample.cu (debug key "bicubic_tile")
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
