@@ -70,7 +70,7 @@ int tu_profile_report(char *buf, size_t cap);
 void tu_profile_reset(void);
 /* bring-up / A-B switches (not part of the stable interface): "tc_base_off_mode" {0,1}, "fused_stack" {0,1} (fused window
  * stack vs per-layer kernels), "conv_2cta" {0,1} (CTA-pair convolution, default off), "conv_stream" {0,1} (streaming ky-stacked N=192 convolution, default on),
- * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0..3} (bicubic kernel: 0 one output column per thread, 1 two columns per thread, 2 [default] the same plus the unrolled circular-window kernel, one 36-row tile per CTA and one (channel, column pair) per thread, where the row schedule is periodic: outH = 3/2 H = 3 rH as in 720p -> 1080p, or outH = n H = 2n rH with n = 2, 3, 4, 6 (720p -> 4K is n = 3), 3 the streaming form (x1.5 outputs only) of that kernel: a CTA walks down a column strip through a ring of TMA stages; measured slower), "bicubic_tile" {0,1,2} (rows per CTA of that kernel: 0 [default] the larger tile when the launch still fills the GPU twice over, 1 the smaller tile, 2 the larger), "resid_fused" {0,1} (ResidualTransformer: LN1 + in_proj and out_proj + LN2 + MLP as two fused kernels per layer, default on; 0 = six kernels), "global_attn_tc" {0,1} (ResidualTransformer: tcgen05 flash attention instead of the mma.sync kernel; default off: measured 6 % / 26 % slower at 2 / 16 frames), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral), "ga_shape" (ResidualTransformer mma.sync attention: -1 automatic by CTA count [default], 0 / 1 / 2 / 3 CTA shapes 4x32 / 2x32 / 4x16 / 8x16 queries, 4 / 5 balanced launches with 64- / 128-query tiles and merged partials; these need the workspace), "stack_var" bit mask (experiments of the dim-128 window stack: 1 = first relative-position bias fetch after the first qkv third instead of before LayerNorm 1) */
+ * "unembed_overlap" {0,1} (unembed starts tile by tile behind the fused window stack, default on), "head_stream" {0,1} (64->3 heads on the streaming kernel; default off: measured slower than the tile kernel), "fuse_conv12" {0,1} (conv1 fused into conv2, default on), "fold_up1" {0,1} (FastTransformer: folded up1 stage + up1_conv, default on; 0 = the unfolded op graph), "fuse_dec12" {0,1} (decoder_conv1 + decoder_conv2 in one kernel, default on), "unembed_areuse" {0,1} (unembed behind the stack: the token tile is loaded once per M tile, default off), "stack_split" {0,1} (window stack: tiles handed between CTAs at block boundaries; default off: bitwise neutral, measured slower together with the unembed overlap), "embed_pair" bit mask (patch embed: 1 one tile per CTA and two CTAs per SM [default, dim 128], 2 filter stages multicast in clusters of two, +4 also at dim 192, +8 L2 prefetch of patch rows), "bicubic_pair" {0..3} (bicubic kernel: 0 one output column per thread, 1 two columns per thread, 2 [default] the same plus the unrolled circular-window kernel, one 36-row tile per CTA and one (channel, column pair) per thread, where the row schedule is periodic: outH = 3/2 H = 3 rH as in 720p -> 1080p, or outH = n H = 2n rH with n = 2, 3, 4, 6 (720p -> 4K is n = 3), 3 the streaming form (x1.5 outputs only) of that kernel: a CTA walks down a column strip through a ring of TMA stages; measured slower), "bicubic_tile" {0,1,2} (rows per CTA of that kernel: 0 [default] the larger tile when it still gives every SM a CTA, 1 the smaller tile, 2 the larger), "resid_fused" {0,1} (ResidualTransformer: LN1 + in_proj and out_proj + LN2 + MLP as two fused kernels per layer, default on; 0 = six kernels), "global_attn_tc" {0,1} (ResidualTransformer: tcgen05 flash attention instead of the mma.sync kernel; default off: measured 6 % / 26 % slower at 2 / 16 frames), "snake" bit mask (reversed work-item order per kernel: 1 downsample, 2 the 64->3 head, 4 window stack + unembed; default 0, measured neutral), "ga_shape" (ResidualTransformer mma.sync attention: -1 automatic by CTA count [default], 0 / 1 / 2 / 3 CTA shapes 4x32 / 2x32 / 4x16 / 8x16 queries, 4 / 5 balanced launches with 64- / 128-query tiles and merged partials; these need the workspace), "stack_var" bit mask (experiments of the dim-128 window stack: 1 = first relative-position bias fetch after the first qkv third instead of before LayerNorm 1) */
 int tu_debug_set(const char *key, int value);
 /* debug only: while device_buffer != NULL the window stack and the unembed GEMM append (globaltimer ns, kind << 48 | smid << 32 | value)
  * pairs behind a 64-bit event counter in word 0 (caller zeroes it); capacity in events; buffer of (1 + 2 * capacity) * 8 bytes */

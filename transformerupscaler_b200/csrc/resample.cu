@@ -561,7 +561,7 @@ constexpr int R32_T = 3 * (BS_W / 2);
 // PAT n = 2, 3, 4, 6: outH = n H = 2n rH (inference.py's --scale values on a 2x-downsampled residual; 3 = 720p -> 4K): the source
 // coordinate (2 oy + 1 - n) / (2n) passes an integer before oy = n m + n / 2 (n even; n odd: AT oy = n m + (n - 1) / 2, where the
 // fp32 rounding decides — the host checks every row), and likewise at ratio 2n for the residual.  A CTA covers whole periods of rows:
-// TILE, or BIG when the launch still fills the GPU twice over with the larger tiles (the per-tile set-up — column filters, vertical
+// TILE, or BIG when the larger tiles still give every SM a CTA (the per-tile set-up — column filters, vertical
 // table, four window rows per source — is 30 % of the instructions at TILE rows; measured at 3:2 / 3:1, profiles/r3_ab_bicubic_tile_rows.log:
 // 36 / 48 / 60 / 72 rows = 0.574 / 0.550 / 0.550 / 0.575 of the pair kernel's time, 72 rows leave three CTAs per SM).
 template <int PAT> struct RowSched {
@@ -1050,12 +1050,13 @@ extern "C" int tu_bicubic_add_clamp(const void *x, int in_dtype, int H, int W, c
                             W <= outW && rW <= outW
                         ? row_pattern(H, rH, outH)
                         : -1;
-    // rows per CTA: the larger tile when the launch still fills the GPU twice over with it (5 CTAs per SM), else the smaller one
+    // rows per CTA: the larger tile as soon as it still gives every SM a CTA (measured at 720p -> 1080p, profiles/r3_ab_bicubic_tile_rows.log:
+    // 1 / 2 / 4 / 8 frames = 16.3 -> 14.8, 23.1 -> 21.8, 34.1 -> 34.7, 63.3 -> 59.2 us), else the smaller one
     int tile_rows = 0;
     bool r32 = false;
     if (pat >= 0) {
         const long ctas_big = (long)ceil_div(outW, BS_W) * ceil_div(outH, sched_tile(pat, true)) * B;
-        tile_rows = sched_tile(pat, g_bicubic_tile ? g_bicubic_tile == 2 : ctas_big >= 2L * 5 * device_sm_count());
+        tile_rows = sched_tile(pat, g_bicubic_tile ? g_bicubic_tile == 2 : ctas_big >= (long)device_sm_count());
         if (!(r32 = plan(tile_rows))) plan(PAIR_H);            // or back to the pair kernel's plan
     }
     static_assert(RowSched<0>::BIG <= R32_MAXTILE && RowSched<2>::BIG <= R32_MAXTILE && RowSched<3>::BIG <= R32_MAXTILE &&
